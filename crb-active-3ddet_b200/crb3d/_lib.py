@@ -1,0 +1,89 @@
+"""ctypes loader for libcrb3d_sm100.so (the C ABI declared in include/crb3d.h).
+
+There is no CPU fallback: if the library is missing or a call returns an error code, a RuntimeError is raised.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcrb3d_sm100.so")
+
+P = c_void_p  # every device/host buffer crosses as a raw address
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+SIGNATURES = {
+    "crb3d_version": [],
+    "crb3d_strerror": [c_int],
+    "crb3d_voxelize_workspace_bytes": [c_int64, c_int, c_int, POINTER(c_size_t)],
+    "crb3d_voxelize": [P, c_int64, c_int, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, P, P, P, P, P, P,
+                       c_size_t, P],
+    "crb3d_subm_rulebook_workspace_bytes": [c_int, POINTER(c_size_t)],
+    "crb3d_subm_rulebook": [P, c_int, P, P, P, P, P, c_size_t, P],
+    "crb3d_conv_out_shape": [P, P, P, P, P, P],
+    "crb3d_sparse_rulebook_workspace_bytes": [c_int, P, POINTER(c_size_t)],
+    "crb3d_sparse_rulebook_coords": [P, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P, c_size_t, P],
+    "crb3d_sparse_rulebook_pairs": [P, c_int, c_int, P, P, P, P, P, P, c_int, P, P, P, c_size_t, P],
+    "crb3d_rulebook_compact_pairs_workspace_bytes": [c_int, c_int, POINTER(c_size_t)],
+    "crb3d_rulebook_compact_pairs": [P, c_int, c_int, c_int, P, P, P, P, c_size_t, P],
+    "crb3d_spconv_forward_f32": [P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, P, P, P, c_int, P, P],
+    "crb3d_spconv_wgrad_workspace_bytes": [c_int, c_int, c_int, c_int, POINTER(c_size_t)],
+    "crb3d_spconv_wgrad_f32": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_size_t, P],
+    "crb3d_sparse_to_dense": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P],
+    "crb3d_dense_to_sparse": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P],
+    "crb3d_boxes_overlap_bev": [P, c_int, P, c_int, P, P],
+    "crb3d_boxes_iou_bev": [P, c_int, P, c_int, P, P],
+    "crb3d_nms_workspace_bytes": [c_int, POINTER(c_size_t)],
+    "crb3d_nms": [P, c_int, c_float, c_int, c_int, P, P, P, c_size_t, P],
+    "crb3d_nms_mask": [P, c_int, c_float, c_int, P, P],
+    "crb3d_boxes_iou_bev_cpu": [P, c_int, P, c_int, P],
+    "crb3d_points_in_boxes": [P, P, c_int, c_int, c_int, P, P],
+    "crb3d_points_in_boxes_stack": [P, c_int, P, c_int, P, P, c_int, c_int, c_int, P, P, P, P],
+    "crb3d_points_in_boxes_cpu": [P, c_int, P, c_int, P],
+    "crb3d_roiaware_pool3d_forward": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, P],
+    "crb3d_roiaware_pool3d_backward": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "crb3d_ball_query_stack": [c_int, c_int, c_float, c_int, P, P, P, P, P, c_int, P],
+    "crb3d_group_points_stack": [c_int, c_int, c_int, c_int, P, P, P, P, P, P],
+    "crb3d_group_points_grad_stack": [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P],
+    "crb3d_farthest_point_sampling": [c_int, c_int, c_int, P, P, P, P],
+    "crb3d_stack_farthest_point_sampling": [c_int, c_int, P, P, P, P, P, P],
+    "crb3d_three_nn_stack": [c_int, c_int, c_int, P, P, P, P, P, P, P],
+    "crb3d_three_interpolate_stack": [c_int, c_int, P, P, P, P, P],
+    "crb3d_three_interpolate_grad_stack": [c_int, c_int, P, P, P, P, P],
+    "crb3d_label_entropy": [P, P, c_int, c_int, P, P, P],
+    "crb3d_pairwise_sqdist_f64": [P, c_int, c_int, P, P],
+    "crb3d_kde_greedy_workspace_bytes": [c_int, c_int, POINTER(c_size_t)],
+    "crb3d_kde_greedy": [P, P, P, c_int, c_int, P, P, c_double, c_int, P, P, P, c_size_t, P],
+}
+_RESTYPES = {"crb3d_version": c_char_p, "crb3d_strerror": c_char_p}
+
+_lib = None
+
+
+def load():
+    """Returns the loaded CDLL; raises RuntimeError (never falls back) when the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libcrb3d_sm100.so not found at %s - build it with `python crb-active-3ddet_b200/build.py` "
+            "(there is no CPU fallback for this path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means header / library drift: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().crb3d_strerror(code).decode()
+        raise RuntimeError("%s failed: %s (code %d)" % (what, msg, code))
+
+
+def call(name, *args):
+    """Calls a C-ABI entry point and raises on a non-zero status."""
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,422 @@
+"""Torch-tensor front end of the C ABI (include/crb3d.h). PyTorch is used for device memory and streams only;
+every function here launches hand-written sm_100a kernels from libcrb3d_sm100.so on the current CUDA stream.
+There is no CPU path: CPU tensors are rejected (except for the two explicit *_cpu host ops).
+"""
+import ctypes
+from ctypes import c_size_t, byref
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_I3 = ctypes.c_int * 3
+_F3 = ctypes.c_float * 3
+_F6 = ctypes.c_float * 6
+
+
+def _i3(v):
+    v = [int(x) for x in (v if isinstance(v, (list, tuple, np.ndarray, torch.Size)) else [v, v, v])]
+    assert len(v) == 3
+    return _I3(*v)
+
+
+def _p(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("crb3d ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _f32c(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+def _i32c(t):
+    return t if (t.dtype == torch.int32 and t.is_contiguous()) else t.int().contiguous()
+
+
+_WS = {}
+
+
+def _ws(nbytes, device):
+    """Grow-only scratch buffer per (device, stream) from torch's caching allocator."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def _ws_bytes(fn, *args):
+    n = c_size_t(0)
+    _lib.call(fn, *args, byref(n))
+    return int(n.value)
+
+
+# ----------------------------------------------------------------------------------------------- voxelize
+def voxelize(points, frame_offsets, batch_size, pc_range, voxel_size, max_pts, max_voxels, xyz_col=0, feat_col=0,
+             n_feat=None, want_voxels=False, want_mean=True):
+    """Hard voxelization + MeanVFE. points (N, S) f32 CUDA; frame_offsets (B+1) int32 CUDA.
+    Returns dict(mean (M,C), voxels (M,P,C) | None, coords (M,4) i32 [b,z,y,x], num_points (M), frame_voxel_offsets (B+1)).
+    One host sync (reads M)."""
+    _need_cuda(points, frame_offsets)
+    points = _f32c(points)
+    frame_offsets = _i32c(frame_offsets)
+    n, stride = points.shape
+    n_feat = stride - feat_col if n_feat is None else n_feat
+    pc_range = [float(x) for x in pc_range]
+    voxel_size = [float(x) for x in voxel_size]
+    grid = [int(round((pc_range[3 + j] - pc_range[j]) / voxel_size[j])) for j in range(3)]
+    cap = max(1, min(n, batch_size * max_voxels))
+    dev = points.device
+    mean = torch.empty((cap, n_feat), dtype=torch.float32, device=dev) if want_mean else None
+    voxels = torch.empty((cap, max_pts, n_feat), dtype=torch.float32, device=dev) if want_voxels else None
+    coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    num = torch.empty((cap,), dtype=torch.int32, device=dev)
+    voff = torch.empty((batch_size + 1,), dtype=torch.int32, device=dev)
+    wsb = _ws_bytes("crb3d_voxelize_workspace_bytes", n, batch_size, max_pts)
+    ws = _ws(wsb, dev)
+    _lib.call("crb3d_voxelize", _p(points), n, stride, xyz_col, feat_col, n_feat, _p(frame_offsets), batch_size,
+              _F6(*pc_range), _F3(*voxel_size), _I3(*grid), max_pts, max_voxels, _p(mean), _p(voxels), _p(coords),
+              _p(num), _p(voff), _p(ws), ws.numel(), _stream(dev))
+    m = int(voff[-1].item())
+    return dict(mean=mean[:m] if mean is not None else None, voxels=voxels[:m] if voxels is not None else None,
+                coords=coords[:m], num_points=num[:m], frame_voxel_offsets=voff, grid_size=grid)
+
+
+# ----------------------------------------------------------------------------------------------- rulebook
+def conv_out_shape(in_shape, ksize, stride, padding, dilation=(1, 1, 1)):
+    out = _I3(0, 0, 0)
+    _lib.call("crb3d_conv_out_shape", _i3(in_shape), _i3(ksize), _i3(stride), _i3(padding), _i3(dilation), out)
+    return [out[0], out[1], out[2]]
+
+
+def subm_rulebook(coords, spatial_shape, ksize, dilation=(1, 1, 1)):
+    """Neighbour table (K, n) int32 for a submanifold conv (output rows == input rows)."""
+    _need_cuda(coords)
+    coords = _i32c(coords)
+    n = coords.shape[0]
+    k = _i3(ksize)
+    K = k[0] * k[1] * k[2]
+    nbr = torch.empty((K, n), dtype=torch.int32, device=coords.device)
+    ws = _ws(_ws_bytes("crb3d_subm_rulebook_workspace_bytes", n), coords.device)
+    _lib.call("crb3d_subm_rulebook", _p(coords), n, _i3(spatial_shape), k, _i3(dilation), _p(nbr), _p(ws), ws.numel(),
+              _stream(coords.device))
+    return nbr
+
+
+def sparse_rulebook(coords, batch_size, in_shape, ksize, stride, padding, dilation=(1, 1, 1), want_transpose=True):
+    """Strided sparse conv rulebook. Returns (out_coords (n_out,4) ascending key order, out_shape, nbr (K,n_out),
+    nbr_t (K,n_in) | None). One host sync (reads n_out)."""
+    _need_cuda(coords)
+    coords = _i32c(coords)
+    dev = coords.device
+    n_in = coords.shape[0]
+    out_shape = conv_out_shape(in_shape, ksize, stride, padding, dilation)
+    k = _i3(ksize)
+    K = k[0] * k[1] * k[2]
+    wsb = _ws_bytes("crb3d_sparse_rulebook_workspace_bytes", batch_size, _i3(out_shape))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)  # private: must survive between the two phases
+    cells = batch_size * out_shape[0] * out_shape[1] * out_shape[2]
+    cap = max(1, min(cells, n_in * K))
+    # most strided layers produce about as many outputs as inputs; retry with the true count if the guess is small
+    guess = max(1, min(cap, 2 * n_in + 1024))
+    n_out_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    out_coords = torch.empty((guess, 4), dtype=torch.int32, device=dev)
+    args = (_p(coords), n_in, batch_size, _i3(in_shape), _i3(out_shape), k, _i3(stride), _i3(padding), _i3(dilation))
+    _lib.call("crb3d_sparse_rulebook_coords", *args, _p(out_coords), guess, _p(n_out_dev), _p(ws), wsb, _stream(dev))
+    n_out = int(n_out_dev.item())
+    if n_out > guess:
+        out_coords = torch.empty((n_out, 4), dtype=torch.int32, device=dev)
+        _lib.call("crb3d_sparse_rulebook_coords", *args, _p(out_coords), n_out, _p(n_out_dev), _p(ws), wsb, _stream(dev))
+    out_coords = out_coords[:n_out]
+    nbr = torch.empty((K, n_out), dtype=torch.int32, device=dev)
+    nbr_t = torch.empty((K, n_in), dtype=torch.int32, device=dev) if want_transpose else None
+    _lib.call("crb3d_sparse_rulebook_pairs", *args, n_out, _p(nbr), _p(nbr_t), _p(ws), wsb, _stream(dev))
+    return out_coords, out_shape, nbr, nbr_t
+
+
+def compact_pairs(nbr):
+    """spconv-format (indice_pairs [2,K,n_out] padded with -1, indice_pair_num [K]) from a neighbour table."""
+    _need_cuda(nbr)
+    K, n_out = nbr.shape
+    dev = nbr.device
+    pairs = torch.full((2, K, max(n_out, 1)), -1, dtype=torch.int32, device=dev)
+    num = torch.zeros((K,), dtype=torch.int32, device=dev)
+    ws = _ws(_ws_bytes("crb3d_rulebook_compact_pairs_workspace_bytes", K, n_out), dev)
+    _lib.call("crb3d_rulebook_compact_pairs", _p(nbr), K, n_out, max(n_out, 1), _p(pairs[0]), _p(pairs[1]), _p(num),
+              _p(ws), ws.numel(), _stream(dev))
+    return pairs[:, :, :n_out] if n_out > 0 else pairs[:, :, :0], num
+
+
+# ----------------------------------------------------------------------------------------------- sparse conv
+def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transpose=False, kmap=None):
+    """out[o] = sum_k feat[nbr[k][o]] @ W_k. weight: [C_out, (kz,ky,kx)|K, C_in] (spconv layout).
+    transpose=True computes the input gradient: feat is dY (rows of the conv OUTPUT), nbr the transposed table."""
+    _need_cuda(feat, nbr, weight)
+    feat = _f32c(feat)
+    nbr = _i32c(nbr)
+    weight = _f32c(weight)
+    K, n_out = nbr.shape
+    cout_w, cin_w = weight.shape[0], weight.shape[-1]
+    assert weight.numel() == cout_w * K * cin_w, "weight does not match the rulebook's kernel volume"
+    if not transpose:
+        cin, cout = cin_w, cout_w
+        strides = (K * cin_w, cin_w, 1)
+    else:
+        cin, cout = cout_w, cin_w
+        strides = (1, cin_w, K * cin_w)
+    assert feat.shape[1] == cin, (feat.shape, cin)
+    out = torch.empty((n_out, cout), dtype=torch.float32, device=feat.device)
+    _lib.call("crb3d_spconv_forward_f32", _p(feat), _p(nbr), _p(weight), n_out, K, cin, cout, strides[0], strides[1],
+              strides[2], _p(kmap), _p(_f32c(scale)) if scale is not None else None,
+              _p(_f32c(shift)) if shift is not None else None, int(bool(relu)), _p(out), _stream(feat.device))
+    return out
+
+
+def spconv_wgrad(feat, dout, nbr, weight_shape, accumulate_into=None):
+    """dW in the spconv layout for out = conv(feat, nbr, W): dW[co,k,ci] = sum_o dY[o,co] * feat[nbr[k][o],ci]."""
+    _need_cuda(feat, dout, nbr)
+    feat = _f32c(feat)
+    dout = _f32c(dout)
+    nbr = _i32c(nbr)
+    K, n_out = nbr.shape
+    cin, cout = feat.shape[1], dout.shape[1]
+    dw = accumulate_into if accumulate_into is not None else torch.empty(weight_shape, dtype=torch.float32, device=feat.device)
+    assert dw.is_contiguous() and dw.numel() == cout * K * cin
+    ws = _ws(_ws_bytes("crb3d_spconv_wgrad_workspace_bytes", n_out, K, cin, cout), feat.device)
+    _lib.call("crb3d_spconv_wgrad_f32", _p(feat), _p(dout), _p(nbr), n_out, K, cin, cout,
+              int(accumulate_into is not None), _p(dw), _p(ws), ws.numel(), _stream(feat.device))
+    return dw
+
+
+# ----------------------------------------------------------------------------------------------- dense
+def sparse_to_dense(feat, coords, batch_size, spatial_shape, channels_last_bev=False):
+    """(B,C,D,H,W) dense tensor (reference .dense()); channels_last_bev=True returns (B,H,W,C*D) memory whose
+    .permute(0,3,1,2) equals dense.view(B, C*D, H, W)."""
+    _need_cuda(feat, coords)
+    feat = _f32c(feat)
+    coords = _i32c(coords)
+    n, C = feat.shape
+    D, H, W = [int(x) for x in spatial_shape]
+    shape = (batch_size, H, W, C * D) if channels_last_bev else (batch_size, C, D, H, W)
+    dense = torch.empty(shape, dtype=torch.float32, device=feat.device)
+    _lib.call("crb3d_sparse_to_dense", _p(feat), _p(coords), n, C, batch_size, D, H, W, int(channels_last_bev), 1,
+              _p(dense), _stream(feat.device))
+    return dense
+
+
+def dense_to_sparse(dense, coords, C, spatial_shape, channels_last_bev=False):
+    _need_cuda(dense, coords)
+    dense = _f32c(dense)
+    coords = _i32c(coords)
+    n = coords.shape[0]
+    D, H, W = [int(x) for x in spatial_shape]
+    B = dense.shape[0]
+    feat = torch.empty((n, C), dtype=torch.float32, device=dense.device)
+    _lib.call("crb3d_dense_to_sparse", _p(dense), _p(coords), n, C, B, D, H, W, int(channels_last_bev), _p(feat),
+              _stream(dense.device))
+    return feat
+
+
+# ----------------------------------------------------------------------------------------------- iou3d / nms
+def boxes_overlap_bev(boxes_a, boxes_b, out=None):
+    _need_cuda(boxes_a, boxes_b)
+    a, b = _f32c(boxes_a[:, :7]), _f32c(boxes_b[:, :7])
+    if out is None:
+        out = torch.zeros((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    _lib.call("crb3d_boxes_overlap_bev", _p(a), a.shape[0], _p(b), b.shape[0], _p(out), _stream(a.device))
+    return out
+
+
+def boxes_iou_bev(boxes_a, boxes_b, out=None):
+    _need_cuda(boxes_a, boxes_b)
+    a, b = _f32c(boxes_a[:, :7]), _f32c(boxes_b[:, :7])
+    if out is None:
+        out = torch.zeros((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    _lib.call("crb3d_boxes_iou_bev", _p(a), a.shape[0], _p(b), b.shape[0], _p(out), _stream(a.device))
+    return out
+
+
+def nms_sorted(boxes_sorted, thresh, rotated=True, max_keep=0):
+    """Greedy NMS over boxes already sorted by descending score. Returns (keep int64 device (n,), num_keep device int)
+    without any host synchronisation."""
+    _need_cuda(boxes_sorted)
+    b = _f32c(boxes_sorted[:, :7])
+    n = b.shape[0]
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=b.device)
+    num = torch.zeros((1,), dtype=torch.int32, device=b.device)
+    ws = _ws(_ws_bytes("crb3d_nms_workspace_bytes", n), b.device)
+    _lib.call("crb3d_nms", _p(b), n, float(thresh), int(bool(rotated)), int(max_keep), _p(keep), _p(num), _p(ws),
+              ws.numel(), _stream(b.device))
+    return keep, num
+
+
+def nms_mask(boxes_sorted, thresh, rotated=True):
+    _need_cuda(boxes_sorted)
+    b = _f32c(boxes_sorted[:, :7])
+    n = b.shape[0]
+    cb = (n + 63) // 64
+    mask = torch.zeros((n, cb), dtype=torch.int64, device=b.device)
+    _lib.call("crb3d_nms_mask", _p(b), n, float(thresh), int(bool(rotated)), _p(mask), _stream(b.device))
+    return mask
+
+
+def boxes_iou_bev_cpu(boxes_a, boxes_b, out):
+    a = boxes_a.float().contiguous()
+    b = boxes_b.float().contiguous()
+    assert not a.is_cuda and not b.is_cuda and not out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+    _lib.call("crb3d_boxes_iou_bev_cpu", _p(a), a.shape[0], _p(b), b.shape[0], _p(out))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- roiaware
+def points_in_boxes(boxes, pts, out=None):
+    """boxes (B,T,7), pts (B,M,3) -> (B,M) int32 index of the first containing box or -1."""
+    _need_cuda(boxes, pts)
+    boxes, pts = _f32c(boxes), _f32c(pts)
+    B, T, _ = boxes.shape
+    M = pts.shape[1]
+    if out is None:
+        out = torch.full((B, M), -1, dtype=torch.int32, device=pts.device)
+    _lib.call("crb3d_points_in_boxes", _p(boxes), _p(pts), B, T, M, _p(out), _stream(pts.device))
+    return out
+
+
+def points_in_boxes_stack(pts, pt_off, boxes, box_off, max_pts_per_frame, want_density=True):
+    """Stacked frames. pts (N,S>=3) xyz first; boxes (T,7). Returns (idx (N,), counts (T,), density (T,) | None)."""
+    _need_cuda(pts, pt_off, boxes, box_off)
+    pts, boxes = _f32c(pts), _f32c(boxes)
+    pt_off, box_off = _i32c(pt_off), _i32c(box_off)
+    N, S = pts.shape
+    T = boxes.shape[0]
+    B = pt_off.numel() - 1
+    idx = torch.empty((N,), dtype=torch.int32, device=pts.device)
+    counts = torch.empty((max(T, 1),), dtype=torch.int32, device=pts.device)
+    dens = torch.empty((max(T, 1),), dtype=torch.float32, device=pts.device) if want_density else None
+    _lib.call("crb3d_points_in_boxes_stack", _p(pts), S, _p(pt_off), int(max_pts_per_frame), _p(boxes), _p(box_off), B,
+              N, T, _p(idx), _p(counts), _p(dens), _stream(pts.device))
+    return idx, counts[:T], (dens[:T] if dens is not None else None)
+
+
+def points_in_boxes_cpu(boxes, pts, out):
+    b = boxes.float().contiguous()
+    p = pts.float().contiguous()
+    assert not b.is_cuda and not p.is_cuda and out.dtype == torch.int32 and out.is_contiguous()
+    _lib.call("crb3d_points_in_boxes_cpu", _p(b), b.shape[0], _p(p), p.shape[0], _p(out))
+    return out
+
+
+def roiaware_pool3d_forward(rois, pts, pts_feature, argmax, pts_idx_of_voxels, pooled, pool_method):
+    _need_cuda(rois, pts, pts_feature, argmax, pts_idx_of_voxels, pooled)
+    rois, pts, pts_feature = _f32c(rois), _f32c(pts), _f32c(pts_feature)
+    n_boxes, ox, oy, oz, C = pooled.shape
+    _lib.call("crb3d_roiaware_pool3d_forward", _p(rois), _p(pts), _p(pts_feature), n_boxes, pts.shape[0], C,
+              pts_idx_of_voxels.shape[4], ox, oy, oz, _p(argmax), _p(pts_idx_of_voxels), _p(pooled), int(pool_method),
+              _stream(pts.device))
+
+
+def roiaware_pool3d_backward(pts_idx_of_voxels, argmax, grad_out, grad_in, pool_method):
+    _need_cuda(pts_idx_of_voxels, argmax, grad_out, grad_in)
+    n_boxes, ox, oy, oz, C = grad_out.shape
+    _lib.call("crb3d_roiaware_pool3d_backward", _p(pts_idx_of_voxels), _p(argmax), _p(_f32c(grad_out)), _p(grad_in),
+              n_boxes, ox, oy, oz, C, pts_idx_of_voxels.shape[4], int(pool_method), _stream(grad_in.device))
+
+
+# ----------------------------------------------------------------------------------------------- pointnet2 (stack)
+def ball_query(B, M, radius, nsample, new_xyz, new_xyz_batch_cnt, xyz, xyz_batch_cnt, idx, max_queries_per_frame=0):
+    _need_cuda(new_xyz, new_xyz_batch_cnt, xyz, xyz_batch_cnt, idx)
+    _lib.call("crb3d_ball_query_stack", B, M, float(radius), int(nsample), _p(new_xyz), _p(new_xyz_batch_cnt), _p(xyz),
+              _p(xyz_batch_cnt), _p(idx), int(max_queries_per_frame), _stream(idx.device))
+
+
+def group_points(B, M, C, nsample, features, features_batch_cnt, idx, idx_batch_cnt, out):
+    _need_cuda(features, features_batch_cnt, idx, idx_batch_cnt, out)
+    _lib.call("crb3d_group_points_stack", B, M, C, nsample, _p(features), _p(features_batch_cnt), _p(idx),
+              _p(idx_batch_cnt), _p(out), _stream(out.device))
+
+
+def group_points_grad(B, M, C, N, nsample, grad_out, idx, idx_batch_cnt, features_batch_cnt, grad_features):
+    _need_cuda(grad_out, idx, idx_batch_cnt, features_batch_cnt, grad_features)
+    _lib.call("crb3d_group_points_grad_stack", B, M, C, N, nsample, _p(grad_out), _p(idx), _p(idx_batch_cnt),
+              _p(features_batch_cnt), _p(grad_features), _stream(grad_out.device))
+
+
+def farthest_point_sampling(b, n, m, points, temp, idx):
+    _need_cuda(points, temp, idx)
+    _lib.call("crb3d_farthest_point_sampling", b, n, m, _p(points), _p(temp), _p(idx), _stream(idx.device))
+
+
+def stack_farthest_point_sampling(points, temp, xyz_batch_cnt, idx, num_sampled_points, n_max=None):
+    _need_cuda(points, temp, xyz_batch_cnt, idx, num_sampled_points)
+    B = xyz_batch_cnt.numel()
+    if n_max is None:
+        n_max = int(xyz_batch_cnt.max().item())
+    _lib.call("crb3d_stack_farthest_point_sampling", B, int(n_max), _p(points), _p(temp), _p(xyz_batch_cnt), _p(idx),
+              _p(num_sampled_points), _stream(idx.device))
+
+
+def three_nn(B, N, M, unknown, unknown_batch_cnt, known, known_batch_cnt, dist2, idx):
+    _need_cuda(unknown, unknown_batch_cnt, known, known_batch_cnt, dist2, idx)
+    _lib.call("crb3d_three_nn_stack", B, N, M, _p(unknown), _p(unknown_batch_cnt), _p(known), _p(known_batch_cnt),
+              _p(dist2), _p(idx), _stream(idx.device))
+
+
+def three_interpolate(N, C, features, idx, weight, out):
+    _need_cuda(features, idx, weight, out)
+    _lib.call("crb3d_three_interpolate_stack", N, C, _p(features), _p(idx), _p(weight), _p(out), _stream(out.device))
+
+
+def three_interpolate_grad(N, C, grad_out, idx, weight, grad_features):
+    _need_cuda(grad_out, idx, weight, grad_features)
+    _lib.call("crb3d_three_interpolate_grad_stack", N, C, _p(grad_out), _p(idx), _p(weight), _p(grad_features),
+              _stream(grad_out.device))
+
+
+# ----------------------------------------------------------------------------------------------- CRB scoring
+def label_entropy(labels, box_off, num_class, want_counts=False):
+    """Per-frame CRB stage-1 entropy of predicted labels (1-based), stacked with box_off (B+1)."""
+    _need_cuda(labels, box_off)
+    labels, box_off = _i32c(labels), _i32c(box_off)
+    B = box_off.numel() - 1
+    ent = torch.empty((B,), dtype=torch.float32, device=labels.device)
+    cc = torch.empty((B, num_class), dtype=torch.int32, device=labels.device) if want_counts else None
+    _lib.call("crb3d_label_entropy", _p(labels), _p(box_off), B, num_class, _p(ent), _p(cc), _stream(labels.device))
+    return (ent, cc) if want_counts else ent
+
+
+def pairwise_sqdist(X):
+    _need_cuda(X)
+    X = _f32c(X)
+    n, d = X.shape
+    D = torch.empty((n, n), dtype=torch.float64, device=X.device)
+    _lib.call("crb3d_pairwise_sqdist_f64", _p(X), n, d, _p(D), _stream(X.device))
+    return D
+
+
+def kde_greedy(dens, labels, cand_off, n_class, axis, prior_n, bandwidth, n_select):
+    """CRB stage-3 greedy selection. Returns (order (n_select,) int32 device, picked_score (n_select,) f64 device)."""
+    _need_cuda(dens, labels, cand_off, axis, prior_n)
+    dens, labels, cand_off = _f32c(dens), _i32c(labels), _i32c(cand_off)
+    axis = axis.double().contiguous()
+    prior_n = prior_n.double().contiguous()
+    n_cand = cand_off.numel() - 1
+    dev = dens.device
+    order = torch.full((n_select,), -1, dtype=torch.int32, device=dev)
+    ps = torch.zeros((n_select,), dtype=torch.float64, device=dev)
+    ws = _ws(_ws_bytes("crb3d_kde_greedy_workspace_bytes", n_cand, n_class), dev)
+    _lib.call("crb3d_kde_greedy", _p(dens), _p(labels), _p(cand_off), n_cand, n_class, _p(axis), _p(prior_n),
+              float(bandwidth), int(n_select), _p(order), _p(ps), _p(ws), ws.numel(), _stream(dev))
+    return order, ps

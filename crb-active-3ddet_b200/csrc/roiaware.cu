@@ -1,0 +1,264 @@
+// points-in-boxes (first containing box per point), fused per-box point density, RoI-aware pool3d fwd/bwd.
+//
+// Replaces (reference, /root/reference):
+//   pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu:16-36   check_pt_in_box3d (MARGIN 1e-5, double compare)
+//   pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu:313-359 points_in_boxes_kernel / launcher
+//   pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu:39-310  generate_pts_mask / collect_inside_pts /
+//                                                                   roiaware_{max,avg}pool3d (+backward)
+//   pcdet/models/detectors/detector3d_template.py:379-387           per-box count -> density (CRB stage-3 input)
+// Differences: boxes are staged once per CTA in shared memory with their sin/cos and double thresholds
+// precomputed; the (N x P) int mask temp + cudaMalloc of the reference is gone (one warp per box walks the points
+// in index order and appends hits directly, which reproduces the serial `collect_inside_pts` list order);
+// pooling threads run channel-fastest so feature reads and pooled writes coalesce.
+#include "common.cuh"
+
+namespace {
+
+struct PBox {
+    float cx, cy, cz, hz, c, s;
+    double tx, ty;  // dx/2.0 + MARGIN, dy/2.0 + MARGIN evaluated in double like the reference
+};
+
+__device__ __forceinline__ void make_pbox(const float* __restrict__ b, PBox& p) {
+    const float margin = 1e-5f;
+    p.cx = b[0]; p.cy = b[1]; p.cz = b[2];
+    p.hz = b[5] * 0.5f;
+    p.tx = (double)b[3] / 2.0 + (double)margin;
+    p.ty = (double)b[4] / 2.0 + (double)margin;
+    p.c = cosf(b[6]);  // cos(-rz) == cos(rz)
+    p.s = sinf(b[6]);  // sin(-rz) == -sin(rz): local_x = sx*c + sy*s, local_y = -sx*s + sy*c
+}
+
+__device__ __forceinline__ bool pt_in_pbox(const PBox& b, float x, float y, float z, float& lx, float& ly) {
+    if (fabsf(z - b.cz) > b.hz) return false;
+    const float sx = x - b.cx, sy = y - b.cy;
+    // contraction pinned to the reference SASS: local_x = fma(sx, cos, sy*(-sina)), local_y = fma(sy, cos, -(sx*(-sina)))
+    lx = __fmaf_rn(sx, b.c, __fmul_rn(sy, b.s));
+    ly = __fmaf_rn(sy, b.c, -__fmul_rn(sx, b.s));
+    return ((double)fabsf(lx) < b.tx) & ((double)fabsf(ly) < b.ty);
+}
+
+__device__ __forceinline__ int seg_of(const int* __restrict__ off, int B, int p) {
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (p >= off[mid]) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+constexpr int PIB_CHUNK = 128;
+
+// Frames are either padded (pt_off == nullptr: frame b owns points [b*M, (b+1)*M) and boxes [b*T, (b+1)*T)) or
+// stacked (offset arrays of length B+1). out_idx is the box index LOCAL to the frame, -1 = background.
+__global__ void __launch_bounds__(256) points_in_boxes_kernel(int B, int M, int T, const float* __restrict__ pts,
+                                                              int pt_stride, const int* __restrict__ pt_off,
+                                                              const float* __restrict__ boxes,
+                                                              const int* __restrict__ box_off, int total_pts,
+                                                              int* __restrict__ out_idx, int* __restrict__ counts) {
+    __shared__ PBox sb[PIB_CHUNK];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    // every thread of a CTA must see the same frame to share the staged boxes: CTAs are launched per frame
+    const int b = blockIdx.y;
+    int p_begin, p_end, b_begin, b_end;
+    if (pt_off) { p_begin = pt_off[b]; p_end = pt_off[b + 1]; b_begin = box_off[b]; b_end = box_off[b + 1]; }
+    else { p_begin = b * M; p_end = p_begin + M; b_begin = b * T; b_end = b_begin + T; }
+    const int pi = p_begin + p;
+    if (blockIdx.x * blockDim.x >= p_end - p_begin) return;  // whole CTA past this frame
+    const bool live = pi < p_end;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (live) { const float* q = pts + (size_t)pi * pt_stride; x = q[0]; y = q[1]; z = q[2]; }
+    int found = -1;
+    for (int c0 = b_begin; c0 < b_end; c0 += PIB_CHUNK) {
+        const int nb = min(PIB_CHUNK, b_end - c0);
+        __syncthreads();
+        if (threadIdx.x < nb) make_pbox(boxes + (size_t)(c0 + threadIdx.x) * 7, sb[threadIdx.x]);
+        __syncthreads();
+        if (live && found < 0) {
+            float lx, ly;
+            for (int k = 0; k < nb; ++k)
+                if (pt_in_pbox(sb[k], x, y, z, lx, ly)) { found = c0 - b_begin + k; break; }
+        }
+        if (__syncthreads_and(!live || found >= 0)) break;
+    }
+    if (live) {
+        if (found >= 0) {
+            out_idx[pi] = found;
+            if (counts) atomicAdd(&counts[b_begin + found], 1);
+        } else if (pt_off) {
+            out_idx[pi] = -1;  // padded API: caller pre-fills -1 (reference contract); stacked API: we own it
+        }
+    }
+    (void)total_pts;
+}
+
+__global__ void __launch_bounds__(256) box_density_kernel(int n_boxes, const float* __restrict__ boxes,
+                                                          const int* __restrict__ counts, float* __restrict__ density) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_boxes) return;
+    const float* b = boxes + (size_t)i * 7;
+    const float vol = __fmul_rn(__fmul_rn(b[3], b[4]), b[5]);
+    density[i] = __fdiv_rn((float)counts[i], vol);
+}
+
+// ------------------------------------------------------------------ RoI-aware pool
+__global__ void __launch_bounds__(128) roiaware_collect_kernel(int n_boxes, int n_pts, int max_pts_each_voxel, int ox,
+                                                               int oy, int oz, const float* __restrict__ rois,
+                                                               const float* __restrict__ pts,
+                                                               int* __restrict__ pts_idx_of_voxels) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_boxes) return;
+    const float* roi = rois + (size_t)warp * 7;
+    PBox pb;
+    make_pbox(roi, pb);
+    const float dx = roi[3], dy = roi[4], dz = roi[5];
+    const float x_res = dx / ox, y_res = dy / oy, z_res = dz / oz;
+    int* lists = pts_idx_of_voxels + (size_t)warp * ox * oy * oz * max_pts_each_voxel;
+    const int max_num = max_pts_each_voxel - 1;
+    for (int k0 = 0; k0 < n_pts; k0 += 32) {
+        const int k = k0 + lane;
+        bool in = false;
+        unsigned int base = 0;
+        if (k < n_pts) {
+            const float* q = pts + (size_t)k * 3;
+            float lx, ly;
+            in = pt_in_pbox(pb, q[0], q[1], q[2], lx, ly);
+            if (in) {
+                const float lz = q[2] - roi[2];
+                unsigned int xi = int((lx + dx / 2) / x_res);
+                unsigned int yi = int((ly + dy / 2) / y_res);
+                unsigned int zi = int((lz + dz / 2) / z_res);
+                // reference: min(max(x_idx, 0), out - 1) on UNSIGNED values, then packed into 8-bit fields
+                xi = min(max(xi, 0u), (unsigned int)(ox - 1));
+                yi = min(max(yi, 0u), (unsigned int)(oy - 1));
+                zi = min(max(zi, 0u), (unsigned int)(oz - 1));
+                xi &= 0xFF; yi &= 0xFF; zi &= 0xFF;
+                base = (xi * oy * oz + yi * oz + zi) * max_pts_each_voxel;
+            }
+        }
+        unsigned int hits = __ballot_sync(0xffffffffu, in);
+        while (hits) {  // append in ascending point index, exactly like the serial collect loop
+            const int l = __ffs(hits) - 1;
+            hits &= hits - 1;
+            if (lane == l) {
+                int cnt = lists[base];
+                if (cnt < max_num) {
+                    lists[base + cnt + 1] = k;
+                    lists[base] = cnt + 1;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) roiaware_pool_kernel(int64_t total, int C, int max_pts_each_voxel, int pool_method,
+                                                            const float* __restrict__ feat,
+                                                            const int* __restrict__ pts_idx_of_voxels,
+                                                            float* __restrict__ pooled, int* __restrict__ argmax) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int c = (int)(t % C);
+    const int64_t vox = t / C;  // flat (box, x, y, z)
+    const int* lst = pts_idx_of_voxels + vox * max_pts_each_voxel;
+    const int n = lst[0];
+    if (pool_method == 0) {
+        int am = -1;
+        float mx = -INFINITY;  // the reference's -1e50 literal saturates to -inf in float
+        for (int k = 1; k <= n; ++k) {
+            float v = __ldg(feat + (size_t)lst[k] * C + c);
+            if (v > mx) { mx = v; am = lst[k]; }
+        }
+        if (am != -1) pooled[t] = mx;
+        argmax[t] = am;
+    } else {
+        float s = 0.f;
+        for (int k = 1; k <= n; ++k) s += __ldg(feat + (size_t)lst[k] * C + c);
+        if (n > 0) pooled[t] = s / n;
+    }
+}
+
+__global__ void __launch_bounds__(256) roiaware_pool_bwd_kernel(int64_t total, int C, int max_pts_each_voxel,
+                                                                int pool_method, const int* __restrict__ pts_idx_of_voxels,
+                                                                const int* __restrict__ argmax,
+                                                                const float* __restrict__ grad_out,
+                                                                float* __restrict__ grad_in) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int c = (int)(t % C);
+    const int64_t vox = t / C;
+    if (pool_method == 0) {
+        const int am = argmax[t];
+        if (am == -1) return;
+        atomicAdd(grad_in + (size_t)am * C + c, grad_out[t]);
+    } else {
+        const int* lst = pts_idx_of_voxels + vox * max_pts_each_voxel;
+        const int n = lst[0];
+        const float g = 1 / fmaxf(float(n), 1.0f);
+        for (int k = 1; k <= n; ++k) atomicAdd(grad_in + (size_t)lst[k] * C + c, grad_out[t] * g);
+    }
+}
+
+}  // namespace
+
+// Padded API (reference points_in_boxes_gpu): boxes (B,T,7), pts (B,M,3), out (B,M) pre-filled with -1 by the caller.
+extern "C" int crb3d_points_in_boxes(const float* boxes, const float* pts, int B, int T, int M, int* out_idx,
+                                     cudaStream_t stream) {
+    if (B < 0 || T < 0 || M < 0 || !out_idx) return CRB3D_ERR_ARG;
+    if (B == 0 || M == 0 || T == 0) return CRB3D_OK;
+    dim3 grid((unsigned)crb3d_divup(M, 256), B);
+    points_in_boxes_kernel<<<grid, 256, 0, stream>>>(B, M, T, pts, 3, nullptr, boxes, nullptr, B * M, out_idx, nullptr);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+// Stacked API used by the scoring path: frame b owns points [pt_off[b], pt_off[b+1]) (row stride pt_stride floats,
+// xyz first) and boxes [box_off[b], box_off[b+1]). Writes out_idx (local box index or -1) for every point, the
+// per-box point counts and (optional) density = count / (dx*dy*dz)  [detector3d_template.py:379-387].
+// max_pts_per_frame bounds the launch grid (host-known).
+extern "C" int crb3d_points_in_boxes_stack(const float* pts, int pt_stride, const int* pt_off, int max_pts_per_frame,
+                                           const float* boxes, const int* box_off, int B, int total_pts,
+                                           int total_boxes, int* out_idx, int* counts, float* density,
+                                           cudaStream_t stream) {
+    if (B <= 0 || !pt_off || !box_off || !out_idx || total_pts < 0 || total_boxes < 0) return CRB3D_ERR_ARG;
+    if (counts && total_boxes > 0) CRB3D_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * total_boxes, stream));
+    if (total_pts > 0 && max_pts_per_frame > 0) {
+        dim3 grid((unsigned)crb3d_divup(max_pts_per_frame, 256), B);
+        points_in_boxes_kernel<<<grid, 256, 0, stream>>>(B, 0, 0, pts, pt_stride, pt_off, boxes, box_off, total_pts,
+                                                         out_idx, counts);
+    }
+    if (density && counts && total_boxes > 0)
+        box_density_kernel<<<(unsigned)crb3d_divup(total_boxes, 256), 256, 0, stream>>>(total_boxes, boxes, counts, density);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+// pool_method: 0 max, 1 avg. argmax / pts_idx_of_voxels / pooled are caller-zeroed (reference contract).
+extern "C" int crb3d_roiaware_pool3d_forward(const float* rois, const float* pts, const float* pts_feature,
+                                             int n_boxes, int n_pts, int C, int max_pts_each_voxel, int ox, int oy,
+                                             int oz, int* argmax, int* pts_idx_of_voxels, float* pooled,
+                                             int pool_method, cudaStream_t stream) {
+    if (n_boxes < 0 || n_pts < 0 || C <= 0 || max_pts_each_voxel <= 1 || ox <= 0 || oy <= 0 || oz <= 0) return CRB3D_ERR_ARG;
+    if (ox > 256 || oy > 256 || oz > 256) return CRB3D_ERR_UNSUPPORTED;  // 8-bit packed voxel index in the reference
+    if (n_boxes == 0) return CRB3D_OK;
+    if (n_pts > 0)
+        roiaware_collect_kernel<<<(unsigned)crb3d_divup((int64_t)n_boxes * 32, 128), 128, 0, stream>>>(
+            n_boxes, n_pts, max_pts_each_voxel, ox, oy, oz, rois, pts, pts_idx_of_voxels);
+    int64_t total = (int64_t)n_boxes * ox * oy * oz * C;
+    roiaware_pool_kernel<<<(unsigned)crb3d_divup(total, 256), 256, 0, stream>>>(total, C, max_pts_each_voxel, pool_method,
+                                                                              pts_feature, pts_idx_of_voxels, pooled, argmax);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+extern "C" int crb3d_roiaware_pool3d_backward(const int* pts_idx_of_voxels, const int* argmax, const float* grad_out,
+                                              float* grad_in, int n_boxes, int ox, int oy, int oz, int C,
+                                              int max_pts_each_voxel, int pool_method, cudaStream_t stream) {
+    if (n_boxes < 0 || C <= 0) return CRB3D_ERR_ARG;
+    int64_t total = (int64_t)n_boxes * ox * oy * oz * C;
+    if (total == 0) return CRB3D_OK;
+    roiaware_pool_bwd_kernel<<<(unsigned)crb3d_divup(total, 256), 256, 0, stream>>>(
+        total, C, max_pts_each_voxel, pool_method, pts_idx_of_voxels, argmax, grad_out, grad_in);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}

@@ -1,0 +1,151 @@
+/*
+ * libcrb3d_sm100 - C ABI of the B200-native (sm_100a) hot path of CRB-active-3Ddet.
+ *
+ * Every entry point takes plain device pointers + sizes + a cudaStream_t, returns 0 on success or a negative
+ * CRB3D_ERR_* code, never allocates (scratch comes in through `ws`, sized by the matching *_workspace_bytes call),
+ * never synchronises the host and keeps no global state. All pointers are DEVICE pointers unless a parameter is
+ * documented as "host". Citations name the reference interface (under /root/reference) each call replaces.
+ */
+#ifndef CRB3D_H_
+#define CRB3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define CRB3D_OK 0
+#define CRB3D_ERR_ARG (-1)         /* invalid argument */
+#define CRB3D_ERR_CUDA (-2)        /* a CUDA call / launch failed */
+#define CRB3D_ERR_WORKSPACE (-3)   /* workspace missing or too small */
+#define CRB3D_ERR_UNSUPPORTED (-4) /* shape outside what the kernels cover */
+
+const char* crb3d_version(void);
+const char* crb3d_strerror(int code);
+
+/* ---- voxelization + MeanVFE ---------------------------------------------------------------------------------
+ * replaces spconv.utils.Point2VoxelCPU3d.point_to_voxel (pcdet/datasets/processor/data_processor.py:15-60,115-143)
+ * fused with MeanVFE.forward (pcdet/models/backbones_3d/vfe/mean_vfe.py:14-31).
+ * points: (n_points, pt_stride) f32, xyz at column xyz_col, the n_feat feature columns start at feat_col.
+ * frame_offsets: (B+1) int32 row offsets of each frame inside `points`. range6/vsize3/grid3: HOST arrays
+ * (xmin,ymin,zmin,xmax,ymax,zmax), (vx,vy,vz), grid (x,y,z).
+ * outputs sized for cap = min(n_points, B*max_voxels) rows: mean_feats (cap,n_feat) [nullable], voxels
+ * (cap,max_pts,n_feat) zero padded [nullable], coords (cap,4) int32 (b,z,y,x), num_points (cap),
+ * frame_voxel_offsets (B+1) int32 (exclusive prefix of per-frame voxel counts; [B] = total rows). */
+int crb3d_voxelize_workspace_bytes(int64_t n_points, int batch_size, int max_pts, size_t* bytes);
+int crb3d_voxelize(const float* points, int64_t n_points, int pt_stride, int xyz_col, int feat_col, int n_feat,
+                   const int* frame_offsets, int batch_size, const float* range6, const float* vsize3,
+                   const int* grid3, int max_pts, int max_voxels, float* mean_feats, float* voxels, int* coords,
+                   int* num_points, int* frame_voxel_offsets, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+/* ---- rulebook ------------------------------------------------------------------------------------------------
+ * replaces spconv 2.1 get_indice_pairs behind SubMConv3d / SparseConv3d
+ * (pcdet/models/backbones_3d/spconv_backbone.py:12-17,77-117). coords: (n,4) int32 (b,z,y,x), unique rows.
+ * Neighbour table nbr[k][o] = input row feeding output row o through kernel offset k = (kz*KY+ky)*KX+kx, or -1.
+ * shape / ksize / stride / pad / dilation arguments are HOST int[3] in (z,y,x) order. */
+int crb3d_subm_rulebook_workspace_bytes(int n, size_t* bytes);
+int crb3d_subm_rulebook(const int* coords, int n, const int* spatial_shape3, const int* ksize3, const int* dilation3,
+                        int* nbr, void* ws, size_t ws_bytes, cudaStream_t stream);
+int crb3d_conv_out_shape(const int* in_shape3, const int* ksize3, const int* stride3, const int* pad3,
+                         const int* dilation3, int* out_shape3);
+int crb3d_sparse_rulebook_workspace_bytes(int batch_size, const int* out_shape3, size_t* bytes);
+/* phase 1: active output coords in ascending linear (b,z,y,x) order; true count -> *n_out_dev (device int). */
+int crb3d_sparse_rulebook_coords(const int* coords_in, int n_in, int batch_size, const int* in_shape3,
+                                 const int* out_shape3, const int* ksize3, const int* stride3, const int* pad3,
+                                 const int* dilation3, int* coords_out, int cap_out, int* n_out_dev, void* ws,
+                                 size_t ws_bytes, cudaStream_t stream);
+/* phase 2 (same ws, untouched since phase 1): nbr [K][n_out], nbr_t [K][n_in] (nullable). */
+int crb3d_sparse_rulebook_pairs(const int* coords_in, int n_in, int batch_size, const int* in_shape3,
+                                const int* out_shape3, const int* ksize3, const int* stride3, const int* pad3,
+                                const int* dilation3, int n_out, int* nbr, int* nbr_t, void* ws, size_t ws_bytes,
+                                cudaStream_t stream);
+/* spconv-format pair lists derived from a table: pairs_in/out [K][pair_cap] (caller pre-fills -1), pair_num [K]. */
+int crb3d_rulebook_compact_pairs_workspace_bytes(int K, int n_out, size_t* bytes);
+int crb3d_rulebook_compact_pairs(const int* nbr, int K, int n_out, int pair_cap, int* pairs_in, int* pairs_out,
+                                 int* pair_num, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+/* ---- sparse convolution --------------------------------------------------------------------------------------
+ * replaces spconv 2.1 SparseConvFunction / SubMConvFunction forward+backward (spconv_backbone.py:77-117;
+ * backward reached from crb_sampling.py:205 and train_active_utils.py:50).
+ * out[o,:] = sum_k feat[nbr[k][o],:] @ W_k ; weight element (co,k,ci) at co*w_co_stride + k*w_k_stride +
+ * ci*w_ci_stride (spconv layout [C_out,K,C_in] = strides (K*cin, cin, 1)). Optional fused epilogue
+ * y = relu(acc*scale[c] + shift[c]) (scale/shift nullable). kmap (nullable, device int[K]) remaps weight slices.
+ * Input gradient = the same call with cin<->cout swapped, the transposed table and strides (1, cin, K*cin). */
+int crb3d_spconv_forward_f32(const float* feat, const int* nbr, const float* weight, int n_out, int K, int cin,
+                             int cout, int64_t w_co_stride, int64_t w_k_stride, int64_t w_ci_stride, const int* kmap,
+                             const float* scale, const float* shift, int relu, float* out, cudaStream_t stream);
+int crb3d_spconv_wgrad_workspace_bytes(int n_out, int K, int cin, int cout, size_t* bytes);
+int crb3d_spconv_wgrad_f32(const float* feat, const float* dout, const int* nbr, int n_out, int K, int cin, int cout,
+                           int accumulate, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+/* ---- SparseConvTensor.dense() (height_compression.py:21-24) ------------------------------------------------
+ * layout 0: (B,C,D,H,W); layout 1: (B,H,W,C*D) channels-last view of the BEV map. */
+int crb3d_sparse_to_dense(const float* feat, const int* coords, int n, int C, int B, int D, int H, int W, int layout,
+                          int zero_fill, float* dense, cudaStream_t stream);
+int crb3d_dense_to_sparse(const float* dense, const int* coords, int n, int C, int B, int D, int H, int W, int layout,
+                          float* feat, cudaStream_t stream);
+
+/* ---- iou3d_nms (pcdet/ops/iou3d_nms/src/iou3d_nms_api.cpp:12-16, iou3d_nms.cpp:49-188) ---------------------
+ * boxes: (n,7) f32 [x,y,z,dx,dy,dz,heading]. */
+int crb3d_boxes_overlap_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* out, cudaStream_t stream);
+int crb3d_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* out, cudaStream_t stream);
+int crb3d_nms_workspace_bytes(int n, size_t* bytes);
+/* boxes sorted by descending score; keep: device int64[n]; num_keep: device int; max_keep <= 0 keeps all. */
+int crb3d_nms(const float* boxes, int n, float thresh, int rotated, int max_keep, long long* keep, int* num_keep,
+              void* ws, size_t ws_bytes, cudaStream_t stream);
+int crb3d_nms_mask(const float* boxes, int n, float thresh, int rotated, unsigned long long* mask, cudaStream_t stream);
+/* host-side (CPU tensors) BEV IoU, replaces boxes_iou_bev_cpu (iou3d_cpu.cpp:232-252): HOST pointers. */
+int crb3d_boxes_iou_bev_cpu(const float* boxes_a, int na, const float* boxes_b, int nb, float* out);
+
+/* ---- roiaware_pool3d (pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:172-177) ---------------------------- */
+int crb3d_points_in_boxes(const float* boxes, const float* pts, int B, int T, int M, int* out_idx, cudaStream_t stream);
+int crb3d_points_in_boxes_stack(const float* pts, int pt_stride, const int* pt_off, int max_pts_per_frame,
+                                const float* boxes, const int* box_off, int B, int total_pts, int total_boxes,
+                                int* out_idx, int* counts, float* density, cudaStream_t stream);
+/* HOST pointers; (n_boxes, n_pts) 0/1 matrix with the CPU op's MARGIN=1e-2 (roiaware_pool3d.cpp:119-168). */
+int crb3d_points_in_boxes_cpu(const float* boxes, int n_boxes, const float* pts, int n_pts, int* out);
+int crb3d_roiaware_pool3d_forward(const float* rois, const float* pts, const float* pts_feature, int n_boxes,
+                                  int n_pts, int C, int max_pts_each_voxel, int ox, int oy, int oz, int* argmax,
+                                  int* pts_idx_of_voxels, float* pooled, int pool_method, cudaStream_t stream);
+int crb3d_roiaware_pool3d_backward(const int* pts_idx_of_voxels, const int* argmax, const float* grad_out,
+                                   float* grad_in, int n_boxes, int ox, int oy, int oz, int C, int max_pts_each_voxel,
+                                   int pool_method, cudaStream_t stream);
+
+/* ---- pointnet2_stack (pcdet/ops/pointnet2/pointnet2_stack/src/pointnet2_api.cpp:13-30) --------------------- */
+int crb3d_ball_query_stack(int B, int M, float radius, int nsample, const float* new_xyz, const int* new_xyz_batch_cnt,
+                           const float* xyz, const int* xyz_batch_cnt, int* idx, int max_queries_per_frame,
+                           cudaStream_t stream);
+int crb3d_group_points_stack(int B, int M, int C, int nsample, const float* features, const int* features_batch_cnt,
+                             const int* idx, const int* idx_batch_cnt, float* out, cudaStream_t stream);
+int crb3d_group_points_grad_stack(int B, int M, int C, int N, int nsample, const float* grad_out, const int* idx,
+                                  const int* idx_batch_cnt, const int* features_batch_cnt, float* grad_features,
+                                  cudaStream_t stream);
+int crb3d_farthest_point_sampling(int b, int n, int m, const float* dataset, float* temp, int* idx, cudaStream_t stream);
+int crb3d_stack_farthest_point_sampling(int B, int n_max, const float* dataset, float* temp, const int* xyz_batch_cnt,
+                                        int* idx, const int* num_sampled_points, cudaStream_t stream);
+int crb3d_three_nn_stack(int B, int N, int M, const float* unknown, const int* unknown_batch_cnt, const float* known,
+                         const int* known_batch_cnt, float* dist2, int* idx, cudaStream_t stream);
+int crb3d_three_interpolate_stack(int N, int C, const float* features, const int* idx, const float* weight, float* out,
+                                  cudaStream_t stream);
+int crb3d_three_interpolate_grad_stack(int N, int C, const float* grad_out, const int* idx, const float* weight,
+                                       float* grad_features, cudaStream_t stream);
+
+/* ---- CRB scoring (pcdet/query_strategies/crb_sampling.py:86-100, 219-226, 276-338) -------------------------- */
+int crb3d_label_entropy(const int* labels, const int* box_off, int B, int num_class, float* entropy, int* class_counts,
+                        cudaStream_t stream);
+int crb3d_pairwise_sqdist_f64(const float* X, int n, int d, double* D, cudaStream_t stream);
+int crb3d_kde_greedy_workspace_bytes(int n_cand, int n_class, size_t* bytes);
+int crb3d_kde_greedy(const float* dens, const int* labels, const int* cand_off, int n_cand, int n_class,
+                     const double* axis, const double* prior_n, double bandwidth, int n_select, int* order,
+                     double* picked_score, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRB3D_H_ */

@@ -1,0 +1,79 @@
+"""Builds the oracle's C restatement (oracle/_build/liboracle.so) and, when /root/reference is present, the
+reference's own sources into oracle/_ref/ (never copied into the repo; outputs are git-ignored but travel with gpurun).
+
+TEST INFRASTRUCTURE ONLY - see oracle/__init__.py.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "_build")
+REFDIR = os.path.join(HERE, "_ref")
+LIB = os.path.join(BUILD, "liboracle.so")
+REFERENCE = "/root/reference"
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+def _newer(dst, srcs):
+    return os.path.exists(dst) and all(os.path.getmtime(dst) >= os.path.getmtime(s) for s in srcs)
+
+
+def build_oracle(force=False):
+    os.makedirs(BUILD, exist_ok=True)
+    src = os.path.join(HERE, "csrc", "oracle.c")
+    if force or not _newer(LIB, [src]):
+        cmd = ["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c99", "-o", LIB, src, "-lm"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle build failed:\n" + r.stderr)
+    return LIB
+
+
+def build_ref(force=False, verbose=False):
+    """Compiles the reference's CUDA kernels (from where they lie under /root/reference) behind extern "C" wrappers
+    (oracle/ref_wrap/*.cu) into oracle/_ref/libpcdet_ref_kernels.so. Returns the path or None when the reference tree is
+    absent (GPU box: the prebuilt file travels with the snapshot)."""
+    out = os.path.join(REFDIR, "libpcdet_ref_kernels.so")
+    if not os.path.isdir(REFERENCE):
+        return out if os.path.exists(out) else None
+    os.makedirs(REFDIR, exist_ok=True)
+    wrap = os.path.join(HERE, "ref_wrap", "ref_kernels_wrap.cu")
+    ops = os.path.join(REFERENCE, "pcdet", "ops")
+    srcs = [
+        wrap,
+        os.path.join(ops, "iou3d_nms", "src", "iou3d_nms_kernel.cu"),
+        os.path.join(ops, "roiaware_pool3d", "src", "roiaware_pool3d_kernel.cu"),
+    ]
+    pn = os.path.join(ops, "pointnet2", "pointnet2_stack", "src")
+    pn_srcs = [os.path.join(pn, f) for f in ("ball_query_gpu.cu", "group_points_gpu.cu", "sampling_gpu.cu", "interpolate_gpu.cu")]
+    if not force and _newer(out, srcs + pn_srcs):
+        return out
+    # the pointnet2 .cu files include headers that pull in <torch/serialize/tensor.h>; give nvcc torch's include dirs
+    import sysconfig
+    import torch.utils.cpp_extension as ext
+    inc = []
+    for p in ext.include_paths():
+        inc += ["-I", p]
+    inc += ["-I", sysconfig.get_paths()["include"], "-I", pn]
+    objs = []
+    os.makedirs(os.path.join(REFDIR, "obj"), exist_ok=True)
+    for i, s in enumerate(srcs + pn_srcs):
+        o = os.path.join(REFDIR, "obj", "%d_%s.o" % (i, os.path.basename(s)[:-3]))
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-w",
+               *inc, "-c", s, "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("reference kernel build failed for %s:\n%s" % (s, r.stderr[-2000:]))
+        objs.append(o)
+    r = subprocess.run([NVCC, "-shared", "-o", out, *objs, "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("reference kernel link failed:\n" + r.stderr[-2000:])
+    if verbose:
+        print("built", out)
+    return out
+
+
+if __name__ == "__main__":
+    print(build_oracle(force="--force" in sys.argv))
+    print(build_ref(force="--force" in sys.argv, verbose=True))
