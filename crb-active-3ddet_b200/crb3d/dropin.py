@@ -1,0 +1,60 @@
+"""Registers the crb3d stand-ins under the import names of the reference's compiled extension modules, so the unmodified
+reference wrappers (`from . import iou3d_nms_cuda` in pcdet/ops/iou3d_nms/iou3d_nms_utils.py:8, `roiaware_pool3d_cuda`
+in roiaware_pool3d_utils.py:6, `pointnet2_stack_cuda` in pointnet2_stack/pointnet2_utils.py:5) and `import spconv` /
+`cumm` resolve to this library. Call before importing pcdet:
+
+    import sys; sys.path.insert(0, "<repo>/crb-active-3ddet_b200")
+    import crb3d.dropin; crb3d.dropin.install()
+"""
+import importlib
+import importlib.abc
+import importlib.machinery
+import sys
+
+ALIASES = {
+    "pcdet.ops.iou3d_nms.iou3d_nms_cuda": "pcdet_ops.iou3d_nms_cuda",
+    "pcdet.ops.roiaware_pool3d.roiaware_pool3d_cuda": "pcdet_ops.roiaware_pool3d_cuda",
+    "pcdet.ops.pointnet2.pointnet2_stack.pointnet2_stack_cuda": "pcdet_ops.pointnet2_stack_cuda",
+    "pcdet.ops.voxel": "pcdet_ops.voxel",
+}
+EXPECTED = {
+    "pcdet.ops.iou3d_nms.iou3d_nms_cuda": ["boxes_overlap_bev_gpu", "boxes_iou_bev_gpu", "nms_gpu", "nms_normal_gpu",
+                                           "boxes_iou_bev_cpu"],
+    "pcdet.ops.roiaware_pool3d.roiaware_pool3d_cuda": ["forward", "backward", "points_in_boxes_gpu", "points_in_boxes_cpu"],
+    "pcdet.ops.pointnet2.pointnet2_stack.pointnet2_stack_cuda": [
+        "ball_query_wrapper", "voxel_query_wrapper", "farthest_point_sampling_wrapper",
+        "stack_farthest_point_sampling_wrapper", "group_points_wrapper", "group_points_grad_wrapper", "three_nn_wrapper",
+        "three_interpolate_wrapper", "three_interpolate_grad_wrapper", "query_stacked_local_neighbor_idxs_wrapper_stack",
+        "query_three_nn_by_stacked_local_idxs_wrapper_stack", "vector_pool_wrapper", "vector_pool_grad_wrapper"],
+    "pcdet.ops.voxel": ["hard_voxelize"],
+}
+
+
+class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """`from . import iou3d_nms_cuda` inside the reference package ends in an import of the fully qualified name; this
+    finder answers it with the stand-in module."""
+
+    def find_spec(self, fullname, path, target=None):
+        if fullname in ALIASES:
+            return importlib.machinery.ModuleSpec(fullname, self)
+        return None
+
+    def create_module(self, spec):
+        return importlib.import_module(ALIASES[spec.name])
+
+    def exec_module(self, module):
+        pass
+
+
+_finder = None
+
+
+def install():
+    """Idempotent. Returns the list of aliased module names."""
+    global _finder
+    if _finder is None:
+        _finder = _AliasFinder()
+        sys.meta_path.insert(0, _finder)
+    for alias, real in ALIASES.items():
+        sys.modules[alias] = importlib.import_module(real)
+    return sorted(ALIASES)

@@ -180,10 +180,25 @@ def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transp
         strides = (1, cin_w, K * cin_w)
     assert feat.shape[1] == cin, (feat.shape, cin)
     out = torch.empty((n_out, cout), dtype=torch.float32, device=feat.device)
+    prof = PROFILE
+    if prof is not None and prof["mode"] == "time":
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(feat.device))
     _lib.call("crb3d_spconv_forward_f32", _p(feat), _p(nbr), _p(weight), n_out, K, cin, cout, strides[0], strides[1],
               strides[2], _p(kmap), _p(_f32c(scale)) if scale is not None else None,
               _p(_f32c(shift)) if shift is not None else None, int(bool(relu)), _p(out), _stream(feat.device))
+    if prof is not None:
+        if prof["mode"] == "time":
+            e1.record(torch.cuda.current_stream(feat.device))
+            prof["records"].append((e0, e1))
+        else:  # "pairs": algorithmic work of this launch (host sync; only used outside timed regions)
+            prof["records"].append(dict(n_out=n_out, K=K, cin=cin, cout=cout, pairs=int((nbr >= 0).sum().item())))
     return out
+
+
+# bench.py hook: None, or {"mode": "time" | "pairs", "records": []} (see bench.py roofline section)
+PROFILE = None
 
 
 def spconv_wgrad(feat, dout, nbr, weight_shape, accumulate_into=None):
@@ -420,3 +435,48 @@ def kde_greedy(dens, labels, cand_off, n_class, axis, prior_n, bandwidth, n_sele
     _lib.call("crb3d_kde_greedy", _p(dens), _p(labels), _p(cand_off), n_cand, n_class, _p(axis), _p(prior_n),
               float(bandwidth), int(n_select), _p(order), _p(ps), _p(ws), ws.numel(), _stream(dev))
     return order, ps
+
+
+# ----------------------------------------------------------------------------------------------- batched scoring path
+def nms_batched(boxes, counts, thresh, rotated=True, max_keep=0):
+    """boxes (B, n_max, 7) (each frame sorted by descending score), counts (B,) int32 device.
+    Returns keep (B, max_keep or n_max) int64 and num_keep (B,) int32 - no host sync."""
+    _need_cuda(boxes, counts)
+    boxes = _f32c(boxes)
+    counts = _i32c(counts)
+    B, n_max, _ = boxes.shape
+    stride = max_keep if max_keep > 0 else n_max
+    keep = torch.zeros((B, max(stride, 1)), dtype=torch.int64, device=boxes.device)
+    num = torch.zeros((B,), dtype=torch.int32, device=boxes.device)
+    ws = _ws(_ws_bytes("crb3d_nms_batched_workspace_bytes", B, n_max), boxes.device)
+    _lib.call("crb3d_nms_batched", _p(boxes), _p(counts), B, n_max, float(thresh), int(bool(rotated)), int(max_keep),
+              _p(keep), max(stride, 1), _p(num), _p(ws), ws.numel(), _stream(boxes.device))
+    return keep, num
+
+
+def points_in_boxes_ranges(pts, pt_begin, pt_end, max_pts_per_frame, boxes, box_begin, box_end, want_density=True):
+    """Like points_in_boxes_stack but with explicit per-frame [begin, end) row ranges into `pts` and `boxes`
+    (padded box tensors). counts/density are indexed like boxes' rows."""
+    _need_cuda(pts, pt_begin, pt_end, boxes, box_begin, box_end)
+    pts = _f32c(pts)
+    boxes2 = _f32c(boxes.reshape(-1, boxes.shape[-1])[:, :7])
+    N, S = pts.shape
+    slots = boxes2.shape[0]
+    B = pt_begin.numel()
+    idx = torch.full((N,), -1, dtype=torch.int32, device=pts.device)
+    counts = torch.zeros((max(slots, 1),), dtype=torch.int32, device=pts.device)
+    dens = torch.zeros((max(slots, 1),), dtype=torch.float32, device=pts.device) if want_density else None
+    _lib.call("crb3d_points_in_boxes_ranges", _p(pts), S, _p(_i32c(pt_begin)), _p(_i32c(pt_end)), int(max_pts_per_frame),
+              _p(boxes2), _p(_i32c(box_begin)), _p(_i32c(box_end)), B, slots, _p(idx), _p(counts), _p(dens),
+              _stream(pts.device))
+    return idx, counts[:slots], (dens[:slots] if dens is not None else None)
+
+
+def label_entropy_ranges(labels, box_begin, box_end, num_class):
+    _need_cuda(labels, box_begin, box_end)
+    labels = _i32c(labels.reshape(-1))
+    B = box_begin.numel()
+    ent = torch.empty((B,), dtype=torch.float32, device=labels.device)
+    _lib.call("crb3d_label_entropy_ranges", _p(labels), _p(_i32c(box_begin)), _p(_i32c(box_end)), B, num_class, _p(ent),
+              None, _stream(labels.device))
+    return ent

@@ -1,0 +1,107 @@
+"""Pool scoring front end (the public call a CRB user makes for stage 1): host frames in, per-frame score records out.
+
+One process per GPU. Frames are sharded round-robin over ranks like the reference's eval DistributedSampler
+(pcdet/datasets/__init__.py:26-46: frame i -> rank i mod W); there is no data-path collective - the only exchange is ONE
+all-gather of the fixed-stride per-frame records at the end, because stage 3's prior needs every pool
+frame's (label, density) pairs (crb_sampling.py:252-258). The reference itself never synchronises ranks in query().
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+RECORD_FIELDS = ("entropy", "num_boxes", "labels", "density")
+
+
+class PoolScorer(object):
+    def __init__(self, model, device, batch_size=4):
+        self.model = model
+        self.device = device
+        self.batch_size = batch_size
+        self.P = model.cfg["nms_post_maxsize"]
+        self.n_feat = model.cfg["data"]["n_feat"]
+        self._pinned = {}
+
+    # -- host staging -------------------------------------------------------------------------------------------
+    def stage_host(self, frames):
+        """Packs a list of (n_i, C) float32 arrays into one pinned (N, C) tensor + int32 offsets (pinned)."""
+        offs = np.zeros(len(frames) + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(f) for f in frames])
+        pts = torch.empty((int(offs[-1]), self.n_feat), dtype=torch.float32).pin_memory()
+        for i, f in enumerate(frames):
+            pts[offs[i]:offs[i + 1]] = torch.from_numpy(np.ascontiguousarray(f[:, -self.n_feat:], dtype=np.float32))
+        return pts, torch.from_numpy(offs).pin_memory(), int(max(len(f) for f in frames)) if frames else 0
+
+    def to_device(self, staged):
+        pts, offs, mx = staged
+        return pts.to(self.device, non_blocking=True), offs.to(self.device, non_blocking=True), mx
+
+    # -- scoring ------------------------------------------------------------------------------------------------
+    def score_device(self, dev_batch):
+        pts, offs, mx = dev_batch
+        return self.model.score_batch(pts, offs, offs.numel() - 1, mx)
+
+    def score_host(self, staged):
+        """End-to-end call: pinned host points -> device -> kernels -> host record (numpy)."""
+        rec = self.score_device(self.to_device(staged))
+        out = {k: rec[k].to("cpu", non_blocking=True) for k in RECORD_FIELDS}
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: v.numpy() for k, v in out.items()}
+
+    def record_tensor(self, rec, frame_ids):
+        """Fixed-stride per-frame record (B, 3 + 2P) float32: [frame_id, num_boxes, entropy, labels..., density...]."""
+        B = rec["entropy"].shape[0]
+        out = torch.zeros((B, 3 + 2 * self.P), dtype=torch.float32, device=self.device)
+        out[:, 0] = torch.as_tensor(frame_ids, dtype=torch.float32, device=self.device)
+        out[:, 1] = rec["num_boxes"].float()
+        out[:, 2] = rec["entropy"]
+        out[:, 3:3 + self.P] = rec["labels"].float()
+        out[:, 3 + self.P:] = rec["density"]
+        return out
+
+    def score_pool(self, frames, frame_ids=None):
+        """Scores this rank's shard of `frames` (all ranks pass the same list) and all-gathers the records.
+        Returns a dict frame_id -> dict(entropy, labels (n,), density (n,)) identical on every rank."""
+        world, rank = _world_rank()
+        ids = list(range(len(frames))) if frame_ids is None else list(frame_ids)
+        mine = shard_indices(len(frames), rank, world)
+        recs = []
+        for s in range(0, len(mine), self.batch_size):
+            sel = mine[s:s + self.batch_size]
+            r = self.score_device(self.to_device(self.stage_host([frames[i] for i in sel])))
+            recs.append(self.record_tensor(r, sel))
+        local = torch.cat(recs) if recs else torch.zeros((0, 3 + 2 * self.P), device=self.device)
+        out = gather_records(local, len(frames), self.P, self.device)
+        return {ids[k]: v for k, v in out.items()}
+
+
+def _world_rank():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def shard_indices(n_frames, rank, world):
+    """frame i -> rank i mod W (the reference's eval DistributedSampler, pcdet/datasets/__init__.py:26-46)."""
+    return list(range(rank, n_frames, world))
+
+
+def gather_records(local, n_frames, P, device):
+    """ONE all-gather of the fixed-stride records (row = [frame index, num_boxes, entropy, P labels, P densities]); rows
+    are padded per rank to ceil(n/W) with frame index -1. Returns {frame index: dict(entropy, labels, density)}."""
+    world, _ = _world_rank()
+    per_rank = (n_frames + world - 1) // world
+    pad = torch.full((per_rank, 3 + 2 * P), -1.0, dtype=torch.float32, device=device)
+    pad[: local.shape[0]] = local
+    if world > 1:
+        gathered = torch.empty((world * per_rank, pad.shape[1]), dtype=torch.float32, device=device)
+        dist.all_gather_into_tensor(gathered, pad)            # the single collective of the scoring path
+    else:
+        gathered = pad
+    out = {}
+    for row in gathered.cpu().numpy():
+        if row[0] < 0:
+            continue
+        n = int(row[1])
+        out[int(row[0])] = dict(entropy=float(row[2]), labels=row[3:3 + n].astype(np.int64),
+                                density=row[3 + P:3 + P + n].astype(np.float32))
+    return out

@@ -1,0 +1,252 @@
+"""SECOND detector + CRB stage-1 scoring on the crb3d kernels.
+
+Module and parameter names mirror the reference so its checkpoints load unchanged
+(pcdet/models/detectors/second_net.py:9-22, detector3d_template.py:24-53 module_topology):
+  vfe (MeanVFE, fused into the voxelizer) -> backbone_3d (VoxelBackBone8x, spconv_backbone.py:69-180) ->
+  map_to_bev_module (HeightCompression) -> backbone_2d (BaseBEVBackbone, base_bev_backbone.py:7-112) ->
+  dense_head (AnchorHeadSingle, anchor_head_single.py:6-76) -> post_processing (detector3d_template.py:186-409).
+`score_batch` is the pool-scoring hot path (forward + per-frame CRB stage-1 record) with no host synchronisation after
+the rulebook phase: max-class scores, top-k, lazy decode, batched rotated NMS, points-in-boxes density and the label
+entropy all stay on the device.
+"""
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+import spconv.pytorch as spconv
+
+from . import head_ops, ops, synth
+
+KITTI_SECOND_CFG = dict(
+    class_names=["Car", "Pedestrian", "Cyclist"],
+    data=synth.KITTI,
+    num_bev_features=256,
+    layer_nums=[5, 5], layer_strides=[1, 2], num_filters=[128, 256], upsample_strides=[1, 2], num_upsample_filters=[256, 256],
+    anchors=[
+        dict(class_name="Car", anchor_sizes=[[3.9, 1.6, 1.56]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-1.78]),
+        dict(class_name="Pedestrian", anchor_sizes=[[0.8, 0.6, 1.73]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-0.6]),
+        dict(class_name="Cyclist", anchor_sizes=[[1.76, 0.6, 1.73]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-0.6]),
+    ],
+    dir_offset=0.78539, dir_limit_offset=0.0, num_dir_bins=2,
+    score_thresh=0.1, nms_thresh=0.01, nms_pre_maxsize=4096, nms_post_maxsize=500,   # second.yaml:88-99
+)
+
+WAYMO_SECOND_CFG = dict(
+    class_names=["Vehicle", "Pedestrian", "Cyclist"],
+    data=synth.WAYMO,
+    num_bev_features=256,
+    layer_nums=[5, 5], layer_strides=[1, 2], num_filters=[128, 256], upsample_strides=[1, 2], num_upsample_filters=[256, 256],
+    anchors=[  # tools/cfgs/waymo_models/second.yaml
+        dict(class_name="Vehicle", anchor_sizes=[[4.7, 2.1, 1.7]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[0]),
+        dict(class_name="Pedestrian", anchor_sizes=[[0.91, 0.86, 1.73]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[0]),
+        dict(class_name="Cyclist", anchor_sizes=[[1.78, 0.84, 1.78]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[0]),
+    ],
+    dir_offset=0.78539, dir_limit_offset=0.0, num_dir_bins=2,
+    score_thresh=0.1, nms_thresh=0.7, nms_pre_maxsize=4096, nms_post_maxsize=500,
+)
+
+
+def post_act_block(in_channels, out_channels, kernel_size, indice_key=None, stride=1, padding=0, conv_type="subm", norm_fn=None):
+    if conv_type == "subm":
+        conv = spconv.SubMConv3d(in_channels, out_channels, kernel_size, bias=False, indice_key=indice_key)
+    elif conv_type == "spconv":
+        conv = spconv.SparseConv3d(in_channels, out_channels, kernel_size, stride=stride, padding=padding, bias=False,
+                                   indice_key=indice_key)
+    elif conv_type == "inverseconv":
+        conv = spconv.SparseInverseConv3d(in_channels, out_channels, kernel_size, indice_key=indice_key, bias=False)
+    else:
+        raise NotImplementedError
+    return spconv.SparseSequential(conv, norm_fn(out_channels), nn.ReLU())
+
+
+class VoxelBackBone8x(nn.Module):
+    def __init__(self, input_channels, grid_size):
+        super().__init__()
+        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        self.sparse_shape = [int(grid_size[2]) + 1, int(grid_size[1]), int(grid_size[0])]   # z gets +1 (spconv_backbone.py:75)
+        self.conv_input = spconv.SparseSequential(
+            spconv.SubMConv3d(input_channels, 16, 3, padding=1, bias=False, indice_key="subm1"), norm_fn(16), nn.ReLU())
+        block = post_act_block
+        self.conv1 = spconv.SparseSequential(block(16, 16, 3, norm_fn=norm_fn, padding=1, indice_key="subm1"))
+        self.conv2 = spconv.SparseSequential(
+            block(16, 32, 3, norm_fn=norm_fn, stride=2, padding=1, indice_key="spconv2", conv_type="spconv"),
+            block(32, 32, 3, norm_fn=norm_fn, padding=1, indice_key="subm2"),
+            block(32, 32, 3, norm_fn=norm_fn, padding=1, indice_key="subm2"))
+        self.conv3 = spconv.SparseSequential(
+            block(32, 64, 3, norm_fn=norm_fn, stride=2, padding=1, indice_key="spconv3", conv_type="spconv"),
+            block(64, 64, 3, norm_fn=norm_fn, padding=1, indice_key="subm3"),
+            block(64, 64, 3, norm_fn=norm_fn, padding=1, indice_key="subm3"))
+        self.conv4 = spconv.SparseSequential(
+            block(64, 64, 3, norm_fn=norm_fn, stride=2, padding=(0, 1, 1), indice_key="spconv4", conv_type="spconv"),
+            block(64, 64, 3, norm_fn=norm_fn, padding=1, indice_key="subm4"),
+            block(64, 64, 3, norm_fn=norm_fn, padding=1, indice_key="subm4"))
+        self.conv_out = spconv.SparseSequential(
+            spconv.SparseConv3d(64, 128, (3, 1, 1), stride=(2, 1, 1), padding=0, bias=False, indice_key="spconv_down2"),
+            norm_fn(128), nn.ReLU())
+        self.num_point_features = 128
+
+    def forward(self, batch_dict):
+        x = spconv.SparseConvTensor(features=batch_dict["voxel_features"], indices=batch_dict["voxel_coords"].int(),
+                                    spatial_shape=self.sparse_shape, batch_size=batch_dict["batch_size"])
+        x = self.conv_input(x)
+        x1 = self.conv1(x)
+        x2 = self.conv2(x1)
+        x3 = self.conv3(x2)
+        x4 = self.conv4(x3)
+        out = self.conv_out(x4)
+        batch_dict.update({"encoded_spconv_tensor": out, "encoded_spconv_tensor_stride": 8,
+                           "multi_scale_3d_features": {"x_conv1": x1, "x_conv2": x2, "x_conv3": x3, "x_conv4": x4},
+                           "multi_scale_3d_strides": {"x_conv1": 1, "x_conv2": 2, "x_conv3": 4, "x_conv4": 8}})
+        return batch_dict
+
+
+class HeightCompression(nn.Module):
+    def __init__(self, num_bev_features):
+        super().__init__()
+        self.num_bev_features = num_bev_features
+
+    def forward(self, batch_dict):
+        t = batch_dict["encoded_spconv_tensor"]
+        # (B, C*D, H, W) values identical to dense().view(N, C*D, H, W); memory is channels-last for the BEV convs
+        batch_dict["spatial_features"] = t.dense_bev_channels_last()
+        batch_dict["spatial_features_stride"] = batch_dict["encoded_spconv_tensor_stride"]
+        return batch_dict
+
+
+class BaseBEVBackbone(nn.Module):
+    def __init__(self, cfg, input_channels):
+        super().__init__()
+        layer_nums, layer_strides, num_filters = cfg["layer_nums"], cfg["layer_strides"], cfg["num_filters"]
+        ups, num_up = cfg["upsample_strides"], cfg["num_upsample_filters"]
+        c_in_list = [input_channels, *num_filters[:-1]]
+        self.blocks, self.deblocks = nn.ModuleList(), nn.ModuleList()
+        for idx in range(len(layer_nums)):
+            layers = [nn.ZeroPad2d(1), nn.Conv2d(c_in_list[idx], num_filters[idx], 3, stride=layer_strides[idx], padding=0, bias=False),
+                      nn.BatchNorm2d(num_filters[idx], eps=1e-3, momentum=0.01), nn.ReLU()]
+            for _ in range(layer_nums[idx]):
+                layers += [nn.Conv2d(num_filters[idx], num_filters[idx], 3, padding=1, bias=False),
+                           nn.BatchNorm2d(num_filters[idx], eps=1e-3, momentum=0.01), nn.ReLU()]
+            self.blocks.append(nn.Sequential(*layers))
+            self.deblocks.append(nn.Sequential(
+                nn.ConvTranspose2d(num_filters[idx], num_up[idx], ups[idx], stride=ups[idx], bias=False),
+                nn.BatchNorm2d(num_up[idx], eps=1e-3, momentum=0.01), nn.ReLU()))
+        self.num_bev_features = sum(num_up)
+
+    def forward(self, batch_dict):
+        x = batch_dict["spatial_features"]
+        ups = []
+        for i in range(len(self.blocks)):
+            x = self.blocks[i](x)
+            ups.append(self.deblocks[i](x))
+        batch_dict["spatial_features_2d"] = torch.cat(ups, dim=1) if len(ups) > 1 else ups[0]
+        return batch_dict
+
+
+class AnchorHeadSingle(nn.Module):
+    def __init__(self, cfg, input_channels, grid_size):
+        super().__init__()
+        self.cfg = cfg
+        self.num_class = len(cfg["class_names"])
+        self.n_loc = sum(len(a["anchor_sizes"]) * len(a["anchor_rotations"]) * len(a["anchor_bottom_heights"]) for a in cfg["anchors"])
+        self.conv_cls = nn.Conv2d(input_channels, self.n_loc * self.num_class, 1)
+        self.conv_box = nn.Conv2d(input_channels, self.n_loc * 7, 1)
+        self.conv_dir_cls = nn.Conv2d(input_channels, self.n_loc * cfg["num_dir_bins"], 1)
+        nn.init.constant_(self.conv_cls.bias, -np.log((1 - 0.01) / 0.01))
+        nn.init.normal_(self.conv_box.weight, mean=0, std=0.001)
+        fm = (int(grid_size[0]) // 8, int(grid_size[1]) // 8)   # feature_map_stride 8
+        self.spec = head_ops.make_anchor_spec(cfg["anchors"], cfg["data"]["pc_range"], fm, cfg["dir_offset"],
+                                              cfg["dir_limit_offset"], cfg["num_dir_bins"])
+        self.num_anchors = fm[0] * fm[1] * self.n_loc
+
+    def forward(self, batch_dict):
+        x = batch_dict["spatial_features_2d"]
+        B = x.shape[0]
+        # NHWC: with channels-last activations permute(0,2,3,1) is a view and .contiguous() is free
+        batch_dict["cls_preds"] = self.conv_cls(x).permute(0, 2, 3, 1).contiguous().view(B, self.num_anchors, self.num_class)
+        batch_dict["box_preds"] = self.conv_box(x).permute(0, 2, 3, 1).contiguous().view(B, self.num_anchors, 7)
+        batch_dict["dir_cls_preds"] = self.conv_dir_cls(x).permute(0, 2, 3, 1).contiguous().view(B, self.num_anchors, -1)
+        return batch_dict
+
+
+class SECONDNet(nn.Module):
+    def __init__(self, cfg=KITTI_SECOND_CFG):
+        super().__init__()
+        self.cfg = cfg
+        d = cfg["data"]
+        rng = np.asarray(d["pc_range"], dtype=np.float64)
+        self.grid_size = np.round((rng[3:6] - rng[0:3]) / np.asarray(d["voxel_size"], dtype=np.float64)).astype(np.int64)
+        self.num_class = len(cfg["class_names"])
+        self.backbone_3d = VoxelBackBone8x(d["n_feat"], self.grid_size)
+        self.map_to_bev_module = HeightCompression(cfg["num_bev_features"])
+        self.backbone_2d = BaseBEVBackbone(cfg, cfg["num_bev_features"])
+        self.dense_head = AnchorHeadSingle(cfg, self.backbone_2d.num_bev_features, self.grid_size)
+
+    def to_device(self, device):
+        self.to(device)
+        self.backbone_2d.to(memory_format=torch.channels_last)
+        self.dense_head.to(memory_format=torch.channels_last)
+        return self
+
+    # ------------------------------------------------------------------------------------------- forward pieces
+    def voxelize(self, points, frame_offsets, batch_size, training=False):
+        d = self.cfg["data"]
+        mv = d["max_voxels_train"] if training else d["max_voxels_test"]
+        return ops.voxelize(points, frame_offsets, batch_size, d["pc_range"], d["voxel_size"], d["max_pts"], mv,
+                            xyz_col=points.shape[1] - d["n_feat"], feat_col=points.shape[1] - d["n_feat"], n_feat=d["n_feat"])
+
+    def forward_features(self, points, frame_offsets, batch_size):
+        """points (N, C) or (N, 1+C) with the batch index in column 0 (collate layout). Returns the head outputs."""
+        vox = self.voxelize(points, frame_offsets, batch_size)
+        bd = dict(batch_size=batch_size, voxel_features=vox["mean"], voxel_coords=vox["coords"])
+        bd = self.backbone_3d(bd)
+        bd = self.map_to_bev_module(bd)
+        bd = self.backbone_2d(bd)
+        bd = self.dense_head(bd)
+        return bd
+
+    @torch.no_grad()
+    def score_batch(self, points, frame_offsets, batch_size, max_pts_per_frame):
+        """CRB stage-1 record of every frame of the batch (crb_sampling.py:72-103 via post_processing):
+        dict(entropy (B,), num_boxes (B,), labels (B,P) int32 1-based (0 pad), density (B,P), boxes (B,P,7), scores (B,P))."""
+        cfg = self.cfg
+        bd = self.forward_features(points, frame_offsets, batch_size)
+        B, A = batch_size, self.dense_head.num_anchors
+        score, label = head_ops.anchor_head_scores(bd["cls_preds"], self.num_class)
+        score, label = score.view(B, A), label.view(B, A, 1)
+        # class_agnostic_nms (model_nms_utils.py:6-25): score >= thresh, top-k(NMS_PRE_MAXSIZE) - valid entries are a prefix
+        k = min(cfg["nms_pre_maxsize"], A)
+        top_scores, top_idx = torch.topk(score, k, dim=1)
+        counts = (top_scores >= cfg["score_thresh"]).sum(dim=1).int()
+        boxes = head_ops.anchor_decode_select(bd["box_preds"], bd["dir_cls_preds"], top_idx, self.dense_head.spec, A)
+        P = cfg["nms_post_maxsize"]
+        keep, num = ops.nms_batched(boxes, counts, cfg["nms_thresh"], rotated=True, max_keep=P)
+        final_boxes = head_ops.gather_rows(boxes, keep, num, 0.0)
+        final_scores = head_ops.gather_rows(top_scores.unsqueeze(-1).contiguous(), keep, num, 0.0).squeeze(-1)
+        anchor_of_kept = head_ops.gather_rows(top_idx.int().unsqueeze(-1).contiguous(), keep, num, 0).squeeze(-1)
+        final_labels = head_ops.gather_rows(label, anchor_of_kept.long(), num, 0).squeeze(-1)
+        # per-box point density (detector3d_template.py:379-387) and label entropy (crb_sampling.py:86-100)
+        box_begin = torch.arange(B, device=points.device, dtype=torch.int32) * P
+        xyz_col = points.shape[1] - cfg["data"]["n_feat"]
+        _, cnt, dens = ops.points_in_boxes_ranges(points[:, xyz_col:], frame_offsets[:-1], frame_offsets[1:], max_pts_per_frame,
+                                                  final_boxes, box_begin, box_begin + num)
+        entropy = ops.label_entropy_ranges(final_labels, box_begin, box_begin + num, self.num_class)
+        return dict(entropy=entropy, num_boxes=num, labels=final_labels, density=dens.view(B, P), point_counts=cnt.view(B, P),
+                    boxes=final_boxes, scores=final_scores)
+
+
+def calibrate_head_bias(model, points, frame_offsets, batch_size, target_fraction=0.03):
+    """Synthetic weights only: the default conv_cls bias (-log(99), anchor_head_single.py:37-38) yields no box above
+    SCORE_THRESH; shift each class's bias so that `target_fraction` of its anchors clear the threshold."""
+    with torch.no_grad():
+        bd = model.forward_features(points, frame_offsets, batch_size)
+        logits = bd["cls_preds"].reshape(-1, model.num_class)
+        thr = float(np.log(model.cfg["score_thresh"] / (1 - model.cfg["score_thresh"])))
+        n_loc = model.dense_head.n_loc
+        for c in range(model.num_class):
+            q = torch.quantile(logits[:: max(1, logits.shape[0] // 200000), c], 1.0 - target_fraction)
+            shift = thr - float(q)
+            bias = model.dense_head.conv_cls.bias.view(n_loc, model.num_class)
+            bias[:, c] += shift
+    return model

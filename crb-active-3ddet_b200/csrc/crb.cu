@@ -19,13 +19,14 @@ constexpr int AXIS = 400;  // crb_sampling.py:259 np.linspace(..., 400)
 
 // ------------------------------------------------------------------ stage 1: label entropy
 __global__ void __launch_bounds__(128) label_entropy_kernel(const int* __restrict__ labels, const int* __restrict__ box_off,
-                                                            int B, int num_class, float* __restrict__ entropy,
+                                                            const int* __restrict__ box_end, int B, int num_class,
+                                                            float* __restrict__ entropy,
                                                             int* __restrict__ class_counts /*B x num_class, optional*/) {
     extern __shared__ int cnt[];  // num_class
     const int b = blockIdx.x;
     for (int c = threadIdx.x; c < num_class; c += blockDim.x) cnt[c] = 0;
     __syncthreads();
-    const int s = box_off[b], e = box_off[b + 1];
+    const int s = box_off[b], e = box_end[b];
     for (int i = s + threadIdx.x; i < e; i += blockDim.x) {
         int l = labels[i] - 1;
         if (l >= 0 && l < num_class) atomicAdd(&cnt[l], 1);
@@ -253,7 +254,17 @@ extern "C" int crb3d_label_entropy(const int* labels, const int* box_off, int B,
                                    int* class_counts, cudaStream_t stream) {
     if (B < 0 || num_class <= 0 || num_class > 4096 || !box_off || !entropy) return CRB3D_ERR_ARG;
     if (B == 0) return CRB3D_OK;
-    label_entropy_kernel<<<B, 128, sizeof(int) * num_class, stream>>>(labels, box_off, B, num_class, entropy, class_counts);
+    label_entropy_kernel<<<B, 128, sizeof(int) * num_class, stream>>>(labels, box_off, box_off + 1, B, num_class, entropy, class_counts);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+// explicit [begin, end) ranges per frame (padded label tensors with per-frame counts)
+extern "C" int crb3d_label_entropy_ranges(const int* labels, const int* box_begin, const int* box_end, int B,
+                                          int num_class, float* entropy, int* class_counts, cudaStream_t stream) {
+    if (B < 0 || num_class <= 0 || num_class > 4096 || !box_begin || !box_end || !entropy) return CRB3D_ERR_ARG;
+    if (B == 0) return CRB3D_OK;
+    label_entropy_kernel<<<B, 128, sizeof(int) * num_class, stream>>>(labels, box_begin, box_end, B, num_class, entropy, class_counts);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }

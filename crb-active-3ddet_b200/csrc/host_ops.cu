@@ -52,3 +52,54 @@ extern "C" int crb3d_points_in_boxes_cpu(const float* boxes, int n_boxes, const 
     }
     return CRB3D_OK;
 }
+
+// Host-side hard voxelizer with the Point2VoxelCPU3d contract (runs inside DataLoader worker processes, where no CUDA
+// context exists): pcdet/datasets/processor/data_processor.py:25,36-42,54-59. HOST pointers. One frame.
+// voxels (max_voxels,max_pts,n_feat) zero-filled here, coords (max_voxels,3) zyx, num (max_voxels). *n_voxels = count.
+#include <vector>
+#include <cstring>
+#include <cmath>
+extern "C" int crb3d_point_to_voxel_cpu(const float* pts, int64_t n, int stride, int n_feat, const float* range6,
+                                        const float* vsize3, const int* grid3, int max_pts, int max_voxels,
+                                        float* voxels, int* coords, int* num, int* n_voxels) {
+    if (n < 0 || stride < 3 || n_feat <= 0 || n_feat > stride || max_pts <= 0 || max_voxels <= 0 || !range6 || !vsize3 ||
+        !grid3 || !voxels || !coords || !num || !n_voxels)
+        return CRB3D_ERR_ARG;
+    size_t cap = 16;
+    while (cap < (size_t)n * 2 + 2) cap <<= 1;
+    std::vector<int64_t> keys(cap, -1);
+    std::vector<int> vals(cap, -1);
+    std::memset(voxels, 0, sizeof(float) * (size_t)max_voxels * max_pts * n_feat);
+    std::memset(num, 0, sizeof(int) * (size_t)max_voxels);
+    int count = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* p = pts + i * stride;
+        int c[3];
+        bool ok = true;
+        for (int j = 0; j < 3 && ok; ++j) {
+            const float f = std::floor((p[j] - range6[j]) / vsize3[j]);
+            ok = (f >= 0.0f) && (f < (float)grid3[j]);
+            c[j] = ok ? (int)f : 0;
+        }
+        if (!ok) continue;
+        const int64_t key = ((int64_t)c[2] * grid3[1] + c[1]) * grid3[0] + c[0];
+        size_t s = (size_t)(((uint64_t)key * 0x9E3779B97F4A7C15ull) >> 17) & (cap - 1);
+        int vid = -1;
+        while (keys[s] != -1) {
+            if (keys[s] == key) { vid = vals[s]; break; }
+            s = (s + 1) & (cap - 1);
+        }
+        if (vid < 0) {
+            if (count >= max_voxels) continue;
+            vid = count++;
+            keys[s] = key; vals[s] = vid;
+            coords[vid * 3] = c[2]; coords[vid * 3 + 1] = c[1]; coords[vid * 3 + 2] = c[0];
+        }
+        if (num[vid] < max_pts) {
+            std::memcpy(voxels + ((size_t)vid * max_pts + num[vid]) * n_feat, p, sizeof(float) * n_feat);
+            ++num[vid];
+        }
+    }
+    *n_voxels = count;
+    return CRB3D_OK;
+}

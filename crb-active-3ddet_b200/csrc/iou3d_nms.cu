@@ -41,11 +41,19 @@ __global__ void __launch_bounds__(256) pairwise_kernel(int na, const float* __re
 // ------------------------------------------------------------------ NMS bitmask (upper-triangular tiles)
 template <bool ROTATED>
 __global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const float* __restrict__ boxes,
-                                                      unsigned long long* __restrict__ mask, int col_blocks) {
+                                                      unsigned long long* __restrict__ mask, int col_blocks,
+                                                      const int* __restrict__ counts, int n_max) {
+    // blockIdx.y = frame (batched NMS: frame b owns boxes[b*n_max ...] and mask[b*n_max*col_blocks ...], n = counts[b])
+    if (counts) {
+        n = min(counts[blockIdx.y], n_max);
+        boxes += (size_t)blockIdx.y * n_max * 7;
+        mask += (size_t)blockIdx.y * n_max * col_blocks;
+    }
     // blockIdx.x enumerates tiles (r, c) with c >= r
     int t = blockIdx.x, r = 0;
     while (t >= col_blocks - r) { t -= col_blocks - r; ++r; }
     const int c = r + t;
+    if (r * 64 >= n || c * 64 >= n) return;  // tile beyond this frame's boxes (uniform per CTA)
     const int row_size = min(n - r * 64, 64), col_size = min(n - c * 64, 64);
     __shared__ RBox cb[64];
     __shared__ float craw[64 * 7];
@@ -79,8 +87,18 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const
 // Equivalent to iou3d_nms.cpp:116-132 (remv bitset, keep[] in ascending box index).
 __global__ void __launch_bounds__(256) nms_reduce_kernel(int n, int col_blocks, const unsigned long long* __restrict__ mask,
                                                          int max_keep, long long* __restrict__ keep,
-                                                         int* __restrict__ num_keep) {
+                                                         int* __restrict__ num_keep, const int* __restrict__ counts,
+                                                         int n_max, int keep_stride) {
     extern __shared__ unsigned long long remv[];  // col_blocks
+    if (counts) {
+        n = min(counts[blockIdx.x], n_max);
+        mask += (size_t)blockIdx.x * n_max * col_blocks;
+        keep += (size_t)blockIdx.x * keep_stride;
+        num_keep += blockIdx.x;
+        col_blocks = (n_max + 63) / 64;
+    }
+    const int row_stride = col_blocks;
+    col_blocks = (n + 63) / 64;
     __shared__ unsigned long long diag[64];
     __shared__ unsigned long long keepbits_s;
     __shared__ int kept_s;
@@ -90,7 +108,7 @@ __global__ void __launch_bounds__(256) nms_reduce_kernel(int n, int col_blocks, 
     __syncthreads();
     for (int c = 0; c < col_blocks; ++c) {
         const int base = c * 64, sz = min(64, n - base);
-        if (tid < 64) diag[tid] = (tid < sz) ? mask[(size_t)(base + tid) * col_blocks + c] : 0ull;
+        if (tid < 64) diag[tid] = (tid < sz) ? mask[(size_t)(base + tid) * row_stride + c] : 0ull;
         __syncthreads();
         if (tid == 0) {
             unsigned long long cur = remv[c], kb = 0ull;
@@ -115,7 +133,7 @@ __global__ void __launch_bounds__(256) nms_reduce_kernel(int n, int col_blocks, 
             while (bits) {
                 int b = __ffsll((long long)bits) - 1;
                 bits &= bits - 1;
-                acc |= mask[(size_t)(base + b) * col_blocks + j];
+                acc |= mask[(size_t)(base + b) * row_stride + j];
             }
             remv[j] |= acc;
         }
@@ -166,14 +184,14 @@ extern "C" int crb3d_nms(const float* boxes, int n, float thresh, int rotated, i
     unsigned long long* mask = c.take<unsigned long long>((size_t)n * cb);
     if (!c.ok) return CRB3D_ERR_WORKSPACE;
     const unsigned tiles = (unsigned)((int64_t)cb * (cb + 1) / 2);
-    if (rotated) nms_mask_kernel<true><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb);
-    else nms_mask_kernel<false><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb);
+    if (rotated) nms_mask_kernel<true><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
+    else nms_mask_kernel<false><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
     size_t smem = sizeof(unsigned long long) * cb;
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return CRB3D_ERR_UNSUPPORTED;
         CRB3D_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    nms_reduce_kernel<<<1, 256, smem, stream>>>(n, cb, mask, max_keep, keep, num_keep);
+    nms_reduce_kernel<<<1, 256, smem, stream>>>(n, cb, mask, max_keep, keep, num_keep, nullptr, 0, 0);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -184,8 +202,43 @@ extern "C" int crb3d_nms_mask(const float* boxes, int n, float thresh, int rotat
     if (n <= 0 || !mask) return CRB3D_ERR_ARG;
     const int cb = (int)crb3d_divup(n, 64);
     const unsigned tiles = (unsigned)((int64_t)cb * (cb + 1) / 2);
-    if (rotated) nms_mask_kernel<true><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb);
-    else nms_mask_kernel<false><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb);
+    if (rotated) nms_mask_kernel<true><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
+    else nms_mask_kernel<false><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+// Batched NMS for the scoring path: frame b owns boxes[b][0..counts[b]) of a padded (B, n_max, 7) tensor (each frame
+// sorted by descending score). keep: (B, keep_stride) int64, num_keep: (B). One mask launch + one reduce launch for
+// the whole batch, no host synchronisation. ws: B * n_max * ceil(n_max/64) * 8 bytes.
+extern "C" int crb3d_nms_batched_workspace_bytes(int B, int n_max, size_t* bytes) {
+    if (!bytes || B < 0 || n_max < 0) return CRB3D_ERR_ARG;
+    size_t cb = (size_t)crb3d_divup(n_max > 0 ? n_max : 1, 64);
+    *bytes = crb3d_align(sizeof(unsigned long long) * (size_t)(B > 0 ? B : 1) * (size_t)(n_max > 0 ? n_max : 1) * cb);
+    return CRB3D_OK;
+}
+
+extern "C" int crb3d_nms_batched(const float* boxes, const int* counts, int B, int n_max, float thresh, int rotated,
+                                 int max_keep, long long* keep, int keep_stride, int* num_keep, void* ws,
+                                 size_t ws_bytes, cudaStream_t stream) {
+    if (B < 0 || n_max < 0 || !counts || !keep || !num_keep || keep_stride <= 0) return CRB3D_ERR_ARG;
+    if (max_keep <= 0 && keep_stride < n_max) return CRB3D_ERR_ARG;
+    if (max_keep > 0 && keep_stride < max_keep) return CRB3D_ERR_ARG;
+    if (B == 0) return CRB3D_OK;
+    if (n_max == 0) { CRB3D_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int) * B, stream)); return CRB3D_OK; }
+    const int cb = (int)crb3d_divup(n_max, 64);
+    WsCursor c(ws, ws_bytes);
+    unsigned long long* mask = c.take<unsigned long long>((size_t)B * n_max * cb);
+    if (!c.ok) return CRB3D_ERR_WORKSPACE;
+    const unsigned tiles = (unsigned)((int64_t)cb * (cb + 1) / 2);
+    if (rotated) nms_mask_kernel<true><<<dim3(tiles, B), 64, 0, stream>>>(0, thresh, boxes, mask, cb, counts, n_max);
+    else nms_mask_kernel<false><<<dim3(tiles, B), 64, 0, stream>>>(0, thresh, boxes, mask, cb, counts, n_max);
+    size_t smem = sizeof(unsigned long long) * cb;
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return CRB3D_ERR_UNSUPPORTED;
+        CRB3D_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    nms_reduce_kernel<<<B, 256, smem, stream>>>(0, cb, mask, max_keep, keep, num_keep, counts, n_max, keep_stride);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }

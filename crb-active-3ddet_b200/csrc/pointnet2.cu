@@ -127,10 +127,14 @@ __global__ void __launch_bounds__(256) group_points_grad_kernel(int B, int M, in
 }
 
 // ------------------------------------------------------------------ farthest point sampling
-// key = (distance bits << 32) | ~tie, tie = (k mod ref_block) << 21 | (k / ref_block): the maximum key is the
-// farthest point, ties resolved like the reference's strided scan (strict '>') + pairwise tree (left wins).
+// key = (distance bits << 32) | ~tie: the maximum key is the farthest point. Ties follow the reference exactly: its
+// strided scan keeps the first maximum per thread (lowest k / block) and its pairwise tree (slot t absorbs slot t+s,
+// left wins ties, s = block/2 ... 1) lets the thread whose id has a 0 at the LOWEST differing bit win, i.e. threads are
+// ordered by their bit-reversed id. tie = bitrev(k mod block) << 21 | (k / block).
 __device__ __forceinline__ unsigned long long fps_key(float d, int k, int ref_block_log2) {
-    const unsigned int tie = ((unsigned int)(k & ((1 << ref_block_log2) - 1)) << 21) | (unsigned int)(k >> ref_block_log2);
+    const unsigned int t = (unsigned int)(k & ((1 << ref_block_log2) - 1));
+    const unsigned int rev = ref_block_log2 ? (__brev(t) >> (32 - ref_block_log2)) : 0u;
+    const unsigned int tie = (rev << 21) | (unsigned int)(k >> ref_block_log2);
     return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(~tie);
 }
 
@@ -213,7 +217,9 @@ __global__ void __launch_bounds__(1024) fps_kernel(int n_fixed, int m_fixed, con
                 int win = 0;
                 if (k2 != 0ull) {
                     const unsigned int tie = ~(unsigned int)(k2 & 0xFFFFFFFFull);
-                    win = (int)((tie & ((1u << 21) - 1u)) << rbl) | (int)(tie >> 21);
+                    const unsigned int rev = tie >> 21;
+                    const unsigned int t = rbl ? (__brev(rev) >> (32 - rbl)) : 0u;
+                    win = (int)((tie & ((1u << 21) - 1u)) << rbl) | (int)t;
                 }
                 cur_s = win;
                 out[j] = win + out_base;

@@ -53,15 +53,17 @@ constexpr int PIB_CHUNK = 128;
 // stacked (offset arrays of length B+1). out_idx is the box index LOCAL to the frame, -1 = background.
 __global__ void __launch_bounds__(256) points_in_boxes_kernel(int B, int M, int T, const float* __restrict__ pts,
                                                               int pt_stride, const int* __restrict__ pt_off,
+                                                              const int* __restrict__ pt_end_arr,
                                                               const float* __restrict__ boxes,
-                                                              const int* __restrict__ box_off, int total_pts,
+                                                              const int* __restrict__ box_off,
+                                                              const int* __restrict__ box_end_arr, int total_pts,
                                                               int* __restrict__ out_idx, int* __restrict__ counts) {
     __shared__ PBox sb[PIB_CHUNK];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     // every thread of a CTA must see the same frame to share the staged boxes: CTAs are launched per frame
     const int b = blockIdx.y;
     int p_begin, p_end, b_begin, b_end;
-    if (pt_off) { p_begin = pt_off[b]; p_end = pt_off[b + 1]; b_begin = box_off[b]; b_end = box_off[b + 1]; }
+    if (pt_off) { p_begin = pt_off[b]; p_end = pt_end_arr[b]; b_begin = box_off[b]; b_end = box_end_arr[b]; }
     else { p_begin = b * M; p_end = p_begin + M; b_begin = b * T; b_end = b_begin + T; }
     const int pi = p_begin + p;
     if (blockIdx.x * blockDim.x >= p_end - p_begin) return;  // whole CTA past this frame
@@ -207,7 +209,7 @@ extern "C" int crb3d_points_in_boxes(const float* boxes, const float* pts, int B
     if (B < 0 || T < 0 || M < 0 || !out_idx) return CRB3D_ERR_ARG;
     if (B == 0 || M == 0 || T == 0) return CRB3D_OK;
     dim3 grid((unsigned)crb3d_divup(M, 256), B);
-    points_in_boxes_kernel<<<grid, 256, 0, stream>>>(B, M, T, pts, 3, nullptr, boxes, nullptr, B * M, out_idx, nullptr);
+    points_in_boxes_kernel<<<grid, 256, 0, stream>>>(B, M, T, pts, 3, nullptr, nullptr, boxes, nullptr, nullptr, B * M, out_idx, nullptr);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -224,11 +226,31 @@ extern "C" int crb3d_points_in_boxes_stack(const float* pts, int pt_stride, cons
     if (counts && total_boxes > 0) CRB3D_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * total_boxes, stream));
     if (total_pts > 0 && max_pts_per_frame > 0) {
         dim3 grid((unsigned)crb3d_divup(max_pts_per_frame, 256), B);
-        points_in_boxes_kernel<<<grid, 256, 0, stream>>>(B, 0, 0, pts, pt_stride, pt_off, boxes, box_off, total_pts,
-                                                         out_idx, counts);
+        points_in_boxes_kernel<<<grid, 256, 0, stream>>>(B, 0, 0, pts, pt_stride, pt_off, pt_off + 1, boxes, box_off,
+                                                         box_off + 1, total_pts, out_idx, counts);
     }
     if (density && counts && total_boxes > 0)
         box_density_kernel<<<(unsigned)crb3d_divup(total_boxes, 256), 256, 0, stream>>>(total_boxes, boxes, counts, density);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+// Same with explicit [begin, end) ranges per frame (padded box tensors with per-frame counts: no compaction, no sync).
+// counts / density are indexed like `boxes` (slots outside a frame's range are left untouched; counts is zeroed here
+// over n_box_slots entries).
+extern "C" int crb3d_points_in_boxes_ranges(const float* pts, int pt_stride, const int* pt_begin, const int* pt_end,
+                                            int max_pts_per_frame, const float* boxes, const int* box_begin,
+                                            const int* box_end, int B, int n_box_slots, int* out_idx, int* counts,
+                                            float* density, cudaStream_t stream) {
+    if (B <= 0 || !pt_begin || !pt_end || !box_begin || !box_end || !out_idx || n_box_slots < 0) return CRB3D_ERR_ARG;
+    if (counts && n_box_slots > 0) CRB3D_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * n_box_slots, stream));
+    if (max_pts_per_frame > 0) {
+        dim3 grid((unsigned)crb3d_divup(max_pts_per_frame, 256), B);
+        points_in_boxes_kernel<<<grid, 256, 0, stream>>>(B, 0, 0, pts, pt_stride, pt_begin, pt_end, boxes, box_begin, box_end,
+                                                         0, out_idx, counts);
+    }
+    if (density && counts && n_box_slots > 0)
+        box_density_kernel<<<(unsigned)crb3d_divup(n_box_slots, 256), 256, 0, stream>>>(n_box_slots, boxes, counts, density);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }

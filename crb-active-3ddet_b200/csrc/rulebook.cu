@@ -191,7 +191,7 @@ extern "C" int crb3d_subm_rulebook_workspace_bytes(int n, size_t* bytes) {
 
 extern "C" int crb3d_subm_rulebook(const int* coords, int n, const int* spatial_shape3, const int* ksize3,
                                    const int* dilation3, int* nbr, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    if (n < 0 || !spatial_shape3 || !ksize3 || !nbr) return CRB3D_ERR_ARG;
+    if (n < 0 || !spatial_shape3 || !ksize3 || (!nbr && n > 0)) return CRB3D_ERR_ARG;
     int pad[3];
     for (int j = 0; j < 3; ++j) {
         if (ksize3[j] % 2 == 0) return CRB3D_ERR_UNSUPPORTED;  // SubM needs odd kernels (centre = identity)
@@ -264,8 +264,13 @@ extern "C" int crb3d_sparse_rulebook_pairs(const int* coords_in, int n_in, int b
                                            const int* pad3, const int* dilation3, int n_out, int* nbr, int* nbr_t,
                                            void* ws, size_t ws_bytes, cudaStream_t stream) {
     ConvGeom g;
-    if (n_in < 0 || n_out < 0 || !nbr || !make_geom(in_shape3, out_shape3, ksize3, stride3, pad3, dilation3, g))
+    if (n_in < 0 || n_out < 0 || (!nbr && n_out > 0) || !make_geom(in_shape3, out_shape3, ksize3, stride3, pad3, dilation3, g))
         return CRB3D_ERR_ARG;
+    if (n_in == 0 || n_out == 0) {  // nothing can pair up
+        if (nbr && n_out > 0) CRB3D_CUDA(cudaMemsetAsync(nbr, 0xFF, sizeof(int) * (size_t)g.K * n_out, stream));
+        if (nbr_t && n_in > 0) CRB3D_CUDA(cudaMemsetAsync(nbr_t, 0xFF, sizeof(int) * (size_t)g.K * n_in, stream));
+        return CRB3D_OK;
+    }
     int64_t nw = bitmap_words(batch_size, out_shape3);
     WsCursor c(ws, ws_bytes);
     unsigned int* bitmap = c.take<unsigned int>(nw);

@@ -44,6 +44,12 @@ int crb3d_voxelize(const float* points, int64_t n_points, int pt_stride, int xyz
                    const int* grid3, int max_pts, int max_voxels, float* mean_feats, float* voxels, int* coords,
                    int* num_points, int* frame_voxel_offsets, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+/* Host-side voxelizer with the same contract for DataLoader workers (no CUDA context there): HOST pointers, one frame.
+ * voxels (max_voxels,max_pts,n_feat), coords (max_voxels,3) zyx, num (max_voxels); *n_voxels = number of voxels. */
+int crb3d_point_to_voxel_cpu(const float* pts, int64_t n, int stride, int n_feat, const float* range6,
+                             const float* vsize3, const int* grid3, int max_pts, int max_voxels, float* voxels,
+                             int* coords, int* num, int* n_voxels);
+
 /* ---- rulebook ------------------------------------------------------------------------------------------------
  * replaces spconv 2.1 get_indice_pairs behind SubMConv3d / SparseConv3d
  * (pcdet/models/backbones_3d/spconv_backbone.py:12-17,77-117). coords: (n,4) int32 (b,z,y,x), unique rows.
@@ -99,6 +105,10 @@ int crb3d_nms_workspace_bytes(int n, size_t* bytes);
 /* boxes sorted by descending score; keep: device int64[n]; num_keep: device int; max_keep <= 0 keeps all. */
 int crb3d_nms(const float* boxes, int n, float thresh, int rotated, int max_keep, long long* keep, int* num_keep,
               void* ws, size_t ws_bytes, cudaStream_t stream);
+/* batched: frame b owns boxes[b][0..counts[b]) of a padded (B,n_max,7) tensor; keep (B,keep_stride) int64, num_keep (B). */
+int crb3d_nms_batched_workspace_bytes(int B, int n_max, size_t* bytes);
+int crb3d_nms_batched(const float* boxes, const int* counts, int B, int n_max, float thresh, int rotated, int max_keep,
+                      long long* keep, int keep_stride, int* num_keep, void* ws, size_t ws_bytes, cudaStream_t stream);
 int crb3d_nms_mask(const float* boxes, int n, float thresh, int rotated, unsigned long long* mask, cudaStream_t stream);
 /* host-side (CPU tensors) BEV IoU, replaces boxes_iou_bev_cpu (iou3d_cpu.cpp:232-252): HOST pointers. */
 int crb3d_boxes_iou_bev_cpu(const float* boxes_a, int na, const float* boxes_b, int nb, float* out);
@@ -108,6 +118,10 @@ int crb3d_points_in_boxes(const float* boxes, const float* pts, int B, int T, in
 int crb3d_points_in_boxes_stack(const float* pts, int pt_stride, const int* pt_off, int max_pts_per_frame,
                                 const float* boxes, const int* box_off, int B, int total_pts, int total_boxes,
                                 int* out_idx, int* counts, float* density, cudaStream_t stream);
+/* explicit [begin,end) row ranges per frame (padded boxes with per-frame counts; no compaction, no sync) */
+int crb3d_points_in_boxes_ranges(const float* pts, int pt_stride, const int* pt_begin, const int* pt_end,
+                                 int max_pts_per_frame, const float* boxes, const int* box_begin, const int* box_end,
+                                 int B, int n_box_slots, int* out_idx, int* counts, float* density, cudaStream_t stream);
 /* HOST pointers; (n_boxes, n_pts) 0/1 matrix with the CPU op's MARGIN=1e-2 (roiaware_pool3d.cpp:119-168). */
 int crb3d_points_in_boxes_cpu(const float* boxes, int n_boxes, const float* pts, int n_pts, int* out);
 int crb3d_roiaware_pool3d_forward(const float* rois, const float* pts, const float* pts_feature, int n_boxes,
@@ -136,9 +150,24 @@ int crb3d_three_interpolate_stack(int N, int C, const float* features, const int
 int crb3d_three_interpolate_grad_stack(int N, int C, const float* grad_out, const int* idx, const float* weight,
                                        float* grad_features, cudaStream_t stream);
 
+/* ---- anchor-head post-processing (anchor_head_template.py:238-285, box_coder_utils.py:45-77,
+ *      detector3d_template.py:281-311): max-class sigmoid score + 1-based label for every anchor, and lazy
+ *      ResidualCoder decoding (+ direction-bin fix) of the selected anchors only. cls/box/dir are channels-last
+ *      (B, H*W*A_loc, n_class | 7 | n_bins). spec: HOST pointer to the AnchorSpec struct of csrc/head.cu. */
+int crb3d_anchor_head_scores(const float* cls_preds, int64_t n_anchor_total, int n_class, float* score, int* label,
+                             cudaStream_t stream);
+int crb3d_anchor_decode_select(const float* box_preds, const float* dir_preds, const long long* sel, int B, int K,
+                               int64_t n_anchor_per_frame, const void* spec, float* out, cudaStream_t stream);
+int crb3d_gather_rows_f32(const float* src, const long long* idx, const int* valid, int B, int K, int64_t n_src,
+                          int width, float fill, float* out, cudaStream_t stream);
+int crb3d_gather_rows_i32(const int* src, const long long* idx, const int* valid, int B, int K, int64_t n_src,
+                          int width, int fill, int* out, cudaStream_t stream);
+
 /* ---- CRB scoring (pcdet/query_strategies/crb_sampling.py:86-100, 219-226, 276-338) -------------------------- */
 int crb3d_label_entropy(const int* labels, const int* box_off, int B, int num_class, float* entropy, int* class_counts,
                         cudaStream_t stream);
+int crb3d_label_entropy_ranges(const int* labels, const int* box_begin, const int* box_end, int B, int num_class,
+                               float* entropy, int* class_counts, cudaStream_t stream);
 int crb3d_pairwise_sqdist_f64(const float* X, int n, int d, double* D, cudaStream_t stream);
 int crb3d_kde_greedy_workspace_bytes(int n_cand, int n_class, size_t* bytes);
 int crb3d_kde_greedy(const float* dens, const int* labels, const int* cand_off, int n_cand, int n_class,

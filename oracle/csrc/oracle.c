@@ -154,6 +154,10 @@ float oracle_box_overlap(const float* a, const float* b) {
 }
 
 float oracle_iou_bev(const float* a, const float* b) {
+    /* boxes further apart than their half diagonals (+ margin slack) cannot touch: overlap is exactly 0 */
+    float ddx = a[0] - b[0], ddy = a[1] - b[1];
+    float reach = 0.5f * (sqrtf(a[3] * a[3] + a[4] * a[4]) + sqrtf(b[3] * b[3] + b[4] * b[4])) + 0.1f;
+    if (ddx * ddx + ddy * ddy > reach * reach) return 0.0f;
     float sa = a[3] * a[4], sb = b[3] * b[4], ov = oracle_box_overlap(a, b);
     return ov / fmaxf(sa + sb - ov, 1e-8f);
 }
@@ -320,10 +324,20 @@ void oracle_group_points(int B, int C, int nsample, const float* feat, const int
 }
 
 /* pointnet2_stack/src/sampling_gpu.cu:17-140. The reference scans with `block` threads (thread t owns k = t, t+block,
- * ...; strict '>' keeps the first maximum) and merges with a pairwise tree in which the LEFT operand wins ties, so
- * the overall tie order is (k mod block, k). block = min(1024, 2^floor(log2 n)) (sampling_gpu.cu:9-13). */
+ * ...; strict '>' keeps the first maximum) and merges with a pairwise tree (slot t absorbs slot t+s for s = block/2..1,
+ * the LEFT operand wins ties). Two tied threads first meet at the lowest bit in which their ids differ and the one
+ * with a 0 there wins, so threads rank by bit-reversed id: tie order = (bitrev(k mod block), k / block).
+ * block = min(1024, 2^floor(log2 n)) (sampling_gpu.cu:9-13). */
+static unsigned bitrev(unsigned v, int bits) {
+    unsigned r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
 void oracle_fps(int n, int m, int block, const float* pts, float* temp, int* idx) {
     if (m <= 0) return;
+    int bits = 0;
+    while ((1 << (bits + 1)) <= block) ++bits;
     int old = 0;
     idx[0] = 0;
     for (int j = 1; j < m; ++j) {
@@ -333,7 +347,7 @@ void oracle_fps(int n, int m, int block, const float* pts, float* temp, int* idx
                              pts[(size_t)old * 3 + 1], pts[(size_t)old * 3 + 2]);
             float d2 = d < temp[k] ? d : temp[k];
             temp[k] = d2;
-            long key = (long)(k % block) * (1l << 32) + k;
+            long key = (long)bitrev((unsigned)(k % block), bits) * (1l << 32) + k / block;
             if (d2 > best || (d2 == best && bestkey >= 0 && key < bestkey)) { best = d2; besti = k; bestkey = key; }
         }
         old = besti;

@@ -1,0 +1,69 @@
+"""-m gpu parity: CRB stage-1 entropy, stage-2 distance matrix, stage-3 greedy KDE/KL - ours vs the reference's own
+library calls (torch Categorical, sklearn euclidean_distances / KernelDensity, scipy entropy) restated in oracle/crb.py."""
+import numpy as np
+import pytest
+import torch
+
+from util import cu
+
+pytestmark = pytest.mark.gpu
+
+
+def test_label_entropy(cuda):
+    from crb3d import ops
+    from oracle import crb as oc
+    rng = np.random.default_rng(1)
+    frames = [rng.integers(1, 4, rng.integers(1, 80)) for _ in range(200)]
+    frames += [np.zeros((0,), np.int64), np.array([2]), np.array([1] * 7 + [3] * 2), np.array([3] * 500), np.array([1, 2, 3])]
+    off = np.cumsum([0] + [len(f) for f in frames]).astype(np.int32)
+    ent = ops.label_entropy(cu(np.concatenate(frames), cuda, torch.int32), cu(off, cuda), 3).cpu().numpy()
+    ref = np.array([oc.label_entropy(f, 3) for f in frames], np.float32)
+    assert np.allclose(ent, ref, rtol=1e-6, atol=1e-7)              # 1e-3 rel is the bar; fp32 rounding only
+    assert ent[-5] == 0.0 and abs(ent[-3] - 0.8018185) < 1e-6
+    # ranking identical to the reference's stable-sort-then-reverse (crb_sampling.py:119-121)
+    ids = list(range(len(frames)))
+    assert oc.stage1_shortlist(ids, list(ent), 50) == oc.stage1_shortlist(ids, list(ref), 50)
+
+
+def test_pairwise_sqdist(cuda):
+    from crb3d import ops
+    from sklearn.metrics.pairwise import euclidean_distances
+    rng = np.random.default_rng(2)
+    X = rng.normal(size=(150, 4099)).astype(np.float32)
+    D = ops.pairwise_sqdist(cu(X, cuda)).cpu().numpy()
+    ref = euclidean_distances(X, X, squared=True)
+    assert np.allclose(D, ref, rtol=1e-6, atol=1e-3)
+
+
+def _pool(rng, n_frames, empty_class_rate=0.2):
+    dens, labs = [], []
+    for _ in range(n_frames):
+        n = int(rng.integers(0, 40))
+        l = rng.integers(1, 4, n)
+        if rng.uniform() < empty_class_rate:
+            l[l == 2] = 1
+        d = np.where(l == 1, rng.gamma(2.0, 8.0, n), np.where(l == 2, rng.gamma(2.0, 30.0, n), rng.gamma(2.0, 15.0, n)))
+        dens.append(d.astype(np.float32)); labs.append(l.astype(np.int64))
+    return dens, labs
+
+
+@pytest.mark.parametrize("seed,n_cand,n_sel", [(0, 24, 8), (1, 40, 12), (2, 12, 12)])
+def test_kde_greedy_vs_sklearn(cuda, seed, n_cand, n_sel):
+    from crb3d import crb_host, ops
+    from oracle import crb as oc
+    rng = np.random.default_rng(seed)
+    pool_d, pool_l = _pool(rng, 300)
+    x_axis, prior = oc.build_prior(np.concatenate(pool_d), np.concatenate(pool_l), 3)
+    ax2, prior2 = crb_host.build_prior(torch.as_tensor(np.concatenate(pool_d)), torch.as_tensor(np.concatenate(pool_l)), 3)
+    assert np.allclose(np.stack(x_axis), ax2.numpy(), rtol=0, atol=0)
+    assert np.allclose(np.stack(prior), prior2.numpy(), rtol=0, atol=0, equal_nan=True)
+    cand_d, cand_l = pool_d[:n_cand], pool_l[:n_cand]
+    picked_o, score_o = oc.greedy_density_balance(list(cand_d), list(cand_l), x_axis, prior, 3, n_sel, bandwidth=5)
+    off = np.cumsum([0] + [len(d) for d in cand_d]).astype(np.int32)
+    prior_n = crb_host.normalise_prior(prior2)
+    order, ps = ops.kde_greedy(cu(np.concatenate(cand_d), cuda), cu(np.concatenate(cand_l), cuda, torch.int32), cu(off, cuda),
+                               3, ax2.to(cuda), prior_n.to(cuda), 5.0, n_sel)
+    assert order.cpu().tolist() == picked_o                                   # identical greedy selection order
+    got = ps.cpu().numpy()[1:]
+    want = np.asarray(score_o[1:], np.float64)
+    assert np.allclose(got, want, rtol=1e-6, atol=1e-9)                       # CRB scores (bar: 1e-3 rel)
