@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exact-fp32", action="store_true", help="sparse convs on the exact-fp32 SIMT kernel instead of tcgen05 TF32")
     return ap.parse_args()
 
 
@@ -163,10 +164,14 @@ def _calibrate_cpu(sd, model, frame, anchors, target_fraction=0.004):
     second_ref.score_frames(sd, model.cfg, [frame], anchors, collect=col)
     logits = col["cls_preds"].reshape(-1, model.num_class)
     thr = float(np.log(model.cfg["score_thresh"] / (1 - model.cfg["score_thresh"])))
-    bias = sd["dense_head.conv_cls.bias"].view(model.dense_head.n_loc, model.num_class)
-    for c in range(model.num_class):
-        q = torch.quantile(logits[:, c], 1.0 - target_fraction)
-        bias[:, c] += thr - float(q)
+    n_loc, nc = model.dense_head.n_loc, model.num_class
+    mean, std = logits.mean(0), logits.std(0).clamp_min(1e-6)
+    z = torch.quantile(((logits - mean) / std).flatten()[:2000000], 1.0 - target_fraction)
+    w = sd["dense_head.conv_cls.weight"].view(n_loc, nc, -1)
+    b = sd["dense_head.conv_cls.bias"].view(n_loc, nc)
+    for c in range(nc):
+        w[:, c] /= std[c]
+        b[:, c] = (b[:, c] - mean[c]) / std[c] - z + thr
 
 
 # ------------------------------------------------------------------------------------------------ own arm
@@ -177,6 +182,7 @@ def run_own(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     model = build_model(device)
+    model.prepare_inference(fold_bev_bn=True, spconv_tf32=not args.exact_fp32)
     frames, batches = make_batches(args.batch)
     ps = scorer.PoolScorer(model, device, args.batch)
     staged = [ps.stage_host(b) for b in batches]

@@ -1,0 +1,149 @@
+"""CRB acquisition strategy on the crb3d kernels: same constructor and `query(leave_pbar, cur_epoch)` contract as
+pcdet/query_strategies/crb_sampling.py:20-342 (registered as 'crb' in pcdet/query_strategies/__init__.py:13-29).
+
+Stage 1 (concise label sampling, :72-121)  - forward + post-processing + per-frame label entropy on the device
+          (PoolScorer.score_pool: frames sharded over ranks, one all-gather of the records); ranking by the reference's
+          stable-sort-then-reverse rule.
+Stage 2 (representative prototypes, :134-226) - gradient embedding per shortlisted frame, pairwise squared distances on
+          the device (crb3d_pairwise_sqdist_f64), k-means++ seeding restated with sklearn's RandomState(0) stream.
+          * detectors with a RoI head: the reference's embedding, roi_head.shared_fc_layer[4].weight.grad (:194-207);
+          * SECOND (no RoI head - the reference's CRB cannot run it, SURVEY.md 8a note G): the in-repo precedent of
+            BADGE (badge_sampling.py:88-91,157-168), the gradient of dense_head.conv_cls.weight under the sigmoid focal
+            loss with the arg-max hypothetical labels. conv_cls is the LAST layer, so its weight gradient is the closed
+            form  dW = delta^T X  (delta = dLoss/dlogits, X = the 512-channel BEV map): no backward pass is needed.
+Stage 3 (greedy density balancing, :247-338) - uniform prior from the WHOLE pool, greedy KDE/KL selection on the device
+          (crb3d_kde_greedy).
+Quirks that define results are kept: pseudo-count 1 for absent classes, `BANDWDITH` typo (bandwidth is always 5 unless
+that misspelt key is set), int() truncation of the density quantiles, strict-'>' first maximum.
+"""
+import numpy as np
+import torch
+
+from . import crb_host, ops
+
+
+def _get(cfg, path, default=None):
+    cur = cfg
+    for key in path.split("."):
+        if cur is None:
+            return default
+        cur = cur.get(key, None) if isinstance(cur, dict) else getattr(cur, key, None)
+    return default if cur is None else cur
+
+
+def sigmoid_focal_loss_grad(logits, labels, alpha=0.25, gamma=2.0):
+    """d/dlogits of pcdet's SigmoidFocalClassificationLoss (loss_utils.py:9-72) summed over anchors with the anchor-head
+    weighting of anchor_head_template.py:95-128 (positives + negatives weighted 1, normalised by the positive count).
+    labels: (A,) int, 0 = background, c > 0 = class c (one-hot column c-1). Returns delta (A, n_class)."""
+    n_class = logits.shape[-1]
+    target = torch.zeros_like(logits)
+    pos = labels > 0
+    target[pos, (labels[pos] - 1).long()] = 1.0
+    p = torch.sigmoid(logits)
+    alpha_w = target * alpha + (1 - target) * (1 - alpha)
+    pt = target * (1.0 - p) + (1.0 - target) * p
+    focal = alpha_w * torch.pow(pt, gamma)
+    # bce = max(x,0) - x*t + log1p(exp(-|x|)); loss = focal * bce ; closed-form derivative (no autograd graph kept)
+    bce = torch.clamp(logits, min=0) - logits * target + torch.log1p(torch.exp(-torch.abs(logits)))
+    dbce = p - target
+    dpt = (1.0 - 2.0 * target) * p * (1.0 - p)
+    dfocal = alpha_w * gamma * torch.pow(pt, gamma - 1.0) * dpt
+    norm = torch.clamp(pos.sum().float(), min=1.0)
+    return (dfocal * bce + focal * dbce) / norm
+
+
+class CRBSampling(object):
+    def __init__(self, model, labelled_loader, unlabelled_loader, rank, active_label_dir, cfg):
+        self.model = model
+        self.labelled_loader = labelled_loader
+        self.unlabelled_loader = unlabelled_loader
+        self.rank = rank
+        self.active_label_dir = active_label_dir
+        self.cfg = cfg
+        self.k1 = _get(cfg, "ACTIVE_TRAIN.ACTIVE_CONFIG.K1", 5)
+        self.k2 = _get(cfg, "ACTIVE_TRAIN.ACTIVE_CONFIG.K2", 3)
+        self.bandwidth = _get(cfg, "ACTIVE_TRAIN.ACTIVE_CONFIG.BANDWDITH", 5)   # sic: the reference reads the typo
+        self.prototype = _get(cfg, "ACTIVE_TRAIN.ACTIVE_CONFIG.CLUSTERING", "kmeans++")
+        self.select_nums = int(_get(cfg, "ACTIVE_TRAIN.SELECT_NUMS", 100))
+        self.alpha = 0.95
+        self.last_stage = {}
+
+    # ------------------------------------------------------------------------------------------------ stage 1
+    def collect_pool(self):
+        """{frame_id: points (n, C) float32}. The loader yields pcdet-style batches: 'frame_id' (B,), 'points'
+        (N, 1+C) with the batch index in column 0 (pcdet/datasets/dataset.py:180-186), or a dict of frames directly."""
+        if isinstance(self.unlabelled_loader, dict):
+            return dict(self.unlabelled_loader)
+        frames = {}
+        for batch in self.unlabelled_loader:
+            pts = np.asarray(batch["points"])
+            for b, fid in enumerate(batch["frame_id"]):
+                frames[fid] = pts[pts[:, 0] == b][:, 1:].astype(np.float32)
+        return frames
+
+    def stage1(self, scorer, frames):
+        ids = list(frames.keys())
+        recs = scorer.score_pool([frames[i] for i in ids], ids)
+        entropies = [recs[i]["entropy"] for i in ids]
+        shortlist = crb_host.shortlist_by_entropy(ids, entropies, int(self.k1 * self.select_nums))
+        return recs, shortlist
+
+    # ------------------------------------------------------------------------------------------------ stage 2
+    @torch.no_grad()
+    def second_gradient_embedding(self, scorer, points):
+        """(n_loc*n_class*512,) embedding of one frame for a SECOND-style detector (see module docstring)."""
+        dev = scorer.device
+        pts = torch.from_numpy(np.ascontiguousarray(points[:, -scorer.n_feat:], dtype=np.float32)).to(dev)
+        offs = torch.tensor([0, pts.shape[0]], dtype=torch.int32, device=dev)
+        bd = self.model.forward_features(pts, offs, 1)
+        logits = bd["cls_preds"][0]                                        # (A, n_class), A = H*W*n_loc
+        labels = torch.argmax(logits, dim=-1)                               # BADGE's hypothetical labels (0 = background)
+        delta = sigmoid_focal_loss_grad(logits, labels)                     # (A, n_class)
+        x = bd["spatial_features_2d"][0].permute(1, 2, 0)                   # (H, W, 512)
+        n_loc, nc = self.model.dense_head.n_loc, logits.shape[-1]
+        d = delta.view(x.shape[0] * x.shape[1], n_loc * nc)                 # channel = type*n_class + class (conv_cls rows)
+        return (d.t() @ x.reshape(-1, x.shape[-1])).reshape(-1)             # conv_cls.weight.grad, flattened
+
+    def stage2(self, scorer, frames, shortlist, embedding_fn=None):
+        fn = embedding_fn or (lambda pts: self.second_gradient_embedding(scorer, pts))
+        emb = torch.stack([fn(frames[fid]).float() for fid in shortlist], 0)
+        n_clusters = int(self.select_nums * self.k2)
+        if self.prototype != "kmeans++":
+            raise NotImplementedError("only the paper's kmeans++ prototype selection is on the hot path")
+        D = ops.pairwise_sqdist(emb)
+        idx = crb_host.kmeans_plusplus_indices(D.cpu().numpy(), n_clusters, seed=0)
+        self.last_stage["embeddings"] = emb
+        return [shortlist[i] for i in idx]
+
+    # ------------------------------------------------------------------------------------------------ stage 3
+    def stage3(self, scorer, recs, prototypes, num_class):
+        dev = scorer.device
+        density_all = torch.from_numpy(np.concatenate([r["density"] for r in recs.values()]))
+        label_all = torch.from_numpy(np.concatenate([r["labels"] for r in recs.values()]))
+        axis, prior = crb_host.build_prior(density_all, label_all, num_class, self.alpha)
+        dens = [recs[f]["density"] for f in prototypes]
+        labs = [recs[f]["labels"] for f in prototypes]
+        off = np.zeros(len(prototypes) + 1, np.int32)
+        off[1:] = np.cumsum([len(d) for d in dens])
+        order, scores = crb_host.greedy_density_balance(
+            torch.from_numpy(np.concatenate(dens).astype(np.float32)).to(dev),
+            torch.from_numpy(np.concatenate(labs).astype(np.int32)).to(dev), torch.from_numpy(off).to(dev), num_class,
+            axis, prior, self.bandwidth, self.select_nums)
+        self.last_stage["stage3_scores"] = scores
+        return [prototypes[i] for i in order]
+
+    # ------------------------------------------------------------------------------------------------ query
+    def query(self, leave_pbar=True, cur_epoch=None, scorer=None, embedding_fn=None):
+        from .scorer import PoolScorer
+        if scorer is None:
+            dev = next(self.model.parameters()).device
+            scorer = PoolScorer(self.model, dev, batch_size=4)
+        num_class = len(self.model.cfg["class_names"]) if hasattr(self.model, "cfg") else len(self.labelled_loader.dataset.class_names)
+        self.model.eval()
+        frames = self.collect_pool()
+        recs, shortlist = self.stage1(scorer, frames)
+        prototypes = self.stage2(scorer, frames, shortlist, embedding_fn)
+        selected = self.stage3(scorer, recs, prototypes, num_class)
+        self.last_stage.update(dict(records=recs, shortlist=shortlist, prototypes=prototypes))
+        self.model.eval()
+        return selected

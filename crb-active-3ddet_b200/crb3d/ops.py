@@ -162,7 +162,7 @@ def compact_pairs(nbr):
 
 
 # ----------------------------------------------------------------------------------------------- sparse conv
-def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transpose=False, kmap=None):
+def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transpose=False, kmap=None, tf32=None):
     """out[o] = sum_k feat[nbr[k][o]] @ W_k. weight: [C_out, (kz,ky,kx)|K, C_in] (spconv layout).
     transpose=True computes the input gradient: feat is dY (rows of the conv OUTPUT), nbr the transposed table."""
     _need_cuda(feat, nbr, weight)
@@ -185,9 +185,19 @@ def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transp
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(feat.device))
-    _lib.call("crb3d_spconv_forward_f32", _p(feat), _p(nbr), _p(weight), n_out, K, cin, cout, strides[0], strides[1],
-              strides[2], _p(kmap), _p(_f32c(scale)) if scale is not None else None,
-              _p(_f32c(shift)) if shift is not None else None, int(bool(relu)), _p(out), _stream(feat.device))
+    use_tc = (SPCONV_TF32 if tf32 is None else tf32) and K <= 27 and cin in (16, 32, 64) and cout in (16, 32, 64, 128)
+    if use_tc:
+        # tcgen05 path wants K-major weight rows [C_out', K, C_in']: the forward layout as is, its transpose for dX
+        w_tc = weight.reshape(cout_w, K, cin_w)
+        if transpose:
+            w_tc = w_tc.permute(2, 1, 0).contiguous()
+        _lib.call("crb3d_spconv_forward_tf32", _p(feat), _p(nbr), _p(w_tc), n_out, K, cin, cout, _p(kmap),
+                  _p(_f32c(scale)) if scale is not None else None, _p(_f32c(shift)) if shift is not None else None,
+                  int(bool(relu)), _p(out), _stream(feat.device))
+    else:
+        _lib.call("crb3d_spconv_forward_f32", _p(feat), _p(nbr), _p(weight), n_out, K, cin, cout, strides[0], strides[1],
+                  strides[2], _p(kmap), _p(_f32c(scale)) if scale is not None else None,
+                  _p(_f32c(shift)) if shift is not None else None, int(bool(relu)), _p(out), _stream(feat.device))
     if prof is not None:
         if prof["mode"] == "time":
             e1.record(torch.cuda.current_stream(feat.device))
@@ -196,6 +206,9 @@ def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transp
             prof["records"].append(dict(n_out=n_out, K=K, cin=cin, cout=cout, pairs=int((nbr >= 0).sum().item())))
     return out
 
+
+# tensor-core (tcgen05, TF32 inputs / fp32 accumulate) sparse conv for the layers it covers; False = exact-fp32 SIMT path
+SPCONV_TF32 = False
 
 # bench.py hook: None, or {"mode": "time" | "pairs", "records": []} (see bench.py roofline section)
 PROFILE = None

@@ -145,6 +145,87 @@ __global__ void __launch_bounds__(256) nms_reduce_kernel(int n, int col_blocks, 
     if (tid == 0) *num_keep = kept_s;
 }
 
+// ------------------------------------------------------------------ fused greedy NMS (no bitmask)
+// Greedy NMS only ever needs IoU(kept box, candidate): a candidate survives iff no PREVIOUSLY KEPT box overlaps it
+// by more than the threshold - identical to the reference's mask + host loop, but with <= n*max_keep pair tests
+// instead of n^2/2 and no n x n/64 mask in memory. One CTA per frame walks the score-sorted candidates in chunks of 64:
+//   A) chunk vs kept list (all threads, quick centre-distance reject first)
+//   B) chunk vs chunk upper triangle -> 64 suppression words in shared memory
+//   C) one thread resolves the 64 candidates in order and appends the survivors to the kept list.
+// IoU argument order is (earlier box, later box) like nms_kernel's iou_bev(cur_box, block_boxes + i*7).
+constexpr int GREEDY_MAX_KEEP = 512;
+constexpr int GREEDY_THREADS = 512;
+
+struct RawBox { float v[7]; };
+__device__ __forceinline__ void load_box(const float* b, RBox& r) { make_rbox(b, r); }
+__device__ __forceinline__ void load_box(const float* b, RawBox& r) {
+#pragma unroll
+    for (int q = 0; q < 7; ++q) r.v[q] = b[q];
+}
+__device__ __forceinline__ float pair_iou(const RBox& a, const RBox& b) { return rbox_iou(a, b); }
+__device__ __forceinline__ float pair_iou(const RawBox& a, const RawBox& b) { return aabb_iou(a.v, b.v); }
+
+template <typename BOX>
+__global__ void __launch_bounds__(GREEDY_THREADS) nms_greedy_kernel(int n_fixed, const int* __restrict__ counts, int n_max,
+                                                                    float thresh, const float* __restrict__ boxes,
+                                                                    int max_keep, long long* __restrict__ keep,
+                                                                    int keep_stride, int* __restrict__ num_keep) {
+    __shared__ BOX kept[GREEDY_MAX_KEEP];
+    __shared__ BOX cand[64];
+    __shared__ int supp[64];
+    __shared__ unsigned long long cmask[64];
+    __shared__ int nk_s;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int n = n_fixed;
+    if (counts) {
+        n = min(counts[b], n_max);
+        boxes += (size_t)b * n_max * 7;
+        keep += (size_t)b * keep_stride;
+        num_keep += b;
+    }
+    if (tid == 0) nk_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += 64) {
+        const int sz = min(64, n - c0);
+        const int nk = nk_s;
+        if (tid < 64) {
+            supp[tid] = 0;
+            cmask[tid] = 0ull;
+            if (tid < sz) load_box(boxes + (size_t)(c0 + tid) * 7, cand[tid]);
+        }
+        __syncthreads();
+        // A) kept (earlier) vs candidates (later); candidate index fastest so a warp shares one kept box
+        for (int p = tid; p < nk * 64; p += GREEDY_THREADS) {
+            const int j = p >> 6, i = p & 63;
+            if (i < sz && !supp[i] && pair_iou(kept[j], cand[i]) > thresh) supp[i] = 1;
+        }
+        __syncthreads();
+        // B) within the chunk: i earlier, j later
+        for (int p = tid; p < 64 * 64; p += GREEDY_THREADS) {
+            const int i = p >> 6, j = p & 63;
+            if (j > i && j < sz && !supp[i] && !supp[j] && pair_iou(cand[i], cand[j]) > thresh)
+                atomicOr(&cmask[i], 1ull << j);
+        }
+        __syncthreads();
+        // C) serial resolve of the chunk
+        if (tid == 0) {
+            unsigned long long removed = 0ull;
+            int k = nk;
+            for (int i = 0; i < sz && k < max_keep; ++i) {
+                if (supp[i] || ((removed >> i) & 1ull)) continue;
+                kept[k] = cand[i];
+                keep[k] = c0 + i;
+                ++k;
+                removed |= cmask[i];
+            }
+            nk_s = k;
+        }
+        __syncthreads();
+        if (nk_s >= max_keep) break;
+    }
+    if (tid == 0) *num_keep = nk_s;
+}
+
 }  // namespace
 
 extern "C" int crb3d_boxes_overlap_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* out,
@@ -179,6 +260,12 @@ extern "C" int crb3d_nms(const float* boxes, int n, float thresh, int rotated, i
                          int* num_keep, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (n < 0 || !keep || !num_keep) return CRB3D_ERR_ARG;
     if (n == 0) { CRB3D_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int), stream)); return CRB3D_OK; }
+    if (max_keep > 0 && max_keep <= GREEDY_MAX_KEEP) {  // bounded keep list: fused greedy kernel, no mask
+        if (rotated) nms_greedy_kernel<RBox><<<1, GREEDY_THREADS, 0, stream>>>(n, nullptr, n, thresh, boxes, max_keep, keep, 0, num_keep);
+        else nms_greedy_kernel<RawBox><<<1, GREEDY_THREADS, 0, stream>>>(n, nullptr, n, thresh, boxes, max_keep, keep, 0, num_keep);
+        CRB3D_CHECK_LAUNCH();
+        return CRB3D_OK;
+    }
     const int cb = (int)crb3d_divup(n, 64);
     WsCursor c(ws, ws_bytes);
     unsigned long long* mask = c.take<unsigned long long>((size_t)n * cb);
@@ -226,6 +313,12 @@ extern "C" int crb3d_nms_batched(const float* boxes, const int* counts, int B, i
     if (max_keep > 0 && keep_stride < max_keep) return CRB3D_ERR_ARG;
     if (B == 0) return CRB3D_OK;
     if (n_max == 0) { CRB3D_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int) * B, stream)); return CRB3D_OK; }
+    if (max_keep > 0 && max_keep <= GREEDY_MAX_KEEP) {  // the scoring path (NMS_POST_MAXSIZE = 500): one CTA per frame
+        if (rotated) nms_greedy_kernel<RBox><<<B, GREEDY_THREADS, 0, stream>>>(0, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep);
+        else nms_greedy_kernel<RawBox><<<B, GREEDY_THREADS, 0, stream>>>(0, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep);
+        CRB3D_CHECK_LAUNCH();
+        return CRB3D_OK;
+    }
     const int cb = (int)crb3d_divup(n_max, 64);
     WsCursor c(ws, ws_bytes);
     unsigned long long* mask = c.take<unsigned long long>((size_t)B * n_max * cb);

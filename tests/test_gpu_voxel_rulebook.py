@@ -160,3 +160,48 @@ def test_dense_roundtrip(cuda):
     assert torch.equal(cl.permute(0, 3, 1, 2).cpu(), ref.view(3, 128 * 2, 25, 22))   # height_compression.py:21-23
     back = ops.dense_to_sparse(d, cu(coords, cuda), 128, shape)
     assert torch.equal(back.cpu(), torch.as_tensor(feat))
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128)])
+def test_spconv_tcgen05_tf32(cuda, cin, cout):
+    """tcgen05 (TF32 in, fp32 accumulate) kernel vs the fp64 oracle. TF32 keeps 10 mantissa bits: the bound is
+    ~2^-11 * sqrt(2) relative per product, averaged over the sum -> 1e-3 of the output scale (north_star tolerance)."""
+    from crb3d import ops
+    from oracle import spconv_ref
+    rng = np.random.default_rng(cin * 7 + cout)
+    shape = [11, 64, 60]
+    coords = _rand_coords(rng, 2, shape, 20000)
+    n = len(coords)
+    feat = rng.normal(size=(n, cin)).astype(np.float32)
+    w = (rng.normal(size=(cout, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.normal(size=cout).astype(np.float32)
+    for kind in ("subm", "sparse", "k311"):
+        if kind == "subm":
+            nbr_ref = spconv_ref.subm_rulebook(coords, shape, (3, 3, 3))
+            nbr = ops.subm_rulebook(cu(coords, cuda), shape, (3, 3, 3))
+            ww = w
+        elif kind == "sparse":
+            _, _, nbr_ref, _ = spconv_ref.sparse_rulebook(coords, 2, shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+            _, _, nbr, nbr_t = ops.sparse_rulebook(cu(coords, cuda), 2, shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+            ww = w
+        else:
+            _, _, nbr_ref, _ = spconv_ref.sparse_rulebook(coords, 2, shape, (3, 1, 1), (2, 1, 1), (0, 0, 0))
+            _, _, nbr, _ = ops.sparse_rulebook(cu(coords, cuda), 2, shape, (3, 1, 1), (2, 1, 1), (0, 0, 0))
+            ww = w[:, :, :1, :1, :].copy()
+        ref = spconv_ref.conv_forward(feat, nbr_ref, ww, dtype=torch.float64)
+        out = ops.spconv_forward(cu(feat, cuda), nbr, cu(ww, cuda), tf32=True)
+        exact = ops.spconv_forward(cu(feat, cuda), nbr, cu(ww, cuda), tf32=False)
+        s = float(ref.abs().max())
+        err = float((out.cpu().double() - ref).abs().max())
+        assert err <= 2e-3 * s, (kind, err / s)
+        assert float((out - exact).abs().max()) > 0 or cin < 8          # it really is a different (TF32) datapath
+        rel_rms = float(((out.cpu().double() - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt())
+        assert rel_rms <= 1e-3, (kind, rel_rms)
+        fused = ops.spconv_forward(cu(feat, cuda), nbr, cu(ww, cuda), scale=cu(scale, cuda), shift=cu(shift, cuda), relu=True, tf32=True)
+        assert torch.allclose(fused, torch.relu(out * cu(scale, cuda) + cu(shift, cuda)), rtol=1e-5, atol=1e-5)
+        if kind == "sparse":   # input gradient through the transposed table with the transposed weight
+            dout = rng.normal(size=tuple(ref.shape)).astype(np.float32)
+            dx_ref, _ = spconv_ref.conv_backward(feat, nbr_ref, ww, dout, dtype=torch.float64)
+            dx = ops.spconv_forward(cu(dout, cuda), nbr_t, cu(ww, cuda), transpose=True, tf32=True)
+            assert float((dx.cpu().double() - dx_ref).abs().max()) <= 2e-3 * float(dx_ref.abs().max())
