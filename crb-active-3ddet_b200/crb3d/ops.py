@@ -231,16 +231,18 @@ def spconv_wgrad(feat, dout, nbr, weight_shape, accumulate_into=None):
 
 
 # ----------------------------------------------------------------------------------------------- dense
-def sparse_to_dense(feat, coords, batch_size, spatial_shape, channels_last_bev=False):
+def sparse_to_dense(feat, coords, batch_size, spatial_shape, channels_last_bev=False, out=None):
     """(B,C,D,H,W) dense tensor (reference .dense()); channels_last_bev=True returns (B,H,W,C*D) memory whose
-    .permute(0,3,1,2) equals dense.view(B, C*D, H, W)."""
+    .permute(0,3,1,2) equals dense.view(B, C*D, H, W). `out`: optional preallocated destination (zero-filled here)."""
     _need_cuda(feat, coords)
     feat = _f32c(feat)
     coords = _i32c(coords)
     n, C = feat.shape
     D, H, W = [int(x) for x in spatial_shape]
     shape = (batch_size, H, W, C * D) if channels_last_bev else (batch_size, C, D, H, W)
-    dense = torch.empty(shape, dtype=torch.float32, device=feat.device)
+    if out is not None:
+        assert tuple(out.shape) == shape and out.is_contiguous() and out.dtype == torch.float32
+    dense = out if out is not None else torch.empty(shape, dtype=torch.float32, device=feat.device)
     _lib.call("crb3d_sparse_to_dense", _p(feat), _p(coords), n, C, batch_size, D, H, W, int(channels_last_bev), 1,
               _p(dense), _stream(feat.device))
     return dense

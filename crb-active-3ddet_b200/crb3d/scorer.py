@@ -47,6 +47,65 @@ class PoolScorer(object):
         torch.cuda.current_stream(self.device).synchronize()
         return {k: v.numpy() for k, v in out.items()}
 
+    def fetch_async(self, rec):
+        """Queues the D2H copy of the record fields into pinned host tensors on the current stream (no sync)."""
+        out = {}
+        for k in RECORD_FIELDS:
+            out[k] = torch.empty(rec[k].shape, dtype=rec[k].dtype, pin_memory=True)
+            out[k].copy_(rec[k], non_blocking=True)
+        return out
+
+    # -- two-stream software pipeline ----------------------------------------------------------------------------
+    def _geom_tensors(self, dev_batch, geom):
+        yield dev_batch[0]
+        yield dev_batch[1]
+        yield geom["voxel_features"]
+        yield geom["voxel_coords"]
+        for d in geom["rulebooks"].values():
+            for t in (d.nbr, d.nbr_t, d.out_indices, d.indices):
+                if t is not None:
+                    yield t
+
+    def score_stream(self, batches, from_host=True, between_steps=None):
+        """Generator over per-batch records. The geometry phase of batch i+1 (H2D copy, voxelize + MeanVFE, 8 rulebooks
+        and their 5 host reads of counts) runs on a side stream while the feature phase of batch i (12 sparse convs, BEV
+        stack, head, NMS, density, entropy) occupies the main stream, so the host reads never drain the GPU.
+        batches: staged host batches (stage_host) when from_host else device batches (to_device)."""
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        side = self._side
+
+        def launch_geometry(b):
+            side.wait_stream(main) if launch_geometry.first else None
+            launch_geometry.first = False
+            with torch.cuda.stream(side):
+                dev = self.to_device(b) if from_host else b
+                geom = self.model.geometry(dev[0], dev[1], dev[1].numel() - 1)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return dev, geom, ev
+
+        launch_geometry.first = True
+        it = iter(batches)
+        try:
+            nxt = launch_geometry(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            dev, geom, ev = nxt
+            main.wait_event(ev)
+            for t in self._geom_tensors(dev, geom):
+                t.record_stream(main)
+            rec = self.model.score_batch(dev[0], dev[1], dev[1].numel() - 1, dev[2], geom=geom)
+            if between_steps is not None:
+                between_steps()
+            try:
+                nxt = launch_geometry(next(it))      # host blocks on side-stream counts while `main` computes
+            except StopIteration:
+                nxt = None
+            yield rec
+
     def record_tensor(self, rec, frame_ids):
         """Fixed-stride per-frame record (B, 3 + 2P) float32: [frame_id, num_boxes, entropy, labels..., density...]."""
         B = rec["entropy"].shape[0]

@@ -87,9 +87,26 @@ class VoxelBackBone8x(nn.Module):
             norm_fn(128), nn.ReLU())
         self.num_point_features = 128
 
+    def build_rulebooks(self, coords, batch_size):
+        """Geometry pass: all 8 rulebooks (4 SubM keys, 4 strided) from the voxel coordinates alone, before any feature
+        kernel is queued. The 4 host reads of n_out then only wait for tiny rulebook kernels, and the 12 conv launches
+        that follow run back to back."""
+        g = spconv.SparseConvTensor(None, coords, self.sparse_shape, batch_size)
+        for seq in (self.conv_input, self.conv1, self.conv2, self.conv3, self.conv4, self.conv_out):
+            for m in seq.modules():
+                if isinstance(m, spconv.SparseConvolution):
+                    d = m._rulebook(g)
+                    if not m.subm:
+                        g = spconv.SparseConvTensor(None, d.out_indices, d.out_spatial_shape, batch_size, indice_dict=g.indice_dict)
+        return g.indice_dict
+
     def forward(self, batch_dict):
-        x = spconv.SparseConvTensor(features=batch_dict["voxel_features"], indices=batch_dict["voxel_coords"].int(),
-                                    spatial_shape=self.sparse_shape, batch_size=batch_dict["batch_size"])
+        coords = batch_dict["voxel_coords"].int()
+        books = batch_dict.get("rulebooks")
+        if books is None:
+            books = self.build_rulebooks(coords, batch_dict["batch_size"])
+        x = spconv.SparseConvTensor(features=batch_dict["voxel_features"], indices=coords,
+                                    spatial_shape=self.sparse_shape, batch_size=batch_dict["batch_size"], indice_dict=books)
         x = self.conv_input(x)
         x1 = self.conv1(x)
         x2 = self.conv2(x1)
@@ -244,10 +261,18 @@ class SECONDNet(nn.Module):
         return ops.voxelize(points, frame_offsets, batch_size, d["pc_range"], d["voxel_size"], d["max_pts"], mv,
                             xyz_col=points.shape[1] - d["n_feat"], feat_col=points.shape[1] - d["n_feat"], n_feat=d["n_feat"])
 
-    def forward_features(self, points, frame_offsets, batch_size):
-        """points (N, C) or (N, 1+C) with the batch index in column 0 (collate layout). Returns the head outputs."""
+    def geometry(self, points, frame_offsets, batch_size):
+        """Everything that needs a host-visible count (voxel count + 4 strided-conv output counts): voxelize + MeanVFE
+        and the 8 rulebooks. Can run on a side stream one batch ahead of the feature phase (PoolScorer.score_stream)."""
         vox = self.voxelize(points, frame_offsets, batch_size)
-        bd = dict(batch_size=batch_size, voxel_features=vox["mean"], voxel_coords=vox["coords"])
+        books = self.backbone_3d.build_rulebooks(vox["coords"], batch_size)
+        return dict(voxel_features=vox["mean"], voxel_coords=vox["coords"], rulebooks=books)
+
+    def forward_features(self, points, frame_offsets, batch_size, geom=None):
+        """points (N, C) or (N, 1+C) with the batch index in column 0 (collate layout). Returns the head outputs."""
+        if geom is None:
+            geom = self.geometry(points, frame_offsets, batch_size)
+        bd = dict(batch_size=batch_size, **geom)
         bd = self.backbone_3d(bd)
         bd = self.map_to_bev_module(bd)
         bd = self.backbone_2d(bd)
@@ -255,12 +280,14 @@ class SECONDNet(nn.Module):
         return bd
 
     @torch.no_grad()
-    def score_batch(self, points, frame_offsets, batch_size, max_pts_per_frame):
-        """CRB stage-1 record of every frame of the batch (crb_sampling.py:72-103 via post_processing):
-        dict(entropy (B,), num_boxes (B,), labels (B,P) int32 1-based (0 pad), density (B,P), boxes (B,P,7), scores (B,P))."""
+    def dense_and_post(self, spatial_features, points_xyz, pt_begin, pt_end, batch_size, max_pts_per_frame):
+        """Static-shape half of the step: BEV backbone -> anchor head -> max-class score / top-k / lazy decode -> batched
+        rotated NMS -> points-in-boxes density -> label entropy. No host synchronisation and no data-dependent shape, so
+        the whole thing is capturable in one CUDA graph (enable_cuda_graph)."""
         cfg = self.cfg
-        bd = self.forward_features(points, frame_offsets, batch_size)
+        bd = self.dense_head(self.backbone_2d(dict(spatial_features=spatial_features)))
         B, A = batch_size, self.dense_head.num_anchors
+        dev = spatial_features.device
         score, label = head_ops.anchor_head_scores(bd["cls_preds"], self.num_class)
         score, label = score.view(B, A), label.view(B, A, 1)
         # class_agnostic_nms (model_nms_utils.py:6-25): score >= thresh, top-k(NMS_PRE_MAXSIZE) - valid entries are a prefix
@@ -275,13 +302,74 @@ class SECONDNet(nn.Module):
         anchor_of_kept = head_ops.gather_rows(top_idx.int().unsqueeze(-1).contiguous(), keep, num, 0).squeeze(-1)
         final_labels = head_ops.gather_rows(label, anchor_of_kept.long(), num, 0).squeeze(-1)
         # per-box point density (detector3d_template.py:379-387) and label entropy (crb_sampling.py:86-100)
-        box_begin = torch.arange(B, device=points.device, dtype=torch.int32) * P
-        xyz_col = points.shape[1] - cfg["data"]["n_feat"]
-        _, cnt, dens = ops.points_in_boxes_ranges(points[:, xyz_col:], frame_offsets[:-1], frame_offsets[1:], max_pts_per_frame,
-                                                  final_boxes, box_begin, box_begin + num)
+        box_begin = torch.arange(B, device=dev, dtype=torch.int32) * P
+        _, cnt, dens = ops.points_in_boxes_ranges(points_xyz, pt_begin, pt_end, max_pts_per_frame, final_boxes, box_begin,
+                                                  box_begin + num)
         entropy = ops.label_entropy_ranges(final_labels, box_begin, box_begin + num, self.num_class)
-        return dict(entropy=entropy, num_boxes=num, labels=final_labels, density=dens.view(B, P), point_counts=cnt.view(B, P),
+        valid = torch.arange(P, device=dev).view(1, P) < num.view(B, 1)
+        dens = torch.where(valid, dens.view(B, P), torch.zeros((), device=dev))   # padded slots: 0, not 0/0
+        return dict(entropy=entropy, num_boxes=num, labels=final_labels, density=dens, point_counts=cnt.view(B, P),
                     boxes=final_boxes, scores=final_scores)
+
+    @torch.no_grad()
+    def enable_cuda_graph(self, batch_size, max_points_per_frame=32768):
+        """Captures dense_and_post for a fixed batch size into a CUDA graph (~150 kernel launches -> 1 graph launch; at
+        batch 4 the eager step is host-launch bound). Inputs live in static buffers: the BEV map the dense() scatter
+        writes into and a point buffer of batch_size*max_points_per_frame rows for the density kernel."""
+        dev = next(self.parameters()).device
+        d = self.cfg["data"]
+        C, (D, H, W) = self.backbone_3d.num_point_features, self.bev_shape()
+        g = dict(B=batch_size, cap=batch_size * max_points_per_frame, max_pts=max_points_per_frame)
+        g["spatial"] = torch.zeros((batch_size, H, W, C * D), device=dev)
+        g["points"] = torch.zeros((g["cap"], d["n_feat"]), device=dev)
+        g["offsets"] = torch.zeros((batch_size + 1,), dtype=torch.int32, device=dev)
+
+        def body():
+            return self.dense_and_post(g["spatial"].permute(0, 3, 1, 2), g["points"], g["offsets"][:-1], g["offsets"][1:],
+                                       batch_size, max_points_per_frame)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):          # warm-up outside capture (cuDNN autotune, workspace allocations)
+            for _ in range(3):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g["out"] = body()
+        g["graph"] = graph
+        self._graph = g
+        return self
+
+    def bev_shape(self):
+        """(D, H, W) of the encoded sparse tensor (z: 41 -> 21 -> 11 -> 5 -> 2; y, x: /8)."""
+        s = list(self.backbone_3d.sparse_shape)
+        for k, st, p in (((3, 3, 3), (2, 2, 2), (1, 1, 1)), ((3, 3, 3), (2, 2, 2), (1, 1, 1)), ((3, 3, 3), (2, 2, 2), (0, 1, 1)),
+                         ((3, 1, 1), (2, 1, 1), (0, 0, 0))):
+            s = ops.conv_out_shape(s, k, st, p)
+        return s
+
+    @torch.no_grad()
+    def score_batch(self, points, frame_offsets, batch_size, max_pts_per_frame, geom=None):
+        """CRB stage-1 record of every frame of the batch (crb_sampling.py:72-103 via post_processing):
+        dict(entropy (B,), num_boxes (B,), labels (B,P) int32 1-based (0 pad), density (B,P), boxes (B,P,7), scores (B,P)).
+        With enable_cuda_graph() and a matching batch the returned tensors are the graph's static outputs: consume (or
+        copy) them on the same stream before the next call."""
+        if geom is None:
+            geom = self.geometry(points, frame_offsets, batch_size)
+        bd = self.backbone_3d(dict(batch_size=batch_size, **geom))
+        enc = bd["encoded_spconv_tensor"]
+        xyz_col = points.shape[1] - self.cfg["data"]["n_feat"]
+        g = getattr(self, "_graph", None)
+        if g is not None and g["B"] == batch_size and points.shape[0] <= g["cap"] and max_pts_per_frame <= g["max_pts"]:
+            ops.sparse_to_dense(enc.features, enc.indices, batch_size, enc.spatial_shape, channels_last_bev=True, out=g["spatial"])
+            g["points"][: points.shape[0]].copy_(points[:, xyz_col:], non_blocking=True)
+            g["offsets"].copy_(frame_offsets, non_blocking=True)
+            g["graph"].replay()
+            return g["out"]
+        spatial = enc.dense_bev_channels_last()
+        return self.dense_and_post(spatial, points[:, xyz_col:], frame_offsets[:-1], frame_offsets[1:], batch_size,
+                                   max_pts_per_frame)
 
 
 def calibrate_head_bias(model, points, frame_offsets, batch_size, target_fraction=0.03):
@@ -291,18 +379,18 @@ def calibrate_head_bias(model, points, frame_offsets, batch_size, target_fractio
     clears the threshold, so all classes get predicted (CRB stage 3 needs every class)."""
     with torch.no_grad():
         bd = model.forward_features(points, frame_offsets, batch_size)
-        logits = bd["cls_preds"].reshape(-1, model.num_class)
-        logits = logits[:: max(1, logits.shape[0] // 400000)]
-        thr = float(np.log(model.cfg["score_thresh"] / (1 - model.cfg["score_thresh"])))
         n_loc, nc = model.dense_head.n_loc, model.num_class
+        logits = bd["cls_preds"].reshape(-1, n_loc * nc)                    # rows = BEV locations, cols = conv_cls channels
+        thr = float(np.log(model.cfg["score_thresh"] / (1 - model.cfg["score_thresh"])))
+        # per output channel (anchor type x class): with random weights the channel MEANS differ far more than the
+        # spatial variation, so anything coarser lets one channel win every arg-max
         mean, std = logits.mean(0), logits.std(0).clamp_min(1e-6)
-        z = torch.quantile(((logits - mean) / std).flatten()[:2000000], 1.0 - target_fraction)
-        w = model.dense_head.conv_cls.weight.view(n_loc, nc, -1)
-        b = model.dense_head.conv_cls.bias.view(n_loc, nc)
-        for c in range(nc):
-            # new logit = (old - mean_c) / std_c - z + thr
-            w[:, c] /= std[c]
-            b[:, c] = (b[:, c] - mean[c]) / std[c] - z + thr
+        zs = ((logits - mean) / std).flatten()
+        z = torch.quantile(zs[:: max(1, zs.numel() // 2000000)], 1.0 - target_fraction)
+        w = model.dense_head.conv_cls.weight.view(n_loc * nc, -1)
+        b = model.dense_head.conv_cls.bias.view(n_loc * nc)
+        w /= std.view(-1, 1)                                                # new logit = (old - mean) / std - z + thr
+        b.copy_((b - mean) / std - z + thr)
         if getattr(model.backbone_2d, "_plan", None) is not None:
             model.backbone_2d.build_inference_plan()
     return model

@@ -164,17 +164,27 @@ __device__ __forceinline__ void load_box(const float* b, RawBox& r) {
 }
 __device__ __forceinline__ float pair_iou(const RBox& a, const RBox& b) { return rbox_iou(a, b); }
 __device__ __forceinline__ float pair_iou(const RawBox& a, const RawBox& b) { return aabb_iou(a.v, b.v); }
+// false only when the overlap is exactly 0 (same centre-distance early-out as rbox_overlap)
+__device__ __forceinline__ bool pair_near(const RBox& a, const RBox& b) {
+    const float dx = a.cx - b.cx, dy = a.cy - b.cy, reach = a.rad + b.rad + 0.1f;
+    return !(dx * dx + dy * dy > reach * reach);
+}
+__device__ __forceinline__ bool pair_near(const RawBox&, const RawBox&) { return true; }
+constexpr int GREEDY_QUEUE = 8192;  // 128 kept boxes x 64 candidates per filtering round
 
 template <typename BOX>
 __global__ void __launch_bounds__(GREEDY_THREADS) nms_greedy_kernel(int n_fixed, const int* __restrict__ counts, int n_max,
                                                                     float thresh, const float* __restrict__ boxes,
                                                                     int max_keep, long long* __restrict__ keep,
                                                                     int keep_stride, int* __restrict__ num_keep) {
-    __shared__ BOX kept[GREEDY_MAX_KEEP];
-    __shared__ BOX cand[64];
+    // dynamic smem: kept[GREEDY_MAX_KEEP] | cand[64] | queue[GREEDY_QUEUE] (u16: kept/first index << 6 | candidate)
+    extern __shared__ __align__(16) unsigned char greedy_smem[];
+    BOX* kept = reinterpret_cast<BOX*>(greedy_smem);
+    BOX* cand = kept + GREEDY_MAX_KEEP;
+    unsigned short* queue = reinterpret_cast<unsigned short*>(cand + 64);
     __shared__ int supp[64];
     __shared__ unsigned long long cmask[64];
-    __shared__ int nk_s;
+    __shared__ int nk_s, qn_s;
     const int b = blockIdx.x, tid = threadIdx.x;
     int n = n_fixed;
     if (counts) {
@@ -193,18 +203,39 @@ __global__ void __launch_bounds__(GREEDY_THREADS) nms_greedy_kernel(int n_fixed,
             cmask[tid] = 0ull;
             if (tid < sz) load_box(boxes + (size_t)(c0 + tid) * 7, cand[tid]);
         }
+        if (tid == 0) qn_s = 0;
         __syncthreads();
-        // A) kept (earlier) vs candidates (later); candidate index fastest so a warp shares one kept box
-        for (int p = tid; p < nk * 64; p += GREEDY_THREADS) {
-            const int j = p >> 6, i = p & 63;
-            if (i < sz && !supp[i] && pair_iou(kept[j], cand[i]) > thresh) supp[i] = 1;
+        // A) kept (earlier) vs candidates (later), 128 kept boxes at a time. A1 filters with the cheap exact-zero
+        //    centre-distance test into a queue, A2 runs the polygon clipping one pair per thread: the expensive,
+        //    divergent work is compacted first, so a warp never idles 31 lanes behind one overlapping pair.
+        for (int j0 = 0; j0 < nk; j0 += GREEDY_QUEUE / 64) {
+            const int jn = min(GREEDY_QUEUE / 64, nk - j0);
+            for (int p = tid; p < jn * 64; p += GREEDY_THREADS) {
+                const int j = j0 + (p >> 6), i = p & 63;
+                if (i < sz && !supp[i] && pair_near(kept[j], cand[i])) queue[atomicAdd(&qn_s, 1)] = (unsigned short)((p >> 6) << 6 | i);
+            }
+            __syncthreads();
+            const int qn = qn_s;
+            for (int t = tid; t < qn; t += GREEDY_THREADS) {
+                const int j = j0 + (queue[t] >> 6), i = queue[t] & 63;
+                if (!supp[i] && pair_iou(kept[j], cand[i]) > thresh) supp[i] = 1;
+            }
+            __syncthreads();
+            if (tid == 0) qn_s = 0;
+            __syncthreads();
         }
-        __syncthreads();
-        // B) within the chunk: i earlier, j later
+        // B) within the chunk: i earlier, j later (same filter-then-evaluate split)
         for (int p = tid; p < 64 * 64; p += GREEDY_THREADS) {
             const int i = p >> 6, j = p & 63;
-            if (j > i && j < sz && !supp[i] && !supp[j] && pair_iou(cand[i], cand[j]) > thresh)
-                atomicOr(&cmask[i], 1ull << j);
+            if (j > i && j < sz && !supp[i] && !supp[j] && pair_near(cand[i], cand[j])) queue[atomicAdd(&qn_s, 1)] = (unsigned short)(p);
+        }
+        __syncthreads();
+        {
+            const int qn = qn_s;
+            for (int t = tid; t < qn; t += GREEDY_THREADS) {
+                const int i = queue[t] >> 6, j = queue[t] & 63;
+                if (pair_iou(cand[i], cand[j]) > thresh) atomicOr(&cmask[i], 1ull << j);
+            }
         }
         __syncthreads();
         // C) serial resolve of the chunk
@@ -224,6 +255,23 @@ __global__ void __launch_bounds__(GREEDY_THREADS) nms_greedy_kernel(int n_fixed,
         if (nk_s >= max_keep) break;
     }
     if (tid == 0) *num_keep = nk_s;
+}
+
+template <typename BOX>
+int launch_greedy_t(int grid, int n_fixed, const int* counts, int n_max, float thresh, const float* boxes, int max_keep,
+                    long long* keep, int keep_stride, int* num_keep, cudaStream_t stream) {
+    const size_t smem = sizeof(BOX) * (GREEDY_MAX_KEEP + 64) + sizeof(unsigned short) * GREEDY_QUEUE;
+    auto kern = nms_greedy_kernel<BOX>;
+    if (smem > 48 * 1024) CRB3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, GREEDY_THREADS, smem, stream>>>(n_fixed, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+int launch_greedy(int rotated, int grid, int n_fixed, const int* counts, int n_max, float thresh, const float* boxes,
+                  int max_keep, long long* keep, int keep_stride, int* num_keep, cudaStream_t stream) {
+    return rotated ? launch_greedy_t<RBox>(grid, n_fixed, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep, stream)
+                   : launch_greedy_t<RawBox>(grid, n_fixed, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep, stream);
 }
 
 }  // namespace
@@ -261,10 +309,7 @@ extern "C" int crb3d_nms(const float* boxes, int n, float thresh, int rotated, i
     if (n < 0 || !keep || !num_keep) return CRB3D_ERR_ARG;
     if (n == 0) { CRB3D_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int), stream)); return CRB3D_OK; }
     if (max_keep > 0 && max_keep <= GREEDY_MAX_KEEP) {  // bounded keep list: fused greedy kernel, no mask
-        if (rotated) nms_greedy_kernel<RBox><<<1, GREEDY_THREADS, 0, stream>>>(n, nullptr, n, thresh, boxes, max_keep, keep, 0, num_keep);
-        else nms_greedy_kernel<RawBox><<<1, GREEDY_THREADS, 0, stream>>>(n, nullptr, n, thresh, boxes, max_keep, keep, 0, num_keep);
-        CRB3D_CHECK_LAUNCH();
-        return CRB3D_OK;
+        return launch_greedy(rotated, 1, n, nullptr, n, thresh, boxes, max_keep, keep, 0, num_keep, stream);
     }
     const int cb = (int)crb3d_divup(n, 64);
     WsCursor c(ws, ws_bytes);
@@ -314,10 +359,7 @@ extern "C" int crb3d_nms_batched(const float* boxes, const int* counts, int B, i
     if (B == 0) return CRB3D_OK;
     if (n_max == 0) { CRB3D_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int) * B, stream)); return CRB3D_OK; }
     if (max_keep > 0 && max_keep <= GREEDY_MAX_KEEP) {  // the scoring path (NMS_POST_MAXSIZE = 500): one CTA per frame
-        if (rotated) nms_greedy_kernel<RBox><<<B, GREEDY_THREADS, 0, stream>>>(0, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep);
-        else nms_greedy_kernel<RawBox><<<B, GREEDY_THREADS, 0, stream>>>(0, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep);
-        CRB3D_CHECK_LAUNCH();
-        return CRB3D_OK;
+        return launch_greedy(rotated, B, 0, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep, stream);
     }
     const int cb = (int)crb3d_divup(n_max, 64);
     WsCursor c(ws, ws_bytes);

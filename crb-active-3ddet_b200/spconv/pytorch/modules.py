@@ -56,10 +56,21 @@ class SparseSequential(SparseModule):
 
     @staticmethod
     def _bn_affine(bn):
-        """eval-mode BatchNorm1d as y = x*scale + shift."""
-        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps) if bn.affine else 1.0 / torch.sqrt(bn.running_var + bn.eps)
-        shift = (bn.bias if bn.affine else 0.0) - bn.running_mean * scale
-        return scale.float().contiguous(), shift.float().contiguous()
+        """eval-mode BatchNorm1d as y = x*scale + shift. Cached on the module (5 tiny kernels otherwise, per layer per
+        call); the cache key is the version counter of every tensor involved, so load_state_dict / optimizer steps /
+        running-stat updates invalidate it."""
+        key = (bn.running_mean._version, bn.running_var._version, bn.weight._version if bn.affine else 0,
+               bn.bias._version if bn.affine else 0, bn.running_mean.data_ptr())
+        cached = getattr(bn, "_crb3d_affine", None)
+        if cached is not None and cached[0] == key:
+            return cached[1], cached[2]
+        with torch.no_grad():
+            inv = 1.0 / torch.sqrt(bn.running_var + bn.eps)
+            scale = bn.weight * inv if bn.affine else inv
+            shift = (bn.bias if bn.affine else 0.0) - bn.running_mean * scale
+            scale, shift = scale.float().contiguous(), shift.float().contiguous()
+        bn._crb3d_affine = (key, scale, shift)
+        return scale, shift
 
     def forward(self, input):
         from .core import SparseConvTensor

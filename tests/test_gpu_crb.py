@@ -67,3 +67,68 @@ def test_kde_greedy_vs_sklearn(cuda, seed, n_cand, n_sel):
     got = ps.cpu().numpy()[1:]
     want = np.asarray(score_o[1:], np.float64)
     assert np.allclose(got, want, rtol=1e-6, atol=1e-9)                       # CRB scores (bar: 1e-3 rel)
+
+
+def test_crb_query_end_to_end_second(cuda):
+    """CRBSampling.query on a small synthetic pool with a SECOND detector: every stage is re-derived with the reference's
+    own library calls (oracle/crb.py) from the same per-frame records / embeddings and must select the same frames."""
+    from crb3d import crb_strategy, scorer, second, synth
+    from oracle import crb as oc
+    torch.manual_seed(0)
+    model = second.SECONDNet().eval().to_device(cuda)
+    frames = {"%06d" % i: synth.make_frame(100 + i)[::2] for i in range(14)}          # ~10k points per frame
+    ps = scorer.PoolScorer(model, cuda, batch_size=4)
+    first = ps.to_device(ps.stage_host(list(frames.values())[:4]))
+    second.calibrate_head_bias(model, first[0], first[1], 4, target_fraction=0.004)
+    cfg = {"ACTIVE_TRAIN": {"SELECT_NUMS": 3, "ACTIVE_CONFIG": {"K1": 3, "K2": 2, "BANDWIDTH": 7}}}   # correct spelling is ignored
+    strat = crb_strategy.CRBSampling(model, None, frames, 0, "/tmp", cfg)
+    assert strat.bandwidth == 5                                                     # the BANDWDITH quirk (SURVEY.md 2.5)
+    selected = strat.query(cur_epoch=0, scorer=ps)
+    st = strat.last_stage
+    recs = st["records"]
+    assert len(selected) == 3 and len(set(selected)) == 3 and set(selected) <= set(frames)
+    ids = list(frames.keys())
+    # stage 1: entropy per frame == torch Categorical on the frame's labels; shortlist == stable sort, reversed
+    ent_o = [oc.label_entropy(recs[i]["labels"], 3) for i in ids]
+    assert np.allclose([recs[i]["entropy"] for i in ids], ent_o, rtol=1e-5, atol=1e-6)
+    assert st["shortlist"] == oc.stage1_shortlist(ids, [recs[i]["entropy"] for i in ids], 9)
+    # stage 2: k-means++ seeding on the embedding matrix == sklearn on the same matrix
+    emb = st["embeddings"].cpu().numpy()
+    assert emb.shape == (9, 18 * 512) and np.isfinite(emb).all() and np.abs(emb).max() > 0
+    want = oc.kmeanspp_indices(emb, 6)
+    assert st["prototypes"] == [st["shortlist"][i] for i in want]
+    # stage 3: greedy KDE/KL on the records == the sklearn/scipy loop
+    x_axis, prior = oc.build_prior(np.concatenate([recs[i]["density"] for i in ids]), np.concatenate([recs[i]["labels"] for i in ids]), 3)
+    picked, _ = oc.greedy_density_balance([recs[f]["density"] for f in st["prototypes"]], [recs[f]["labels"] for f in st["prototypes"]],
+                                          x_axis, prior, 3, 3, bandwidth=5)
+    assert selected == [st["prototypes"][i] for i in picked]
+
+
+def test_second_gradient_embedding_is_conv_cls_weight_grad(cuda):
+    """The closed-form last-layer embedding (delta^T X) == autograd's conv_cls.weight.grad of the focal loss."""
+    from crb3d import crb_strategy, scorer, second, synth
+    torch.manual_seed(1)
+    model = second.SECONDNet().eval().to_device(cuda)
+    ps = scorer.PoolScorer(model, cuda, batch_size=1)
+    pts = synth.make_frame(7)[::3]
+    strat = crb_strategy.CRBSampling(model, None, {}, 0, "/tmp", {})
+    emb = strat.second_gradient_embedding(ps, pts)
+    with torch.no_grad():
+        p = torch.from_numpy(pts).to(cuda)
+        offs = torch.tensor([0, len(pts)], dtype=torch.int32, device=cuda)
+        bd = model.forward_features(p, offs, 1)
+    x = bd["spatial_features_2d"].detach()
+    w = model.dense_head.conv_cls.weight.detach().clone().requires_grad_(True)
+    logits = torch.nn.functional.conv2d(x, w, model.dense_head.conv_cls.bias).permute(0, 2, 3, 1).reshape(-1, 3)
+    labels = torch.argmax(logits, -1)
+    target = torch.zeros_like(logits)
+    pos = labels > 0
+    target[pos, labels[pos] - 1] = 1.0
+    prob = torch.sigmoid(logits)
+    aw = target * 0.25 + (1 - target) * 0.75
+    pt = target * (1 - prob) + (1 - target) * prob
+    bce = torch.clamp(logits, min=0) - logits * target + torch.log1p(torch.exp(-torch.abs(logits)))
+    loss = (aw * pt ** 2 * bce).sum() / torch.clamp(pos.sum().float(), min=1.0)
+    loss.backward()
+    ref = w.grad.reshape(-1)
+    assert float((emb - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
