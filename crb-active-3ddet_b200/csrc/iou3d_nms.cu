@@ -1,19 +1,23 @@
-// Rotated BEV overlap / IoU and NMS (rotated + axis-aligned) with an ON-DEVICE greedy reduce.
+// Rotated BEV overlap / IoU and NMS (rotated + axis-aligned) with an ON-DEVICE greedy pass.
 //
 // Replaces (reference, /root/reference):
 //   pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu:236-265  boxes_overlap_kernel / boxes_iou_bev_kernel
 //   pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu:267-372  nms_kernel / nms_normal_kernel (64x64 suppression bitmask)
 //   pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:90-188         nms_gpu / nms_normal_gpu host side: D2H of the mask +
 //                                                        serial CPU greedy loop (iou3d_nms.cpp:121-132)
-// The polygon arithmetic (edge crossings, corner containment with MARGIN=1e-2, angular sort about the centroid,
-// shoelace sum) follows iou3d_nms_kernel.cu:36-234 operation for operation because the kept-index list is a
-// bit-exact target. What is different:
+// The polygon arithmetic (rbox.cuh) follows iou3d_nms_kernel.cu:36-234 operation for operation because the kept-index
+// list is a bit-exact target. What is different:
 //   * per-box data (corners, sin/cos) is computed once per tile in shared memory instead of once per pair;
-//   * pairs whose centres are further apart than the two half-diagonals (+slack) are rejected before any polygon
-//     work (their overlap is exactly 0 in the reference as well);
+//   * FILTER THEN EVALUATE: every tile first runs the cheap exact-zero centre-distance test on its 64x64 pairs and
+//     compacts the survivors into a shared-memory queue; only then is the divergent polygon clipping run, one queued
+//     pair per thread, so a warp never idles 31 lanes behind one overlapping pair (the reference evaluates 64 pairs
+//     serially per thread);
 //   * only the upper-triangular tiles of the bitmask are produced (the reference's host loop never reads the rest);
-//   * the greedy pass runs on the GPU in 64-box chunks and writes `keep` / `num_keep` in device memory, so the
-//     2 MB mask never crosses PCIe and there is no host synchronisation.
+//   * the greedy pass runs on the GPU: per 64-box chunk it PULLS the suppression word of every already-kept box
+//     (<= keep-count loads spread over the CTA + one OR-reduction) and resolves the chunk against its diagonal tile,
+//     writing `keep` / `num_keep` in device memory - the mask never crosses PCIe, there is no host synchronisation,
+//     and a bounded keep list (NMS_POST_MAXSIZE) stops the pass early;
+//   * a batched entry point runs all frames of a batch in one mask launch + one reduce launch.
 #include "common.cuh"
 #include "rbox.cuh"
 
@@ -38,12 +42,20 @@ __global__ void __launch_bounds__(256) pairwise_kernel(int na, const float* __re
     out[(size_t)ia * nb + ib] = IOU ? rbox_iou(sa[ty], sb[tx]) : rbox_overlap(sa[ty], sb[tx]);
 }
 
-// ------------------------------------------------------------------ NMS bitmask (upper-triangular tiles)
+// false only when the overlap is exactly 0 (same centre-distance early-out as rbox_overlap)
+__device__ __forceinline__ bool rbox_near(const RBox& a, const RBox& b) {
+    const float dx = a.cx - b.cx, dy = a.cy - b.cy, reach = a.rad + b.rad + 0.1f;
+    return !(dx * dx + dy * dy > reach * reach);
+}
+
+// ------------------------------------------------------------------ NMS bitmask (upper-triangular 64x64 tiles)
+constexpr int MASK_THREADS = 256;
+
 template <bool ROTATED>
-__global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const float* __restrict__ boxes,
-                                                      unsigned long long* __restrict__ mask, int col_blocks,
-                                                      const int* __restrict__ counts, int n_max) {
-    // blockIdx.y = frame (batched NMS: frame b owns boxes[b*n_max ...] and mask[b*n_max*col_blocks ...], n = counts[b])
+__global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int n, float thresh, const float* __restrict__ boxes,
+                                                                unsigned long long* __restrict__ mask, int col_blocks,
+                                                                const int* __restrict__ counts, int n_max) {
+    // blockIdx.y = frame (batched: frame b owns boxes[b*n_max ...] and mask[b*n_max*col_blocks ...], n = counts[b])
     if (counts) {
         n = min(counts[blockIdx.y], n_max);
         boxes += (size_t)blockIdx.y * n_max * 7;
@@ -55,223 +67,124 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const
     const int c = r + t;
     if (r * 64 >= n || c * 64 >= n) return;  // tile beyond this frame's boxes (uniform per CTA)
     const int row_size = min(n - r * 64, 64), col_size = min(n - c * 64, 64);
-    __shared__ RBox cb[64];
-    __shared__ float craw[64 * 7];
-    const int tid = threadIdx.x;
-    if (tid < col_size) {
-        const float* src = boxes + (size_t)(c * 64 + tid) * 7;
-        if (ROTATED) make_rbox(src, cb[tid]);
-        else
-            for (int q = 0; q < 7; ++q) craw[tid * 7 + q] = src[q];
+    __shared__ RBox rb[64], cb[64];
+    __shared__ float rraw[64 * 7], craw[64 * 7];
+    __shared__ unsigned short queue[4096];
+    __shared__ unsigned long long bits[64];
+    __shared__ int qn;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 64) {
+        bits[tid] = 0ull;
+        if (tid < row_size) {
+            const float* src = boxes + (size_t)(r * 64 + tid) * 7;
+            if (ROTATED) make_rbox(src, rb[tid]);
+            else
+                for (int q = 0; q < 7; ++q) rraw[tid * 7 + q] = src[q];
+        }
+    } else if (tid < 128) {
+        const int u = tid - 64;
+        if (u < col_size) {
+            const float* src = boxes + (size_t)(c * 64 + u) * 7;
+            if (ROTATED) make_rbox(src, cb[u]);
+            else
+                for (int q = 0; q < 7; ++q) craw[u * 7 + q] = src[q];
+        }
+    }
+    if (tid == 0) qn = 0;
+    __syncthreads();
+    // filter: row i (earlier box) vs column j (later box); diagonal tile keeps j > i only
+    for (int p = tid; p < 64 * 64; p += MASK_THREADS) {
+        const int i = p >> 6, j = p & 63;
+        bool near = i < row_size && j < col_size && (r != c || j > i);
+        if (ROTATED) near = near && rbox_near(rb[i], cb[j]);
+        const unsigned int m = __ballot_sync(0xffffffffu, near);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&qn, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (near) queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)p;
+        }
     }
     __syncthreads();
-    if (tid >= row_size) return;
-    const int i = r * 64 + tid;
-    unsigned long long bits = 0;
-    const int start = (r == c) ? tid + 1 : 0;
-    if (ROTATED) {
-        RBox me;
-        make_rbox(boxes + (size_t)i * 7, me);
-        for (int j = start; j < col_size; ++j)
-            if (rbox_iou(me, cb[j]) > thresh) bits |= 1ull << j;
-    } else {
-        float me[7];
-        for (int q = 0; q < 7; ++q) me[q] = boxes[(size_t)i * 7 + q];
-        for (int j = start; j < col_size; ++j)
-            if (aabb_iou(me, craw + j * 7) > thresh) bits |= 1ull << j;
+    const int nq = qn;
+    for (int q = tid; q < nq; q += MASK_THREADS) {
+        const int i = queue[q] >> 6, j = queue[q] & 63;
+        const float v = ROTATED ? rbox_iou(rb[i], cb[j]) : aabb_iou(rraw + i * 7, craw + j * 7);
+        if (v > thresh) atomicOr(&bits[i], 1ull << j);
     }
-    mask[(size_t)i * col_blocks + c] = bits;
+    __syncthreads();
+    if (tid < row_size) mask[(size_t)(r * 64 + tid) * col_blocks + c] = bits[tid];
 }
 
 // ------------------------------------------------------------------ greedy pass on the device
-// Equivalent to iou3d_nms.cpp:116-132 (remv bitset, keep[] in ascending box index).
-__global__ void __launch_bounds__(256) nms_reduce_kernel(int n, int col_blocks, const unsigned long long* __restrict__ mask,
-                                                         int max_keep, long long* __restrict__ keep,
-                                                         int* __restrict__ num_keep, const int* __restrict__ counts,
-                                                         int n_max, int keep_stride) {
-    extern __shared__ unsigned long long remv[];  // col_blocks
+// Equivalent to iou3d_nms.cpp:116-132 (remv bitset, keep[] in ascending box index). Box i of chunk c is kept iff no
+// kept box j < i suppresses it: kept boxes of EARLIER chunks are pulled (mask[j][c], one word each, all in flight at
+// once), kept boxes of the same chunk come from the diagonal tile.
+constexpr int REDUCE_THREADS = 256;
+
+__global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(int n, int col_blocks, const unsigned long long* __restrict__ mask,
+                                                                    int max_keep, long long* __restrict__ keep,
+                                                                    int* __restrict__ num_keep, const int* __restrict__ counts,
+                                                                    int n_max, int keep_stride) {
+    extern __shared__ int kept_list[];  // up to n entries
     if (counts) {
         n = min(counts[blockIdx.x], n_max);
         mask += (size_t)blockIdx.x * n_max * col_blocks;
         keep += (size_t)blockIdx.x * keep_stride;
         num_keep += blockIdx.x;
-        col_blocks = (n_max + 63) / 64;
     }
     const int row_stride = col_blocks;
-    col_blocks = (n + 63) / 64;
+    const int chunks = (n + 63) / 64;
     __shared__ unsigned long long diag[64];
-    __shared__ unsigned long long keepbits_s;
+    __shared__ unsigned long long wor[REDUCE_THREADS / 32];
     __shared__ int kept_s;
-    const int tid = threadIdx.x;
-    for (int j = tid; j < col_blocks; j += blockDim.x) remv[j] = 0ull;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) kept_s = 0;
     __syncthreads();
-    for (int c = 0; c < col_blocks; ++c) {
+    for (int c = 0; c < chunks; ++c) {
         const int base = c * 64, sz = min(64, n - base);
-        if (tid < 64) diag[tid] = (tid < sz) ? mask[(size_t)(base + tid) * row_stride + c] : 0ull;
+        const int nk = kept_s;
+        unsigned long long part = 0ull;
+        for (int t = tid; t < nk; t += REDUCE_THREADS) part |= __ldg(&mask[(size_t)kept_list[t] * row_stride + c]);
+        if (tid < 64) diag[tid] = (tid < sz) ? __ldg(&mask[(size_t)(base + tid) * row_stride + c]) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part |= __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) wor[warp] = part;
         __syncthreads();
         if (tid == 0) {
-            unsigned long long cur = remv[c], kb = 0ull;
-            int kept = kept_s;
+            unsigned long long cur = 0ull;
+            for (int w = 0; w < REDUCE_THREADS / 32; ++w) cur |= wor[w];
+            // kept boxes that belong to THIS chunk were appended below in earlier iterations only, so `cur` holds the
+            // earlier chunks' verdict; the diagonal tile adds the within-chunk suppressions in index order
+            int k = nk;
             for (int b = 0; b < sz; ++b) {
-                if (!((cur >> b) & 1ull)) {
-                    if (max_keep > 0 && kept >= max_keep) break;
-                    kb |= 1ull << b;
-                    cur |= diag[b];
-                    ++kept;
-                }
+                if ((cur >> b) & 1ull) continue;
+                if (max_keep > 0 && k >= max_keep) break;
+                kept_list[k] = base + b;
+                keep[k] = base + b;
+                ++k;
+                cur |= diag[b];
             }
-            keepbits_s = kb;
+            kept_s = k;
         }
-        __syncthreads();
-        const unsigned long long kb = keepbits_s;
-        const int kept0 = kept_s;
-        if (tid < 64 && ((kb >> tid) & 1ull))
-            keep[kept0 + __popcll(kb & ((1ull << tid) - 1ull))] = base + tid;
-        for (int j = c + 1 + tid; j < col_blocks; j += blockDim.x) {
-            unsigned long long acc = 0ull, bits = kb;
-            while (bits) {
-                int b = __ffsll((long long)bits) - 1;
-                bits &= bits - 1;
-                acc |= mask[(size_t)(base + b) * row_stride + j];
-            }
-            remv[j] |= acc;
-        }
-        __syncthreads();
-        if (tid == 0) kept_s = kept0 + __popcll(kb);
         __syncthreads();
         if (max_keep > 0 && kept_s >= max_keep) break;
     }
     if (tid == 0) *num_keep = kept_s;
 }
 
-// ------------------------------------------------------------------ fused greedy NMS (no bitmask)
-// Greedy NMS only ever needs IoU(kept box, candidate): a candidate survives iff no PREVIOUSLY KEPT box overlaps it
-// by more than the threshold - identical to the reference's mask + host loop, but with <= n*max_keep pair tests
-// instead of n^2/2 and no n x n/64 mask in memory. One CTA per frame walks the score-sorted candidates in chunks of 64:
-//   A) chunk vs kept list (all threads, quick centre-distance reject first)
-//   B) chunk vs chunk upper triangle -> 64 suppression words in shared memory
-//   C) one thread resolves the 64 candidates in order and appends the survivors to the kept list.
-// IoU argument order is (earlier box, later box) like nms_kernel's iou_bev(cur_box, block_boxes + i*7).
-constexpr int GREEDY_MAX_KEEP = 512;
-constexpr int GREEDY_THREADS = 512;
-
-struct RawBox { float v[7]; };
-__device__ __forceinline__ void load_box(const float* b, RBox& r) { make_rbox(b, r); }
-__device__ __forceinline__ void load_box(const float* b, RawBox& r) {
-#pragma unroll
-    for (int q = 0; q < 7; ++q) r.v[q] = b[q];
-}
-__device__ __forceinline__ float pair_iou(const RBox& a, const RBox& b) { return rbox_iou(a, b); }
-__device__ __forceinline__ float pair_iou(const RawBox& a, const RawBox& b) { return aabb_iou(a.v, b.v); }
-// false only when the overlap is exactly 0 (same centre-distance early-out as rbox_overlap)
-__device__ __forceinline__ bool pair_near(const RBox& a, const RBox& b) {
-    const float dx = a.cx - b.cx, dy = a.cy - b.cy, reach = a.rad + b.rad + 0.1f;
-    return !(dx * dx + dy * dy > reach * reach);
-}
-__device__ __forceinline__ bool pair_near(const RawBox&, const RawBox&) { return true; }
-constexpr int GREEDY_QUEUE = 8192;  // 128 kept boxes x 64 candidates per filtering round
-
-template <typename BOX>
-__global__ void __launch_bounds__(GREEDY_THREADS) nms_greedy_kernel(int n_fixed, const int* __restrict__ counts, int n_max,
-                                                                    float thresh, const float* __restrict__ boxes,
-                                                                    int max_keep, long long* __restrict__ keep,
-                                                                    int keep_stride, int* __restrict__ num_keep) {
-    // dynamic smem: kept[GREEDY_MAX_KEEP] | cand[64] | queue[GREEDY_QUEUE] (u16: kept/first index << 6 | candidate)
-    extern __shared__ __align__(16) unsigned char greedy_smem[];
-    BOX* kept = reinterpret_cast<BOX*>(greedy_smem);
-    BOX* cand = kept + GREEDY_MAX_KEEP;
-    unsigned short* queue = reinterpret_cast<unsigned short*>(cand + 64);
-    __shared__ int supp[64];
-    __shared__ unsigned long long cmask[64];
-    __shared__ int nk_s, qn_s;
-    const int b = blockIdx.x, tid = threadIdx.x;
-    int n = n_fixed;
-    if (counts) {
-        n = min(counts[b], n_max);
-        boxes += (size_t)b * n_max * 7;
-        keep += (size_t)b * keep_stride;
-        num_keep += b;
-    }
-    if (tid == 0) nk_s = 0;
-    __syncthreads();
-    for (int c0 = 0; c0 < n; c0 += 64) {
-        const int sz = min(64, n - c0);
-        const int nk = nk_s;
-        if (tid < 64) {
-            supp[tid] = 0;
-            cmask[tid] = 0ull;
-            if (tid < sz) load_box(boxes + (size_t)(c0 + tid) * 7, cand[tid]);
-        }
-        if (tid == 0) qn_s = 0;
-        __syncthreads();
-        // A) kept (earlier) vs candidates (later), 128 kept boxes at a time. A1 filters with the cheap exact-zero
-        //    centre-distance test into a queue, A2 runs the polygon clipping one pair per thread: the expensive,
-        //    divergent work is compacted first, so a warp never idles 31 lanes behind one overlapping pair.
-        for (int j0 = 0; j0 < nk; j0 += GREEDY_QUEUE / 64) {
-            const int jn = min(GREEDY_QUEUE / 64, nk - j0);
-            for (int p = tid; p < jn * 64; p += GREEDY_THREADS) {
-                const int j = j0 + (p >> 6), i = p & 63;
-                if (i < sz && !supp[i] && pair_near(kept[j], cand[i])) queue[atomicAdd(&qn_s, 1)] = (unsigned short)((p >> 6) << 6 | i);
-            }
-            __syncthreads();
-            const int qn = qn_s;
-            for (int t = tid; t < qn; t += GREEDY_THREADS) {
-                const int j = j0 + (queue[t] >> 6), i = queue[t] & 63;
-                if (!supp[i] && pair_iou(kept[j], cand[i]) > thresh) supp[i] = 1;
-            }
-            __syncthreads();
-            if (tid == 0) qn_s = 0;
-            __syncthreads();
-        }
-        // B) within the chunk: i earlier, j later (same filter-then-evaluate split)
-        for (int p = tid; p < 64 * 64; p += GREEDY_THREADS) {
-            const int i = p >> 6, j = p & 63;
-            if (j > i && j < sz && !supp[i] && !supp[j] && pair_near(cand[i], cand[j])) queue[atomicAdd(&qn_s, 1)] = (unsigned short)(p);
-        }
-        __syncthreads();
-        {
-            const int qn = qn_s;
-            for (int t = tid; t < qn; t += GREEDY_THREADS) {
-                const int i = queue[t] >> 6, j = queue[t] & 63;
-                if (pair_iou(cand[i], cand[j]) > thresh) atomicOr(&cmask[i], 1ull << j);
-            }
-        }
-        __syncthreads();
-        // C) serial resolve of the chunk
-        if (tid == 0) {
-            unsigned long long removed = 0ull;
-            int k = nk;
-            for (int i = 0; i < sz && k < max_keep; ++i) {
-                if (supp[i] || ((removed >> i) & 1ull)) continue;
-                kept[k] = cand[i];
-                keep[k] = c0 + i;
-                ++k;
-                removed |= cmask[i];
-            }
-            nk_s = k;
-        }
-        __syncthreads();
-        if (nk_s >= max_keep) break;
-    }
-    if (tid == 0) *num_keep = nk_s;
-}
-
-template <typename BOX>
-int launch_greedy_t(int grid, int n_fixed, const int* counts, int n_max, float thresh, const float* boxes, int max_keep,
-                    long long* keep, int keep_stride, int* num_keep, cudaStream_t stream) {
-    const size_t smem = sizeof(BOX) * (GREEDY_MAX_KEEP + 64) + sizeof(unsigned short) * GREEDY_QUEUE;
-    auto kern = nms_greedy_kernel<BOX>;
-    if (smem > 48 * 1024) CRB3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, GREEDY_THREADS, smem, stream>>>(n_fixed, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep);
+int launch_nms(const float* boxes, const int* counts, int B, int n, float thresh, int rotated, int max_keep, long long* keep,
+               int keep_stride, int* num_keep, unsigned long long* mask, cudaStream_t stream) {
+    const int cb = (int)crb3d_divup(n, 64);
+    const unsigned tiles = (unsigned)((int64_t)cb * (cb + 1) / 2);
+    if (rotated) nms_mask_kernel<true><<<dim3(tiles, B), MASK_THREADS, 0, stream>>>(n, thresh, boxes, mask, cb, counts, n);
+    else nms_mask_kernel<false><<<dim3(tiles, B), MASK_THREADS, 0, stream>>>(n, thresh, boxes, mask, cb, counts, n);
+    const size_t smem = sizeof(int) * (size_t)(max_keep > 0 ? (max_keep < n ? max_keep : n) : n);
+    if (smem > 200 * 1024) return CRB3D_ERR_UNSUPPORTED;
+    if (smem > 40 * 1024) CRB3D_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_reduce_kernel<<<B, REDUCE_THREADS, smem, stream>>>(n, cb, mask, max_keep, keep, num_keep, counts, n, keep_stride);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
-}
-
-int launch_greedy(int rotated, int grid, int n_fixed, const int* counts, int n_max, float thresh, const float* boxes,
-                  int max_keep, long long* keep, int keep_stride, int* num_keep, cudaStream_t stream) {
-    return rotated ? launch_greedy_t<RBox>(grid, n_fixed, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep, stream)
-                   : launch_greedy_t<RawBox>(grid, n_fixed, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep, stream);
 }
 
 }  // namespace
@@ -308,34 +221,21 @@ extern "C" int crb3d_nms(const float* boxes, int n, float thresh, int rotated, i
                          int* num_keep, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (n < 0 || !keep || !num_keep) return CRB3D_ERR_ARG;
     if (n == 0) { CRB3D_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int), stream)); return CRB3D_OK; }
-    if (max_keep > 0 && max_keep <= GREEDY_MAX_KEEP) {  // bounded keep list: fused greedy kernel, no mask
-        return launch_greedy(rotated, 1, n, nullptr, n, thresh, boxes, max_keep, keep, 0, num_keep, stream);
-    }
-    const int cb = (int)crb3d_divup(n, 64);
     WsCursor c(ws, ws_bytes);
-    unsigned long long* mask = c.take<unsigned long long>((size_t)n * cb);
+    unsigned long long* mask = c.take<unsigned long long>((size_t)n * crb3d_divup(n, 64));
     if (!c.ok) return CRB3D_ERR_WORKSPACE;
-    const unsigned tiles = (unsigned)((int64_t)cb * (cb + 1) / 2);
-    if (rotated) nms_mask_kernel<true><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
-    else nms_mask_kernel<false><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
-    size_t smem = sizeof(unsigned long long) * cb;
-    if (smem > 48 * 1024) {
-        if (smem > 200 * 1024) return CRB3D_ERR_UNSUPPORTED;
-        CRB3D_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    nms_reduce_kernel<<<1, 256, smem, stream>>>(n, cb, mask, max_keep, keep, num_keep, nullptr, 0, 0);
-    CRB3D_CHECK_LAUNCH();
-    return CRB3D_OK;
+    return launch_nms(boxes, nullptr, 1, n, thresh, rotated, max_keep, keep, 0, num_keep, mask, stream);
 }
 
-// Raw suppression bitmask (full upper triangle), for parity checks against the reference nms_kernel.
+// Raw suppression bitmask (upper-triangular tiles; the rest is left untouched), for parity checks against the
+// reference nms_kernel.
 extern "C" int crb3d_nms_mask(const float* boxes, int n, float thresh, int rotated, unsigned long long* mask,
                               cudaStream_t stream) {
     if (n <= 0 || !mask) return CRB3D_ERR_ARG;
     const int cb = (int)crb3d_divup(n, 64);
     const unsigned tiles = (unsigned)((int64_t)cb * (cb + 1) / 2);
-    if (rotated) nms_mask_kernel<true><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
-    else nms_mask_kernel<false><<<tiles, 64, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
+    if (rotated) nms_mask_kernel<true><<<tiles, MASK_THREADS, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
+    else nms_mask_kernel<false><<<tiles, MASK_THREADS, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -358,22 +258,8 @@ extern "C" int crb3d_nms_batched(const float* boxes, const int* counts, int B, i
     if (max_keep > 0 && keep_stride < max_keep) return CRB3D_ERR_ARG;
     if (B == 0) return CRB3D_OK;
     if (n_max == 0) { CRB3D_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int) * B, stream)); return CRB3D_OK; }
-    if (max_keep > 0 && max_keep <= GREEDY_MAX_KEEP) {  // the scoring path (NMS_POST_MAXSIZE = 500): one CTA per frame
-        return launch_greedy(rotated, B, 0, counts, n_max, thresh, boxes, max_keep, keep, keep_stride, num_keep, stream);
-    }
-    const int cb = (int)crb3d_divup(n_max, 64);
     WsCursor c(ws, ws_bytes);
-    unsigned long long* mask = c.take<unsigned long long>((size_t)B * n_max * cb);
+    unsigned long long* mask = c.take<unsigned long long>((size_t)B * n_max * crb3d_divup(n_max, 64));
     if (!c.ok) return CRB3D_ERR_WORKSPACE;
-    const unsigned tiles = (unsigned)((int64_t)cb * (cb + 1) / 2);
-    if (rotated) nms_mask_kernel<true><<<dim3(tiles, B), 64, 0, stream>>>(0, thresh, boxes, mask, cb, counts, n_max);
-    else nms_mask_kernel<false><<<dim3(tiles, B), 64, 0, stream>>>(0, thresh, boxes, mask, cb, counts, n_max);
-    size_t smem = sizeof(unsigned long long) * cb;
-    if (smem > 48 * 1024) {
-        if (smem > 200 * 1024) return CRB3D_ERR_UNSUPPORTED;
-        CRB3D_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    nms_reduce_kernel<<<B, 256, smem, stream>>>(0, cb, mask, max_keep, keep, num_keep, counts, n_max, keep_stride);
-    CRB3D_CHECK_LAUNCH();
-    return CRB3D_OK;
+    return launch_nms(boxes, counts, B, n_max, thresh, rotated, max_keep, keep, keep_stride, num_keep, mask, stream);
 }

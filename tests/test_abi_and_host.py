@@ -170,3 +170,42 @@ def test_record_all_gather_world2_gloo():
     assert res[0][1] == res[1][1] == list(range(7))
     assert res[0][2] == res[1][2]
     assert res[0][2][5] == (0.5, [1, 2], [50.0, 50.0])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pcdet"), reason="reference tree not present")
+def test_reference_wrappers_import_unmodified_on_dropin():
+    """The REFERENCE's own pcdet/ops/*_utils.py files, loaded as they are, resolve `from . import *_cuda` to the crb3d
+    stand-ins - exercised here through their CPU entry points (no GPU in this container)."""
+    import importlib.util
+    import types
+    from crb3d import dropin
+    from oracle import boxes as ob
+    dropin.install()
+    for name in ("pcdet", "pcdet.ops", "pcdet.ops.iou3d_nms", "pcdet.ops.roiaware_pool3d", "pcdet.utils"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = ["/root/reference/" + name.replace(".", "/")]
+            sys.modules[name] = m
+    cu_mod = types.ModuleType("pcdet.utils.common_utils")       # the wrappers only use check_numpy_to_torch from it
+    cu_mod.check_numpy_to_torch = lambda x: (torch.from_numpy(x).float(), True) if isinstance(x, np.ndarray) else (x, False)
+    sys.modules["pcdet.utils.common_utils"] = cu_mod
+    sys.modules["pcdet.utils"].common_utils = cu_mod
+
+    def load(mod, path):
+        spec = importlib.util.spec_from_file_location(mod, path)
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[mod] = m
+        spec.loader.exec_module(m)
+        return m
+    iou_utils = load("pcdet.ops.iou3d_nms.iou3d_nms_utils", "/root/reference/pcdet/ops/iou3d_nms/iou3d_nms_utils.py")
+    roi_utils = load("pcdet.ops.roiaware_pool3d.roiaware_pool3d_utils", "/root/reference/pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py")
+    assert iou_utils.iou3d_nms_cuda.__name__ == "pcdet_ops.iou3d_nms_cuda"
+    from util import rand_boxes
+    rng = np.random.default_rng(5)
+    a, b = rand_boxes(rng, 30, 8, True), rand_boxes(rng, 20, 8, True)
+    assert np.abs(iou_utils.boxes_bev_iou_cpu(a, b) - ob.boxes_iou_bev(a, b)).max() < 1e-5
+    pts = rng.uniform(-10, 10, (300, 3)).astype(np.float32)
+    assert np.array_equal(roi_utils.points_in_boxes_cpu(pts, a), ob.points_in_boxes_cpu(a, pts))
+    for fn in ("boxes_iou3d_gpu", "nms_gpu", "nms_normal_gpu", "boxes_iou_bev"):
+        assert callable(getattr(iou_utils, fn))
+    assert callable(roi_utils.points_in_boxes_gpu) and callable(roi_utils.RoIAwarePool3d)
