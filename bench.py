@@ -332,6 +332,11 @@ def cpu_baseline(model, frames, n_frames):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner, cuDNN logs) are sent to
+    # stderr for the whole run and the result line is written to the saved descriptor at the end
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

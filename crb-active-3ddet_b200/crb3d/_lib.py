@@ -28,7 +28,7 @@ SIGNATURES = {
     "crb3d_rulebook_compact_pairs_workspace_bytes": [c_int, c_int, POINTER(c_size_t)],
     "crb3d_rulebook_compact_pairs": [P, c_int, c_int, c_int, P, P, P, P, c_size_t, P],
     "crb3d_spconv_forward_f32": [P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, P, P, P, c_int, P, P],
-    "crb3d_spconv_forward_tf32": [P, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P],
+    "crb3d_spconv_forward_tf32": [P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P],
     "crb3d_spconv_wgrad_workspace_bytes": [c_int, c_int, c_int, c_int, POINTER(c_size_t)],
     "crb3d_spconv_wgrad_f32": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_size_t, P],
     "crb3d_sparse_to_dense": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P],

@@ -185,13 +185,14 @@ def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transp
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(feat.device))
-    use_tc = (SPCONV_TF32 if tf32 is None else tf32) and K <= 27 and cin in (16, 32, 64) and cout in (16, 32, 64, 128)
+    use_tc = ((SPCONV_TF32 if tf32 is None else tf32) and K <= 27 and cin in (16, 32, 64) and cout in (16, 32, 64, 128)
+              and feat.shape[0] > 0)
     if use_tc:
         # tcgen05 path wants K-major weight rows [C_out', K, C_in']: the forward layout as is, its transpose for dX
         w_tc = weight.reshape(cout_w, K, cin_w)
         if transpose:
             w_tc = w_tc.permute(2, 1, 0).contiguous()
-        _lib.call("crb3d_spconv_forward_tf32", _p(feat), _p(nbr), _p(w_tc), n_out, K, cin, cout, _p(kmap),
+        _lib.call("crb3d_spconv_forward_tf32", _p(feat), feat.shape[0], _p(nbr), _p(w_tc), n_out, K, cin, cout, _p(kmap),
                   _p(_f32c(scale)) if scale is not None else None, _p(_f32c(shift)) if shift is not None else None,
                   int(bool(relu)), _p(out), _stream(feat.device))
     else:

@@ -1,26 +1,33 @@
-// Sparse 3D convolution on the 5th-gen tensor cores (tcgen05, TF32 inputs, fp32 accumulate in TMEM).
+// Sparse 3D convolution on the 5th-gen tensor cores (tcgen05, TF32 inputs, fp32 accumulate in TMEM) fed by TMA.
 //
 // Replaces the external spconv-cu113==2.1.21 implicit-GEMM forward reached from
 //   pcdet/models/backbones_3d/spconv_backbone.py:77-117   (C_in >= 16 layers of VoxelBackBone8x)
 // Same contract as csrc/spconv_simt.cu:  out[o,:] = sum_k in[nbr[k][o],:] @ W[:,k,:]^T, W = [C_out, K, C_in].
 //
-// One CTA owns 128 consecutive output rows (the UMMA M). Warp-specialised, mbarrier pipelined:
-//   producers (warps 0-6): for every kernel offset k that has a neighbour in the tile, gather the 128 input rows
-//       (cp.async 16 B, zero-fill for missing neighbours) and the C_out x C_in weight slice into a 128B-swizzled
-//       K-major shared-memory stage; `cp.async.mbarrier.arrive.noinc` signals full[stage] when the copies land.
-//   MMA issuer (warp 7, one lane): waits full[stage], issues C_in/8 tcgen05.mma (M=128, N=C_out, K=8, kind::tf32)
-//       accumulating ALL offsets into one TMEM tile, tcgen05.commit -> empty[stage] (and -> acc_full at the end).
-//   epilogue (warps 0-3): tcgen05.ld 32 lanes x 32 columns, optional scale/shift/ReLU, one store per output row.
-// The output is written once, there are no atomics and the summation order is fixed (k ascending).
+// One CTA owns 128 consecutive output rows (the UMMA M). Six warps, mbarrier pipelined:
+//   warp 0 (producer): for every kernel offset k that has a neighbour in the tile, lane g gathers tile rows 4g..4g+3
+//       with ONE `cp.async.bulk.tensor.2d ... tile::gather4` per 32-channel block - the four row coordinates come
+//       straight from the neighbour table, an absent neighbour (-1) is out of bounds and is zero-filled by the TMA
+//       unit, the 128-byte swizzle of the UMMA K-major layout is applied by the hardware. The C_out x C_in weight
+//       slice is one 3-D TMA box. A 4-row group that has no neighbour now and had none when the stage was last used is
+//       skipped (the buffers start out zeroed), so ~85 % of the padded rows cost nothing.
+//   warp 1 (one lane): waits full[stage], issues C_in/8 tcgen05.mma (M=128, N=C_out, K=8, kind::tf32) accumulating ALL
+//       offsets into one TMEM tile, tcgen05.commit -> empty[stage] (and -> acc_full at the end).
+//   warps 2-5 (epilogue): tcgen05.ld 32 lanes x 32 columns, optional scale/shift/ReLU, one store per output row.
+// The output is written once, there are no atomics and the summation order is fixed (k ascending). No LSU gather at
+// all: an earlier cp.async version spent ~3000 cycles per stage just ISSUING 16-byte copies (tools/trace_spconv.py).
 #include "common.cuh"
 #include <cuda.h>
 
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int THREADS = 256;
-constexpr int PRODUCERS = 224;  // warps 0..6
+constexpr int THREADS = 192;
 constexpr int MAX_K = 27;
+
+// optional timeline trace of one CTA (clock64 stamps per offset: producer after empty-wait / after issuing its copies,
+// MMA thread after full-wait / after issuing + committing); set through crb3d_debug_set_tc_trace, null in production
+__device__ long long* g_tc_trace = nullptr;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -35,13 +42,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity));
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes));
-}
-// arrive on `bar` once all cp.async issued so far by this thread have completed (does not bump the pending count)
-__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)));
 }
 
 // K-major, 128B-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
@@ -68,10 +68,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)));
 }
 
-// NKB = ceil(C_in / 32) k-blocks (one 128-byte swizzle row holds 32 floats; C_in = 16 is zero-padded to 32).
+// NKB = ceil(C_in / 32) k-blocks (one 128-byte swizzle row holds 32 floats; C_in = 16 is zero-padded by the TMA unit).
 template <int NKB, int COUT, int STAGES, int MIN_CTAS>
-__global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* __restrict__ feat, const int* __restrict__ nbr,
-                                                                   const __grid_constant__ CUtensorMap wmap, int n_out, int K, int cin,
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_constant__ CUtensorMap fmap,
+                                                                   const __grid_constant__ CUtensorMap wmap,
+                                                                   const int* __restrict__ nbr, int n_out, int K,
                                                                    const int* __restrict__ kmap, const float* __restrict__ scale,
                                                                    const float* __restrict__ shift, int relu,
                                                                    float* __restrict__ out) {
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
     constexpr int TMEM_COLS = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ int rows[MAX_K][TILE_M];
+    __shared__ __align__(16) int rows[MAX_K][TILE_M];
     __shared__ int act[MAX_K];
     __shared__ int n_act_s;
     __shared__ uint64_t full_bar[STAGES];
@@ -92,20 +93,20 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * TILE_M;
 
-    // ---- setup: barriers, TMEM, neighbour rows of this tile for every offset
+    // ---- setup: barriers, TMEM, zeroed stages, neighbour rows of this tile for every offset
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], PRODUCERS + 1);  // 224 cp.async arrivals + the TMA expect_tx arrive
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&full_bar[s], 1);   // the producer's arrive.expect_tx; the TMA units complete the byte count
+            mbar_init(&empty_bar[s], 1);  // tcgen05.commit
         }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    if (warp == 7) {
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    {   // stage A buffers start out zeroed (absent neighbours are never written, see the producer loop)
+    {
         float4* z = reinterpret_cast<float4*>(smem);
         for (int t = tid; t < STAGES * STAGE_BYTES / 16; t += THREADS) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
         const int o = row0 + r;
         rows[k][r] = (o < n_out) ? __ldg(&nbr[(size_t)k * n_out + o]) : -1;
     }
+    asm volatile("fence.proxy.async.shared::cta;");  // the zero fill (generic proxy) precedes TMA writes / MMA reads
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
@@ -122,8 +124,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
     if (warp == 0) {
         int n = 0;
         for (int k = 0; k < K; ++k) {
-            bool any = false;
-            for (int r = lane; r < TILE_M; r += 32) any |= rows[k][r] >= 0;
+            const int4 v = reinterpret_cast<const int4*>(rows[k])[lane];
+            const bool any = (v.x & v.y & v.z & v.w) >= 0;  // some entry is non-negative <=> the AND has a clear sign bit
             if (__any_sync(0xffffffffu, any)) { if (lane == 0) act[n] = k; ++n; }
         }
         if (lane == 0) n_act_s = n;
@@ -132,47 +134,55 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
     const int n_act = n_act_s;
     const uint32_t smem_base = smem_u32(smem);
 
-    if (warp < 7) {
-        // ================================ producers ================================
-        const int vec_per_row = cin >> 2;  // real 16-byte chunks per row (cin % 4 == 0)
+    if (warp == 0) {
+        // ================================ producer warp: TMA gather4 + weight box ================================
         for (int it = 0; it < n_act; ++it) {
             const int stage = it % STAGES;
             if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1);
+            long long* trace = (g_tc_trace && blockIdx.x == gridDim.x / 2 && lane == 0) ? g_tc_trace + 128 : nullptr;
+            if (trace) trace[it * 4 + 0] = clock64();
             const int k = act[it];
             const int kw = kmap ? kmap[k] : k;
             const uint32_t a_base = smem_base + stage * STAGE_BYTES, b_base = a_base + A_BYTES;
-            // B: the C_out x C_in weight slice of offset kw = one TMA box per k-block (3-D map {ci, k, co}, 128B swizzle)
-            if (tid == 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full_bar[stage])), "r"((uint32_t)B_BYTES));
+            const uint32_t bar = smem_u32(&full_bar[stage]);
+            // lane g owns tile rows 4g..4g+3
+            const int4 cur = reinterpret_cast<const int4*>(rows[k])[lane];
+            bool need = (cur.x & cur.y & cur.z & cur.w) >= 0;
+            if (!need && it >= STAGES) {  // stale data from the stage's previous tenant must be cleared
+                const int4 prev = reinterpret_cast<const int4*>(rows[act[it - STAGES]])[lane];
+                need = (prev.x & prev.y & prev.z & prev.w) >= 0;
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, need);
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)B_BYTES + (uint32_t)__popc(m) * (uint32_t)(NKB * 512);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes));
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb)
                     asm volatile(
                         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                         ::"r"(b_base + kb * (COUT * 128)), "l"(reinterpret_cast<uint64_t>(&wmap)), "r"(kb * 32), "r"(kw), "r"(0),
-                        "r"(smem_u32(&full_bar[stage])) : "memory");
+                        "r"(bar) : "memory");
             }
-            // A: 128 rows x (NKB*8) chunks of 16 B; consecutive threads copy consecutive chunks of one row. ~85 % of the
-            // (offset, row) slots have no neighbour: such a row is only re-zeroed if the stage's previous tenant left
-            // data there (stage buffers start out zeroed), which cuts the copy instructions ~3.5x.
-            const int k_prev = (it >= STAGES) ? act[it - STAGES] : -1;
-            for (int q = tid; q < TILE_M * NKB * 8; q += PRODUCERS) {
-                const int r = q / (NKB * 8), c16 = q - r * (NKB * 8);
-                const int kb = c16 >> 3, c = c16 & 7;
-                const int src = rows[k][r];
-                const bool ok = src >= 0 && c16 < vec_per_row;
-                if (!ok && (k_prev < 0 || rows[k_prev][r] < 0)) continue;   // already zero
-                const float* g = ok ? feat + (size_t)src * cin + c16 * 4 : feat;
-                cp_async16(a_base + kb * (TILE_M * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), g, ok ? 16u : 0u);
+            __syncwarp();
+            if (need) {
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb)
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
+                        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                        ::"r"(a_base + kb * (TILE_M * 128) + lane * 512), "l"(reinterpret_cast<uint64_t>(&fmap)), "r"(kb * 32),
+                        "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w), "r"(bar) : "memory");
             }
-            cp_async_arrive(&full_bar[stage]);
+            if (trace) trace[it * 4 + 1] = clock64();
         }
-    } else if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
         // ================================ MMA issuer ================================
         const uint32_t idesc = make_idesc_tf32(TILE_M, COUT);
         for (int it = 0; it < n_act; ++it) {
             const int stage = it % STAGES;
             mbar_wait(&full_bar[stage], (it / STAGES) & 1);
-            asm volatile("fence.proxy.async.shared::cta;");   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+            long long* trace = (g_tc_trace && blockIdx.x == gridDim.x / 2) ? g_tc_trace : nullptr;
+            if (trace) trace[it * 4 + 2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t a_base = smem_base + stage * STAGE_BYTES, b_base = a_base + A_BYTES;
 #pragma unroll
@@ -186,22 +196,24 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
             }
             umma_commit(&empty_bar[stage]);                   // frees the stage when these MMAs retire
             if (it == n_act - 1) umma_commit(&acc_bar);       // accumulator complete
+            if (trace) trace[it * 4 + 3] = clock64();
         }
     }
 
-    // ---- epilogue: TMEM -> registers -> global (warps 0..3 own TMEM lanes 32w..32w+31 = tile rows)
-    if (warp < 4) {
+    // ---- epilogue: TMEM -> registers -> global (warps 2..5; a warp may only touch TMEM lanes 32*(warp%4)..+31)
+    if (warp >= 2) {
         if (n_act > 0) {
             mbar_wait(&acc_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;");
         }
-        const int r = warp * 32 + lane;
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
         const int o = row0 + r;
 #pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 32) {
             uint32_t v[32];
             if (n_act > 0) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + c0;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + c0;
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -239,7 +251,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 7) {
+    if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
 }
@@ -274,40 +286,55 @@ int make_weight_map(const float* weight, int K, int cin, int cout, CUtensorMap* 
     return r == CUDA_SUCCESS ? CRB3D_OK : CRB3D_ERR_CUDA;
 }
 
+// 2-D view {ci, row} of the (n_in, C_in) feature matrix for tile::gather4: box {32, 1} (four rows are named per
+// instruction), 128-byte swizzle, out-of-bounds rows / columns read as zero (verified by tools/probe/gather4_probe.cu)
+int make_feature_map(const float* feat, int n_in, int cin, CUtensorMap* map) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return CRB3D_ERR_CUDA;
+    cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)n_in};
+    cuuint64_t strides[1] = {(cuuint64_t)cin * 4};
+    cuuint32_t box[2] = {32, 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(feat), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? CRB3D_OK : CRB3D_ERR_CUDA;
+}
+
 template <int NKB, int COUT, int STAGES, int MIN_CTAS>
-int launch_tc(const float* feat, const int* nbr, const float* weight, int n_out, int K, int cin, const int* kmap,
+int launch_tc(const float* feat, int n_in, const int* nbr, const float* weight, int n_out, int K, int cin, const int* kmap,
               const float* scale, const float* shift, int relu, float* out, cudaStream_t stream) {
     constexpr size_t smem = (size_t)STAGES * (NKB * TILE_M * 128 + NKB * COUT * 128) + 1024;
-    CUtensorMap wmap;
+    CUtensorMap wmap, fmap;
     int rc = make_weight_map(weight, K, cin, COUT, &wmap);
     if (rc) return rc;
+    rc = make_feature_map(feat, n_in, cin, &fmap);
+    if (rc) return rc;
     auto kern = spconv_fwd_tc<NKB, COUT, STAGES, MIN_CTAS>;
-    static bool attr_set = false;  // per instantiation; the attribute is per function (and per device - single-GPU processes)
+    static bool attr_set = false;  // per instantiation; the attribute is per function (single-GPU processes)
     if (!attr_set) {
         CRB3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    kern<<<(unsigned)crb3d_divup(n_out, TILE_M), THREADS, smem, stream>>>(feat, nbr, wmap, n_out, K, cin, kmap, scale, shift,
-                                                                         relu, out);
+    kern<<<(unsigned)crb3d_divup(n_out, TILE_M), THREADS, smem, stream>>>(fmap, wmap, nbr, n_out, K, kmap, scale, shift, relu, out);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
 
 }  // namespace
 
-// TF32 tensor-core forward. weight must be contiguous [C_out, K, C_in] (for the input gradient pass the transposed
-// weight [C_in, K, C_out] and the transposed table). Supported: C_in a multiple of 4 up to 64, C_out in
+// TF32 tensor-core forward. feat: (n_in, C_in) contiguous; weight: contiguous [C_out, K, C_in] (for the input gradient
+// pass the transposed weight [C_in, K, C_out] and the transposed table). Supported: C_in in {16, 32, 64}, C_out in
 // {16, 32, 64, 128}, K <= 27; anything else returns CRB3D_ERR_UNSUPPORTED (callers use crb3d_spconv_forward_f32).
-// Stage counts are sized so that two CTAs fit one SM (<= ~110 KB each) wherever possible: the second CTA hides the
-// first one's gather latency and a 150-tile layer fits one wave of 296 CTA slots.
-extern "C" int crb3d_spconv_forward_tf32(const float* feat, const int* nbr, const float* weight, int n_out, int K, int cin,
-                                         int cout, const int* kmap, const float* scale, const float* shift, int relu,
-                                         float* out, cudaStream_t stream) {
-    if (n_out < 0 || K <= 0 || cin <= 0 || cout <= 0 || !weight || !out) return CRB3D_ERR_ARG;
+// Stage counts are sized so that two or three CTAs fit one SM: the co-resident CTAs hide each other's TMA round trips.
+extern "C" int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int* nbr, const float* weight, int n_out, int K,
+                                         int cin, int cout, const int* kmap, const float* scale, const float* shift,
+                                         int relu, float* out, cudaStream_t stream) {
+    if (n_out < 0 || n_in < 0 || K <= 0 || cin <= 0 || cout <= 0 || !weight || !out) return CRB3D_ERR_ARG;
     if (n_out == 0) return CRB3D_OK;
-    if (!feat || !nbr) return CRB3D_ERR_ARG;
-    if (K > MAX_K || (cin & 3)) return CRB3D_ERR_UNSUPPORTED;
-#define TC_ARGS feat, nbr, weight, n_out, K, cin, kmap, scale, shift, relu, out, stream
+    if (!feat || !nbr || n_in == 0) return CRB3D_ERR_ARG;
+    if (K > MAX_K || (cin != 16 && cin != 32 && cin != 64)) return CRB3D_ERR_UNSUPPORTED;
+#define TC_ARGS feat, n_in, nbr, weight, n_out, K, cin, kmap, scale, shift, relu, out, stream
     const int nkb = (cin + 31) / 32;
     if (nkb == 1) {                                        // stage = 16 KB + C_out*128 B
         if (cout == 16) return launch_tc<1, 16, 4, 2>(TC_ARGS);
@@ -322,4 +349,9 @@ extern "C" int crb3d_spconv_forward_tf32(const float* feat, const int* nbr, cons
     }
 #undef TC_ARGS
     return CRB3D_ERR_UNSUPPORTED;
+}
+
+// Debug hook (not part of include/crb3d.h): buf = device array of >= 256 int64, or null to switch tracing off.
+extern "C" int crb3d_debug_set_tc_trace(long long* buf) {
+    return cudaMemcpyToSymbol(g_tc_trace, &buf, sizeof(buf)) == cudaSuccess ? CRB3D_OK : CRB3D_ERR_CUDA;
 }
