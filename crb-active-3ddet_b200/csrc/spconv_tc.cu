@@ -22,7 +22,8 @@
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int THREADS = 192;
+constexpr int PW = 4;            // producer warps (also the epilogue warps)
+constexpr int THREADS = (PW + 1) * 32;
 constexpr int MAX_K = 27;
 
 // optional timeline trace of one CTA (clock64 stamps per offset: producer after empty-wait / after issuing its copies,
@@ -96,13 +97,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
     // ---- setup: barriers, TMEM, zeroed stages, neighbour rows of this tile for every offset
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);   // the producer's arrive.expect_tx; the TMA units complete the byte count
+            mbar_init(&full_bar[s], PW);  // one arrive.expect_tx per producer warp; the TMA unit completes the byte count
             mbar_init(&empty_bar[s], 1);  // tcgen05.commit
         }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    if (warp == 1) {
+    if (warp == PW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -134,28 +135,38 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
     const int n_act = n_act_s;
     const uint32_t smem_base = smem_u32(smem);
 
-    if (warp == 0) {
-        // ================================ producer warp: TMA gather4 + weight box ================================
+    if (warp < PW) {
+        // ================================ producer warps: TMA gather4 + weight box ================================
+        // warp w, lane l < 32/PW owns the 4-row group g = l*PW + w (the per-thread TMA issue cost is spread over PW warps)
+        const int g = lane * PW + warp;
+        const bool owner = lane < 32 / PW;
         for (int it = 0; it < n_act; ++it) {
             const int stage = it % STAGES;
             if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1);
-            long long* trace = (g_tc_trace && blockIdx.x == gridDim.x / 2 && lane == 0) ? g_tc_trace + 128 : nullptr;
+            long long* trace = (g_tc_trace && blockIdx.x == gridDim.x / 2 && tid == 0) ? g_tc_trace + 128 : nullptr;
             if (trace) trace[it * 4 + 0] = clock64();
             const int k = act[it];
-            const int kw = kmap ? kmap[k] : k;
             const uint32_t a_base = smem_base + stage * STAGE_BYTES, b_base = a_base + A_BYTES;
             const uint32_t bar = smem_u32(&full_bar[stage]);
-            // lane g owns tile rows 4g..4g+3
-            const int4 cur = reinterpret_cast<const int4*>(rows[k])[lane];
-            bool need = (cur.x & cur.y & cur.z & cur.w) >= 0;
-            if (!need && it >= STAGES) {  // stale data from the stage's previous tenant must be cleared
-                const int4 prev = reinterpret_cast<const int4*>(rows[act[it - STAGES]])[lane];
-                need = (prev.x & prev.y & prev.z & prev.w) >= 0;
+            int4 cur = make_int4(-1, -1, -1, -1);
+            bool need = false;
+            if (owner) {
+                cur = reinterpret_cast<const int4*>(rows[k])[g];
+                need = (cur.x & cur.y & cur.z & cur.w) >= 0;
+                if (!need && it >= STAGES) {  // stale data from the stage's previous tenant must be cleared
+                    const int4 prev = reinterpret_cast<const int4*>(rows[act[it - STAGES]])[g];
+                    need = (prev.x & prev.y & prev.z & prev.w) >= 0;
+                }
             }
             const unsigned int m = __ballot_sync(0xffffffffu, need);
             if (lane == 0) {
-                const uint32_t bytes = (uint32_t)B_BYTES + (uint32_t)__popc(m) * (uint32_t)(NKB * 512);
+                uint32_t bytes = (uint32_t)__popc(m) * (uint32_t)(NKB * 512);
+                if (warp == 0) bytes += (uint32_t)B_BYTES;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes));
+            }
+            __syncwarp();
+            if (warp == PW - 1 && lane == 31) {   // an otherwise idle lane fetches the weight slice
+                const int kw = kmap ? kmap[k] : k;
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb)
                     asm volatile(
@@ -163,19 +174,18 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
                         ::"r"(b_base + kb * (COUT * 128)), "l"(reinterpret_cast<uint64_t>(&wmap)), "r"(kb * 32), "r"(kw), "r"(0),
                         "r"(bar) : "memory");
             }
-            __syncwarp();
             if (need) {
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb)
                     asm volatile(
                         "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
                         "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                        ::"r"(a_base + kb * (TILE_M * 128) + lane * 512), "l"(reinterpret_cast<uint64_t>(&fmap)), "r"(kb * 32),
+                        ::"r"(a_base + kb * (TILE_M * 128) + g * 512), "l"(reinterpret_cast<uint64_t>(&fmap)), "r"(kb * 32),
                         "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w), "r"(bar) : "memory");
             }
             if (trace) trace[it * 4 + 1] = clock64();
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == PW && lane == 0) {
         // ================================ MMA issuer ================================
         const uint32_t idesc = make_idesc_tf32(TILE_M, COUT);
         for (int it = 0; it < n_act; ++it) {
@@ -200,8 +210,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
         }
     }
 
-    // ---- epilogue: TMEM -> registers -> global (warps 2..5; a warp may only touch TMEM lanes 32*(warp%4)..+31)
-    if (warp >= 2) {
+    // ---- epilogue: TMEM -> registers -> global (warps 0..3; a warp may only touch TMEM lanes 32*(warp%4)..+31)
+    if (warp < 4) {
         if (n_act > 0) {
             mbar_wait(&acc_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;");
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 1) {
+    if (warp == PW) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
 }

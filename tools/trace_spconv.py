@@ -26,10 +26,10 @@ for key, cin, cout in (("subm3", 64, 64), ("subm1", 16, 16)):
     lib.crb3d_debug_set_tc_trace(None)
     t = buf.cpu().numpy()
     a, b = t[:128].reshape(32, 4), t[128:].reshape(32, 4)
-    t0 = a[0, 0]
+    t0 = b[0, 0]
     print(key, cin, cout, "rows", d.nbr.shape[1])
-    print(" it | p0 empty-done  p0 issued | p223 empty-done p223 issued | mma full-done  mma committed")
+    print(" it | producer: stage free   TMA issued | mma: stage full   issued+committed")
     for it in range(27):
-        if a[it, 0] == 0:
+        if b[it, 0] == 0:
             break
-        print("%3d | %8d %10d | %8d %10d | %8d %10d" % (it, a[it, 0] - t0, a[it, 1] - t0, b[it, 0] - t0, b[it, 1] - t0, a[it, 2] - t0, a[it, 3] - t0))
+        print("%3d | %10d %12d | %10d %12d" % (it, b[it, 0] - t0, b[it, 1] - t0, a[it, 2] - t0, a[it, 3] - t0))
