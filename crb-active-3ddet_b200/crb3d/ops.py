@@ -231,6 +231,50 @@ def spconv_wgrad(feat, dout, nbr, weight_shape, accumulate_into=None):
     return dw
 
 
+# ----------------------------------------------------------------------------------------------- BEV GEMMs (tcgen05)
+def bev_gemm(a, weight, bias, relu, segs, n_sub=1, up=0, in_hw=(0, 0)):
+    """D = A @ W^T (+bias) (ReLU) on the tensor cores with fused output placement (csrc/bev_gemm_tc.cu).
+    a: (M, K) fp32 CUDA, unit column stride (row stride = a.stride(0)); weight: contiguous (n_sub*N, K);
+    bias: (N,) or None; segs: [(out_tensor, col_begin, width, row_stride_floats)] - column segment -> out_tensor's
+    storage starting at its data_ptr(). up=2: the four (dy,dx) slices of a k=s=2 transposed conv, in_hw = input (H, W)."""
+    _need_cuda(a, weight)
+    assert a.dtype == torch.float32 and a.dim() == 2 and a.stride(1) == 1
+    weight = _f32c(weight)
+    M, K = a.shape
+    N = weight.shape[0] // n_sub
+    assert weight.shape[1] == K and 1 <= len(segs) <= 3
+    ptrs = (ctypes.c_void_p * 3)(*[s[0].data_ptr() for s in segs], *([None] * (3 - len(segs))))
+    cb = (ctypes.c_int * 3)(*[int(s[1]) for s in segs], *([0] * (3 - len(segs))))
+    wd = (ctypes.c_int * 3)(*[int(s[2]) for s in segs], *([0] * (3 - len(segs))))
+    rs = (ctypes.c_longlong * 3)(*[int(s[3]) for s in segs], *([0] * (3 - len(segs))))
+    _lib.call("crb3d_bev_gemm_tf32", _p(a), M, K, a.stride(0), _p(weight), N, n_sub, _p(_f32c(bias)) if bias is not None else None,
+              int(bool(relu)), len(segs), ptrs, cb, wd, rs, int(up), int(in_hw[0]), int(in_hw[1]), _stream(a.device))
+
+
+def pack_conv3x3_weight(weight):
+    """(C_out, C_in, 3, 3) conv weight -> the slab layout of csrc/bev_conv_tc.cu:
+    [C_out/128][tap = ky*3+kx][C_in/16][4 slabs][128 co][4 ci] (contiguous fp32)."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    assert tuple(weight.shape[2:]) == (3, 3) and cout % 128 == 0 and cin % 16 == 0
+    w = weight.detach().float().permute(0, 2, 3, 1).reshape(cout // 128, 128, 9, cin // 16, 4, 4)
+    return w.permute(0, 2, 3, 4, 1, 5).contiguous()
+
+
+def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None):
+    """3x3 / stride 1 / pad 1 conv (+bias, ReLU) on the tensor cores. x_nhwc: (B, H, W, C_in) contiguous fp32 CUDA;
+    wpack: pack_conv3x3_weight(...). Returns (B, H, W, C_out) contiguous."""
+    _need_cuda(x_nhwc, wpack)
+    assert x_nhwc.dtype == torch.float32 and x_nhwc.is_contiguous() and wpack.is_contiguous()
+    B, H, W, cin = x_nhwc.shape
+    cout = wpack.shape[0] * 128
+    assert wpack.shape[2] * 16 == cin
+    if out is None:
+        out = torch.empty((B, H, W, cout), dtype=torch.float32, device=x_nhwc.device)
+    _lib.call("crb3d_bev_conv3x3_tf32", _p(x_nhwc), B, H, W, cin, _p(wpack), cout, _p(_f32c(bias)) if bias is not None else None,
+              int(bool(relu)), _p(out), _stream(x_nhwc.device))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- dense
 def sparse_to_dense(feat, coords, batch_size, spatial_shape, channels_last_bev=False, out=None):
     """(B,C,D,H,W) dense tensor (reference .dense()); channels_last_bev=True returns (B,H,W,C*D) memory whose
@@ -301,7 +345,8 @@ def nms_mask(boxes_sorted, thresh, rotated=True):
     n = b.shape[0]
     cb = (n + 63) // 64
     mask = torch.zeros((n, cb), dtype=torch.int64, device=b.device)
-    _lib.call("crb3d_nms_mask", _p(b), n, float(thresh), int(bool(rotated)), _p(mask), _stream(b.device))
+    ws = _ws(_ws_bytes("crb3d_nms_workspace_bytes", n), b.device)
+    _lib.call("crb3d_nms_mask", _p(b), n, float(thresh), int(bool(rotated)), _p(mask), _p(ws), ws.numel(), _stream(b.device))
     return mask
 
 

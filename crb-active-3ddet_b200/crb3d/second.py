@@ -48,6 +48,10 @@ WAYMO_SECOND_CFG = dict(
 )
 
 
+# tcgen05 halo-tile kernel for the 3x3 stride-1 BEV convs: "auto" (when its CTA count fills whole waves), True, False
+BEV_CONV_TC = "auto"
+
+
 def post_act_block(in_channels, out_channels, kernel_size, indice_key=None, stride=1, padding=0, conv_type="subm", norm_fn=None):
     if conv_type == "subm":
         conv = spconv.SubMConv3d(in_channels, out_channels, kernel_size, bias=False, indice_key=indice_key)
@@ -160,29 +164,75 @@ class BaseBEVBackbone(nn.Module):
         return w.contiguous(memory_format=torch.channels_last), shift.contiguous()
 
     def build_inference_plan(self):
-        """[(kind, weight, bias, stride, padding)] per block; rebuilt whenever parameters change (call after loading
-        a checkpoint / moving the module)."""
+        """[(conv layers, deblock, deblock GEMM)] per block; rebuilt whenever parameters change (call after loading a
+        checkpoint / moving the module). 3x3 stride-1 convs get a packed weight for crb3d's tcgen05 halo-tile conv
+        (ops.bev_conv3x3); deblocks with kernel == stride in {1, 2} run on the tcgen05 GEMM (ops.bev_gemm) and write
+        their channel slice of the concatenated map directly. Everything else stays on cuDNN."""
         plan = []
         with torch.no_grad():
             for blk, de in zip(self.blocks, self.deblocks):
                 layers = []
                 mods = list(blk)
-                w, b = self._fold(mods[1].weight, mods[2])
-                layers.append((w, b, mods[1].stride, (1, 1)))           # ZeroPad2d(1) + conv(pad 0) == conv(pad 1)
-                for j in range(4, len(mods), 3):
-                    w, b = self._fold(mods[j].weight, mods[j + 1])
-                    layers.append((w, b, mods[j].stride, mods[j].padding))
+                convs = [(mods[1], mods[2], (1, 1))] + [(mods[j], mods[j + 1], mods[j].padding) for j in range(4, len(mods), 3)]
+                for conv, bn, pad in convs:                              # ZeroPad2d(1) + conv(pad 0) == conv(pad 1)
+                    w, b = self._fold(conv.weight, bn)
+                    wpack = None
+                    if (conv.kernel_size == (3, 3) and conv.stride == (1, 1) and tuple(pad) == (1, 1) and w.shape[0] % 128 == 0
+                            and w.shape[1] % 16 == 0 and w.is_cuda):
+                        wpack = ops.pack_conv3x3_weight(w)
+                    layers.append((w, b, conv.stride, tuple(pad), wpack))
                 dw, db = self._fold(de[0].weight, de[1], transposed=True)
-                plan.append((layers, (dw, db, de[0].stride)))
+                st = de[0].stride[0] if isinstance(de[0], nn.ConvTranspose2d) else 0
+                cin, cout = dw.shape[0], dw.shape[1]
+                gemm = None
+                if (st in (1, 2) and de[0].stride == (st, st) and de[0].kernel_size == (st, st) and cin % 32 == 0
+                        and cout in (128, 256) and dw.is_cuda):
+                    # ConvTranspose2d weight (C_in, C_out, kh, kw) -> [(dy,dx)][C_out][C_in]
+                    gemm = (dw.permute(2, 3, 1, 0).reshape(st * st * cout, cin).contiguous(), db, st)
+                plan.append((layers, (dw, db, de[0].stride), gemm))
         self._plan = plan
         return plan
 
+    @staticmethod
+    def _tc_conv_pays(B, H, W, cout):
+        """The halo-tile kernel runs one CTA (4 tiles of 128 pixels x 128 channels) per SM: use it when its CTA count
+        fills whole waves of the 148 SMs, otherwise cuDNN's finer tiles win (BEV_CONV_TC = True/False overrides)."""
+        if BEV_CONV_TC != "auto":
+            return bool(BEV_CONV_TC)
+        u, v = (H, W) if H % 8 == 0 or W % 8 != 0 else (W, H)
+        ctas = -(-(B * -(-u // 8) * -(-v // 16)) // 4) * (cout // 128)
+        return ctas / (-(-ctas // 148) * 148.0) >= 0.8
+
     def forward_inference(self, x):
-        ups = []
-        for layers, (dw, db, ds) in self._plan:
-            for w, b, stride, pad in layers:
-                x = torch.cudnn_convolution_relu(x, w, b, stride, pad, (1, 1), 1)
-            ups.append(torch.relu_(torch.nn.functional.conv_transpose2d(x, dw, db, stride=ds)))
+        B = x.shape[0]
+        gemm_ok = all(g is not None for _, _, g in self._plan)
+        if gemm_ok:
+            ctot = sum(g[0].shape[0] // (g[2] * g[2]) for _, _, g in self._plan)
+            cat = None
+        xh = x.permute(0, 2, 3, 1)                                   # (B, H, W, C): the memory order of channels-last
+        xh = xh if xh.is_contiguous() else xh.contiguous()
+        ups, c0 = [], 0
+        for layers, (dw, db, ds), gemm in self._plan:
+            for w, b, stride, pad, wpack in layers:
+                if wpack is not None and self._tc_conv_pays(B, xh.shape[1], xh.shape[2], w.shape[0]):
+                    xh = ops.bev_conv3x3(xh, wpack, b, True)
+                else:
+                    xh = torch.cudnn_convolution_relu(xh.permute(0, 3, 1, 2), w, b, stride, pad, (1, 1), 1).permute(0, 2, 3, 1)
+                    xh = xh if xh.is_contiguous() else xh.contiguous()
+            if not gemm_ok:
+                ups.append(torch.relu_(torch.nn.functional.conv_transpose2d(xh.permute(0, 3, 1, 2), dw, db, stride=ds)))
+                continue
+            gw, gb, st = gemm
+            cout = gw.shape[0] // (st * st)
+            h, wd = xh.shape[1], xh.shape[2]
+            if cat is None:   # (B, H_out, W_out, sum C) channels-last; every deblock lands on the same output grid
+                cat = torch.empty((B, h * st, wd * st, ctot), dtype=torch.float32, device=x.device)
+            assert cat.shape[1] == h * st and cat.shape[2] == wd * st
+            ops.bev_gemm(xh.view(B * h * wd, xh.shape[3]), gw, gb, True, [(cat.view(-1, ctot)[:, c0:], 0, cout, ctot)],
+                         n_sub=st * st, up=2 if st == 2 else 0, in_hw=(h, wd))
+            c0 += cout
+        if gemm_ok:
+            return cat.permute(0, 3, 1, 2)
         return torch.cat(ups, dim=1) if len(ups) > 1 else ups[0]
 
     def forward(self, batch_dict):
@@ -214,9 +264,39 @@ class AnchorHeadSingle(nn.Module):
                                               cfg["dir_limit_offset"], cfg["num_dir_bins"])
         self.num_anchors = fm[0] * fm[1] * self.n_loc
 
+    def build_inference_plan(self):
+        """The three 1x1 head convs as one [n_cls + n_box + n_dir (padded to 80)][C_in] weight for ops.bev_gemm."""
+        self._plan = None
+        with torch.no_grad():
+            ws = [m.weight.reshape(m.weight.shape[0], -1) for m in (self.conv_cls, self.conv_box, self.conv_dir_cls)]
+            bs = [m.bias for m in (self.conv_cls, self.conv_box, self.conv_dir_cls)]
+            n, k = sum(w.shape[0] for w in ws), ws[0].shape[1]
+            if n <= 80 and k % 32 == 0:
+                w = torch.zeros((80, k), dtype=torch.float32, device=ws[0].device)
+                b = torch.zeros((80,), dtype=torch.float32, device=ws[0].device)
+                w[:n] = torch.cat(ws, 0)
+                b[:n] = torch.cat(bs, 0)
+                self._plan = (w.contiguous(), b, [x.shape[0] for x in ws])
+        return self._plan
+
     def forward(self, batch_dict):
         x = batch_dict["spatial_features_2d"]
         B = x.shape[0]
+        plan = getattr(self, "_plan", None)
+        if plan is not None and not self.training and not torch.is_grad_enabled() and x.is_cuda:
+            w, b, widths = plan
+            a = x.permute(0, 2, 3, 1)
+            a = (a if a.is_contiguous() else a.contiguous()).view(-1, x.shape[1])
+            outs = [torch.empty((a.shape[0], n), dtype=torch.float32, device=x.device) for n in widths]
+            segs, c0 = [], 0
+            for o, n in zip(outs, widths):
+                segs.append((o, c0, n, n))
+                c0 += n
+            ops.bev_gemm(a, w, b, False, segs)
+            batch_dict["cls_preds"] = outs[0].view(B, self.num_anchors, self.num_class)
+            batch_dict["box_preds"] = outs[1].view(B, self.num_anchors, 7)
+            batch_dict["dir_cls_preds"] = outs[2].view(B, self.num_anchors, -1)
+            return batch_dict
         # NHWC: with channels-last activations permute(0,2,3,1) is a view and .contiguous() is free
         batch_dict["cls_preds"] = self.conv_cls(x).permute(0, 2, 3, 1).contiguous().view(B, self.num_anchors, self.num_class)
         batch_dict["box_preds"] = self.conv_box(x).permute(0, 2, 3, 1).contiguous().view(B, self.num_anchors, 7)
@@ -248,8 +328,10 @@ class SECONDNet(nn.Module):
         with C_in >= 16 to the tcgen05 TF32 kernel (None = leave the global crb3d.ops.SPCONV_TF32 setting alone)."""
         self.eval()
         self.backbone_2d._plan = None
+        self.dense_head._plan = None
         if fold_bev_bn:
             self.backbone_2d.build_inference_plan()
+            self.dense_head.build_inference_plan()
         if spconv_tf32 is not None:
             ops.SPCONV_TF32 = bool(spconv_tf32)
         return self
@@ -393,4 +475,6 @@ def calibrate_head_bias(model, points, frame_offsets, batch_size, target_fractio
         b.copy_((b - mean) / std - z + thr)
         if getattr(model.backbone_2d, "_plan", None) is not None:
             model.backbone_2d.build_inference_plan()
+        if getattr(model.dense_head, "_plan", None) is not None:
+            model.dense_head.build_inference_plan()
     return model

@@ -7,17 +7,17 @@
 //                                                        serial CPU greedy loop (iou3d_nms.cpp:121-132)
 // The polygon arithmetic (rbox.cuh) follows iou3d_nms_kernel.cu:36-234 operation for operation because the kept-index
 // list is a bit-exact target. What is different:
-//   * per-box data (corners, sin/cos) is computed once per tile in shared memory instead of once per pair;
-//   * FILTER THEN EVALUATE: every tile first runs the cheap exact-zero centre-distance test on its 64x64 pairs and
-//     compacts the survivors into a shared-memory queue; only then is the divergent polygon clipping run, one queued
-//     pair per thread, so a warp never idles 31 lanes behind one overlapping pair (the reference evaluates 64 pairs
-//     serially per thread);
-//   * only the upper-triangular tiles of the bitmask are produced (the reference's host loop never reads the rest);
-//   * the greedy pass runs on the GPU: per 64-box chunk it PULLS the suppression word of every already-kept box
-//     (<= keep-count loads spread over the CTA + one OR-reduction) and resolves the chunk against its diagonal tile,
-//     writing `keep` / `num_keep` in device memory - the mask never crosses PCIe, there is no host synchronisation,
-//     and a bounded keep list (NMS_POST_MAXSIZE) stops the pass early;
-//   * a batched entry point runs all frames of a batch in one mask launch + one reduce launch.
+//   * per-box data (corners, sin/cos) is computed once per box by a prep kernel instead of once per pair;
+//   * FILTER THEN EVALUATE: a CTA owns 64 rows x 512 columns; warps sweep the cheap exact-zero centre-distance test
+//     over 16-byte filter records in shared memory and compact the survivors into a queue; only then is the divergent
+//     polygon clipping run, one queued pair per thread, so a warp never idles 31 lanes behind one overlapping pair
+//     (the reference evaluates 64 pairs serially per thread);
+//   * only the blocks on/above the diagonal of the bitmask are produced (the reference's host loop never reads the
+//     rest), stored column-block major so the greedy pass streams them with contiguous copies;
+//   * the greedy pass runs on the GPU, one CTA per frame: column block c+1 is prefetched (cp.async, double buffer)
+//     while chunk c is resolved from shared memory, writing `keep` / `num_keep` in device memory - the mask never
+//     crosses PCIe, there is no host synchronisation, and a bounded keep list (NMS_POST_MAXSIZE) stops the pass early;
+//   * a batched entry point runs all frames of a batch in one prep + one mask + one reduce launch.
 #include "common.cuh"
 #include "rbox.cuh"
 
@@ -43,110 +43,186 @@ __global__ void __launch_bounds__(256) pairwise_kernel(int na, const float* __re
 }
 
 // false only when the overlap is exactly 0 (same centre-distance early-out as rbox_overlap)
-__device__ __forceinline__ bool rbox_near(const RBox& a, const RBox& b) {
-    const float dx = a.cx - b.cx, dy = a.cy - b.cy, reach = a.rad + b.rad + 0.1f;
+__device__ __forceinline__ bool circ_near(const float4& a, const float4& b) {
+    const float dx = a.x - b.x, dy = a.y - b.y, reach = a.z + b.z + 0.1f;
     return !(dx * dx + dy * dy > reach * reach);
 }
+// axis-aligned: (left, right, top, bottom) with the expressions of aabb_iou; false only when inter == 0 exactly
+__device__ __forceinline__ bool aabb_near(const float4& a, const float4& b) {
+    return fminf(a.y, b.y) - fmaxf(a.x, b.x) > 0.f && fminf(a.w, b.w) - fmaxf(a.z, b.z) > 0.f;
+}
 
-// ------------------------------------------------------------------ NMS bitmask (upper-triangular 64x64 tiles)
+// ------------------------------------------------------------------ NMS step 1: per-box precompute
+// One thread per box: the rotated-box record (corners, sin/cos: 64 B) once per box instead of once per tile, and a
+// 16-byte filter record (rotated: centre + half diagonal; axis-aligned: the four edges).
+template <bool ROTATED>
+__global__ void __launch_bounds__(256) nms_prep_kernel(int n, const float* __restrict__ boxes, const int* __restrict__ counts,
+                                                       int n_max, RBox* __restrict__ rb, float4* __restrict__ circ) {
+    const int f = blockIdx.y;
+    if (counts) n = min(counts[f], n_max);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* src = boxes + ((size_t)f * n_max + i) * 7;
+    const size_t o = (size_t)f * n_max + i;
+    if (ROTATED) {
+        RBox r;
+        make_rbox(src, r);
+        const float4* p = reinterpret_cast<const float4*>(&r);
+        float4* d = reinterpret_cast<float4*>(rb + o);
+        d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
+        circ[o] = make_float4(r.cx, r.cy, r.rad, 0.f);
+    } else {
+        circ[o] = make_float4(src[0] - src[3] / 2, src[0] + src[3] / 2, src[1] - src[4] / 2, src[1] + src[4] / 2);
+    }
+}
+
+// ------------------------------------------------------------------ NMS step 2: suppression bitmask
+// CTA = 64 rows (earlier boxes) x up to MASK_CW*64 columns (later boxes). FILTER THEN EVALUATE: a warp sweeps one row's
+// columns with the 16-byte filter records (shared memory) and compacts the surviving pairs into a queue; then the CTA
+// runs the divergent polygon clipping one queued pair per thread. Words are stored column-block major
+// (maskT[c][row]) so that the greedy pass can stream a whole column block with contiguous 16-byte copies.
 constexpr int MASK_THREADS = 256;
+constexpr int MASK_CW = 8;
 
 template <bool ROTATED>
 __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int n, float thresh, const float* __restrict__ boxes,
-                                                                unsigned long long* __restrict__ mask, int col_blocks,
+                                                                const RBox* __restrict__ rb, const float4* __restrict__ circ,
+                                                                unsigned long long* __restrict__ maskT, int rows_pad,
                                                                 const int* __restrict__ counts, int n_max) {
-    // blockIdx.y = frame (batched: frame b owns boxes[b*n_max ...] and mask[b*n_max*col_blocks ...], n = counts[b])
-    if (counts) {
-        n = min(counts[blockIdx.y], n_max);
-        boxes += (size_t)blockIdx.y * n_max * 7;
-        mask += (size_t)blockIdx.y * n_max * col_blocks;
-    }
-    // blockIdx.x enumerates tiles (r, c) with c >= r
-    int t = blockIdx.x, r = 0;
-    while (t >= col_blocks - r) { t -= col_blocks - r; ++r; }
-    const int c = r + t;
-    if (r * 64 >= n || c * 64 >= n) return;  // tile beyond this frame's boxes (uniform per CTA)
-    const int row_size = min(n - r * 64, 64), col_size = min(n - c * 64, 64);
-    __shared__ RBox rb[64], cb[64];
-    __shared__ float rraw[64 * 7], craw[64 * 7];
-    __shared__ unsigned short queue[4096];
-    __shared__ unsigned long long bits[64];
+    const int f = blockIdx.z;
+    if (counts) n = min(counts[f], n_max);
+    const int cbn = (n + 63) >> 6;
+    const int r = blockIdx.y, c0 = max((int)blockIdx.x * MASK_CW, r), c1 = min(((int)blockIdx.x + 1) * MASK_CW, cbn);
+    if (r >= cbn || c1 <= c0) return;  // uniform per CTA
+    boxes += (size_t)f * n_max * 7;
+    rb += (size_t)f * n_max;
+    circ += (size_t)f * n_max;
+    maskT += (size_t)f * rows_pad * (rows_pad >> 6);
+    __shared__ RBox rrow[64];
+    __shared__ float4 rcirc[64];
+    __shared__ float4 ccirc[MASK_CW * 64];
+    __shared__ unsigned long long bits[MASK_CW][64];
+    __shared__ unsigned int queue[(MASK_THREADS / 32) * MASK_CW * 64];
     __shared__ int qn;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncols = min(n - c0 * 64, (c1 - c0) * 64);
+    const bool all_near = thresh < 0.f;  // then even a zero IoU suppresses: nothing may be filtered out
     if (tid < 64) {
-        bits[tid] = 0ull;
-        if (tid < row_size) {
-            const float* src = boxes + (size_t)(r * 64 + tid) * 7;
-            if (ROTATED) make_rbox(src, rb[tid]);
-            else
-                for (int q = 0; q < 7; ++q) rraw[tid * 7 + q] = src[q];
-        }
-    } else if (tid < 128) {
-        const int u = tid - 64;
-        if (u < col_size) {
-            const float* src = boxes + (size_t)(c * 64 + u) * 7;
-            if (ROTATED) make_rbox(src, cb[u]);
-            else
-                for (int q = 0; q < 7; ++q) craw[u * 7 + q] = src[q];
+        const int i = r * 64 + tid;
+        if (i < n) {
+            rcirc[tid] = circ[i];
+            if (ROTATED) {
+                const float4* p = reinterpret_cast<const float4*>(rb + i);
+                float4* d = reinterpret_cast<float4*>(&rrow[tid]);
+                d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
+            }
         }
     }
-    if (tid == 0) qn = 0;
+    for (int t = tid; t < ncols; t += MASK_THREADS) ccirc[t] = circ[c0 * 64 + t];
+    for (int t = tid; t < MASK_CW * 64; t += MASK_THREADS) (&bits[0][0])[t] = 0ull;
     __syncthreads();
-    // filter: row i (earlier box) vs column j (later box); diagonal tile keeps j > i only
-    for (int p = tid; p < 64 * 64; p += MASK_THREADS) {
-        const int i = p >> 6, j = p & 63;
-        bool near = i < row_size && j < col_size && (r != c || j > i);
-        if (ROTATED) near = near && rbox_near(rb[i], cb[j]);
-        const unsigned int m = __ballot_sync(0xffffffffu, near);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&qn, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (near) queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)p;
+    for (int i0 = 0; i0 < 64; i0 += MASK_THREADS / 32) {
+        if (tid == 0) qn = 0;
+        __syncthreads();
+        const int il = i0 + warp, ig = r * 64 + il;  // one row per warp
+        if (ig < n) {
+            const float4 me = rcirc[il];
+            for (int jj = lane; jj < ((ncols + 31) & ~31); jj += 32) {
+                const int jg = c0 * 64 + jj;
+                bool near = jj < ncols && jg > ig;
+                if (near && !all_near) near = ROTATED ? circ_near(me, ccirc[jj]) : aabb_near(me, ccirc[jj]);
+                const unsigned int m = __ballot_sync(0xffffffffu, near);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&qn, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (near) queue[base + __popc(m & ((1u << lane) - 1u))] = ((unsigned int)il << 16) | (unsigned int)jj;
+                }
+            }
         }
+        __syncthreads();
+        const int nq = qn;
+        for (int q = tid; q < nq; q += MASK_THREADS) {
+            const int il2 = queue[q] >> 16, jj = queue[q] & 0xffff, jg = c0 * 64 + jj;
+            float v;
+            if (ROTATED) {
+                RBox cbx;
+                const float4* p = reinterpret_cast<const float4*>(rb + jg);
+                float4* d = reinterpret_cast<float4*>(&cbx);
+                d[0] = __ldg(p); d[1] = __ldg(p + 1); d[2] = __ldg(p + 2); d[3] = __ldg(p + 3);
+                v = rbox_iou(rrow[il2], cbx);
+            } else {
+                v = aabb_iou(boxes + (size_t)(r * 64 + il2) * 7, boxes + (size_t)jg * 7);
+            }
+            if (v > thresh) atomicOr(&bits[jj >> 6][il2], 1ull << (jj & 63));
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const int nq = qn;
-    for (int q = tid; q < nq; q += MASK_THREADS) {
-        const int i = queue[q] >> 6, j = queue[q] & 63;
-        const float v = ROTATED ? rbox_iou(rb[i], cb[j]) : aabb_iou(rraw + i * 7, craw + j * 7);
-        if (v > thresh) atomicOr(&bits[i], 1ull << j);
-    }
-    __syncthreads();
-    if (tid < row_size) mask[(size_t)(r * 64 + tid) * col_blocks + c] = bits[tid];
+    for (int t = tid; t < (c1 - c0) * 64; t += MASK_THREADS)
+        maskT[(size_t)(c0 + (t >> 6)) * rows_pad + r * 64 + (t & 63)] = bits[t >> 6][t & 63];
 }
 
-// ------------------------------------------------------------------ greedy pass on the device
+// maskT[c][row] -> the reference's row-major mask[row][c] (parity checks only); cells below the diagonal are not written
+__global__ void nms_mask_transpose_kernel(int n, int cb, int rows_pad, const unsigned long long* __restrict__ maskT,
+                                          unsigned long long* __restrict__ mask) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (row < n && c >= (row >> 6)) mask[(size_t)row * cb + c] = maskT[(size_t)c * rows_pad + row];
+}
+
+// ------------------------------------------------------------------ NMS step 3: greedy pass on the device
 // Equivalent to iou3d_nms.cpp:116-132 (remv bitset, keep[] in ascending box index). Box i of chunk c is kept iff no
-// kept box j < i suppresses it: kept boxes of EARLIER chunks are pulled (mask[j][c], one word each, all in flight at
-// once), kept boxes of the same chunk come from the diagonal tile.
+// kept box j < i suppresses it. One CTA per frame walks the chunks; column block c+1 of maskT (the words of ALL
+// earlier rows, <= 32 KB) is prefetched with cp.async into the other half of a double buffer while chunk c is being
+// resolved, so no global-memory latency sits on the serial chain: the verdict of the kept boxes of earlier chunks is
+// an OR over <= keep-count shared-memory words, and the within-chunk resolve visits only the boxes that survive
+// (find-first-set over the not-yet-suppressed bits) instead of all 64.
 constexpr int REDUCE_THREADS = 256;
 
-__global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(int n, int col_blocks, const unsigned long long* __restrict__ mask,
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+
+// STREAM = false (very large n: the double buffer does not fit): words are pulled from global memory instead.
+template <bool STREAM>
+__global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(int n, int rows_pad, const unsigned long long* __restrict__ maskT,
                                                                     int max_keep, long long* __restrict__ keep,
                                                                     int* __restrict__ num_keep, const int* __restrict__ counts,
                                                                     int n_max, int keep_stride) {
-    extern __shared__ int kept_list[];  // up to n entries
+    extern __shared__ __align__(16) unsigned char dyn[];
+    // layout: two column-block buffers of rows_pad words each, then the kept list (up to n ints)
+    unsigned long long* buf0 = reinterpret_cast<unsigned long long*>(dyn);
+    unsigned long long* buf1 = buf0 + (STREAM ? rows_pad : 0);
+    int* kept_list = reinterpret_cast<int*>(buf1 + (STREAM ? rows_pad : 0));
+    const int f = blockIdx.x;
     if (counts) {
-        n = min(counts[blockIdx.x], n_max);
-        mask += (size_t)blockIdx.x * n_max * col_blocks;
-        keep += (size_t)blockIdx.x * keep_stride;
-        num_keep += blockIdx.x;
+        n = min(counts[f], n_max);
+        maskT += (size_t)f * rows_pad * (rows_pad >> 6);
+        keep += (size_t)f * keep_stride;
+        num_keep += f;
     }
-    const int row_stride = col_blocks;
     const int chunks = (n + 63) / 64;
-    __shared__ unsigned long long diag[64];
     __shared__ unsigned long long wor[REDUCE_THREADS / 32];
     __shared__ int kept_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) kept_s = 0;
+    auto prefetch = [&](int c, unsigned long long* dst) {  // rows [0, (c+1)*64) of column block c: (c+1)*512 bytes
+        if (!STREAM) return;
+        const unsigned long long* src = maskT + (size_t)c * rows_pad;
+        for (int t = tid; t < (c + 1) * 32; t += REDUCE_THREADS) cp_async16(dst + 2 * t, src + 2 * t);
+    };
+    if (chunks > 0) prefetch(0, buf0);
+    asm volatile("cp.async.commit_group;");
     __syncthreads();
     for (int c = 0; c < chunks; ++c) {
+        const unsigned long long* cur_buf = STREAM ? ((c & 1) ? buf1 : buf0) : maskT + (size_t)c * rows_pad;
+        if (c + 1 < chunks) prefetch(c + 1, (c & 1) ? buf0 : buf1);
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 1;");
+        __syncthreads();
         const int base = c * 64, sz = min(64, n - base);
         const int nk = kept_s;
         unsigned long long part = 0ull;
-        for (int t = tid; t < nk; t += REDUCE_THREADS) part |= __ldg(&mask[(size_t)kept_list[t] * row_stride + c]);
-        if (tid < 64) diag[tid] = (tid < sz) ? __ldg(&mask[(size_t)(base + tid) * row_stride + c]) : 0ull;
+        for (int t = tid; t < nk; t += REDUCE_THREADS) part |= cur_buf[kept_list[t]];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part |= __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) wor[warp] = part;
@@ -154,35 +230,278 @@ __global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(int n, int c
         if (tid == 0) {
             unsigned long long cur = 0ull;
             for (int w = 0; w < REDUCE_THREADS / 32; ++w) cur |= wor[w];
-            // kept boxes that belong to THIS chunk were appended below in earlier iterations only, so `cur` holds the
-            // earlier chunks' verdict; the diagonal tile adds the within-chunk suppressions in index order
+            const unsigned long long valid = sz == 64 ? ~0ull : ((1ull << sz) - 1ull);
             int k = nk;
-            for (int b = 0; b < sz; ++b) {
-                if ((cur >> b) & 1ull) continue;
+            unsigned long long avail = ~cur & valid;
+            while (avail) {
                 if (max_keep > 0 && k >= max_keep) break;
+                const int b = __ffsll((long long)avail) - 1;
                 kept_list[k] = base + b;
                 keep[k] = base + b;
                 ++k;
-                cur |= diag[b];
+                cur |= cur_buf[base + b];                               // diagonal tile: bits above b only
+                avail = ~cur & valid & ~((2ull << b) - 1ull);          // (2<<63) wraps to 0 -> mask 0xFF..FF, avail 0
             }
             kept_s = k;
         }
         __syncthreads();
         if (max_keep > 0 && kept_s >= max_keep) break;
     }
+    asm volatile("cp.async.wait_group 0;");
     if (tid == 0) *num_keep = kept_s;
 }
 
-int launch_nms(const float* boxes, const int* counts, int B, int n, float thresh, int rotated, int max_keep, long long* keep,
-               int keep_stride, int* num_keep, unsigned long long* mask, cudaStream_t stream) {
+// ------------------------------------------------------------------ kept-driven greedy NMS (the scoring path)
+// The bitmask needs n^2/2 pair tests although the host loop only ever reads the rows of KEPT boxes (1-2 % of them).
+// Here one CTA per frame walks the score-sorted boxes in groups of 512 and only evaluates
+//   (A) group boxes against the boxes kept so far (filter -> queue -> polygon clipping, skipping boxes that are
+//       already suppressed), then (B) the survivors of the group against each other (a <= 512 x 512 bit matrix in
+//       shared memory) and (C) a serial resolve of that matrix by one warp.
+// Identical keep list (same rbox_iou on the same ordered pairs (earlier, later), same greedy rule), ~20x fewer
+// polygon evaluations, no n^2 workspace traffic; stops as soon as max_keep boxes are kept.
+constexpr int GR_THREADS = 1024;
+constexpr int GR_G = 512;
+constexpr int GR_QCAP = 8192;
+
+template <bool ROTATED>
+__device__ __forceinline__ float pair_iou(const float* __restrict__ boxes, const RBox* __restrict__ rb, int j, int i) {
+    if (ROTATED) {
+        RBox a, b;
+        const float4* pa = reinterpret_cast<const float4*>(rb + j);
+        const float4* pb = reinterpret_cast<const float4*>(rb + i);
+        float4* da = reinterpret_cast<float4*>(&a);
+        float4* db = reinterpret_cast<float4*>(&b);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { da[u] = __ldg(pa + u); db[u] = __ldg(pb + u); }
+        return rbox_iou(a, b);
+    }
+    return aabb_iou(boxes + (size_t)j * 7, boxes + (size_t)i * 7);
+}
+
+template <bool ROTATED>
+__global__ void __launch_bounds__(GR_THREADS) nms_greedy_kernel(int n, float thresh, const float* __restrict__ boxes,
+                                                                const RBox* __restrict__ rb, const float4* __restrict__ circ,
+                                                                int max_keep, long long* __restrict__ keep,
+                                                                int* __restrict__ num_keep, const int* __restrict__ counts,
+                                                                int n_max, int keep_stride, int kcap) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    float4* gcirc = reinterpret_cast<float4*>(dyn);                       // GR_G
+    float4* kcirc = gcirc + GR_G;                                          // kcap
+    unsigned int* queue = reinterpret_cast<unsigned int*>(kcirc + kcap);   // GR_QCAP
+    unsigned int* msk = queue + GR_QCAP;                                   // GR_G x GR_G/32
+    int* surv = reinterpret_cast<int*>(msk + GR_G * (GR_G / 32));          // GR_G
+    int* supp = surv + GR_G;                                               // GR_G
+    int* kept_idx = supp + GR_G;                                           // kcap
+    __shared__ int qn, nk_s, ns_s, overflow, wcnt[GR_THREADS / 32];
+    const int f = blockIdx.x;
+    if (counts) {
+        n = min(counts[f], n_max);
+        boxes += (size_t)f * n_max * 7;
+        rb += (size_t)f * n_max;
+        circ += (size_t)f * n_max;
+        keep += (size_t)f * keep_stride;
+        num_keep += f;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool all_near = thresh < 0.f;
+    if (tid == 0) nk_s = 0;
+    __syncthreads();
+
+    // filter pairs [p_lo, p_hi) of the current phase into the queue; phase 0: p = k * gsz + t (kept k vs group box t),
+    // phase 1: p = a * ns + b (survivor a vs survivor b > a). Pairs that do not fit set `overflow`.
+    auto filter = [&](int phase, int p_lo, int p_hi, int gsz, int ns) {
+        for (int p0 = p_lo; p0 < p_hi; p0 += GR_THREADS) {
+            const int p = p0 + tid;
+            bool near = false;
+            unsigned int code = 0;
+            if (p < p_hi) {
+                if (phase == 0) {
+                    const int k = p / gsz, t = p - k * gsz;
+                    near = supp[t] == 0 && (all_near || (ROTATED ? circ_near(kcirc[k], gcirc[t]) : aabb_near(kcirc[k], gcirc[t])));
+                    code = ((unsigned int)k << 9) | (unsigned int)t;
+                } else {
+                    const int a = p / ns, b = p - a * ns;
+                    near = b > a && (all_near || (ROTATED ? circ_near(gcirc[surv[a]], gcirc[surv[b]]) : aabb_near(gcirc[surv[a]], gcirc[surv[b]])));
+                    code = ((unsigned int)a << 9) | (unsigned int)b;
+                }
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, near);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&qn, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (near) {
+                    if (slot < GR_QCAP) queue[slot] = code;
+                    else overflow = 1;
+                }
+            }
+        }
+    };
+    auto evaluate = [&](int phase, int g0) {
+        const int nq = min(qn, GR_QCAP);
+        for (int q = tid; q < nq; q += GR_THREADS) {
+            const unsigned int code = queue[q];
+            const int hi = code >> 9, lo = code & 511;
+            if (phase == 0) {
+                if (supp[lo]) continue;             // benign race: a stale 0 only costs one evaluation
+                if (pair_iou<ROTATED>(boxes, rb, kept_idx[hi], g0 + lo) > thresh) supp[lo] = 1;
+            } else {
+                if (pair_iou<ROTATED>(boxes, rb, g0 + surv[hi], g0 + surv[lo]) > thresh) atomicOr(&msk[hi * (GR_G / 32) + (lo >> 5)], 1u << (lo & 31));
+            }
+        }
+    };
+    // one phase = one filter pass over all pairs (normally a single evaluation round); if the queue overflowed the pairs
+    // are re-walked in chunks that cannot overflow (already-decided pairs are re-evaluated to the same verdict)
+    auto run_phase = [&](int phase, int total, int g0, int gsz, int ns) {
+        if (tid == 0) { qn = 0; overflow = 0; }
+        __syncthreads();
+        filter(phase, 0, total, gsz, ns);
+        __syncthreads();
+        evaluate(phase, g0);
+        const bool again = overflow != 0;
+        __syncthreads();
+        if (again) {
+            for (int lo = 0; lo < total; lo += GR_QCAP) {
+                if (tid == 0) qn = 0;
+                __syncthreads();
+                filter(phase, lo, min(total, lo + GR_QCAP), gsz, ns);
+                __syncthreads();
+                evaluate(phase, g0);
+                __syncthreads();
+            }
+        }
+    };
+
+    for (int g0 = 0; g0 < n; g0 += GR_G) {
+        const int gsz = min(GR_G, n - g0);
+        const int nk = nk_s;
+        if (tid < gsz) { gcirc[tid] = circ[g0 + tid]; supp[tid] = 0; }
+        __syncthreads();
+        if (nk > 0) run_phase(0, nk * gsz, g0, gsz, 0);
+        // ordered compaction of the survivors
+        {
+            const bool alive = tid < gsz && supp[tid] == 0;
+            const unsigned int m = __ballot_sync(0xffffffffu, alive);
+            if (lane == 0) wcnt[warp] = __popc(m);
+            __syncthreads();
+            if (warp == 0) {
+                const int c = wcnt[lane];
+                const int incl = warp_incl_scan(c);
+                wcnt[lane] = incl - c;
+                if (lane == 31) ns_s = incl;
+            }
+            __syncthreads();
+            if (alive) surv[wcnt[warp] + __popc(m & ((1u << lane) - 1u))] = tid;
+        }
+        for (int t = tid; t < GR_G * (GR_G / 32); t += GR_THREADS) msk[t] = 0u;
+        __syncthreads();
+        const int ns = ns_s;
+        if (ns > 1) run_phase(1, ns * ns, g0, gsz, ns);
+        // serial resolve of the survivor matrix (warp 0; lane w holds word w of the removed set)
+        if (warp == 0) {
+            unsigned int removed = 0u;
+            int k = nk;
+            for (int a = 0; a < ns; ++a) {
+                const unsigned int w = __shfl_sync(0xffffffffu, removed, a >> 5);
+                if ((w >> (a & 31)) & 1u) continue;
+                if (max_keep > 0 && k >= max_keep) break;
+                if (lane == 0) {
+                    const int t = surv[a];
+                    kept_idx[k] = g0 + t;
+                    kcirc[k] = gcirc[t];
+                    keep[k] = g0 + t;
+                }
+                ++k;
+                if (lane < GR_G / 32) removed |= msk[a * (GR_G / 32) + lane];
+            }
+            if (lane == 0) nk_s = k;
+        }
+        __syncthreads();
+        if (max_keep > 0 && nk_s >= max_keep) break;
+    }
+    if (tid == 0) *num_keep = nk_s;
+}
+
+struct NmsWs {
+    unsigned long long* maskT;
+    RBox* rb;
+    float4* circ;
+    int rows_pad;
+};
+
+size_t nms_ws_bytes(int B, int n_max) {
+    const size_t cb = (size_t)crb3d_divup(n_max > 0 ? n_max : 1, 64), nb = (size_t)(B > 0 ? B : 1);
+    return crb3d_align(8 * nb * cb * cb * 64) + crb3d_align(sizeof(RBox) * nb * cb * 64) + crb3d_align(16 * nb * cb * 64);
+}
+
+bool nms_ws_take(void* ws, size_t ws_bytes, int B, int n_max, NmsWs& w) {
+    WsCursor c(ws, ws_bytes);
+    const size_t cb = (size_t)crb3d_divup(n_max, 64);
+    w.rows_pad = (int)(cb * 64);
+    w.maskT = c.take<unsigned long long>((size_t)B * cb * cb * 64);
+    w.rb = c.take<RBox>((size_t)B * cb * 64);
+    w.circ = c.take<float4>((size_t)B * cb * 64);
+    return c.ok;
+}
+
+int launch_mask(const float* boxes, const int* counts, int B, int n, float thresh, int rotated, const NmsWs& w, cudaStream_t stream) {
     const int cb = (int)crb3d_divup(n, 64);
-    const unsigned tiles = (unsigned)((int64_t)cb * (cb + 1) / 2);
-    if (rotated) nms_mask_kernel<true><<<dim3(tiles, B), MASK_THREADS, 0, stream>>>(n, thresh, boxes, mask, cb, counts, n);
-    else nms_mask_kernel<false><<<dim3(tiles, B), MASK_THREADS, 0, stream>>>(n, thresh, boxes, mask, cb, counts, n);
-    const size_t smem = sizeof(int) * (size_t)(max_keep > 0 ? (max_keep < n ? max_keep : n) : n);
+    const dim3 pg((unsigned)crb3d_divup(n, 256), B), mg((unsigned)crb3d_divup(cb, MASK_CW), cb, B);
+    if (rotated) {
+        nms_prep_kernel<true><<<pg, 256, 0, stream>>>(n, boxes, counts, n, w.rb, w.circ);
+        nms_mask_kernel<true><<<mg, MASK_THREADS, 0, stream>>>(n, thresh, boxes, w.rb, w.circ, w.maskT, w.rows_pad, counts, n);
+    } else {
+        nms_prep_kernel<false><<<pg, 256, 0, stream>>>(n, boxes, counts, n, w.rb, w.circ);
+        nms_mask_kernel<false><<<mg, MASK_THREADS, 0, stream>>>(n, thresh, boxes, w.rb, w.circ, w.maskT, w.rows_pad, counts, n);
+    }
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+size_t greedy_smem(int kcap) {
+    return (size_t)GR_G * 16 + (size_t)kcap * 16 + (size_t)GR_QCAP * 4 + (size_t)GR_G * (GR_G / 32) * 4 + (size_t)GR_G * 8 + (size_t)kcap * 4;
+}
+
+int launch_nms(const float* boxes, const int* counts, int B, int n, float thresh, int rotated, int max_keep, long long* keep,
+               int keep_stride, int* num_keep, const NmsWs& w, cudaStream_t stream) {
+    const int kcap = max_keep > 0 ? (max_keep < n ? max_keep : n) : n;
+    if ((max_keep > 0 || n <= 2048) && greedy_smem(kcap) <= 200 * 1024) {
+        // kept-driven path: prep + one CTA per frame
+        const dim3 pg((unsigned)crb3d_divup(n, 256), B);
+        const size_t smem = greedy_smem(kcap);
+        static size_t smem_set[2] = {0, 0};
+        if (smem > smem_set[rotated ? 1 : 0]) {
+            if (rotated) CRB3D_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CRB3D_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set[rotated ? 1 : 0] = smem;
+        }
+        if (rotated) {
+            nms_prep_kernel<true><<<pg, 256, 0, stream>>>(n, boxes, counts, n, w.rb, w.circ);
+            nms_greedy_kernel<true><<<B, GR_THREADS, smem, stream>>>(n, thresh, boxes, w.rb, w.circ, max_keep, keep, num_keep, counts, n, keep_stride, kcap);
+        } else {
+            nms_prep_kernel<false><<<pg, 256, 0, stream>>>(n, boxes, counts, n, w.rb, w.circ);
+            nms_greedy_kernel<false><<<B, GR_THREADS, smem, stream>>>(n, thresh, boxes, w.rb, w.circ, max_keep, keep, num_keep, counts, n, keep_stride, kcap);
+        }
+        CRB3D_CHECK_LAUNCH();
+        return CRB3D_OK;
+    }
+    int rc = launch_mask(boxes, counts, B, n, thresh, rotated, w, stream);
+    if (rc) return rc;
+    const size_t list = sizeof(int) * (size_t)kcap + 16;
+    const bool stream_mode = 16 * (size_t)w.rows_pad + list <= 200 * 1024;
+    const size_t smem = (stream_mode ? 16 * (size_t)w.rows_pad : 0) + list;
     if (smem > 200 * 1024) return CRB3D_ERR_UNSUPPORTED;
-    if (smem > 40 * 1024) CRB3D_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_reduce_kernel<<<B, REDUCE_THREADS, smem, stream>>>(n, cb, mask, max_keep, keep, num_keep, counts, n, keep_stride);
+    static size_t smem_set[2] = {0, 0};
+    if (smem > 40 * 1024 && smem > smem_set[stream_mode]) {
+        if (stream_mode) CRB3D_CUDA(cudaFuncSetAttribute(nms_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CRB3D_CUDA(cudaFuncSetAttribute(nms_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[stream_mode] = smem;
+    }
+    if (stream_mode)
+        nms_reduce_kernel<true><<<B, REDUCE_THREADS, smem, stream>>>(n, w.rows_pad, w.maskT, max_keep, keep, num_keep, counts, n, keep_stride);
+    else
+        nms_reduce_kernel<false><<<B, REDUCE_THREADS, smem, stream>>>(n, w.rows_pad, w.maskT, max_keep, keep, num_keep, counts, n, keep_stride);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -211,8 +530,7 @@ extern "C" int crb3d_boxes_iou_bev(const float* boxes_a, int na, const float* bo
 
 extern "C" int crb3d_nms_workspace_bytes(int n, size_t* bytes) {
     if (!bytes || n < 0) return CRB3D_ERR_ARG;
-    size_t cb = (size_t)crb3d_divup(n > 0 ? n : 1, 64);
-    *bytes = crb3d_align(sizeof(unsigned long long) * (size_t)(n > 0 ? n : 1) * cb);
+    *bytes = nms_ws_bytes(1, n);
     return CRB3D_OK;
 }
 
@@ -221,32 +539,32 @@ extern "C" int crb3d_nms(const float* boxes, int n, float thresh, int rotated, i
                          int* num_keep, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (n < 0 || !keep || !num_keep) return CRB3D_ERR_ARG;
     if (n == 0) { CRB3D_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int), stream)); return CRB3D_OK; }
-    WsCursor c(ws, ws_bytes);
-    unsigned long long* mask = c.take<unsigned long long>((size_t)n * crb3d_divup(n, 64));
-    if (!c.ok) return CRB3D_ERR_WORKSPACE;
-    return launch_nms(boxes, nullptr, 1, n, thresh, rotated, max_keep, keep, 0, num_keep, mask, stream);
+    NmsWs w;
+    if (!nms_ws_take(ws, ws_bytes, 1, n, w)) return CRB3D_ERR_WORKSPACE;
+    return launch_nms(boxes, nullptr, 1, n, thresh, rotated, max_keep, keep, 0, num_keep, w, stream);
 }
 
-// Raw suppression bitmask (upper-triangular tiles; the rest is left untouched), for parity checks against the
-// reference nms_kernel.
-extern "C" int crb3d_nms_mask(const float* boxes, int n, float thresh, int rotated, unsigned long long* mask,
-                              cudaStream_t stream) {
+// Raw suppression bitmask in the reference's row-major layout mask[n][ceil(n/64)] (cells on and above the diagonal
+// block; the rest is left untouched), for parity checks against the reference nms_kernel. ws: crb3d_nms_workspace_bytes(n).
+extern "C" int crb3d_nms_mask(const float* boxes, int n, float thresh, int rotated, unsigned long long* mask, void* ws,
+                              size_t ws_bytes, cudaStream_t stream) {
     if (n <= 0 || !mask) return CRB3D_ERR_ARG;
+    NmsWs w;
+    if (!nms_ws_take(ws, ws_bytes, 1, n, w)) return CRB3D_ERR_WORKSPACE;
+    int rc = launch_mask(boxes, nullptr, 1, n, thresh, rotated, w, stream);
+    if (rc) return rc;
     const int cb = (int)crb3d_divup(n, 64);
-    const unsigned tiles = (unsigned)((int64_t)cb * (cb + 1) / 2);
-    if (rotated) nms_mask_kernel<true><<<tiles, MASK_THREADS, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
-    else nms_mask_kernel<false><<<tiles, MASK_THREADS, 0, stream>>>(n, thresh, boxes, mask, cb, nullptr, 0);
+    nms_mask_transpose_kernel<<<dim3((unsigned)crb3d_divup(n, 256), cb), 256, 0, stream>>>(n, cb, w.rows_pad, w.maskT, mask);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
 
 // Batched NMS for the scoring path: frame b owns boxes[b][0..counts[b]) of a padded (B, n_max, 7) tensor (each frame
-// sorted by descending score). keep: (B, keep_stride) int64, num_keep: (B). One mask launch + one reduce launch for
-// the whole batch, no host synchronisation. ws: B * n_max * ceil(n_max/64) * 8 bytes.
+// sorted by descending score). keep: (B, keep_stride) int64, num_keep: (B). prep + mask + reduce launches for the whole
+// batch, no host synchronisation.
 extern "C" int crb3d_nms_batched_workspace_bytes(int B, int n_max, size_t* bytes) {
     if (!bytes || B < 0 || n_max < 0) return CRB3D_ERR_ARG;
-    size_t cb = (size_t)crb3d_divup(n_max > 0 ? n_max : 1, 64);
-    *bytes = crb3d_align(sizeof(unsigned long long) * (size_t)(B > 0 ? B : 1) * (size_t)(n_max > 0 ? n_max : 1) * cb);
+    *bytes = nms_ws_bytes(B, n_max);
     return CRB3D_OK;
 }
 
@@ -258,8 +576,7 @@ extern "C" int crb3d_nms_batched(const float* boxes, const int* counts, int B, i
     if (max_keep > 0 && keep_stride < max_keep) return CRB3D_ERR_ARG;
     if (B == 0) return CRB3D_OK;
     if (n_max == 0) { CRB3D_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int) * B, stream)); return CRB3D_OK; }
-    WsCursor c(ws, ws_bytes);
-    unsigned long long* mask = c.take<unsigned long long>((size_t)B * n_max * crb3d_divup(n_max, 64));
-    if (!c.ok) return CRB3D_ERR_WORKSPACE;
-    return launch_nms(boxes, counts, B, n_max, thresh, rotated, max_keep, keep, keep_stride, num_keep, mask, stream);
+    NmsWs w;
+    if (!nms_ws_take(ws, ws_bytes, B, n_max, w)) return CRB3D_ERR_WORKSPACE;
+    return launch_nms(boxes, counts, B, n_max, thresh, rotated, max_keep, keep, keep_stride, num_keep, w, stream);
 }

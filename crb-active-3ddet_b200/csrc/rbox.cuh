@@ -11,7 +11,7 @@
 
 constexpr float kEps = 1e-8f;
 
-struct RBox {
+struct alignas(16) RBox {  // 64 bytes: moved as four float4
     float cx, cy, hx, hy, c, s;  // centre, half extents, cos/sin(heading)
     float px[4], py[4];          // rotated corners
     float area, rad;             // dx*dy, half diagonal

@@ -115,7 +115,10 @@ int crb3d_nms(const float* boxes, int n, float thresh, int rotated, int max_keep
 int crb3d_nms_batched_workspace_bytes(int B, int n_max, size_t* bytes);
 int crb3d_nms_batched(const float* boxes, const int* counts, int B, int n_max, float thresh, int rotated, int max_keep,
                       long long* keep, int keep_stride, int* num_keep, void* ws, size_t ws_bytes, cudaStream_t stream);
-int crb3d_nms_mask(const float* boxes, int n, float thresh, int rotated, unsigned long long* mask, cudaStream_t stream);
+/* raw suppression bitmask, row-major mask[n][ceil(n/64)] like the reference nms_kernel (blocks on/above the diagonal only);
+ * ws: crb3d_nms_workspace_bytes(n). */
+int crb3d_nms_mask(const float* boxes, int n, float thresh, int rotated, unsigned long long* mask, void* ws, size_t ws_bytes,
+                   cudaStream_t stream);
 /* host-side (CPU tensors) BEV IoU, replaces boxes_iou_bev_cpu (iou3d_cpu.cpp:232-252): HOST pointers. */
 int crb3d_boxes_iou_bev_cpu(const float* boxes_a, int na, const float* boxes_b, int nb, float* out);
 
@@ -155,6 +158,25 @@ int crb3d_three_interpolate_stack(int N, int C, const float* features, const int
                                   cudaStream_t stream);
 int crb3d_three_interpolate_grad_stack(int N, int C, const float* grad_out, const int* idx, const float* weight,
                                        float* grad_features, cudaStream_t stream);
+
+/* ---- dense BEV GEMMs on tcgen05 (TF32 in, fp32 accumulate): the deblocks of BaseBEVBackbone
+ *      (base_bev_backbone.py:60-78,100-108: ConvTranspose2d(k = stride) + BN + ReLU + torch.cat) and the three 1x1
+ *      head convs of AnchorHeadSingle (anchor_head_single.py:18-32,41-58) with bias/ReLU/placement fused.
+ *      D[m,n] = sum_k A[m,k] W[n,k]; A: (M,K) rows lda floats apart; W: contiguous [n_sub][N][K]; bias: N or null.
+ *      Column segment s = [col_begin[s], +width[s]) is written to out_ptr[s] + row * row_stride[s] (1 <= n_seg <= 3).
+ *      up = 0: n_sub = 1, output row = GEMM row. up = 2: n_sub = 4 (dy,dx) slices of a kernel=stride=2 transposed
+ *      conv; GEMM row (b,y,x) of an in_h x in_w map lands on output pixel (b, 2y+dy, 2x+dx).
+ *      Supported: K % 32 == 0, N in {80, 128, 256}, lda % 4 == 0. */
+int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long lda, const float* W, int N, int n_sub,
+                        const float* bias, int relu, int n_seg, float* const* out_ptr, const int* col_begin,
+                        const int* width, const long long* row_stride, int up, int in_h, int in_w, cudaStream_t stream);
+
+/* ---- 3x3 / stride 1 / pad 1 BEV convolution on tcgen05 (halo-tile implicit GEMM, TF32 in, fp32 accumulate) with
+ *      the folded BatchNorm shift + ReLU fused (base_bev_backbone.py:33-50,96-99).
+ *      in: (B,H,W,C_in) channels-last; wpack: [C_out/128][ky*3+kx][C_in/16][4][128][4] (crb3d.ops.pack_conv3x3_weight);
+ *      bias: C_out or null; out: (B,H,W,C_out) channels-last. Supported: C_in % 16 == 0, C_out % 128 == 0. */
+int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int cin, const float* wpack, int cout, const float* bias,
+                           int relu, float* out, cudaStream_t stream);
 
 /* ---- anchor-head post-processing (anchor_head_template.py:238-285, box_coder_utils.py:45-77,
  *      detector3d_template.py:281-311): max-class sigmoid score + 1-based label for every anchor, and lazy

@@ -50,7 +50,8 @@ def test_pairwise_bitwise_vs_reference_kernels(cuda):
 
 
 @pytest.mark.parametrize("n,thr,rotated", [(4096, 0.01, True), (1024, 0.7, True), (9000, 0.8, True), (777, 0.1, True),
-                                           (2000, 0.5, False), (1, 0.5, True), (64, 0.3, True), (65, 0.3, True)])
+                                           (2000, 0.5, False), (1, 0.5, True), (64, 0.3, True), (65, 0.3, True),
+                                           (15000, 0.5, True), (513, -1.0, True)])
 def test_nms_vs_reference_kernels(cuda, n, thr, rotated):
     """keep list == the reference's mask kernel + the host greedy loop of iou3d_nms.cpp:116-132 (restated in numpy)."""
     from crb3d import ops

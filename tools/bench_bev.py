@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Micro-benchmark + parity probe for the tcgen05 BEV kernels (run on the GPU box):
+  python tools/bench_bev.py            -> one line per shape: max/rms error vs fp32 torch, us own kernel, us cuDNN TF32
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "crb-active-3ddet_b200"), ROOT):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+from crb3d import ops  # noqa: E402
+
+
+ONCE = len(sys.argv) > 1 and sys.argv[1] == "once"     # one launch per case (for ncu captures)
+
+
+def timeit(fn, n=20):
+    if ONCE:
+        fn()
+        torch.cuda.synchronize()
+        return 1.0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(n):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def conv_case(B, H, W, cin, cout, check=True):
+    g = torch.Generator().manual_seed(cin + cout + H)
+    x = torch.randn(B, H, W, cin, generator=g).cuda()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    wp = ops.pack_conv3x3_weight(w)
+    out = ops.bev_conv3x3(x, wp, b, True)
+    torch.cuda.synchronize()
+    msg = ""
+    if check and not ONCE:
+        torch.backends.cudnn.allow_tf32 = False
+        ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w, b, padding=1)).permute(0, 2, 3, 1)
+        err = (out - ref).abs()
+        rms = ref.pow(2).mean().sqrt()
+        msg = "max_err/rms %.2e rms_err/rms %.2e" % (float(err.max() / rms), float(err.pow(2).mean().sqrt() / rms))
+    torch.backends.cudnn.allow_tf32 = True
+    xc = x.permute(0, 3, 1, 2)
+    wc = w.contiguous(memory_format=torch.channels_last)
+    t_own = timeit(lambda: ops.bev_conv3x3(x, wp, b, True, out=out))
+    t_dnn = 1.0 if ONCE else timeit(lambda: torch.cudnn_convolution_relu(xc, wc, b, (1, 1), (1, 1), (1, 1), 1))
+    fl = 2.0 * 9 * cin * cout * B * H * W
+    print("conv3x3 B%d %dx%d %d->%d: %s | own %.1f us (%.0f TF/s) cudnn %.1f us (%.0f TF/s)" %
+          (B, H, W, cin, cout, msg, t_own, fl / t_own / 1e6, t_dnn, fl / t_dnn / 1e6), flush=True)
+
+
+def gemm_case(name, M, K, N, n_sub=1, up=0, in_hw=(0, 0), segs_w=None, ctot=None):
+    g = torch.Generator().manual_seed(M % 1000 + K + N)
+    a = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(n_sub * N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    if segs_w is None:
+        ctot = ctot or N
+        out = torch.empty((M * n_sub, ctot), device="cuda")
+        segs = [(out, 0, N, ctot)]
+        out_bytes = M * n_sub * N * 4
+    else:
+        outs = [torch.empty((M, n), device="cuda") for n in segs_w]
+        segs, c0 = [], 0
+        for o, n in zip(outs, segs_w):
+            segs.append((o, c0, n, n))
+            c0 += n
+        out_bytes = M * sum(segs_w) * 4
+    t = timeit(lambda: ops.bev_gemm(a, w, b, True, segs, n_sub=n_sub, up=up, in_hw=in_hw))
+    byts = M * K * 4 + out_bytes + w.numel() * 4
+    print("gemm %s M%d K%d N%d x%d: own %.1f us, %.0f GB/s algorithmic, %.0f TF/s" %
+          (name, M, K, N, n_sub, t, byts / t / 1e3, 2.0 * M * K * N * n_sub / t / 1e6), flush=True)
+
+
+if __name__ == "__main__":
+    gemm_case("deconv1", 4 * 200 * 176, 128, 256, ctot=512)
+    gemm_case("deconv2", 4 * 100 * 88, 256, 256, n_sub=4, up=2, in_hw=(100, 88), ctot=512)
+    gemm_case("heads", 4 * 200 * 176, 512, 80, segs_w=(18, 42, 12))
+    conv_case(1, 16, 16, 16, 128)
+    conv_case(2, 24, 40, 32, 128)
+    conv_case(1, 37, 29, 64, 256)
+    conv_case(4, 200, 176, 128, 128)
+    conv_case(4, 200, 176, 256, 128)
+    conv_case(4, 100, 88, 256, 256)
+    conv_case(8, 100, 88, 256, 256, check=False)
+    conv_case(2, 188, 188, 128, 128, check=False)
