@@ -58,6 +58,7 @@ SIGNATURES = {
     "crb3d_bev_gemm_tf32": [P, c_int64, c_int, c_int64, P, c_int, c_int, P, c_int, c_int, P, P, P, P, c_int, c_int, c_int, P],
     "crb3d_bev_conv3x3_tf32": [P, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, P],
     "crb3d_anchor_head_scores": [P, c_int64, c_int, P, P, P],
+    "crb3d_anchor_head_scores_topk": [P, c_int, c_int64, c_int, c_float, c_int, P, P, P, P, P, P, P, P],
     "crb3d_anchor_decode_select": [P, P, P, c_int, c_int, c_int64, P, P, P],
     "crb3d_gather_rows_f32": [P, P, P, c_int, c_int, c_int64, c_int, c_float, P, P],
     "crb3d_gather_rows_i32": [P, P, P, c_int, c_int, c_int64, c_int, c_int, P, P],
@@ -102,14 +103,14 @@ KERNELS_PER_CALL = {
     "crb3d_voxelize": 12, "crb3d_subm_rulebook": 2, "crb3d_sparse_rulebook_coords": 6, "crb3d_sparse_rulebook_pairs": 1,
     "crb3d_rulebook_compact_pairs": 6, "crb3d_spconv_forward_f32": 1, "crb3d_spconv_wgrad_f32": 2,
     "crb3d_sparse_to_dense": 1, "crb3d_dense_to_sparse": 1, "crb3d_boxes_overlap_bev": 1, "crb3d_boxes_iou_bev": 1,
-    "crb3d_nms": 3, "crb3d_nms_batched": 3, "crb3d_nms_mask": 3, "crb3d_points_in_boxes": 1,
+    "crb3d_nms": 7, "crb3d_nms_batched": 7, "crb3d_nms_mask": 3, "crb3d_points_in_boxes": 1,
     "crb3d_points_in_boxes_stack": 2, "crb3d_points_in_boxes_ranges": 2, "crb3d_roiaware_pool3d_forward": 2,
     "crb3d_roiaware_pool3d_backward": 1, "crb3d_ball_query_stack": 1, "crb3d_group_points_stack": 1,
     "crb3d_group_points_grad_stack": 1, "crb3d_farthest_point_sampling": 1, "crb3d_stack_farthest_point_sampling": 1,
     "crb3d_three_nn_stack": 1, "crb3d_three_interpolate_stack": 1, "crb3d_three_interpolate_grad_stack": 1,
     "crb3d_label_entropy": 1, "crb3d_label_entropy_ranges": 1, "crb3d_pairwise_sqdist_f64": 1,
     "crb3d_bev_gemm_tf32": [P, c_int64, c_int, c_int64, P, c_int, c_int, P, c_int, c_int, P, P, P, P, c_int, c_int, c_int, P],
-    "crb3d_anchor_head_scores": 1, "crb3d_anchor_decode_select": 1, "crb3d_gather_rows_f32": 1, "crb3d_gather_rows_i32": 1,
+    "crb3d_anchor_head_scores": 1, "crb3d_anchor_head_scores_topk": 2, "crb3d_anchor_decode_select": 1, "crb3d_gather_rows_f32": 1, "crb3d_gather_rows_i32": 1,
     "crb3d_spconv_forward_tf32": 1, "crb3d_bev_gemm_tf32": 1, "crb3d_bev_conv3x3_tf32": 1,
 }
 LAUNCHES = {"kernels": 0, "calls": 0}

@@ -75,6 +75,28 @@ def anchor_head_scores(cls_preds, n_class):
     return score, label
 
 
+def anchor_head_scores_topk(cls_preds, n_class, batch_size, thresh, k):
+    """Fused score pass + candidate selection (class_agnostic_nms front half, model_nms_utils.py:6-25).
+    cls_preds (B, A, n_class) channels-last logits. Returns score (B*A,), label (B*A,) int32 (1-based) for every anchor and,
+    per frame, the anchors with score >= thresh sorted by descending score (ties: ascending anchor index), cut at k:
+    top_scores (B, k) float32, top_idx (B, k) int64, counts (B,) int32 (valid prefix length; the tail is zero)."""
+    _need_cuda(cls_preds)
+    cls_preds = _f32c(cls_preds)
+    dev = cls_preds.device
+    B = int(batch_size)
+    A = cls_preds.numel() // n_class // max(B, 1)
+    score = torch.empty((B * A,), dtype=torch.float32, device=dev)
+    label = torch.empty((B * A,), dtype=torch.int32, device=dev)
+    cand = torch.empty((B, A), dtype=torch.int64, device=dev)
+    cand_count = torch.empty((B,), dtype=torch.int32, device=dev)
+    top_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+    top_idx = torch.empty((B, k), dtype=torch.int64, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    _lib.call("crb3d_anchor_head_scores_topk", _p(cls_preds), B, A, n_class, float(thresh), int(k), _p(score), _p(label),
+              _p(cand), _p(cand_count), _p(top_scores), _p(top_idx), _p(counts), _stream(dev))
+    return score, label, top_scores, top_idx, counts
+
+
 def anchor_decode_select(box_preds, dir_preds, sel, spec, n_anchor_per_frame):
     """Decode only the selected anchors. box_preds (B, A, 7), dir_preds (B, A, bins) | None, sel (B, K) int64."""
     _need_cuda(box_preds, sel)

@@ -232,7 +232,14 @@ def spconv_wgrad(feat, dout, nbr, weight_shape, accumulate_into=None):
 
 
 # ----------------------------------------------------------------------------------------------- BEV GEMMs (tcgen05)
-def bev_gemm(a, weight, bias, relu, segs, n_sub=1, up=0, in_hw=(0, 0)):
+def round_tf32(t):
+    """fp32 -> nearest TF32 value (10 mantissa bits), kept in fp32 storage. The tensor cores truncate fp32 operands;
+    weights rounded once here (and activations rounded by the producing epilogue) are read exactly instead."""
+    i = t.detach().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def bev_gemm(a, weight, bias, relu, segs, n_sub=1, up=0, in_hw=(0, 0), round_out=False):
     """D = A @ W^T (+bias) (ReLU) on the tensor cores with fused output placement (csrc/bev_gemm_tc.cu).
     a: (M, K) fp32 CUDA, unit column stride (row stride = a.stride(0)); weight: contiguous (n_sub*N, K);
     bias: (N,) or None; segs: [(out_tensor, col_begin, width, row_stride_floats)] - column segment -> out_tensor's
@@ -248,7 +255,8 @@ def bev_gemm(a, weight, bias, relu, segs, n_sub=1, up=0, in_hw=(0, 0)):
     wd = (ctypes.c_int * 3)(*[int(s[2]) for s in segs], *([0] * (3 - len(segs))))
     rs = (ctypes.c_longlong * 3)(*[int(s[3]) for s in segs], *([0] * (3 - len(segs))))
     _lib.call("crb3d_bev_gemm_tf32", _p(a), M, K, a.stride(0), _p(weight), N, n_sub, _p(_f32c(bias)) if bias is not None else None,
-              int(bool(relu)), len(segs), ptrs, cb, wd, rs, int(up), int(in_hw[0]), int(in_hw[1]), _stream(a.device))
+              int(bool(relu)) | (2 if round_out else 0), len(segs), ptrs, cb, wd, rs, int(up), int(in_hw[0]), int(in_hw[1]),
+              _stream(a.device))
 
 
 def pack_conv3x3_weight(weight):
@@ -256,11 +264,11 @@ def pack_conv3x3_weight(weight):
     [C_out/128][tap = ky*3+kx][C_in/16][4 slabs][128 co][4 ci] (contiguous fp32)."""
     cout, cin = weight.shape[0], weight.shape[1]
     assert tuple(weight.shape[2:]) == (3, 3) and cout % 128 == 0 and cin % 16 == 0
-    w = weight.detach().float().permute(0, 2, 3, 1).reshape(cout // 128, 128, 9, cin // 16, 4, 4)
+    w = round_tf32(weight.detach().float()).permute(0, 2, 3, 1).reshape(cout // 128, 128, 9, cin // 16, 4, 4)
     return w.permute(0, 2, 3, 4, 1, 5).contiguous()
 
 
-def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None):
+def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None, round_out=False):
     """3x3 / stride 1 / pad 1 conv (+bias, ReLU) on the tensor cores. x_nhwc: (B, H, W, C_in) contiguous fp32 CUDA;
     wpack: pack_conv3x3_weight(...). Returns (B, H, W, C_out) contiguous."""
     _need_cuda(x_nhwc, wpack)
@@ -271,7 +279,7 @@ def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None):
     if out is None:
         out = torch.empty((B, H, W, cout), dtype=torch.float32, device=x_nhwc.device)
     _lib.call("crb3d_bev_conv3x3_tf32", _p(x_nhwc), B, H, W, cin, _p(wpack), cout, _p(_f32c(bias)) if bias is not None else None,
-              int(bool(relu)), _p(out), _stream(x_nhwc.device))
+              int(bool(relu)) | (2 if round_out else 0), _p(out), _stream(x_nhwc.device))
     return out
 
 

@@ -188,17 +188,19 @@ class BaseBEVBackbone(nn.Module):
                 if (st in (1, 2) and de[0].stride == (st, st) and de[0].kernel_size == (st, st) and cin % 32 == 0
                         and cout in (128, 256) and dw.is_cuda):
                     # ConvTranspose2d weight (C_in, C_out, kh, kw) -> [(dy,dx)][C_out][C_in]
-                    gemm = (dw.permute(2, 3, 1, 0).reshape(st * st * cout, cin).contiguous(), db, st)
+                    gemm = (ops.round_tf32(dw.permute(2, 3, 1, 0).reshape(st * st * cout, cin).contiguous()), db, st)
                 plan.append((layers, (dw, db, de[0].stride), gemm))
         self._plan = plan
         return plan
 
     @staticmethod
-    def _tc_conv_pays(B, H, W, cout):
+    def _tc_conv_pays(B, H, W, cout, cin=128):
         """The halo-tile kernel runs one CTA (4 tiles of 128 pixels x 128 channels) per SM: use it when its CTA count
         fills whole waves of the 148 SMs, otherwise cuDNN's finer tiles win (BEV_CONV_TC = True/False overrides)."""
         if BEV_CONV_TC != "auto":
             return bool(BEV_CONV_TC)
+        if cin > 128:      # measured on B200 (tools/bench_bev.py): cuDNN's 256-channel kernels reach 650-690 TF/s, ours ~490
+            return False
         u, v = (H, W) if H % 8 == 0 or W % 8 != 0 else (W, H)
         ctas = -(-(B * -(-u // 8) * -(-v // 16)) // 4) * (cout // 128)
         return ctas / (-(-ctas // 148) * 148.0) >= 0.8
@@ -214,8 +216,8 @@ class BaseBEVBackbone(nn.Module):
         ups, c0 = [], 0
         for layers, (dw, db, ds), gemm in self._plan:
             for w, b, stride, pad, wpack in layers:
-                if wpack is not None and self._tc_conv_pays(B, xh.shape[1], xh.shape[2], w.shape[0]):
-                    xh = ops.bev_conv3x3(xh, wpack, b, True)
+                if wpack is not None and self._tc_conv_pays(B, xh.shape[1], xh.shape[2], w.shape[0], w.shape[1]):
+                    xh = ops.bev_conv3x3(xh, wpack, b, True, round_out=True)   # the next layer reads TF32 exactly
                 else:
                     xh = torch.cudnn_convolution_relu(xh.permute(0, 3, 1, 2), w, b, stride, pad, (1, 1), 1).permute(0, 2, 3, 1)
                     xh = xh if xh.is_contiguous() else xh.contiguous()
@@ -229,7 +231,7 @@ class BaseBEVBackbone(nn.Module):
                 cat = torch.empty((B, h * st, wd * st, ctot), dtype=torch.float32, device=x.device)
             assert cat.shape[1] == h * st and cat.shape[2] == wd * st
             ops.bev_gemm(xh.view(B * h * wd, xh.shape[3]), gw, gb, True, [(cat.view(-1, ctot)[:, c0:], 0, cout, ctot)],
-                         n_sub=st * st, up=2 if st == 2 else 0, in_hw=(h, wd))
+                         n_sub=st * st, up=2 if st == 2 else 0, in_hw=(h, wd), round_out=True)
             c0 += cout
         if gemm_ok:
             return cat.permute(0, 3, 1, 2)
@@ -276,7 +278,7 @@ class AnchorHeadSingle(nn.Module):
                 b = torch.zeros((80,), dtype=torch.float32, device=ws[0].device)
                 w[:n] = torch.cat(ws, 0)
                 b[:n] = torch.cat(bs, 0)
-                self._plan = (w.contiguous(), b, [x.shape[0] for x in ws])
+                self._plan = (ops.round_tf32(w), b, [x.shape[0] for x in ws])
         return self._plan
 
     def forward(self, batch_dict):
@@ -370,12 +372,17 @@ class SECONDNet(nn.Module):
         bd = self.dense_head(self.backbone_2d(dict(spatial_features=spatial_features)))
         B, A = batch_size, self.dense_head.num_anchors
         dev = spatial_features.device
-        score, label = head_ops.anchor_head_scores(bd["cls_preds"], self.num_class)
-        score, label = score.view(B, A), label.view(B, A, 1)
         # class_agnostic_nms (model_nms_utils.py:6-25): score >= thresh, top-k(NMS_PRE_MAXSIZE) - valid entries are a prefix
         k = min(cfg["nms_pre_maxsize"], A)
-        top_scores, top_idx = torch.topk(score, k, dim=1)
-        counts = (top_scores >= cfg["score_thresh"]).sum(dim=1).int()
+        if k <= 4096:
+            score, label, top_scores, top_idx, counts = head_ops.anchor_head_scores_topk(bd["cls_preds"], self.num_class, B,
+                                                                                         cfg["score_thresh"], k)
+            label = label.view(B, A, 1)
+        else:
+            score, label = head_ops.anchor_head_scores(bd["cls_preds"], self.num_class)
+            score, label = score.view(B, A), label.view(B, A, 1)
+            top_scores, top_idx = torch.topk(score, k, dim=1)
+            counts = (top_scores >= cfg["score_thresh"]).sum(dim=1).int()
         boxes = head_ops.anchor_decode_select(bd["box_preds"], bd["dir_cls_preds"], top_idx, self.dense_head.spec, A)
         P = cfg["nms_post_maxsize"]
         keep, num = ops.nms_batched(boxes, counts, cfg["nms_thresh"], rotated=True, max_keep=P)

@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(192, 1) bev_conv3x3_tc(const __grid_constant__
                     for (int e = 0; e < 4; ++e) {
                         float x = __uint_as_float(vv[j + e]);
                         if (bias_n) x += __ldg(&bias_n[c0 + j + e]);
-                        if (relu) x = fmaxf(x, 0.0f);
+                        if (relu & 1) x = fmaxf(x, 0.0f);
+                        if (relu & 2) x = tf32_rn(x);
                         wp[e] = x;
                     }
                     *reinterpret_cast<float4*>(stage_f + (size_t)lane * PITCH + c0 + j) = w;
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(192, 1) bev_conv3x3_tc(const __grid_constant__
 
 // in: (B, H, W, C_in) channels-last fp32; wpack: weights packed by crb3d.ops.pack_conv3x3_weight into
 // [C_out/128][tap = ky*3+kx][C_in/16][slab 4][128 co][4 ci]; bias: C_out or null; out: (B, H, W, C_out) channels-last.
-// Supported: C_in % 16 == 0, C_out % 128 == 0. The 8-pixel tile edge runs along H when H % 8 == 0 (else along W).
+// relu: bit 0 = ReLU, bit 1 = round the stored values to TF32 (round-to-nearest). Supported: C_in % 16 == 0, C_out % 128 == 0. The 8-pixel tile edge runs along H when H % 8 == 0 (else along W).
 extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int cin, const float* wpack, int cout,
                                       const float* bias, int relu, float* out, cudaStream_t stream) {
     if (!in || !wpack || !out || B <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) return CRB3D_ERR_ARG;

@@ -13,13 +13,14 @@
 // A ConvTranspose2d with kernel == stride == 2 is four such GEMMs (one per output sub-position dy,dx), selected by
 // blockIdx.x, whose rows land on the interleaved output pixels (2y+dy, 2x+dx).
 //
-// One CTA = one 128-row tile x all N columns. Warp roles (mbarrier pipelined, STAGES deep):
-//   warp 0, one lane : TMA producer - per 32-channel k-block one 128x32 box of A and one Nx32 box of W, 128B swizzle
-//   warp 1, one lane : tcgen05.mma issuer (4 x M128 x N x K8 per k-block), tcgen05.commit frees the stage
-//   warps 2-5        : epilogue - tcgen05.ld, bias/ReLU, rows staged in shared memory (aliasing the drained pipeline
-//                      buffers) and written out as whole 128-byte lines
-// Two CTAs are resident per SM (TMEM 2 x 256 columns), so one CTA's epilogue overlaps the other's main loop; the
-// kernels are HBM-bound (K <= 512): bytes/row = 4*(K + N).
+// Persistent CTAs (one per SM), each walking 128-row tiles of one weight slice. Warp roles (mbarrier pipelined):
+//   warp 0, one lane : TMA producer - per 32-channel k-block one 128x32 box of A (and, when the weights are not
+//                      resident, one Nx32 box of W), 128B swizzle, STAGES deep across tile boundaries
+//   warp 1, one lane : tcgen05.mma issuer (4 x M128 x N x K8 per k-block) into one of TWO TMEM accumulators
+//   warps 2-5        : epilogue of the other accumulator - tcgen05.ld, bias/ReLU, rows staged in shared memory and written
+//                      out as whole 128-byte lines
+// The kernels are HBM-bound (K <= 512): bytes/row = 4*(K + N); a first one-tile-per-CTA version spent most of its time
+// in per-CTA prologue/epilogue latency (24 % of the DRAM peak in ncu, profiles/r01_bev_gemm_v1.txt).
 #include "tc_common.cuh"
 
 namespace {
@@ -41,149 +42,239 @@ struct GemmOut {
 
 template <int N>
 struct Cfg {
-    static constexpr int CH = N < 128 ? N : 128;             // columns staged per epilogue pass
-    static constexpr int PITCH = CH + 4;                     // floats; +4 keeps float4 rows conflict-free
-    static constexpr int TMEM_COLS = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+    static constexpr int TMEM_N = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));   // columns per accumulator
     static constexpr int A_BYTES = TILE_M * 128;
-    static constexpr int B_BYTES = N * 128;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int B_BYTES = N * 128;           // one 32-channel k-block of the weights
+    static constexpr int CH = 32;                     // columns staged per epilogue pass
+    static constexpr int PITCH = CH + 4;              // floats; +4 keeps float4 rows conflict-free
+    // ROWS mode: 8 warps x 32 rows x PITCH; DENSE mode: 4 quarters x 32 rows x N
+    static constexpr int staging_bytes(bool dense) { return ((dense ? 4 * 32 * N * 4 : 8 * 32 * PITCH * 4) + 1023) & ~1023; }
 };
 
-template <int N, int STAGES>
-__global__ void __launch_bounds__(192) bev_gemm_tc(const __grid_constant__ CUtensorMap amap,
-                                                   const __grid_constant__ CUtensorMap wmap, int M, int K,
-                                                   const float* __restrict__ bias, int relu,
-                                                   const __grid_constant__ GemmOut out) {
+// PERSISTENT: gridDim.x = n_slices * ctas_per_slice. A CTA serves ONE weight slice (N output columns of one
+// sub-position) and walks the 128-row tiles  t = rank, rank + ctas_per_slice, ...  of the activation matrix:
+//   BRES = true : the slice's whole [N][K] weight block is loaded once and stays in shared memory; only activation
+//                 k-blocks stream through the STAGES-deep ring;
+//   BRES = false: weight k-blocks stream with the activations (L2 hits) - used when N*K*4 does not fit.
+// Two TMEM accumulators: the MMA warp fills one while the epilogue warps drain the other, so loads, MMAs and stores of
+// consecutive tiles overlap and the kernel runs at the HBM rate of its activation read + output write.
+template <int N, int STAGES, bool BRES, bool DENSE>
+__global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CUtensorMap amap,
+                                                      const __grid_constant__ CUtensorMap wmap, int M, int K,
+                                                      int ctas_per_slice, int halves, const float* __restrict__ bias, int relu,
+                                                      const __grid_constant__ GemmOut out) {
     using C = Cfg<N>;
-    static_assert(STAGES * C::STAGE_BYTES >= TILE_M * C::PITCH * 4, "staging must fit in the pipeline buffers");
+    constexpr int STAGE_BYTES = C::A_BYTES + (BRES ? 0 : C::B_BYTES);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full_bar[STAGES];
-    __shared__ uint64_t empty_bar[STAGES];
-    __shared__ uint64_t acc_bar;
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2], b_full;
     __shared__ uint32_t tmem_base_s;
+    __shared__ long long rowoff_s[8][32];          // ROWS mode: output offset of each staged row, per epilogue warp
+    __shared__ int colbase_s[DENSE ? N : 1], colw_s[DENSE ? N : 1];   // DENSE mode: column -> staging offset / segment width
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int sub = blockIdx.x;                 // output sub-position of a 2x2 transposed conv (0 otherwise)
-    const int m0 = blockIdx.y * TILE_M;
+    const int slice = blockIdx.x / ctas_per_slice, rank = blockIdx.x - slice * ctas_per_slice;
+    const int sub = slice / halves, half = slice - sub * halves;   // transposed-conv sub-position, column block
     const int nkb = K / BK;
+    const int n_tiles = (M + TILE_M - 1) / TILE_M;
+    const int my_tiles = rank < n_tiles ? (n_tiles - rank + ctas_per_slice - 1) / ctas_per_slice : 0;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&acc_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+        mbar_init(&b_full, 1);
         mbar_fence_init();
         tma_prefetch_desc(&amap);
         tma_prefetch_desc(&wmap);
     }
-    if (warp == 1) tmem_alloc<C::TMEM_COLS>(&tmem_base_s);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-    const uint32_t smem_base = smem_u32(smem);
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int stage = kb % STAGES;
-                if (kb >= STAGES) mbar_wait(&empty_bar[stage], ((kb / STAGES) - 1) & 1);
-                const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES, b_dst = a_dst + C::A_BYTES;
-                mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-                tma_load_2d(a_dst, &amap, kb * BK, m0, &full_bar[stage]);
-                tma_load_2d(b_dst, &wmap, kb * BK, sub * N, &full_bar[stage]);
+    if (warp == 1) tmem_alloc<2 * C::TMEM_N>(&tmem_base_s);
+    if (DENSE) {
+        for (int c = tid; c < N; c += blockDim.x) {
+            int base = 0, cb = -1, w = 0;
+            for (int sgi = 0; sgi < out.n_seg; ++sgi) {
+                if (c >= out.col_begin[sgi] && c < out.col_begin[sgi] + out.width[sgi]) { cb = base + (c - out.col_begin[sgi]); w = out.width[sgi]; }
+                base += 32 * out.width[sgi];
             }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(TILE_M, N);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int stage = kb % STAGES;
-                mbar_wait(&full_bar[stage], (kb / STAGES) & 1);
-                tc_fence_after();
-                const uint32_t a_base = smem_base + stage * C::STAGE_BYTES, b_base = a_base + C::A_BYTES;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    umma_tf32(tmem_base, desc_sw128(a_base + j * 32), desc_sw128(b_base + j * 32), idesc, (kb > 0 || j > 0) ? 1u : 0u);
-                umma_commit(&empty_bar[stage]);
-                if (kb == nkb - 1) umma_commit(&acc_bar);
-            }
-        }
-    } else {
-        // ================================ epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =========================
-        const int q = warp & 3;
-        const int r = q * 32 + lane;              // tile row owned by this thread in the TMEM read
-        mbar_wait(&acc_bar, 0);
-        tc_fence_after();
-        float* stage_f = reinterpret_cast<float*>(smem) + (size_t)q * 32 * C::PITCH;  // this warp's 32 staged rows
-        // output row offsets of this warp's rows (lane l holds row q*32 + l); -1 = beyond M
-        long long orow;
-        {
-            const long long m = (long long)m0 + r;
-            if (m >= M) orow = -1;
-            else if (out.up == 2) {
-                const int hw = out.in_w * out.in_h;
-                const int b = (int)(m / hw), rem = (int)(m - (long long)b * hw);
-                const int y = rem / out.in_w, x = rem - y * out.in_w;
-                orow = ((long long)b * (2 * out.in_h) + 2 * y + (sub >> 1)) * (2 * out.in_w) + 2 * x + (sub & 1);
-            } else orow = m;
-        }
-#pragma unroll 1
-        for (int c_begin = 0; c_begin < N; c_begin += C::CH) {
-#pragma unroll 1
-            for (int c0 = 0; c0 < C::CH; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_begin + c0), v);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (c0 + j >= C::CH) break;
-                    float4 w;
-                    float* wp = reinterpret_cast<float*>(&w);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float x = __uint_as_float(v[j + u]);
-                        if (bias) x += __ldg(&bias[c_begin + c0 + j + u]);
-                        if (relu) x = fmaxf(x, 0.0f);
-                        wp[u] = x;
-                    }
-                    *reinterpret_cast<float4*>(stage_f + (size_t)lane * C::PITCH + c0 + j) = w;
-                }
-            }
-            __syncwarp();
-            for (int s = 0; s < out.n_seg; ++s) {
-                const int lo = max(out.col_begin[s], c_begin), hi = min(out.col_begin[s] + out.width[s], c_begin + C::CH);
-                const int w = hi - lo;
-                if (w <= 0) continue;
-                float* base = out.ptr[s] + (lo - out.col_begin[s]);
-                const long long stride = out.row_stride[s];
-                const int soff = lo - c_begin;
-                if (((w | soff | (lo - out.col_begin[s])) & 3) == 0 && (stride & 3) == 0 && ((uintptr_t)out.ptr[s] & 15) == 0) {
-                    const int w4 = w >> 2;                      // float4 per row
-                    for (int e = lane; e < 32 * w4; e += 32) {
-                        const int rr = e / w4, c4 = e - rr * w4;
-                        const long long orr = __shfl_sync(0xffffffffu, orow, rr);
-                        if (orr >= 0)
-                            *reinterpret_cast<float4*>(base + orr * stride + c4 * 4) =
-                                *reinterpret_cast<const float4*>(stage_f + (size_t)rr * C::PITCH + soff + c4 * 4);
-                    }
-                } else {
-                    for (int e = lane; e < 32 * w; e += 32) {
-                        const int rr = e / w, c = e - rr * w;
-                        const long long orr = __shfl_sync(0xffffffffu, orow, rr);
-                        if (orr >= 0) base[orr * stride + c] = stage_f[(size_t)rr * C::PITCH + soff + c];
-                    }
-                }
-            }
-            __syncwarp();
+            colbase_s[c] = cb;
+            colw_s[c] = w;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    // layout: [staging][resident weights (BRES)][stage ring]
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bres_base = smem_base + C::staging_bytes(DENSE);
+    const uint32_t ring_base = bres_base + (BRES ? (uint32_t)nkb * C::B_BYTES : 0u);
+    const int wrow = slice * N;                  // first weight row of this slice
+
+    if (warp == 0) {
+        if (lane == 0 && my_tiles > 0) {
+            if (BRES) {
+                mbar_expect_tx(&b_full, (uint32_t)nkb * C::B_BYTES);
+                for (int kb = 0; kb < nkb; ++kb) tma_load_2d(bres_base + kb * C::B_BYTES, &wmap, kb * BK, wrow, &b_full);
+            }
+            int it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int m0 = (rank + i * ctas_per_slice) * TILE_M;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int stage = it % STAGES;
+                    if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1);
+                    const uint32_t a_dst = ring_base + stage * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    tma_load_2d(a_dst, &amap, kb * BK, m0, &full_bar[stage]);
+                    if (!BRES) tma_load_2d(a_dst + C::A_BYTES, &wmap, kb * BK, wrow, &full_bar[stage]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && my_tiles > 0) {
+            const uint32_t idesc = idesc_tf32(TILE_M, N);
+            if (BRES) mbar_wait(&b_full, 0);
+            int it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int acc = i & 1;
+                if (i >= 2) mbar_wait(&acc_empty[acc], ((i >> 1) - 1) & 1);   // the epilogue has drained this accumulator
+                tc_fence_after();
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int stage = it % STAGES;
+                    mbar_wait(&full_bar[stage], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_base = ring_base + stage * STAGE_BYTES;
+                    const uint32_t b_base = BRES ? bres_base + kb * C::B_BYTES : a_base + C::A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        umma_tf32(tmem_base + acc * C::TMEM_N, desc_sw128(a_base + j * 32), desc_sw128(b_base + j * 32), idesc,
+                                  (kb > 0 || j > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        // ================================ epilogue: 8 warps, two per TMEM lane quarter ================================
+        const int q = warp & 3, h = (warp - 2) >> 2;      // quarter (TMEM lanes 32q..32q+31), which half of the columns
+        const int r = q * 32 + lane;                      // tile row owned by this thread in the TMEM read
+        const int col0 = half * N;                        // first output column of this slice (within the logical N_total)
+        float* stage_base = reinterpret_cast<float*>(smem);
+        if (!DENSE) {
+            // ---- one segment of full rows: each warp stages 32 rows x 32 columns and stores whole 128-byte lines
+            float* stage_w = stage_base + (size_t)(warp - 2) * 32 * C::PITCH;
+            long long* rowoff = rowoff_s[warp - 2];
+            const long long stride = out.row_stride[0];
+            float* obase = out.ptr[0] + col0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int acc = i & 1;
+                const long long m = (long long)(rank + i * ctas_per_slice) * TILE_M + r;
+                long long orow = -1;                      // output row of this lane's tile row; -1 = beyond M
+                if (m < M) {
+                    if (out.up == 2) {
+                        const int hw = out.in_w * out.in_h;
+                        const int b = (int)(m / hw), rem = (int)(m - (long long)b * hw);
+                        const int y = rem / out.in_w, x = rem - y * out.in_w;
+                        orow = ((long long)b * (2 * out.in_h) + 2 * y + (sub >> 1)) * (2 * out.in_w) + 2 * x + (sub & 1);
+                    } else orow = m;
+                }
+                rowoff[lane] = orow < 0 ? -1 : orow * stride;
+                mbar_wait(&acc_full[acc], (i >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = h * 32; c0 < N; c0 += 64) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::TMEM_N + c0), v);
+                    if (c0 + 64 >= N) {           // this warp's last TMEM read of the tile: hand the accumulator back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 w;
+                        float* wp = reinterpret_cast<float*>(&w);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float x = __uint_as_float(v[j + u]);
+                            if (bias) x += __ldg(&bias[col0 + c0 + j + u]);
+                            if (relu & 1) x = fmaxf(x, 0.0f);
+                            if (relu & 2) x = tf32_rn(x);
+                            wp[u] = x;
+                        }
+                        *reinterpret_cast<float4*>(stage_w + (size_t)lane * C::PITCH + j) = w;
+                    }
+                    __syncwarp();
+                    float4 val[8];
+                    long long off[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {      // 4 rows x 128 bytes per warp instruction
+                        const int rr = it * 4 + (lane >> 3);
+                        off[it] = rowoff[rr];
+                        val[it] = *reinterpret_cast<const float4*>(stage_w + (size_t)rr * C::PITCH + (lane & 7) * 4);
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it)
+                        if (off[it] >= 0) *reinterpret_cast<float4*>(obase + off[it] + c0 + (lane & 7) * 4) = val[it];
+                    __syncwarp();
+                }
+            }
+        } else {
+            // ---- contiguous-row segments (row_stride == width): the quarter's two warps fill one dense [segment][32 rows][w]
+            // staging block, then copy each segment out as one contiguous run of float4
+            float* stage_q = stage_base + (size_t)q * 32 * N;
+            const int tq = h * 32 + lane;                 // thread index within the quarter (0..63)
+            for (int i = 0; i < my_tiles; ++i) {
+                const int acc = i & 1;
+                const long long mrow0 = (long long)(rank + i * ctas_per_slice) * TILE_M + q * 32;   // first row of the quarter
+                mbar_wait(&acc_full[acc], (i >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = h * 16; c0 < N; c0 += 32) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::TMEM_N + c0), v);
+                    if (c0 + 32 >= N) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = c0 + j;
+                        const int cbse = colbase_s[c];
+                        if (cbse < 0) continue;            // padding column
+                        float x = __uint_as_float(v[j]);
+                        if (bias) x += __ldg(&bias[col0 + c]);
+                        if (relu & 1) x = fmaxf(x, 0.0f);
+                        if (relu & 2) x = tf32_rn(x);
+                        stage_q[cbse + lane * colw_s[c]] = x;
+                    }
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q));
+                const int rows_valid = (int)max(0ll, min(32ll, (long long)M - mrow0));
+                int sbase = 0;
+                for (int sgi = 0; sgi < out.n_seg; ++sgi) {
+                    const int w = out.width[sgi];
+                    float* dst = out.ptr[sgi] + mrow0 * w;
+                    const float* src = stage_q + sbase;
+                    if (rows_valid == 32) {
+                        for (int e = tq; e < 8 * w; e += 64)
+                            reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(src)[e];
+                    } else {
+                        for (int e = tq; e < rows_valid * w; e += 64) dst[e] = src[e];
+                    }
+                    sbase += 32 * w;
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<2 * C::TMEM_N>(tmem_base);
 }
 
-template <int N, int STAGES>
-int launch_gemm(const float* A, long long M, int K, long long lda, const float* W, int n_sub, const float* bias, int relu,
-                const GemmOut& out, cudaStream_t stream) {
+template <int N, int STAGES, bool BRES, bool DENSE>
+int launch_gemm(const float* A, long long M, int K, long long lda, const float* W, int n_slices, int halves, const float* bias,
+                int relu, const GemmOut& out, cudaStream_t stream) {
     using C = Cfg<N>;
     CUtensorMap amap, wmap;
     {
@@ -193,19 +284,25 @@ int launch_gemm(const float* A, long long M, int K, long long lda, const float* 
         if (rc) return rc;
     }
     {
-        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N * n_sub}, strides[1] = {(uint64_t)K * 4};
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N * n_slices}, strides[1] = {(uint64_t)K * 4};
         const uint32_t box[2] = {BK, (uint32_t)N};
         int rc = make_map_f32(&wmap, W, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    constexpr size_t smem = (size_t)STAGES * C::STAGE_BYTES + 1024;
-    auto kern = bev_gemm_tc<N, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    const size_t smem = 1024 + C::staging_bytes(DENSE) + (BRES ? (size_t)(K / BK) * C::B_BYTES : 0) +
+                        (size_t)STAGES * (C::A_BYTES + (BRES ? 0 : C::B_BYTES));
+    if (smem > 227 * 1024) return CRB3D_ERR_UNSUPPORTED;
+    auto kern = bev_gemm_tc<N, STAGES, BRES, DENSE>;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
         CRB3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        smem_set = smem;
     }
-    kern<<<dim3((unsigned)n_sub, (unsigned)crb3d_divup(M, TILE_M)), 192, smem, stream>>>(amap, wmap, (int)M, K, bias, relu, out);
+    const int n_tiles = (int)crb3d_divup(M, TILE_M);
+    int per_slice = CRB3D_NUM_SMS / n_slices;
+    if (per_slice < 1) per_slice = 1;
+    if (per_slice > n_tiles) per_slice = n_tiles;
+    kern<<<(unsigned)(n_slices * per_slice), 320, smem, stream>>>(amap, wmap, (int)M, K, per_slice, halves, bias, relu, out);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -216,7 +313,8 @@ int launch_gemm(const float* A, long long M, int K, long long lda, const float* 
 // Output: n_seg column segments (seg s = columns [col_begin[s], col_begin[s]+width[s]) -> out_ptr[s] + row*row_stride[s]).
 // up = 0: output row = GEMM row, n_sub must be 1. up = 2: ConvTranspose2d(kernel = stride = 2): n_sub = 4 weight slices
 // ordered (dy, dx), GEMM row (b, y, x) of an in_h x in_w map lands on output pixel (b, 2y+dy, 2x+dx).
-// Supported: K % 32 == 0, N in {80, 128, 256} (pad weights/bias with zero rows to reach a supported N).
+// relu: bit 0 = ReLU, bit 1 = round the stored values to TF32 (round-to-nearest) so that a following tensor-core layer
+// reads them exactly. Supported: K % 32 == 0, N in {80, 128, 256} (pad weights/bias with zero rows to reach a supported N).
 extern "C" int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long lda, const float* W, int N, int n_sub,
                                    const float* bias, int relu, int n_seg, float* const* out_ptr, const int* col_begin,
                                    const int* width, const long long* row_stride, int up, int in_h, int in_w,
@@ -234,8 +332,22 @@ extern "C" int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long
         if (!out_ptr[s] || col_begin[s] < 0 || width[s] <= 0 || col_begin[s] + width[s] > N) return CRB3D_ERR_ARG;
         o.ptr[s] = out_ptr[s]; o.col_begin[s] = col_begin[s]; o.width[s] = width[s]; o.row_stride[s] = row_stride[s];
     }
-    if (N == 256) return launch_gemm<256, 2>(A, M, K, lda, W, n_sub, bias, relu, o, stream);   // 2 x 48 KB
-    if (N == 128) return launch_gemm<128, 3>(A, M, K, lda, W, n_sub, bias, relu, o, stream);   // 3 x 32 KB
-    if (N == 80) return launch_gemm<80, 3>(A, M, K, lda, W, n_sub, bias, relu, o, stream);     // 3 x 26 KB
+    // output placement modes: ROWS = one segment holding all N columns (rows row_stride apart); DENSE = consecutive
+    // segments of contiguous rows (row_stride == width), N = 80 only
+    bool rows = n_seg == 1 && col_begin[0] == 0 && width[0] == N && row_stride[0] % 4 == 0 && ((uintptr_t)out_ptr[0] & 15) == 0;
+    bool dense = up == 0;
+    for (int s = 0, c = 0; s < n_seg; ++s) {
+        dense = dense && col_begin[s] == c && row_stride[s] == width[s] && ((uintptr_t)out_ptr[s] & 15) == 0;
+        c += width[s];
+    }
+    // slices = (sub-positions) x (column blocks of the per-CTA width); resident weights when N_cta * K * 4 <= 128 KB
+    if (rows) {
+        if (N == 256 && K <= 128) return launch_gemm<256, 3, true, false>(A, M, K, lda, W, n_sub, 1, bias, relu, o, stream);
+        if (N == 256 && K <= 256) return launch_gemm<128, 3, true, false>(A, M, K, lda, W, n_sub * 2, 2, bias, relu, o, stream);
+        if (N == 256) return launch_gemm<128, 5, false, false>(A, M, K, lda, W, n_sub * 2, 2, bias, relu, o, stream);
+        if (N == 128 && K <= 256) return launch_gemm<128, 3, true, false>(A, M, K, lda, W, n_sub, 1, bias, relu, o, stream);
+        if (N == 128) return launch_gemm<128, 5, false, false>(A, M, K, lda, W, n_sub, 1, bias, relu, o, stream);
+    }
+    if (dense && N == 80) return launch_gemm<80, 6, false, true>(A, M, K, lda, W, n_sub, 1, bias, relu, o, stream);
     return CRB3D_ERR_UNSUPPORTED;
 }

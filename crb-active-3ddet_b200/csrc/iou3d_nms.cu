@@ -52,6 +52,21 @@ __device__ __forceinline__ bool aabb_near(const float4& a, const float4& b) {
     return fminf(a.y, b.y) - fmaxf(a.x, b.x) > 0.f && fminf(a.w, b.w) - fmaxf(a.z, b.z) > 0.f;
 }
 
+template <bool ROTATED>
+__device__ __forceinline__ float pair_iou(const float* __restrict__ boxes, const RBox* __restrict__ rb, int j, int i) {
+    if (ROTATED) {
+        RBox a, b;
+        const float4* pa = reinterpret_cast<const float4*>(rb + j);
+        const float4* pb = reinterpret_cast<const float4*>(rb + i);
+        float4* da = reinterpret_cast<float4*>(&a);
+        float4* db = reinterpret_cast<float4*>(&b);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { da[u] = __ldg(pa + u); db[u] = __ldg(pb + u); }
+        return rbox_iou(a, b);
+    }
+    return aabb_iou(boxes + (size_t)j * 7, boxes + (size_t)i * 7);
+}
+
 // ------------------------------------------------------------------ NMS step 1: per-box precompute
 // One thread per box: the rotated-box record (corners, sin/cos: 64 B) once per box instead of once per tile, and a
 // 16-byte filter record (rotated: centre + half diagonal; axis-aligned: the four edges).
@@ -88,9 +103,18 @@ template <bool ROTATED>
 __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int n, float thresh, const float* __restrict__ boxes,
                                                                 const RBox* __restrict__ rb, const float4* __restrict__ circ,
                                                                 unsigned long long* __restrict__ maskT, int rows_pad,
-                                                                const int* __restrict__ counts, int n_max) {
+                                                                const int* __restrict__ counts, int n_max, int prefix,
+                                                                const int* __restrict__ idx, const int* __restrict__ m_dev,
+                                                                unsigned int* __restrict__ gq, int* __restrict__ gq_count, int gq_cap) {
+    // gq != null: surviving pairs are appended to a GLOBAL queue (frame:4 | row:14 | column:14 bits) that nms_eval_kernel
+    // drains with every SM of the chip - a tile whose pairs pile up (the top-scored boxes of a frame sit on a few objects)
+    // would otherwise serialise thousands of ~15 us polygon clippings on its eight warps. A reservation that does not fit
+    // is evaluated here instead.
+    // level selection: prefix > 0 -> only the first `prefix` boxes; idx/m_dev -> the m_dev[f] boxes listed in idx
     const int f = blockIdx.z;
     if (counts) n = min(counts[f], n_max);
+    if (prefix > 0) n = min(n, prefix);
+    if (m_dev) { n = m_dev[f]; idx += (size_t)f * n_max; }
     const int cbn = (n + 63) >> 6;
     const int r = blockIdx.y, c0 = max((int)blockIdx.x * MASK_CW, r), c1 = min(((int)blockIdx.x + 1) * MASK_CW, cbn);
     if (r >= cbn || c1 <= c0) return;  // uniform per CTA
@@ -103,22 +127,23 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int n, float thr
     __shared__ float4 ccirc[MASK_CW * 64];
     __shared__ unsigned long long bits[MASK_CW][64];
     __shared__ unsigned int queue[(MASK_THREADS / 32) * MASK_CW * 64];
-    __shared__ int qn;
+    __shared__ int qn, gbase_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncols = min(n - c0 * 64, (c1 - c0) * 64);
     const bool all_near = thresh < 0.f;  // then even a zero IoU suppresses: nothing may be filtered out
     if (tid < 64) {
         const int i = r * 64 + tid;
         if (i < n) {
-            rcirc[tid] = circ[i];
+            const int bi = idx ? idx[i] : i;
+            rcirc[tid] = circ[bi];
             if (ROTATED) {
-                const float4* p = reinterpret_cast<const float4*>(rb + i);
+                const float4* p = reinterpret_cast<const float4*>(rb + bi);
                 float4* d = reinterpret_cast<float4*>(&rrow[tid]);
                 d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
             }
         }
     }
-    for (int t = tid; t < ncols; t += MASK_THREADS) ccirc[t] = circ[c0 * 64 + t];
+    for (int t = tid; t < ncols; t += MASK_THREADS) ccirc[t] = circ[idx ? idx[c0 * 64 + t] : c0 * 64 + t];
     for (int t = tid; t < MASK_CW * 64; t += MASK_THREADS) (&bits[0][0])[t] = 0ull;
     __syncthreads();
     for (int i0 = 0; i0 < 64; i0 += MASK_THREADS / 32) {
@@ -142,8 +167,29 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int n, float thr
         }
         __syncthreads();
         const int nq = qn;
+        if (gq) {
+            if (tid == 0) {
+                gbase_s = -1;
+                if (nq > 0) {
+                    const int b = atomicAdd(gq_count, nq);
+                    if (b + nq <= gq_cap) gbase_s = b;
+                    else if (b < gq_cap) gbase_s = -2 - b;   // straddles the end: pad the tail with skip markers
+                }
+            }
+            __syncthreads();
+            const int gb = gbase_s;
+            if (gb >= 0) {
+                for (int q = tid; q < nq; q += MASK_THREADS)
+                    gq[gb + q] = ((unsigned int)f << 28) | ((unsigned int)(r * 64 + (queue[q] >> 16)) << 14) |
+                                 (unsigned int)(c0 * 64 + (queue[q] & 0xffff));
+                __syncthreads();
+                continue;
+            }
+            if (gb <= -2) for (int t = -2 - gb + tid; t < gq_cap; t += MASK_THREADS) gq[t] = 0xFFFFFFFFu;
+        }
         for (int q = tid; q < nq; q += MASK_THREADS) {
-            const int il2 = queue[q] >> 16, jj = queue[q] & 0xffff, jg = c0 * 64 + jj;
+            const int il2 = queue[q] >> 16, jj = queue[q] & 0xffff;
+            const int jg = idx ? idx[c0 * 64 + jj] : c0 * 64 + jj;
             float v;
             if (ROTATED) {
                 RBox cbx;
@@ -152,7 +198,7 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int n, float thr
                 d[0] = __ldg(p); d[1] = __ldg(p + 1); d[2] = __ldg(p + 2); d[3] = __ldg(p + 3);
                 v = rbox_iou(rrow[il2], cbx);
             } else {
-                v = aabb_iou(boxes + (size_t)(r * 64 + il2) * 7, boxes + (size_t)jg * 7);
+                v = aabb_iou(boxes + (size_t)(idx ? idx[r * 64 + il2] : r * 64 + il2) * 7, boxes + (size_t)jg * 7);
             }
             if (v > thresh) atomicOr(&bits[jj >> 6][il2], 1ull << (jj & 63));
         }
@@ -160,6 +206,24 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int n, float thr
     }
     for (int t = tid; t < (c1 - c0) * 64; t += MASK_THREADS)
         maskT[(size_t)(c0 + (t >> 6)) * rows_pad + r * 64 + (t & 63)] = bits[t >> 6][t & 63];
+}
+
+// drains the global pair queue of nms_mask_kernel: one pair per thread, the whole chip
+template <bool ROTATED>
+__global__ void __launch_bounds__(256) nms_eval_kernel(const unsigned int* __restrict__ gq, const int* __restrict__ gq_count,
+                                                       int gq_cap, float thresh, const float* __restrict__ boxes,
+                                                       const RBox* __restrict__ rb, const int* __restrict__ idx, int n_max,
+                                                       unsigned long long* __restrict__ maskT, int rows_pad) {
+    const int total = min(*gq_count, gq_cap);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const unsigned int e = gq[q];
+        if (e == 0xFFFFFFFFu) continue;
+        const int f = e >> 28, i = (e >> 14) & 0x3FFF, j = e & 0x3FFF;
+        const int bi = idx ? idx[(size_t)f * n_max + i] : i, bj = idx ? idx[(size_t)f * n_max + j] : j;
+        const float v = pair_iou<ROTATED>(boxes + (size_t)f * n_max * 7, rb + (size_t)f * n_max, bi, bj);
+        if (v > thresh)
+            atomicOr(&maskT[(size_t)f * rows_pad * (rows_pad >> 6) + (size_t)(j >> 6) * rows_pad + i], 1ull << (j & 63));
+    }
 }
 
 // maskT[c][row] -> the reference's row-major mask[row][c] (parity checks only); cells below the diagonal are not written
@@ -187,7 +251,10 @@ template <bool STREAM>
 __global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(int n, int rows_pad, const unsigned long long* __restrict__ maskT,
                                                                     int max_keep, long long* __restrict__ keep,
                                                                     int* __restrict__ num_keep, const int* __restrict__ counts,
-                                                                    int n_max, int keep_stride) {
+                                                                    int n_max, int keep_stride, int prefix,
+                                                                    const int* __restrict__ idx, const int* __restrict__ m_dev) {
+    // idx/m_dev: second level - positions map to box indices through idx and the kept boxes are APPENDED after the
+    // *num_keep boxes the first level kept (their indices are all smaller, so the list stays ascending)
     extern __shared__ __align__(16) unsigned char dyn[];
     // layout: two column-block buffers of rows_pad words each, then the kept list (up to n ints)
     unsigned long long* buf0 = reinterpret_cast<unsigned long long*>(dyn);
@@ -200,6 +267,9 @@ __global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(int n, int r
         keep += (size_t)f * keep_stride;
         num_keep += f;
     }
+    if (prefix > 0) n = min(n, prefix);
+    int kbase = 0;
+    if (m_dev) { n = m_dev[f]; idx += (size_t)f * n_max; kbase = *num_keep; }
     const int chunks = (n + 63) / 64;
     __shared__ unsigned long long wor[REDUCE_THREADS / 32];
     __shared__ int kept_s;
@@ -234,10 +304,10 @@ __global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(int n, int r
             int k = nk;
             unsigned long long avail = ~cur & valid;
             while (avail) {
-                if (max_keep > 0 && k >= max_keep) break;
+                if (max_keep > 0 && kbase + k >= max_keep) break;
                 const int b = __ffsll((long long)avail) - 1;
                 kept_list[k] = base + b;
-                keep[k] = base + b;
+                keep[kbase + k] = idx ? idx[base + b] : base + b;
                 ++k;
                 cur |= cur_buf[base + b];                               // diagonal tile: bits above b only
                 avail = ~cur & valid & ~((2ull << b) - 1ull);          // (2<<63) wraps to 0 -> mask 0xFF..FF, avail 0
@@ -245,194 +315,138 @@ __global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(int n, int r
             kept_s = k;
         }
         __syncthreads();
-        if (max_keep > 0 && kept_s >= max_keep) break;
+        if (max_keep > 0 && kbase + kept_s >= max_keep) break;
     }
     asm volatile("cp.async.wait_group 0;");
-    if (tid == 0) *num_keep = kept_s;
+    if (tid == 0) *num_keep = kbase + kept_s;
 }
 
-// ------------------------------------------------------------------ kept-driven greedy NMS (the scoring path)
-// The bitmask needs n^2/2 pair tests although the host loop only ever reads the rows of KEPT boxes (1-2 % of them).
-// Here one CTA per frame walks the score-sorted boxes in groups of 512 and only evaluates
-//   (A) group boxes against the boxes kept so far (filter -> queue -> polygon clipping, skipping boxes that are
-//       already suppressed), then (B) the survivors of the group against each other (a <= 512 x 512 bit matrix in
-//       shared memory) and (C) a serial resolve of that matrix by one warp.
-// Identical keep list (same rbox_iou on the same ordered pairs (earlier, later), same greedy rule), ~20x fewer
-// polygon evaluations, no n^2 workspace traffic; stops as soon as max_keep boxes are kept.
-constexpr int GR_THREADS = 1024;
-constexpr int GR_G = 512;
-constexpr int GR_QCAP = 8192;
+// ------------------------------------------------------------------ two-level NMS: prefix, wide suppression, survivors
+// The bitmask costs n^2/2 pair tests although the greedy rule only ever reads the rows of KEPT boxes. Greedy NMS over a
+// score-sorted list has the prefix property (the kept boxes of the first P boxes are exactly the kept boxes < P of the
+// whole list), so: (1) mask + reduce over the first P boxes; (2) every later box is tested against those few kept boxes
+// only (k-major rounds, already-suppressed boxes are skipped) - typically most of the list dies here; (3) the survivors
+// are compacted in index order and (4) mask + reduce run over the survivors alone, appending to the keep list. The keep
+// list is identical to the full-mask result: a survivor can only be suppressed by a kept survivor.
+constexpr int SUP_THREADS = 1024;
+constexpr int SUP_CAND = 512;     // candidates per CTA
+constexpr int SUP_KCH = 16;       // kept boxes per round: SUP_CAND * SUP_KCH pairs never overflow the queue
 
 template <bool ROTATED>
-__device__ __forceinline__ float pair_iou(const float* __restrict__ boxes, const RBox* __restrict__ rb, int j, int i) {
-    if (ROTATED) {
-        RBox a, b;
-        const float4* pa = reinterpret_cast<const float4*>(rb + j);
-        const float4* pb = reinterpret_cast<const float4*>(rb + i);
-        float4* da = reinterpret_cast<float4*>(&a);
-        float4* db = reinterpret_cast<float4*>(&b);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { da[u] = __ldg(pa + u); db[u] = __ldg(pb + u); }
-        return rbox_iou(a, b);
+__global__ void __launch_bounds__(SUP_THREADS) nms_suppress_kernel(int n, float thresh, const float* __restrict__ boxes,
+                                                                   const RBox* __restrict__ rb, const float4* __restrict__ circ,
+                                                                   const long long* __restrict__ keep, const int* __restrict__ num_keep,
+                                                                   const int* __restrict__ counts, int n_max, int keep_stride,
+                                                                   int prefix, int* __restrict__ alive) {
+    const int f = blockIdx.y;
+    if (counts) n = min(counts[f], n_max);
+    const int i0 = prefix + blockIdx.x * SUP_CAND;
+    boxes += (size_t)f * n_max * 7;
+    rb += (size_t)f * n_max;
+    circ += (size_t)f * n_max;
+    alive += (size_t)f * n_max;
+    if (counts) { keep += (size_t)f * keep_stride; num_keep += f; }
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (i0 >= n) {   // nothing (left) in this slice: still clear the flags the compaction reads
+        for (int t = tid; t < SUP_CAND; t += SUP_THREADS) if (i0 + t < n_max) alive[i0 + t] = 0;
+        return;
     }
-    return aabb_iou(boxes + (size_t)j * 7, boxes + (size_t)i * 7);
-}
-
-template <bool ROTATED>
-__global__ void __launch_bounds__(GR_THREADS) nms_greedy_kernel(int n, float thresh, const float* __restrict__ boxes,
-                                                                const RBox* __restrict__ rb, const float4* __restrict__ circ,
-                                                                int max_keep, long long* __restrict__ keep,
-                                                                int* __restrict__ num_keep, const int* __restrict__ counts,
-                                                                int n_max, int keep_stride, int kcap) {
-    extern __shared__ __align__(16) unsigned char dyn[];
-    float4* gcirc = reinterpret_cast<float4*>(dyn);                       // GR_G
-    float4* kcirc = gcirc + GR_G;                                          // kcap
-    unsigned int* queue = reinterpret_cast<unsigned int*>(kcirc + kcap);   // GR_QCAP
-    unsigned int* msk = queue + GR_QCAP;                                   // GR_G x GR_G/32
-    int* surv = reinterpret_cast<int*>(msk + GR_G * (GR_G / 32));          // GR_G
-    int* supp = surv + GR_G;                                               // GR_G
-    int* kept_idx = supp + GR_G;                                           // kcap
-    __shared__ int qn, nk_s, ns_s, overflow, wcnt[GR_THREADS / 32];
-    const int f = blockIdx.x;
-    if (counts) {
-        n = min(counts[f], n_max);
-        boxes += (size_t)f * n_max * 7;
-        rb += (size_t)f * n_max;
-        circ += (size_t)f * n_max;
-        keep += (size_t)f * keep_stride;
-        num_keep += f;
-    }
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ float4 ccirc[SUP_CAND];
+    __shared__ float4 kcirc[SUP_KCH];
+    __shared__ int kidx[SUP_KCH];
+    __shared__ int supp[SUP_CAND];
+    __shared__ unsigned int queue[SUP_CAND * SUP_KCH];
+    __shared__ int qn;
+    const int gsz = min(SUP_CAND, n - i0), nk = *num_keep;
     const bool all_near = thresh < 0.f;
-    if (tid == 0) nk_s = 0;
-    __syncthreads();
-
-    // filter pairs [p_lo, p_hi) of the current phase into the queue; phase 0: p = k * gsz + t (kept k vs group box t),
-    // phase 1: p = a * ns + b (survivor a vs survivor b > a). Pairs that do not fit set `overflow`.
-    auto filter = [&](int phase, int p_lo, int p_hi, int gsz, int ns) {
-        for (int p0 = p_lo; p0 < p_hi; p0 += GR_THREADS) {
+    for (int t = tid; t < SUP_CAND; t += SUP_THREADS) { supp[t] = 0; if (t < gsz) ccirc[t] = circ[i0 + t]; }
+    for (int k0 = 0; k0 < nk; k0 += SUP_KCH) {
+        const int kn = min(SUP_KCH, nk - k0);
+        __syncthreads();
+        if (tid < kn) { const int b = (int)keep[k0 + tid]; kidx[tid] = b; kcirc[tid] = circ[b]; }
+        if (tid == 0) qn = 0;
+        __syncthreads();
+        for (int p0 = 0; p0 < kn * gsz; p0 += SUP_THREADS) {
             const int p = p0 + tid;
             bool near = false;
-            unsigned int code = 0;
-            if (p < p_hi) {
-                if (phase == 0) {
-                    const int k = p / gsz, t = p - k * gsz;
-                    near = supp[t] == 0 && (all_near || (ROTATED ? circ_near(kcirc[k], gcirc[t]) : aabb_near(kcirc[k], gcirc[t])));
-                    code = ((unsigned int)k << 9) | (unsigned int)t;
-                } else {
-                    const int a = p / ns, b = p - a * ns;
-                    near = b > a && (all_near || (ROTATED ? circ_near(gcirc[surv[a]], gcirc[surv[b]]) : aabb_near(gcirc[surv[a]], gcirc[surv[b]])));
-                    code = ((unsigned int)a << 9) | (unsigned int)b;
-                }
+            int k = 0, t = 0;
+            if (p < kn * gsz) {
+                k = p / gsz; t = p - k * gsz;
+                near = supp[t] == 0 && (all_near || (ROTATED ? circ_near(kcirc[k], ccirc[t]) : aabb_near(kcirc[k], ccirc[t])));
             }
             const unsigned int m = __ballot_sync(0xffffffffu, near);
             if (m) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(&qn, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                const int slot = base + __popc(m & ((1u << lane) - 1u));
-                if (near) {
-                    if (slot < GR_QCAP) queue[slot] = code;
-                    else overflow = 1;
-                }
+                if (near) queue[base + __popc(m & ((1u << lane) - 1u))] = ((unsigned int)k << 9) | (unsigned int)t;
             }
         }
-    };
-    auto evaluate = [&](int phase, int g0) {
-        const int nq = min(qn, GR_QCAP);
-        for (int q = tid; q < nq; q += GR_THREADS) {
-            const unsigned int code = queue[q];
-            const int hi = code >> 9, lo = code & 511;
-            if (phase == 0) {
-                if (supp[lo]) continue;             // benign race: a stale 0 only costs one evaluation
-                if (pair_iou<ROTATED>(boxes, rb, kept_idx[hi], g0 + lo) > thresh) supp[lo] = 1;
-            } else {
-                if (pair_iou<ROTATED>(boxes, rb, g0 + surv[hi], g0 + surv[lo]) > thresh) atomicOr(&msk[hi * (GR_G / 32) + (lo >> 5)], 1u << (lo & 31));
-            }
+        __syncthreads();
+        const int nq = qn;
+        for (int q = tid; q < nq; q += SUP_THREADS) {
+            const int k = queue[q] >> 9, t = queue[q] & 511;
+            if (supp[t]) continue;                 // benign race: a stale 0 only costs one evaluation
+            if (pair_iou<ROTATED>(boxes, rb, kidx[k], i0 + t) > thresh) supp[t] = 1;
         }
-    };
-    // one phase = one filter pass over all pairs (normally a single evaluation round); if the queue overflowed the pairs
-    // are re-walked in chunks that cannot overflow (already-decided pairs are re-evaluated to the same verdict)
-    auto run_phase = [&](int phase, int total, int g0, int gsz, int ns) {
-        if (tid == 0) { qn = 0; overflow = 0; }
-        __syncthreads();
-        filter(phase, 0, total, gsz, ns);
-        __syncthreads();
-        evaluate(phase, g0);
-        const bool again = overflow != 0;
-        __syncthreads();
-        if (again) {
-            for (int lo = 0; lo < total; lo += GR_QCAP) {
-                if (tid == 0) qn = 0;
-                __syncthreads();
-                filter(phase, lo, min(total, lo + GR_QCAP), gsz, ns);
-                __syncthreads();
-                evaluate(phase, g0);
-                __syncthreads();
-            }
-        }
-    };
-
-    for (int g0 = 0; g0 < n; g0 += GR_G) {
-        const int gsz = min(GR_G, n - g0);
-        const int nk = nk_s;
-        if (tid < gsz) { gcirc[tid] = circ[g0 + tid]; supp[tid] = 0; }
-        __syncthreads();
-        if (nk > 0) run_phase(0, nk * gsz, g0, gsz, 0);
-        // ordered compaction of the survivors
-        {
-            const bool alive = tid < gsz && supp[tid] == 0;
-            const unsigned int m = __ballot_sync(0xffffffffu, alive);
-            if (lane == 0) wcnt[warp] = __popc(m);
-            __syncthreads();
-            if (warp == 0) {
-                const int c = wcnt[lane];
-                const int incl = warp_incl_scan(c);
-                wcnt[lane] = incl - c;
-                if (lane == 31) ns_s = incl;
-            }
-            __syncthreads();
-            if (alive) surv[wcnt[warp] + __popc(m & ((1u << lane) - 1u))] = tid;
-        }
-        for (int t = tid; t < GR_G * (GR_G / 32); t += GR_THREADS) msk[t] = 0u;
-        __syncthreads();
-        const int ns = ns_s;
-        if (ns > 1) run_phase(1, ns * ns, g0, gsz, ns);
-        // serial resolve of the survivor matrix (warp 0; lane w holds word w of the removed set)
-        if (warp == 0) {
-            unsigned int removed = 0u;
-            int k = nk;
-            for (int a = 0; a < ns; ++a) {
-                const unsigned int w = __shfl_sync(0xffffffffu, removed, a >> 5);
-                if ((w >> (a & 31)) & 1u) continue;
-                if (max_keep > 0 && k >= max_keep) break;
-                if (lane == 0) {
-                    const int t = surv[a];
-                    kept_idx[k] = g0 + t;
-                    kcirc[k] = gcirc[t];
-                    keep[k] = g0 + t;
-                }
-                ++k;
-                if (lane < GR_G / 32) removed |= msk[a * (GR_G / 32) + lane];
-            }
-            if (lane == 0) nk_s = k;
-        }
-        __syncthreads();
-        if (max_keep > 0 && nk_s >= max_keep) break;
     }
-    if (tid == 0) *num_keep = nk_s;
+    __syncthreads();
+    for (int t = tid; t < SUP_CAND; t += SUP_THREADS)
+        if (i0 + t < n_max) alive[i0 + t] = (t < gsz && supp[t] == 0) ? 1 : 0;
+}
+
+// ordered compaction of the alive flags (positions >= prefix) into idx; m = 0 when the keep list is already full
+__global__ void __launch_bounds__(1024) nms_compact_kernel(int n, const int* __restrict__ counts, int n_max, int prefix,
+                                                           int max_keep, const int* __restrict__ num_keep,
+                                                           const int* __restrict__ alive, int* __restrict__ idx,
+                                                           int* __restrict__ m_dev) {
+    const int f = blockIdx.x;
+    if (counts) { n = min(counts[f], n_max); num_keep += f; }
+    alive += (size_t)f * n_max;
+    idx += (size_t)f * n_max;
+    __shared__ int scan_s[33];
+    __shared__ int run;
+    if (threadIdx.x == 0) run = 0;
+    __syncthreads();
+    const bool full = max_keep > 0 && *num_keep >= max_keep;
+    if (!full) {
+        for (int i0 = prefix; i0 < n; i0 += 1024) {
+            const int i = i0 + threadIdx.x;
+            const int a = (i < n) ? alive[i] : 0;
+            int total;
+            const int ex = block_excl_scan(a, scan_s, &total);
+            if (a) idx[run + ex] = i;
+            __syncthreads();
+            if (threadIdx.x == 0) run += total;
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) m_dev[f] = run;
 }
 
 struct NmsWs {
     unsigned long long* maskT;
     RBox* rb;
     float4* circ;
+    int* alive;   // (B, rows_pad) survivor flags of the two-level path
+    int* idx;     // (B, rows_pad) compacted survivor indices
+    int* m_dev;   // (B) survivor counts
+    unsigned int* gq;   // global pair queue (null when n or B exceed its bit fields)
+    int* gq_count;      // two counters: level 1 / level 2
+    int gq_cap;
     int rows_pad;
 };
 
+size_t nms_gq_cap(int B, int n) {   // pairs; 0 = no global queue
+    if (B > 16 || n > 16384) return 0;
+    const size_t all = (size_t)B * n * n / 2;
+    return all < ((size_t)4 << 20) ? (all < 1024 ? 1024 : all) : ((size_t)4 << 20);
+}
+
 size_t nms_ws_bytes(int B, int n_max) {
     const size_t cb = (size_t)crb3d_divup(n_max > 0 ? n_max : 1, 64), nb = (size_t)(B > 0 ? B : 1);
-    return crb3d_align(8 * nb * cb * cb * 64) + crb3d_align(sizeof(RBox) * nb * cb * 64) + crb3d_align(16 * nb * cb * 64);
+    return crb3d_align(8 * nb * cb * cb * 64) + crb3d_align(sizeof(RBox) * nb * cb * 64) + crb3d_align(16 * nb * cb * 64) +
+           2 * crb3d_align(4 * nb * cb * 64) + crb3d_align(4 * nb) + crb3d_align(4 * nms_gq_cap((int)nb, (int)cb * 64)) + crb3d_align(8);
 }
 
 bool nms_ws_take(void* ws, size_t ws_bytes, int B, int n_max, NmsWs& w) {
@@ -442,52 +456,46 @@ bool nms_ws_take(void* ws, size_t ws_bytes, int B, int n_max, NmsWs& w) {
     w.maskT = c.take<unsigned long long>((size_t)B * cb * cb * 64);
     w.rb = c.take<RBox>((size_t)B * cb * 64);
     w.circ = c.take<float4>((size_t)B * cb * 64);
+    w.alive = c.take<int>((size_t)B * cb * 64);
+    w.idx = c.take<int>((size_t)B * cb * 64);
+    w.m_dev = c.take<int>((size_t)B);
+    w.gq_cap = (int)nms_gq_cap(B, w.rows_pad);
+    w.gq = c.take<unsigned int>((size_t)w.gq_cap);
+    w.gq_count = c.take<int>(2);
+    if (w.gq_cap == 0) w.gq = nullptr;
     return c.ok;
 }
 
-int launch_mask(const float* boxes, const int* counts, int B, int n, float thresh, int rotated, const NmsWs& w, cudaStream_t stream) {
-    const int cb = (int)crb3d_divup(n, 64);
-    const dim3 pg((unsigned)crb3d_divup(n, 256), B), mg((unsigned)crb3d_divup(cb, MASK_CW), cb, B);
-    if (rotated) {
-        nms_prep_kernel<true><<<pg, 256, 0, stream>>>(n, boxes, counts, n, w.rb, w.circ);
-        nms_mask_kernel<true><<<mg, MASK_THREADS, 0, stream>>>(n, thresh, boxes, w.rb, w.circ, w.maskT, w.rows_pad, counts, n);
-    } else {
-        nms_prep_kernel<false><<<pg, 256, 0, stream>>>(n, boxes, counts, n, w.rb, w.circ);
-        nms_mask_kernel<false><<<mg, MASK_THREADS, 0, stream>>>(n, thresh, boxes, w.rb, w.circ, w.maskT, w.rows_pad, counts, n);
+// level: prefix > 0 -> first `prefix` boxes; idx/m_dev -> survivors (second level); both 0/null -> all boxes
+int launch_mask(const float* boxes, const int* counts, int B, int n, float thresh, int rotated, const NmsWs& w, int prefix,
+                const int* idx, const int* m_dev, int level, cudaStream_t stream) {
+    const int cb = (int)crb3d_divup(prefix > 0 ? (prefix < n ? prefix : n) : n, 64);
+    const dim3 mg((unsigned)crb3d_divup(cb, MASK_CW), cb, B);
+    int* cnt = w.gq ? w.gq_count + level : nullptr;
+    if (rotated)
+        nms_mask_kernel<true><<<mg, MASK_THREADS, 0, stream>>>(n, thresh, boxes, w.rb, w.circ, w.maskT, w.rows_pad, counts, n, prefix, idx, m_dev, w.gq, cnt, w.gq_cap);
+    else
+        nms_mask_kernel<false><<<mg, MASK_THREADS, 0, stream>>>(n, thresh, boxes, w.rb, w.circ, w.maskT, w.rows_pad, counts, n, prefix, idx, m_dev, w.gq, cnt, w.gq_cap);
+    if (w.gq) {
+        if (rotated) nms_eval_kernel<true><<<CRB3D_NUM_SMS * 4, 256, 0, stream>>>(w.gq, cnt, w.gq_cap, thresh, boxes, w.rb, idx, n, w.maskT, w.rows_pad);
+        else nms_eval_kernel<false><<<CRB3D_NUM_SMS * 4, 256, 0, stream>>>(w.gq, cnt, w.gq_cap, thresh, boxes, w.rb, idx, n, w.maskT, w.rows_pad);
     }
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
 
-size_t greedy_smem(int kcap) {
-    return (size_t)GR_G * 16 + (size_t)kcap * 16 + (size_t)GR_QCAP * 4 + (size_t)GR_G * (GR_G / 32) * 4 + (size_t)GR_G * 8 + (size_t)kcap * 4;
+int launch_prep(const float* boxes, const int* counts, int B, int n, int rotated, const NmsWs& w, cudaStream_t stream) {
+    if (w.gq) CRB3D_CUDA(cudaMemsetAsync(w.gq_count, 0, 2 * sizeof(int), stream));
+    const dim3 pg((unsigned)crb3d_divup(n, 256), B);
+    if (rotated) nms_prep_kernel<true><<<pg, 256, 0, stream>>>(n, boxes, counts, n, w.rb, w.circ);
+    else nms_prep_kernel<false><<<pg, 256, 0, stream>>>(n, boxes, counts, n, w.rb, w.circ);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
 }
 
-int launch_nms(const float* boxes, const int* counts, int B, int n, float thresh, int rotated, int max_keep, long long* keep,
-               int keep_stride, int* num_keep, const NmsWs& w, cudaStream_t stream) {
+int launch_reduce(const int* counts, int B, int n, int max_keep, long long* keep, int keep_stride, int* num_keep, const NmsWs& w,
+                  int prefix, const int* idx, const int* m_dev, cudaStream_t stream) {
     const int kcap = max_keep > 0 ? (max_keep < n ? max_keep : n) : n;
-    if ((max_keep > 0 || n <= 2048) && greedy_smem(kcap) <= 200 * 1024) {
-        // kept-driven path: prep + one CTA per frame
-        const dim3 pg((unsigned)crb3d_divup(n, 256), B);
-        const size_t smem = greedy_smem(kcap);
-        static size_t smem_set[2] = {0, 0};
-        if (smem > smem_set[rotated ? 1 : 0]) {
-            if (rotated) CRB3D_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else CRB3D_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set[rotated ? 1 : 0] = smem;
-        }
-        if (rotated) {
-            nms_prep_kernel<true><<<pg, 256, 0, stream>>>(n, boxes, counts, n, w.rb, w.circ);
-            nms_greedy_kernel<true><<<B, GR_THREADS, smem, stream>>>(n, thresh, boxes, w.rb, w.circ, max_keep, keep, num_keep, counts, n, keep_stride, kcap);
-        } else {
-            nms_prep_kernel<false><<<pg, 256, 0, stream>>>(n, boxes, counts, n, w.rb, w.circ);
-            nms_greedy_kernel<false><<<B, GR_THREADS, smem, stream>>>(n, thresh, boxes, w.rb, w.circ, max_keep, keep, num_keep, counts, n, keep_stride, kcap);
-        }
-        CRB3D_CHECK_LAUNCH();
-        return CRB3D_OK;
-    }
-    int rc = launch_mask(boxes, counts, B, n, thresh, rotated, w, stream);
-    if (rc) return rc;
     const size_t list = sizeof(int) * (size_t)kcap + 16;
     const bool stream_mode = 16 * (size_t)w.rows_pad + list <= 200 * 1024;
     const size_t smem = (stream_mode ? 16 * (size_t)w.rows_pad : 0) + list;
@@ -499,11 +507,41 @@ int launch_nms(const float* boxes, const int* counts, int B, int n, float thresh
         smem_set[stream_mode] = smem;
     }
     if (stream_mode)
-        nms_reduce_kernel<true><<<B, REDUCE_THREADS, smem, stream>>>(n, w.rows_pad, w.maskT, max_keep, keep, num_keep, counts, n, keep_stride);
+        nms_reduce_kernel<true><<<B, REDUCE_THREADS, smem, stream>>>(n, w.rows_pad, w.maskT, max_keep, keep, num_keep, counts, n, keep_stride, prefix, idx, m_dev);
     else
-        nms_reduce_kernel<false><<<B, REDUCE_THREADS, smem, stream>>>(n, w.rows_pad, w.maskT, max_keep, keep, num_keep, counts, n, keep_stride);
+        nms_reduce_kernel<false><<<B, REDUCE_THREADS, smem, stream>>>(n, w.rows_pad, w.maskT, max_keep, keep, num_keep, counts, n, keep_stride, prefix, idx, m_dev);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
+}
+
+constexpr int NMS_PREFIX = 256;
+
+int launch_nms(const float* boxes, const int* counts, int B, int n, float thresh, int rotated, int max_keep, long long* keep,
+               int keep_stride, int* num_keep, const NmsWs& w, cudaStream_t stream) {
+    int rc = launch_prep(boxes, counts, B, n, rotated, w, stream);
+    if (rc) return rc;
+    if (n <= 2 * NMS_PREFIX) {   // short lists: one level
+        rc = launch_mask(boxes, counts, B, n, thresh, rotated, w, 0, nullptr, nullptr, 0, stream);
+        if (rc) return rc;
+        return launch_reduce(counts, B, n, max_keep, keep, keep_stride, num_keep, w, 0, nullptr, nullptr, stream);
+    }
+    // level 1: the first NMS_PREFIX boxes
+    rc = launch_mask(boxes, counts, B, n, thresh, rotated, w, NMS_PREFIX, nullptr, nullptr, 0, stream);
+    if (rc) return rc;
+    rc = launch_reduce(counts, B, n, max_keep, keep, keep_stride, num_keep, w, NMS_PREFIX, nullptr, nullptr, stream);
+    if (rc) return rc;
+    // every later box against the boxes kept so far, then the ordered list of survivors
+    const dim3 sg((unsigned)crb3d_divup(n - NMS_PREFIX, SUP_CAND), B);
+    if (rotated)
+        nms_suppress_kernel<true><<<sg, SUP_THREADS, 0, stream>>>(n, thresh, boxes, w.rb, w.circ, keep, num_keep, counts, n, keep_stride, NMS_PREFIX, w.alive);
+    else
+        nms_suppress_kernel<false><<<sg, SUP_THREADS, 0, stream>>>(n, thresh, boxes, w.rb, w.circ, keep, num_keep, counts, n, keep_stride, NMS_PREFIX, w.alive);
+    nms_compact_kernel<<<B, 1024, 0, stream>>>(n, counts, n, NMS_PREFIX, max_keep, num_keep, w.alive, w.idx, w.m_dev);
+    CRB3D_CHECK_LAUNCH();
+    // level 2: the survivors among themselves, appended to the keep list
+    rc = launch_mask(boxes, counts, B, n, thresh, rotated, w, 0, w.idx, w.m_dev, 1, stream);
+    if (rc) return rc;
+    return launch_reduce(counts, B, n, max_keep, keep, keep_stride, num_keep, w, 0, w.idx, w.m_dev, stream);
 }
 
 }  // namespace
@@ -541,7 +579,7 @@ extern "C" int crb3d_nms(const float* boxes, int n, float thresh, int rotated, i
     if (n == 0) { CRB3D_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int), stream)); return CRB3D_OK; }
     NmsWs w;
     if (!nms_ws_take(ws, ws_bytes, 1, n, w)) return CRB3D_ERR_WORKSPACE;
-    return launch_nms(boxes, nullptr, 1, n, thresh, rotated, max_keep, keep, 0, num_keep, w, stream);
+    return launch_nms(boxes, nullptr, 1, n, thresh, rotated, max_keep, keep, n, num_keep, w, stream);
 }
 
 // Raw suppression bitmask in the reference's row-major layout mask[n][ceil(n/64)] (cells on and above the diagonal
@@ -551,7 +589,9 @@ extern "C" int crb3d_nms_mask(const float* boxes, int n, float thresh, int rotat
     if (n <= 0 || !mask) return CRB3D_ERR_ARG;
     NmsWs w;
     if (!nms_ws_take(ws, ws_bytes, 1, n, w)) return CRB3D_ERR_WORKSPACE;
-    int rc = launch_mask(boxes, nullptr, 1, n, thresh, rotated, w, stream);
+    int rc = launch_prep(boxes, nullptr, 1, n, rotated, w, stream);
+    if (rc) return rc;
+    rc = launch_mask(boxes, nullptr, 1, n, thresh, rotated, w, 0, nullptr, nullptr, 0, stream);
     if (rc) return rc;
     const int cb = (int)crb3d_divup(n, 64);
     nms_mask_transpose_kernel<<<dim3((unsigned)crb3d_divup(n, 256), cb), 256, 0, stream>>>(n, cb, w.rows_pad, w.maskT, mask);

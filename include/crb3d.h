@@ -184,6 +184,12 @@ int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int cin, const 
  *      (B, H*W*A_loc, n_class | 7 | n_bins). spec: HOST pointer to the AnchorSpec struct of csrc/head.cu. */
 int crb3d_anchor_head_scores(const float* cls_preds, int64_t n_anchor_total, int n_class, float* score, int* label,
                              cudaStream_t stream);
+/* scores + labels of every anchor and, per frame, the anchors with score >= thresh sorted by descending score (ties:
+ * ascending index) cut at K <= 4096 - the front half of class_agnostic_nms (model_nms_utils.py:6-25) without a full top-k.
+ * cand (B, n_per_frame) uint64 and cand_count (B) are scratch; counts[b] = valid prefix of top_score/top_idx (B, K). */
+int crb3d_anchor_head_scores_topk(const float* cls_preds, int B, int64_t n_per_frame, int n_class, float thresh, int K,
+                                  float* score, int* label, unsigned long long* cand, int* cand_count, float* top_score,
+                                  long long* top_idx, int* counts, cudaStream_t stream);
 int crb3d_anchor_decode_select(const float* box_preds, const float* dir_preds, const long long* sel, int B, int K,
                                int64_t n_anchor_per_frame, const void* spec, float* out, cudaStream_t stream);
 int crb3d_gather_rows_f32(const float* src, const long long* idx, const int* valid, int B, int K, int64_t n_src,

@@ -23,7 +23,8 @@ def _check(out, ref, what):
 
 
 @pytest.mark.parametrize("M,K,N,relu", [(128 * 7 + 5, 128, 256, True), (1000, 256, 128, False), (35200, 512, 80, False),
-                                        (1, 32, 256, True), (129, 64, 80, True)])
+                                        (1, 32, 256, True), (129, 64, 80, True), (128 * 300 + 17, 256, 256, True),
+                                        (20000, 512, 256, False), (5000, 384, 128, True)])
 def test_bev_gemm_plain(cuda, M, K, N, relu):
     from crb3d import ops
     _fp32_reference_mode()
@@ -31,13 +32,19 @@ def test_bev_gemm_plain(cuda, M, K, N, relu):
     a = torch.randn(M, K, generator=g).to(cuda)
     w = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(cuda)
     b = torch.randn(N, generator=g).to(cuda)
-    out = torch.full((M, N + 8), -7.0, device=cuda)
-    ops.bev_gemm(a, w, b, relu, [(out[:, 4:], 0, N, N + 8)])
+    if N == 80:      # N = 80 is the dense-rows placement (row_stride == width)
+        out = torch.full((M, N), -7.0, device=cuda)
+        ops.bev_gemm(a, w, b, relu, [(out, 0, N, N)])
+        got = out
+    else:            # full rows inside a wider buffer: columns [4, 4+N) of an (M, N+8) tensor
+        out = torch.full((M, N + 8), -7.0, device=cuda)
+        ops.bev_gemm(a, w, b, relu, [(out[:, 4:], 0, N, N + 8)])
+        got = out[:, 4:4 + N]
+        assert float(out[:, :4].min()) == -7.0 and float(out[:, 4 + N:].max()) == -7.0   # nothing outside the segment is touched
     ref = a.double() @ w.double().t() + b.double()
     if relu:
         ref = ref.clamp_min(0)
-    _check(out[:, 4:4 + N], ref, "gemm")
-    assert float(out[:, :4].min()) == -7.0 and float(out[:, 4 + N:].max()) == -7.0   # nothing outside the segment is touched
+    _check(got, ref, "gemm")
 
 
 def test_bev_gemm_three_segments(cuda):
@@ -120,3 +127,27 @@ def test_bev_conv3x3_halo_tile(cuda, B, H, W, cin, cout):
     _check(out, ref, "conv3x3")
     lin = ops.bev_conv3x3(x, ops.pack_conv3x3_weight(w), None, False)
     _check(lin, torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), None, padding=1).permute(0, 2, 3, 1), "conv3x3 linear")
+
+
+@pytest.mark.parametrize("B,A,thr,k,shift", [(4, 211200, 0.1, 4096, 0.0), (2, 5000, 0.5, 4096, 4.0), (3, 30000, 0.2, 512, 0.0),
+                                             (1, 100, 0.9, 64, 0.0), (2, 70000, 0.6, 4096, 0.0), (2, 64, 0.0, 4096, 0.0)])
+def test_head_scores_topk(cuda, B, A, thr, k, shift):
+    """Fused score pass + candidate top-k == (score >= thr) then sort by (score desc, anchor index asc), cut at k - both
+    the few-candidates path and the radix-select path (more than k candidates); duplicates in the scores included."""
+    from crb3d import head_ops
+    g = torch.Generator(device="cpu").manual_seed(A + k)
+    cls = (torch.randn(B, A, 3, generator=g) * 2 - 3 + shift).to(cuda)
+    m = (A // 7) * 7
+    cls[:, 0:m:7] = cls[:, 1:m:7]                                   # exact score ties between different anchors
+    s, l, ts, ti, c = head_ops.anchor_head_scores_topk(cls, 3, B, thr, k)
+    s2, l2 = head_ops.anchor_head_scores(cls, 3)
+    assert torch.equal(s, s2) and torch.equal(l, l2)
+    sc = s.view(B, A).cpu().numpy()
+    for b in range(B):
+        cand = np.nonzero(sc[b] >= np.float32(thr))[0]
+        order = cand[np.lexsort((cand, -sc[b][cand].astype(np.float64)))][:k]
+        n = len(order)
+        assert int(c[b]) == n
+        assert np.array_equal(ti[b, :n].cpu().numpy(), order)
+        assert np.array_equal(ts[b, :n].cpu().numpy(), sc[b][order])
+        assert float(ts[b, n:].abs().sum()) == 0

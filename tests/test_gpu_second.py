@@ -180,6 +180,7 @@ def test_second_inference_plan_tf32_vs_exact(setup, cuda):
             rec = model.score_batch(pts, offs_t, 2, max(len(f) for f in frames))
         finally:
             model.backbone_2d._plan = None
+            model.dense_head._plan = None
             ops.SPCONV_TF32 = False
     for k in ("cls_preds", "box_preds", "dir_cls_preds"):
         a, b = fast[k].double(), exact[k].double()

@@ -86,6 +86,7 @@ def gemm_case(name, M, K, N, n_sub=1, up=0, in_hw=(0, 0), segs_w=None, ctot=None
 
 
 if __name__ == "__main__":
+    gemm_case("deconv1-contig", 4 * 200 * 176, 128, 256, ctot=256)
     gemm_case("deconv1", 4 * 200 * 176, 128, 256, ctot=512)
     gemm_case("deconv2", 4 * 100 * 88, 256, 256, n_sub=4, up=2, in_hw=(100, 88), ctot=512)
     gemm_case("heads", 4 * 200 * 176, 512, 80, segs_w=(18, 42, 12))
