@@ -40,8 +40,9 @@ def parse():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="launch the dense half eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--no-pipeline", action="store_true", help="one batch at a time on one stream (no geometry/feature overlap)")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the whole-step CUDA graph")
+    ap.add_argument("--half-graph", action="store_true", help="round-1 mode: only the dense half in a CUDA graph, geometry pipelined on a side stream")
+    ap.add_argument("--no-pipeline", action="store_true", help="(with --half-graph/--no-graph) one batch at a time on one stream")
     ap.add_argument("--exact-fp32", action="store_true", help="sparse convs on the exact-fp32 SIMT kernel instead of tcgen05 TF32")
     return ap.parse_args()
 
@@ -190,7 +191,10 @@ def run_own(args, rank, world, local_rank):
     staged = [ps.stage_host(b) for b in batches]
     resident = [ps.to_device(s) for s in staged]
     second.calibrate_head_bias(model, resident[0][0], resident[0][1], args.batch, target_fraction=0.004)
-    if not args.no_graph:   # BEV backbone + head + post-processing (static shapes) as one CUDA graph
+    full_graph = not args.no_graph and not args.half_graph
+    if full_graph:          # the WHOLE step (voxelize .. entropy) as one CUDA graph, every count device-side
+        model.enable_full_graph(args.batch, max_points_per_frame=max(s[2] for s in staged) + 1024)
+    elif not args.no_graph:  # BEV backbone + head + post-processing (static shapes) as one CUDA graph
         model.enable_cuda_graph(args.batch, max_points_per_frame=max(s[2] for s in staged) + 1024)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     nb = len(resident)
@@ -201,13 +205,18 @@ def run_own(args, rank, world, local_rank):
         torch.cuda.synchronize(device)
 
     # pair counts of every sparse-conv launch of every distinct batch (outside any timed region)
+    def dynamic_score(dev_batch):   # eager path with host-visible counts (the instrumented passes need per-launch hooks)
+        geom = model.geometry(dev_batch[0], dev_batch[1], dev_batch[1].numel() - 1)
+        return model.score_batch(dev_batch[0], dev_batch[1], dev_batch[1].numel() - 1, dev_batch[2], geom=geom)
+
     pair_records = []
     for b in range(nb):
         ops.PROFILE = {"mode": "pairs", "records": []}
-        ps.score_device(resident[b])
+        dynamic_score(resident[b])
         pair_records.append(ops.PROFILE["records"])
     ops.PROFILE = None
-    if args.no_pipeline:
+    serial = args.no_pipeline or full_graph
+    if serial:
         for i in range(args.warmup):
             ps.score_device(resident[i % nb])
     else:  # warm the side stream's allocator pool too: same code path as the timed region
@@ -219,7 +228,6 @@ def run_own(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ops.PROFILE = {"mode": "time", "records": []}
     k0 = _lib.LAUNCHES["kernels"]
     rec = None
     fill = [0]
@@ -230,7 +238,7 @@ def run_own(args, rank, world, local_rank):
 
     barrier()
     ev0.record()
-    if args.no_pipeline:
+    if serial:
         for i in range(args.steps):
             rec = ps.score_device(resident[i % nb])
             l2_flush()
@@ -244,10 +252,10 @@ def run_own(args, rank, world, local_rank):
     ev1.record()
     barrier()
     launches = _lib.LAUNCHES["kernels"] - k0
-    conv_events = ops.PROFILE["records"]
-    ops.PROFILE = None
     total_ms = ev0.elapsed_time(ev1)
-    step_ms = [total_ms / max(args.steps, 1)] * args.steps
+    overflow = False
+    if full_graph:
+        overflow = not bool((rec["counts"].cpu().numpy() <= np.asarray(model._full_graph["caps"])).all())
 
     # ---- timed region 2: end to end through the public API (pinned host -> device -> host record) --------------
     for i in range(min(args.warmup, 2)):
@@ -255,7 +263,12 @@ def run_own(args, rank, world, local_rank):
     barrier()
     e2e_t0 = time.perf_counter()
     outs = []
-    if args.no_pipeline:
+    if full_graph:      # H2D of the points into the static buffers, one graph launch, D2H of the record - all asynchronous
+        for i in range(args.steps):
+            outs.append(ps.fetch_async(model.full_graph_replay(staged[i % nb][0], staged[i % nb][1])))
+        torch.cuda.synchronize(device)
+        out = {k: v.numpy() for k, v in outs[-1].items() if k != "counts"}
+    elif args.no_pipeline:
         for i in range(args.steps):
             out = ps.score_host(staged[i % nb])
     else:
@@ -270,6 +283,15 @@ def run_own(args, rank, world, local_rank):
     h2d = int(np.mean([s[0].numel() * 4 + s[1].numel() * 4 for s in staged]))
     d2h = int(sum(v.nbytes for v in out.values()))
 
+    # ---- instrumented pass (outside both timed regions): per-launch events of the heaviest kernels, eager path
+    prof_records = {"mode": "time", "records": [], "conv2d": []}
+    ops.PROFILE = prof_records
+    for i in range(args.steps):
+        dynamic_score(resident[i % nb])
+        l2_flush()
+    ops.PROFILE = None
+    torch.cuda.synchronize(device)
+
     # max over ranks
     if world > 1:
         t = torch.tensor([total_ms, e2e_ms], device=device, dtype=torch.float64)
@@ -281,32 +303,58 @@ def run_own(args, rank, world, local_rank):
     value = frames_total / (total_ms / 1e3)
     e2e_value = frames_total / (e2e_ms / 1e3)
 
-    # ---- roofline of the dominant kernel family of this library: sparse-conv forward (HBM bound) ---------------
-    conv_ms = [a.elapsed_time(b) for a, b in conv_events]
-    per_step = len(pair_records[0])
-    alg_bytes = 0
-    for i in range(args.steps):
-        alg_bytes += sum(spconv_algorithmic_bytes(r) for r in pair_records[i % nb])
-    conv_total_ms = sum(conv_ms)
+    # ---- roofline: per-launch CUDA events of the two heaviest kernel families of this library --------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes / (conv_total_ms / 1e3) / 1e9 if conv_total_ms > 0 else 0.0
-    roofline = {"kernel": "spconv_fwd (12 sparse-conv launches per step, aggregated)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "launches_per_step": per_step,
-                "algorithmic_bytes_per_step": alg_bytes / max(args.steps, 1), "kernel_ms_per_step": conv_total_ms / max(args.steps, 1),
-                "share_of_step": conv_total_ms / max(sum(step_ms), 1e-9)}
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    step_ms_avg = total_ms / max(args.steps, 1)
+    # (a) sparse-conv forward, HBM bound: algorithmic bytes / time
+    conv_total_ms = sum(a.elapsed_time(b) for a, b in prof_records["records"])
+    alg_bytes = sum(sum(spconv_algorithmic_bytes(r) for r in pair_records[i % nb]) for i in range(args.steps))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sp_ach = alg_bytes / (conv_total_ms / 1e3) / 1e9 if conv_total_ms > 0 else 0.0
+    roof_sp = {"kernel": "spconv_fwd_tc / spconv_fwd_simt (12 sparse-conv launches per step, aggregated)", "bound": "hbm",
+               "achieved": sp_ach, "peak": hbm_peak,
+               "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+               "unit": "GB/s", "frac": sp_ach / hbm_peak, "traffic": traffic.get("spconv_fwd_bytes_per_step"),
+               "launches_per_step": len(pair_records[0]), "algorithmic_bytes_per_step": alg_bytes / max(args.steps, 1),
+               "kernel_ms_per_step": conv_total_ms / max(args.steps, 1),
+               "share_of_step": conv_total_ms / max(args.steps, 1) / step_ms_avg}
+    # (b) bev_conv3x3_tc, tensor bound: 2*9*C_in*C_out*pixels flops / time; TF32 peak = half the measured bf16 rate
+    c2 = prof_records["conv2d"]
+    c2_ms = sum(a.elapsed_time(b) for a, b, _ in c2)
+    c2_flops = sum(f for _, _, f in c2)
+    tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+    c2_ach = c2_flops / (c2_ms / 1e3) / 1e12 if c2_ms > 0 else 0.0
+    roof_c2 = {"kernel": "bev_conv3x3_tc (halo-tile tcgen05 TF32 conv, %d launches per step)" % (len(c2) // max(args.steps, 1)),
+               "bound": "tensor", "achieved": c2_ach, "peak": tf32_peak,
+               "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 = half the bf16 rate; of measured)" if peaks
+                               else "fallback 1400/2 TFLOP/s (of fallback)"),
+               "unit": "TFLOP/s", "frac": c2_ach / tf32_peak, "traffic": traffic.get("bev_conv3x3_bytes_per_launch"),
+               "launches_per_step": len(c2) // max(args.steps, 1), "flops_per_step": c2_flops / max(args.steps, 1),
+               "kernel_ms_per_step": c2_ms / max(args.steps, 1), "share_of_step": c2_ms / max(args.steps, 1) / step_ms_avg}
+    roofline, roofline2 = (roof_c2, roof_sp) if c2_ms > conv_total_ms else (roof_sp, roof_c2)
+    roofline["measured"] = roofline2["measured"] = ("CUDA events around every launch of the kernel on its launching stream during an "
+                                                    "instrumented eager pass of the same %d steps (the headline region replays one CUDA "
+                                                    "graph per step, which has no per-kernel events); L2 flushed between steps" % args.steps)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (sparse convs fp32 FFMA; dense BEV convs TF32 via cuDNN, the reference's PyTorch default)",
+            "dtype": ("f32 storage; tensor-core layers multiply in TF32 with fp32 accumulation (sparse convs, BEV convs, deblock/head "
+                      "GEMMs; cuDNN TF32 where it is used is the reference's PyTorch default); --exact-fp32 switches the sparse "
+                      "convs to fp32 FFMA") if not args.exact_fp32 else "f32 (sparse convs fp32 FFMA; BEV stack TF32)",
             "data": "synthetic", "config": workload_config(args.batch, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline}
+            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "roofline_secondary": roofline2}
+    line["config"]["graph"] = ("whole step = one CUDA graph (device-side counts); static capacities exceeded: %s" % overflow) if full_graph \
+        else ("dense half in a CUDA graph" if not args.no_graph else "eager")
 
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(model, frames, args.cpu_sample_frames)

@@ -20,18 +20,18 @@ SIGNATURES = {
                        c_size_t, P],
     "crb3d_point_to_voxel_cpu": [P, c_int64, c_int, c_int, P, P, P, c_int, c_int, P, P, P, P],
     "crb3d_subm_rulebook_workspace_bytes": [c_int, POINTER(c_size_t)],
-    "crb3d_subm_rulebook": [P, c_int, P, P, P, P, P, c_size_t, P],
+    "crb3d_subm_rulebook": [P, c_int, P, P, P, P, P, P, c_size_t, P],
     "crb3d_conv_out_shape": [P, P, P, P, P, P],
     "crb3d_sparse_rulebook_workspace_bytes": [c_int, P, POINTER(c_size_t)],
-    "crb3d_sparse_rulebook_coords": [P, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P, c_size_t, P],
-    "crb3d_sparse_rulebook_pairs": [P, c_int, c_int, P, P, P, P, P, P, c_int, P, P, P, c_size_t, P],
+    "crb3d_sparse_rulebook_coords": [P, c_int, P, c_int, P, P, P, P, P, P, P, c_int, P, P, c_size_t, P],
+    "crb3d_sparse_rulebook_pairs": [P, c_int, P, c_int, P, P, P, P, P, P, c_int, P, P, P, c_size_t, P],
     "crb3d_rulebook_compact_pairs_workspace_bytes": [c_int, c_int, POINTER(c_size_t)],
     "crb3d_rulebook_compact_pairs": [P, c_int, c_int, c_int, P, P, P, P, c_size_t, P],
-    "crb3d_spconv_forward_f32": [P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, P, P, P, c_int, P, P],
-    "crb3d_spconv_forward_tf32": [P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P],
+    "crb3d_spconv_forward_f32": [P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, P, P, P, c_int, P, P, P],
+    "crb3d_spconv_forward_tf32": [P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P],
     "crb3d_spconv_wgrad_workspace_bytes": [c_int, c_int, c_int, c_int, POINTER(c_size_t)],
     "crb3d_spconv_wgrad_f32": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_size_t, P],
-    "crb3d_sparse_to_dense": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P],
+    "crb3d_sparse_to_dense": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P],
     "crb3d_dense_to_sparse": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P],
     "crb3d_boxes_overlap_bev": [P, c_int, P, c_int, P, P],
     "crb3d_boxes_iou_bev": [P, c_int, P, c_int, P, P],

@@ -67,10 +67,11 @@ def _ws_bytes(fn, *args):
 
 # ----------------------------------------------------------------------------------------------- voxelize
 def voxelize(points, frame_offsets, batch_size, pc_range, voxel_size, max_pts, max_voxels, xyz_col=0, feat_col=0,
-             n_feat=None, want_voxels=False, want_mean=True):
+             n_feat=None, want_voxels=False, want_mean=True, sync=True):
     """Hard voxelization + MeanVFE. points (N, S) f32 CUDA; frame_offsets (B+1) int32 CUDA.
     Returns dict(mean (M,C), voxels (M,P,C) | None, coords (M,4) i32 [b,z,y,x], num_points (M), frame_voxel_offsets (B+1)).
-    One host sync (reads M)."""
+    One host sync (reads M) unless sync=False (capacity-sized outputs + device-side count, CUDA-graph capturable; rows of
+    `points` at or beyond frame_offsets[B] are ignored)."""
     _need_cuda(points, frame_offsets)
     points = _f32c(points)
     frame_offsets = _i32c(frame_offsets)
@@ -91,6 +92,9 @@ def voxelize(points, frame_offsets, batch_size, pc_range, voxel_size, max_pts, m
     _lib.call("crb3d_voxelize", _p(points), n, stride, xyz_col, feat_col, n_feat, _p(frame_offsets), batch_size,
               _F6(*pc_range), _F3(*voxel_size), _I3(*grid), max_pts, max_voxels, _p(mean), _p(voxels), _p(coords),
               _p(num), _p(voff), _p(ws), ws.numel(), _stream(dev))
+    if not sync:   # static mode: capacity-sized outputs, the voxel count stays on the device (frame_voxel_offsets[B])
+        return dict(mean=mean, voxels=voxels, coords=coords, num_points=num, frame_voxel_offsets=voff, grid_size=grid,
+                    n_dev=voff[batch_size:])
     m = int(voff[-1].item())
     return dict(mean=mean[:m] if mean is not None else None, voxels=voxels[:m] if voxels is not None else None,
                 coords=coords[:m], num_points=num[:m], frame_voxel_offsets=voff, grid_size=grid)
@@ -103,8 +107,9 @@ def conv_out_shape(in_shape, ksize, stride, padding, dilation=(1, 1, 1)):
     return [out[0], out[1], out[2]]
 
 
-def subm_rulebook(coords, spatial_shape, ksize, dilation=(1, 1, 1)):
-    """Neighbour table (K, n) int32 for a submanifold conv (output rows == input rows)."""
+def subm_rulebook(coords, spatial_shape, ksize, dilation=(1, 1, 1), n_dev=None):
+    """Neighbour table (K, n) int32 for a submanifold conv (output rows == input rows). n_dev: device int32 row count when
+    `coords` is a capacity-sized static buffer (rows beyond it are not written)."""
     _need_cuda(coords)
     coords = _i32c(coords)
     n = coords.shape[0]
@@ -112,7 +117,7 @@ def subm_rulebook(coords, spatial_shape, ksize, dilation=(1, 1, 1)):
     K = k[0] * k[1] * k[2]
     nbr = torch.empty((K, n), dtype=torch.int32, device=coords.device)
     ws = _ws(_ws_bytes("crb3d_subm_rulebook_workspace_bytes", n), coords.device)
-    _lib.call("crb3d_subm_rulebook", _p(coords), n, _i3(spatial_shape), k, _i3(dilation), _p(nbr), _p(ws), ws.numel(),
+    _lib.call("crb3d_subm_rulebook", _p(coords), n, _p(n_dev), _i3(spatial_shape), k, _i3(dilation), _p(nbr), _p(ws), ws.numel(),
               _stream(coords.device))
     return nbr
 
@@ -135,7 +140,7 @@ def sparse_rulebook(coords, batch_size, in_shape, ksize, stride, padding, dilati
     guess = max(1, min(cap, 2 * n_in + 1024))
     n_out_dev = torch.zeros(1, dtype=torch.int32, device=dev)
     out_coords = torch.empty((guess, 4), dtype=torch.int32, device=dev)
-    args = (_p(coords), n_in, batch_size, _i3(in_shape), _i3(out_shape), k, _i3(stride), _i3(padding), _i3(dilation))
+    args = (_p(coords), n_in, None, batch_size, _i3(in_shape), _i3(out_shape), k, _i3(stride), _i3(padding), _i3(dilation))
     _lib.call("crb3d_sparse_rulebook_coords", *args, _p(out_coords), guess, _p(n_out_dev), _p(ws), wsb, _stream(dev))
     n_out = int(n_out_dev.item())
     if n_out > guess:
@@ -146,6 +151,28 @@ def sparse_rulebook(coords, batch_size, in_shape, ksize, stride, padding, dilati
     nbr_t = torch.empty((K, n_in), dtype=torch.int32, device=dev) if want_transpose else None
     _lib.call("crb3d_sparse_rulebook_pairs", *args, n_out, _p(nbr), _p(nbr_t), _p(ws), wsb, _stream(dev))
     return out_coords, out_shape, nbr, nbr_t
+
+
+def sparse_rulebook_static(coords, n_in_dev, batch_size, in_shape, ksize, stride, padding, cap_out, dilation=(1, 1, 1)):
+    """Strided sparse conv rulebook without any host synchronisation (CUDA-graph capturable): `coords` (cap_in, 4) holds
+    n_in_dev[0] valid rows; returns (out_coords (cap_out, 4), out_shape, nbr (K, cap_out), n_out_dev (1,) int32 device).
+    n_out_dev is the TRUE count - if it exceeds cap_out the extra outputs were dropped (callers check it afterwards)."""
+    _need_cuda(coords, n_in_dev)
+    coords = _i32c(coords)
+    dev = coords.device
+    cap_in = coords.shape[0]
+    out_shape = conv_out_shape(in_shape, ksize, stride, padding, dilation)
+    k = _i3(ksize)
+    K = k[0] * k[1] * k[2]
+    wsb = _ws_bytes("crb3d_sparse_rulebook_workspace_bytes", batch_size, _i3(out_shape))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    n_out_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    out_coords = torch.zeros((cap_out, 4), dtype=torch.int32, device=dev)
+    nbr = torch.empty((K, cap_out), dtype=torch.int32, device=dev)
+    args = (_p(coords), cap_in, _p(n_in_dev), batch_size, _i3(in_shape), _i3(out_shape), k, _i3(stride), _i3(padding), _i3(dilation))
+    _lib.call("crb3d_sparse_rulebook_coords", *args, _p(out_coords), cap_out, _p(n_out_dev), _p(ws), wsb, _stream(dev))
+    _lib.call("crb3d_sparse_rulebook_pairs", *args, cap_out, _p(nbr), None, _p(ws), wsb, _stream(dev))
+    return out_coords, out_shape, nbr, n_out_dev
 
 
 def compact_pairs(nbr):
@@ -162,7 +189,7 @@ def compact_pairs(nbr):
 
 
 # ----------------------------------------------------------------------------------------------- sparse conv
-def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transpose=False, kmap=None, tf32=None):
+def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transpose=False, kmap=None, tf32=None, n_dev=None):
     """out[o] = sum_k feat[nbr[k][o]] @ W_k. weight: [C_out, (kz,ky,kx)|K, C_in] (spconv layout).
     transpose=True computes the input gradient: feat is dY (rows of the conv OUTPUT), nbr the transposed table."""
     _need_cuda(feat, nbr, weight)
@@ -179,6 +206,7 @@ def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transp
         cin, cout = cout_w, cin_w
         strides = (1, cin_w, K * cin_w)
     assert feat.shape[1] == cin, (feat.shape, cin)
+    # n_dev: device row count of a capacity-sized table; rows beyond it are left untouched (no consumer reads them)
     out = torch.empty((n_out, cout), dtype=torch.float32, device=feat.device)
     prof = PROFILE
     if prof is not None and prof["mode"] == "time":
@@ -194,11 +222,11 @@ def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transp
             w_tc = w_tc.permute(2, 1, 0).contiguous()
         _lib.call("crb3d_spconv_forward_tf32", _p(feat), feat.shape[0], _p(nbr), _p(w_tc), n_out, K, cin, cout, _p(kmap),
                   _p(_f32c(scale)) if scale is not None else None, _p(_f32c(shift)) if shift is not None else None,
-                  int(bool(relu)), _p(out), _stream(feat.device))
+                  int(bool(relu)), _p(out), _p(n_dev), _stream(feat.device))
     else:
         _lib.call("crb3d_spconv_forward_f32", _p(feat), _p(nbr), _p(weight), n_out, K, cin, cout, strides[0], strides[1],
                   strides[2], _p(kmap), _p(_f32c(scale)) if scale is not None else None,
-                  _p(_f32c(shift)) if shift is not None else None, int(bool(relu)), _p(out), _stream(feat.device))
+                  _p(_f32c(shift)) if shift is not None else None, int(bool(relu)), _p(out), _p(n_dev), _stream(feat.device))
     if prof is not None:
         if prof["mode"] == "time":
             e1.record(torch.cuda.current_stream(feat.device))
@@ -278,13 +306,21 @@ def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None, round_out=False):
     assert wpack.shape[2] * 16 == cin
     if out is None:
         out = torch.empty((B, H, W, cout), dtype=torch.float32, device=x_nhwc.device)
+    prof = PROFILE
+    timed = prof is not None and prof.get("mode") == "time" and "conv2d" in prof
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(x_nhwc.device))
     _lib.call("crb3d_bev_conv3x3_tf32", _p(x_nhwc), B, H, W, cin, _p(wpack), cout, _p(_f32c(bias)) if bias is not None else None,
               int(bool(relu)) | (2 if round_out else 0), _p(out), _stream(x_nhwc.device))
+    if timed:
+        e1.record(torch.cuda.current_stream(x_nhwc.device))
+        prof["conv2d"].append((e0, e1, 2.0 * 9 * cin * cout * B * H * W))
     return out
 
 
 # ----------------------------------------------------------------------------------------------- dense
-def sparse_to_dense(feat, coords, batch_size, spatial_shape, channels_last_bev=False, out=None):
+def sparse_to_dense(feat, coords, batch_size, spatial_shape, channels_last_bev=False, out=None, n_dev=None):
     """(B,C,D,H,W) dense tensor (reference .dense()); channels_last_bev=True returns (B,H,W,C*D) memory whose
     .permute(0,3,1,2) equals dense.view(B, C*D, H, W). `out`: optional preallocated destination (zero-filled here)."""
     _need_cuda(feat, coords)
@@ -297,7 +333,7 @@ def sparse_to_dense(feat, coords, batch_size, spatial_shape, channels_last_bev=F
         assert tuple(out.shape) == shape and out.is_contiguous() and out.dtype == torch.float32
     dense = out if out is not None else torch.empty(shape, dtype=torch.float32, device=feat.device)
     _lib.call("crb3d_sparse_to_dense", _p(feat), _p(coords), n, C, batch_size, D, H, W, int(channels_last_bev), 1,
-              _p(dense), _stream(feat.device))
+              _p(dense), _p(n_dev), _stream(feat.device))
     return dense
 
 

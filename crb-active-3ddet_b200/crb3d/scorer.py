@@ -41,8 +41,21 @@ class PoolScorer(object):
         return self.model.score_batch(pts, offs, offs.numel() - 1, mx)
 
     def score_host(self, staged):
-        """End-to-end call: pinned host points -> device -> kernels -> host record (numpy)."""
-        rec = self.score_device(self.to_device(staged))
+        """End-to-end call: pinned host points -> device -> kernels -> host record (numpy). With the whole-step CUDA
+        graph (SECONDNet.enable_full_graph) this is one H2D copy into the static buffers, one graph launch and one D2H of
+        the record; a batch that exceeds a static capacity is re-scored on the dynamic path."""
+        fg = getattr(self.model, "_full_graph", None)
+        if fg is not None and fg["B"] == staged[1].numel() - 1 and staged[0].shape[0] <= fg["cap"] and staged[2] <= fg["max_pts"]:
+            rec = self.model.full_graph_replay(staged[0], staged[1])
+            out = {k: rec[k].to("cpu", non_blocking=True) for k in RECORD_FIELDS + ("counts",)}
+            torch.cuda.current_stream(self.device).synchronize()
+            if bool((out["counts"].numpy() <= np.asarray(fg["caps"])).all()):
+                return {k: out[k].numpy() for k in RECORD_FIELDS}
+            dev = self.to_device(staged)   # capacity exceeded (never seen on KITTI-shaped clouds): dynamic path
+            geom = self.model.geometry(dev[0], dev[1], dev[1].numel() - 1)
+            rec = self.model.score_batch(dev[0], dev[1], dev[1].numel() - 1, dev[2], geom=geom)
+        else:
+            rec = self.score_device(self.to_device(staged))
         out = {k: rec[k].to("cpu", non_blocking=True) for k in RECORD_FIELDS}
         torch.cuda.current_stream(self.device).synchronize()
         return {k: v.numpy() for k, v in out.items()}
@@ -50,7 +63,7 @@ class PoolScorer(object):
     def fetch_async(self, rec):
         """Queues the D2H copy of the record fields into pinned host tensors on the current stream (no sync)."""
         out = {}
-        for k in RECORD_FIELDS:
+        for k in RECORD_FIELDS + (("counts",) if "counts" in rec else ()):
             out[k] = torch.empty(rec[k].shape, dtype=rec[k].dtype, pin_memory=True)
             out[k].copy_(rec[k], non_blocking=True)
         return out
@@ -123,11 +136,19 @@ class PoolScorer(object):
         world, rank = _world_rank()
         ids = list(range(len(frames))) if frame_ids is None else list(frame_ids)
         mine = shard_indices(len(frames), rank, world)
-        recs = []
+        recs, checks = [], []
+        fg = getattr(self.model, "_full_graph", None)
         for s in range(0, len(mine), self.batch_size):
             sel = mine[s:s + self.batch_size]
-            r = self.score_device(self.to_device(self.stage_host([frames[i] for i in sel])))
+            dev = self.to_device(self.stage_host([frames[i] for i in sel]))
+            r = self.score_device(dev)
             recs.append(self.record_tensor(r, sel))
+            if "counts" in r:                      # whole-step graph: remember the device-side counts of this batch
+                checks.append((len(recs) - 1, sel, dev, r["counts"].clone()))
+        for i, sel, dev, counts in checks:         # a static capacity was exceeded: re-score on the dynamic path
+            if not bool((counts.cpu().numpy() <= np.asarray(fg["caps"])).all()):
+                geom = self.model.geometry(dev[0], dev[1], dev[1].numel() - 1)
+                recs[i] = self.record_tensor(self.model.score_batch(dev[0], dev[1], dev[1].numel() - 1, dev[2], geom=geom), sel)
         local = torch.cat(recs) if recs else torch.zeros((0, 3 + 2 * self.P), device=self.device)
         out = gather_records(local, len(frames), self.P, self.device)
         return {ids[k]: v for k, v in out.items()}

@@ -430,6 +430,102 @@ class SECONDNet(nn.Module):
         self._graph = g
         return self
 
+    # ------------------------------------------------------------------------------------------- whole-step CUDA graph
+    def _sparse_layers(self):
+        """[(conv, bn, relu)] of the 3-D backbone in execution order (spconv_backbone.py:77-117)."""
+        layers = []
+        bb = self.backbone_3d
+        for seq in (bb.conv_input, bb.conv1, bb.conv2, bb.conv3, bb.conv4, bb.conv_out):
+            for m in seq.modules():
+                if isinstance(m, spconv.SparseConvolution):
+                    layers.append([m, None, False])
+                elif isinstance(m, nn.BatchNorm1d):
+                    layers[-1][1] = m
+                elif isinstance(m, nn.ReLU):
+                    layers[-1][2] = True
+        return layers
+
+    def _static_step(self, g):
+        """One whole scoring step on capacity-sized static buffers with DEVICE-side row counts: voxelize + MeanVFE, the 8
+        rulebooks, 12 sparse convs (BN + ReLU fused), dense(), BEV stack, head, top-k, NMS, density, entropy. No host
+        synchronisation anywhere, so the step is one CUDA graph (enable_full_graph). Counts that exceed their capacity
+        are reported in `counts` (true values) next to `caps`; the caller re-scores such a batch on the dynamic path."""
+        B = g["B"]
+        d = self.cfg["data"]
+        vox = ops.voxelize(g["points"], g["offsets"], B, d["pc_range"], d["voxel_size"], d["max_pts"], d["max_voxels_test"],
+                           xyz_col=0, feat_col=0, n_feat=d["n_feat"], sync=False)
+        feat, coords, n_dev = vox["mean"], vox["coords"], vox["n_dev"]
+        shape = list(self.backbone_3d.sparse_shape)
+        books, counts, caps = {}, [n_dev], [coords.shape[0]]
+        for conv, bn, relu in self._sparse_layers():
+            if conv.subm:
+                key = (conv.indice_key, tuple(conv.kernel_size))
+                if key not in books:
+                    books[key] = ops.subm_rulebook(coords, shape, conv.kernel_size, conv.dilation, n_dev=n_dev)
+                nbr = books[key]
+            else:
+                cap_out = int(min(B * np.prod(ops.conv_out_shape(shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)),
+                                  g["growth"][len(caps) - 1] * coords.shape[0]))
+                coords, shape, nbr, n_dev = ops.sparse_rulebook_static(coords, n_dev, B, shape, conv.kernel_size, conv.stride,
+                                                                       conv.padding, cap_out, conv.dilation)
+                counts.append(n_dev)
+                caps.append(cap_out)
+            scale, shift = spconv.SparseSequential._bn_affine(bn) if bn is not None else (None, None)
+            if conv.bias is not None:
+                shift = conv.bias if shift is None else shift + scale * conv.bias
+            feat = ops.spconv_forward(feat, nbr, conv.weight, scale=scale, shift=shift, relu=relu, n_dev=n_dev)
+        ops.sparse_to_dense(feat, coords, B, shape, channels_last_bev=True, out=g["spatial"], n_dev=n_dev)
+        out = self.dense_and_post(g["spatial"].permute(0, 3, 1, 2), g["points"], g["offsets"][:-1], g["offsets"][1:], B,
+                                  g["max_pts"])
+        out["counts"] = torch.cat(counts)
+        g["caps"] = caps
+        return out
+
+    @torch.no_grad()
+    def enable_full_graph(self, batch_size, max_points_per_frame=32768, growth=(2.0, 1.0, 1.0, 1.0)):
+        """Captures the WHOLE scoring step (_static_step) for a fixed batch size into one CUDA graph: every count stays on
+        the device, so one replay replaces ~250 kernel launches and 5 host synchronisations (the eager step is host-bound).
+        growth[i]: capacity of the i-th strided conv's output rows relative to its input capacity."""
+        dev = next(self.parameters()).device
+        d = self.cfg["data"]
+        C, (D, H, W) = self.backbone_3d.num_point_features, self.bev_shape()
+        g = dict(B=batch_size, cap=batch_size * max_points_per_frame, max_pts=max_points_per_frame, growth=list(growth))
+        g["spatial"] = torch.zeros((batch_size, H, W, C * D), device=dev)
+        g["points"] = torch.zeros((g["cap"], d["n_feat"]), device=dev)
+        g["offsets"] = torch.zeros((batch_size + 1,), dtype=torch.int32, device=dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):          # warm-up outside capture (cuDNN autotune, workspace allocations)
+            for _ in range(3):
+                self._static_step(g)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import _lib
+        k0 = _lib.LAUNCHES["kernels"]
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g["out"] = self._static_step(g)
+        g["kernels"] = _lib.LAUNCHES["kernels"] - k0      # kernels of libcrb3d_sm100 recorded in the graph (per replay)
+        g["graph"] = graph
+        self._full_graph = g
+        return self
+
+    def full_graph_replay(self, points, frame_offsets):
+        """Copies one batch into the static buffers and replays the whole-step graph. Returns the static output dict
+        (consume or copy it on the same stream before the next call); out["counts"] vs self._full_graph["caps"] tells
+        whether a capacity was exceeded."""
+        g = self._full_graph
+        n = points.shape[0]
+        if n > g["cap"] or frame_offsets.numel() != g["B"] + 1:
+            raise ValueError("batch does not fit the captured graph")
+        xyz_col = points.shape[1] - self.cfg["data"]["n_feat"]
+        g["points"][:n].copy_(points[:, xyz_col:], non_blocking=True)
+        g["offsets"].copy_(frame_offsets, non_blocking=True)
+        g["graph"].replay()
+        from . import _lib
+        _lib.LAUNCHES["kernels"] += g["kernels"]
+        return g["out"]
+
     def bev_shape(self):
         """(D, H, W) of the encoded sparse tensor (z: 41 -> 21 -> 11 -> 5 -> 2; y, x: /8)."""
         s = list(self.backbone_3d.sparse_shape)
@@ -444,6 +540,10 @@ class SECONDNet(nn.Module):
         dict(entropy (B,), num_boxes (B,), labels (B,P) int32 1-based (0 pad), density (B,P), boxes (B,P,7), scores (B,P)).
         With enable_cuda_graph() and a matching batch the returned tensors are the graph's static outputs: consume (or
         copy) them on the same stream before the next call."""
+        fg = getattr(self, "_full_graph", None)
+        if (geom is None and fg is not None and fg["B"] == batch_size and points.shape[0] <= fg["cap"]
+                and max_pts_per_frame <= fg["max_pts"]):
+            return self.full_graph_replay(points, frame_offsets)
         if geom is None:
             geom = self.geometry(points, frame_offsets, batch_size)
         bd = self.backbone_3d(dict(batch_size=batch_size, **geom))

@@ -11,7 +11,8 @@ namespace {
 
 template <bool GATHER>
 __global__ void __launch_bounds__(256) dense_kernel(const int* __restrict__ coords, int n, int C, int D, int H, int W,
-                                                    int layout, float* __restrict__ feat, float* __restrict__ dense) {
+                                                    int layout, float* __restrict__ feat, float* __restrict__ dense,
+                                                    const int* __restrict__ n_dev) {
     // warp = 32 consecutive rows of one channel for layout 0 (writes land on neighbouring x);
     // for layout 1 a warp covers 32 consecutive channels of one row.
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -19,6 +20,7 @@ __global__ void __launch_bounds__(256) dense_kernel(const int* __restrict__ coor
     int row, c;
     if (layout == 0) { row = (int)(t % n); c = (int)(t / n); }
     else { c = (int)(t % C); row = (int)(t / C); }
+    if (n_dev && row >= *n_dev) return;   // n is only the capacity of a static buffer
     const int4 q = __ldg(reinterpret_cast<const int4*>(coords) + row);
     size_t off;
     if (layout == 0) off = ((((size_t)q.x * C + c) * D + q.y) * H + q.z) * W + q.w;
@@ -30,12 +32,12 @@ __global__ void __launch_bounds__(256) dense_kernel(const int* __restrict__ coor
 }  // namespace
 
 extern "C" int crb3d_sparse_to_dense(const float* feat, const int* coords, int n, int C, int B, int D, int H, int W,
-                                     int layout, int zero_fill, float* dense, cudaStream_t stream) {
+                                     int layout, int zero_fill, float* dense, const int* n_dev, cudaStream_t stream) {
     if (n < 0 || C <= 0 || B <= 0 || D <= 0 || H <= 0 || W <= 0 || !dense || (layout != 0 && layout != 1)) return CRB3D_ERR_ARG;
     if (zero_fill) CRB3D_CUDA(cudaMemsetAsync(dense, 0, sizeof(float) * (size_t)B * C * D * H * W, stream));
     if (n == 0) return CRB3D_OK;
     dense_kernel<false><<<(unsigned)crb3d_divup((int64_t)n * C, 256), 256, 0, stream>>>(coords, n, C, D, H, W, layout,
-                                                                                       const_cast<float*>(feat), dense);
+                                                                                       const_cast<float*>(feat), dense, n_dev);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -45,7 +47,7 @@ extern "C" int crb3d_dense_to_sparse(const float* dense, const int* coords, int 
     if (n < 0 || C <= 0 || B <= 0 || !feat || (layout != 0 && layout != 1)) return CRB3D_ERR_ARG;
     if (n == 0) return CRB3D_OK;
     dense_kernel<true><<<(unsigned)crb3d_divup((int64_t)n * C, 256), 256, 0, stream>>>(coords, n, C, D, H, W, layout, feat,
-                                                                                      const_cast<float*>(dense));
+                                                                                      const_cast<float*>(dense), nullptr);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }

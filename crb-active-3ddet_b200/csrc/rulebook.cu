@@ -30,11 +30,13 @@ __device__ __forceinline__ unsigned long long lin_key(int b, int z, int y, int x
 }
 
 // ---------------------------------------------------------------- SubM ------------------------
+// n_dev (nullable): device-side row count - the host-side n is then only the capacity / row stride of the tables, so a
+// whole step can be recorded in a CUDA graph without reading any count back
 __global__ void __launch_bounds__(256) subm_insert(const int* __restrict__ coords, int n, ConvGeom g,
                                                    unsigned long long* __restrict__ keys, int* __restrict__ vals,
-                                                   uint32_t cap_mask) {
+                                                   uint32_t cap_mask, const int* __restrict__ n_dev) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || (n_dev && i >= *n_dev)) return;
     int4 c = reinterpret_cast<const int4*>(coords)[i];
     uint32_t s = hash_insert(keys, cap_mask, lin_key(c.x, c.y, c.z, c.w, g.in_shape));
     vals[s] = i;  // coordinates are unique (voxelizer / previous rulebook guarantee it)
@@ -44,10 +46,10 @@ __global__ void __launch_bounds__(256) subm_insert(const int* __restrict__ coord
 __global__ void __launch_bounds__(256) subm_lookup(const int* __restrict__ coords, int n, ConvGeom g,
                                                    const unsigned long long* __restrict__ keys,
                                                    const int* __restrict__ vals, uint32_t cap_mask,
-                                                   int* __restrict__ nbr) {
+                                                   int* __restrict__ nbr, const int* __restrict__ n_dev) {
     int o = blockIdx.x * blockDim.x + threadIdx.x;
     int k = blockIdx.y;
-    if (o >= n) return;
+    if (o >= n || (n_dev && o >= *n_dev)) return;
     int4 c = __ldg(reinterpret_cast<const int4*>(coords) + o);
     int kx = k % g.k[2], ky = (k / g.k[2]) % g.k[1], kz = k / (g.k[2] * g.k[1]);
     int z = c.y - g.p[0] + kz * g.d[0];
@@ -75,10 +77,10 @@ __device__ __forceinline__ bool out_coord(const ConvGeom& g, int4 c, int k, int&
 }
 
 __global__ void __launch_bounds__(256) sparse_mark(const int* __restrict__ coords, int n, ConvGeom g,
-                                                   unsigned int* __restrict__ bitmap) {
+                                                   unsigned int* __restrict__ bitmap, const int* __restrict__ n_dev) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int k = blockIdx.y;
-    if (i >= n) return;
+    if (i >= n || (n_dev && i >= *n_dev)) return;
     int4 c = __ldg(reinterpret_cast<const int4*>(coords) + i);
     int oz, oy, ox;
     if (!out_coord(g, c, k, oz, oy, ox)) return;
@@ -116,10 +118,11 @@ __global__ void __launch_bounds__(256) sparse_emit_coords(const unsigned int* __
 __global__ void __launch_bounds__(256) sparse_fill_pairs(const int* __restrict__ coords, int n, ConvGeom g,
                                                          const unsigned int* __restrict__ bitmap,
                                                          const int* __restrict__ rank, int n_out,
-                                                         int* __restrict__ nbr, int* __restrict__ nbr_t) {
+                                                         int* __restrict__ nbr, int* __restrict__ nbr_t,
+                                                         const int* __restrict__ n_dev) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int k = blockIdx.y;
-    if (i >= n) return;
+    if (i >= n || (n_dev && i >= *n_dev)) return;
     int4 c = __ldg(reinterpret_cast<const int4*>(coords) + i);
     int oz, oy, ox;
     int o = -1;
@@ -189,7 +192,7 @@ extern "C" int crb3d_subm_rulebook_workspace_bytes(int n, size_t* bytes) {
     return CRB3D_OK;
 }
 
-extern "C" int crb3d_subm_rulebook(const int* coords, int n, const int* spatial_shape3, const int* ksize3,
+extern "C" int crb3d_subm_rulebook(const int* coords, int n, const int* n_dev, const int* spatial_shape3, const int* ksize3,
                                    const int* dilation3, int* nbr, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (n < 0 || !spatial_shape3 || !ksize3 || (!nbr && n > 0)) return CRB3D_ERR_ARG;
     int pad[3];
@@ -207,8 +210,8 @@ extern "C" int crb3d_subm_rulebook(const int* coords, int n, const int* spatial_
     if (!c.ok) return CRB3D_ERR_WORKSPACE;
     CRB3D_CUDA(cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * cap, stream));
     const unsigned nb = (unsigned)crb3d_divup(n, 256);
-    subm_insert<<<nb, 256, 0, stream>>>(coords, n, g, keys, vals, cap - 1);
-    subm_lookup<<<dim3(nb, g.K), 256, 0, stream>>>(coords, n, g, keys, vals, cap - 1, nbr);
+    subm_insert<<<nb, 256, 0, stream>>>(coords, n, g, keys, vals, cap - 1, n_dev);
+    subm_lookup<<<dim3(nb, g.K), 256, 0, stream>>>(coords, n, g, keys, vals, cap - 1, nbr, n_dev);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -231,9 +234,11 @@ extern "C" int crb3d_sparse_rulebook_workspace_bytes(int batch_size, const int* 
     return CRB3D_OK;
 }
 
+// n_in_dev (nullable, both phases): device-side input row count; n_in is then the capacity of coords_in / stride of nbr_t,
+// and n_out of phase 2 the capacity of coords_out / stride of nbr (rows beyond the true counts are never written).
 // Phase 1: active output coordinates in ascending key order. Writes min(count, cap_out) rows of coords_out and the
 // true count to n_out_dev. The bitmap + ranks stay in `ws` for phase 2 (same ws, untouched in between).
-extern "C" int crb3d_sparse_rulebook_coords(const int* coords_in, int n_in, int batch_size, const int* in_shape3,
+extern "C" int crb3d_sparse_rulebook_coords(const int* coords_in, int n_in, const int* n_in_dev, int batch_size, const int* in_shape3,
                                             const int* out_shape3, const int* ksize3, const int* stride3,
                                             const int* pad3, const int* dilation3, int* coords_out, int cap_out,
                                             int* n_out_dev, void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -248,7 +253,7 @@ extern "C" int crb3d_sparse_rulebook_coords(const int* coords_in, int n_in, int 
     int* scan_ws = c.take<int>(crb3d_scan_ws_ints(nw));
     if (!c.ok) return CRB3D_ERR_WORKSPACE;
     CRB3D_CUDA(cudaMemsetAsync(bitmap, 0, sizeof(unsigned int) * nw, stream));
-    if (n_in > 0) sparse_mark<<<dim3((unsigned)crb3d_divup(n_in, 256), g.K), 256, 0, stream>>>(coords_in, n_in, g, bitmap);
+    if (n_in > 0) sparse_mark<<<dim3((unsigned)crb3d_divup(n_in, 256), g.K), 256, 0, stream>>>(coords_in, n_in, g, bitmap, n_in_dev);
     const unsigned nbw = (unsigned)crb3d_divup(nw, 256);
     bitmap_popc<<<nbw, 256, 0, stream>>>(bitmap, nw, rank);
     int rc = crb3d_scan_exclusive_i32(rank, rank, nw, scan_ws, n_out_dev, stream);
@@ -259,7 +264,7 @@ extern "C" int crb3d_sparse_rulebook_coords(const int* coords_in, int n_in, int 
 }
 
 // Phase 2: neighbour tables. nbr is [K][n_out], nbr_t (optional) is [K][n_in].
-extern "C" int crb3d_sparse_rulebook_pairs(const int* coords_in, int n_in, int batch_size, const int* in_shape3,
+extern "C" int crb3d_sparse_rulebook_pairs(const int* coords_in, int n_in, const int* n_in_dev, int batch_size, const int* in_shape3,
                                            const int* out_shape3, const int* ksize3, const int* stride3,
                                            const int* pad3, const int* dilation3, int n_out, int* nbr, int* nbr_t,
                                            void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -279,7 +284,7 @@ extern "C" int crb3d_sparse_rulebook_pairs(const int* coords_in, int n_in, int b
     CRB3D_CUDA(cudaMemsetAsync(nbr, 0xFF, sizeof(int) * (size_t)g.K * n_out, stream));
     if (n_in > 0)
         sparse_fill_pairs<<<dim3((unsigned)crb3d_divup(n_in, 256), g.K), 256, 0, stream>>>(coords_in, n_in, g, bitmap,
-                                                                                          rank, n_out, nbr, nbr_t);
+                                                                                          rank, n_out, nbr, nbr_t, n_in_dev);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }

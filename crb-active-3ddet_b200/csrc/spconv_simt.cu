@@ -23,7 +23,10 @@ __global__ void __launch_bounds__(THREADS) spconv_fwd_simt(const float* __restri
                                                            int cout, int w_k_stride, int w_co_stride, int w_ci_stride,
                                                            const int* __restrict__ kmap, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, int relu,
-                                                           float* __restrict__ out) {
+                                                           float* __restrict__ out, const int* __restrict__ n_dev) {
+    // n_dev (nullable): device-side row count; n_out is then only the capacity / row stride of the neighbour table
+    const int nv = n_dev ? min(n_out, *n_dev) : n_out;
+    if ((int)blockIdx.x * TM >= nv) return;
     extern __shared__ float smem[];
     constexpr int COUTP = 16 * RN + 1;
     float* As = smem;                   // [TM][CK + 4]
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(THREADS) spconv_fwd_simt(const float* __restri
         int my = -1;
         if (tid < TM) {
             int o = row0 + tid;
-            my = (o < n_out) ? __ldg(&nbr[(size_t)k * n_out + o]) : -1;
+            my = (o < nv) ? __ldg(&nbr[(size_t)k * n_out + o]) : -1;
             rows[tid] = my;
         }
         if (!__syncthreads_or(my >= 0)) continue;  // nobody in this tile has a neighbour at offset k
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(THREADS) spconv_fwd_simt(const float* __restri
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
         int o = row0 + ty * RM + r;
-        if (o >= n_out) continue;
+        if (o >= nv) continue;
 #pragma unroll
         for (int j = 0; j < RN; ++j) {
             int c = tx + 16 * j;
@@ -184,12 +187,12 @@ __global__ void __launch_bounds__(256) spconv_wgrad_reduce(const float* __restri
 template <int RN>
 int launch_fwd(const float* feat, const int* nbr, const float* weight, int n_out, int K, int cin, int cout,
                int w_k_stride, int w_co_stride, int w_ci_stride, const int* kmap, const float* scale, const float* shift,
-               int relu, float* out, cudaStream_t stream) {
+               int relu, float* out, const int* n_dev, cudaStream_t stream) {
     size_t smem = sizeof(float) * (TM * (CK + 4) + CK * (16 * RN + 1));
     auto kern = spconv_fwd_simt<RN>;
     if (smem > 48 * 1024) CRB3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)crb3d_divup(n_out, TM), THREADS, smem, stream>>>(feat, nbr, weight, n_out, K, cin, cout, w_k_stride,
-                                                                     w_co_stride, w_ci_stride, kmap, scale, shift, relu, out);
+                                                                     w_co_stride, w_ci_stride, kmap, scale, shift, relu, out, n_dev);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -200,18 +203,19 @@ int launch_fwd(const float* feat, const int* nbr, const float* weight, int n_out
 // weight element (co, k, ci) at co*w_co_stride + k*w_k_stride + ci*w_ci_stride.
 // forward: (K*cin, cin, 1) for the spconv layout [C_out, K, C_in]; input-gradient: call with cin<->cout swapped,
 // the transposed table and strides (1, cin, K*cin).
+// n_dev (device, optional): true row count when n_out is only the capacity / stride of a static neighbour table.
 // kmap (device, optional): offset k of the table uses weight slice kmap[k] (used to run dX of a SubM conv on the
 // forward table with flipped offsets).
 extern "C" int crb3d_spconv_forward_f32(const float* feat, const int* nbr, const float* weight, int n_out, int K,
                                         int cin, int cout, int64_t w_co_stride, int64_t w_k_stride, int64_t w_ci_stride,
                                         const int* kmap,
-                                        const float* scale, const float* shift, int relu, float* out,
+                                        const float* scale, const float* shift, int relu, float* out, const int* n_dev,
                                         cudaStream_t stream) {
     if (n_out < 0 || K <= 0 || cin <= 0 || cout <= 0 || !weight || !out) return CRB3D_ERR_ARG;
     if (n_out == 0) return CRB3D_OK;
     if (!feat || !nbr) return CRB3D_ERR_ARG;
     if (cout > 256) return CRB3D_ERR_UNSUPPORTED;
-#define ARGS feat, nbr, weight, n_out, K, cin, cout, (int)w_k_stride, (int)w_co_stride, (int)w_ci_stride, kmap, scale, shift, relu, out, stream
+#define ARGS feat, nbr, weight, n_out, K, cin, cout, (int)w_k_stride, (int)w_co_stride, (int)w_ci_stride, kmap, scale, shift, relu, out, n_dev, stream
     if (cout <= 16) return launch_fwd<1>(ARGS);
     if (cout <= 32) return launch_fwd<2>(ARGS);
     if (cout <= 64) return launch_fwd<4>(ARGS);

@@ -76,7 +76,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
                                                                    const int* __restrict__ nbr, int n_out, int K,
                                                                    const int* __restrict__ kmap, const float* __restrict__ scale,
                                                                    const float* __restrict__ shift, int relu,
-                                                                   float* __restrict__ out) {
+                                                                   float* __restrict__ out, const int* __restrict__ n_dev) {
+    // n_dev (nullable): device-side row count; n_out is then only the capacity / row stride of the neighbour table
+    const int nv = n_dev ? min(n_out, *n_dev) : n_out;
+    if ((int)blockIdx.x * TILE_M >= nv) return;   // uniform per CTA, before any barrier / TMEM allocation
     constexpr int A_BYTES = NKB * TILE_M * 128;
     constexpr int B_BYTES = NKB * COUT * 128;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
     for (int t = tid; t < K * TILE_M; t += THREADS) {
         const int k = t / TILE_M, r = t - k * TILE_M;
         const int o = row0 + r;
-        rows[k][r] = (o < n_out) ? __ldg(&nbr[(size_t)k * n_out + o]) : -1;
+        rows[k][r] = (o < nv) ? __ldg(&nbr[(size_t)k * n_out + o]) : -1;
     }
     asm volatile("fence.proxy.async.shared::cta;");  // the zero fill (generic proxy) precedes TMA writes / MMA reads
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            if (o < n_out) {
+            if (o < nv) {
                 float* dst = out + (size_t)o * COUT + c0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -313,7 +316,7 @@ int make_feature_map(const float* feat, int n_in, int cin, CUtensorMap* map) {
 
 template <int NKB, int COUT, int STAGES, int MIN_CTAS>
 int launch_tc(const float* feat, int n_in, const int* nbr, const float* weight, int n_out, int K, int cin, const int* kmap,
-              const float* scale, const float* shift, int relu, float* out, cudaStream_t stream) {
+              const float* scale, const float* shift, int relu, float* out, const int* n_dev, cudaStream_t stream) {
     constexpr size_t smem = (size_t)STAGES * (NKB * TILE_M * 128 + NKB * COUT * 128) + 1024;
     CUtensorMap wmap, fmap;
     int rc = make_weight_map(weight, K, cin, COUT, &wmap);
@@ -326,7 +329,7 @@ int launch_tc(const float* feat, int n_in, const int* nbr, const float* weight, 
         CRB3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    kern<<<(unsigned)crb3d_divup(n_out, TILE_M), THREADS, smem, stream>>>(fmap, wmap, nbr, n_out, K, kmap, scale, shift, relu, out);
+    kern<<<(unsigned)crb3d_divup(n_out, TILE_M), THREADS, smem, stream>>>(fmap, wmap, nbr, n_out, K, kmap, scale, shift, relu, out, n_dev);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -339,12 +342,12 @@ int launch_tc(const float* feat, int n_in, const int* nbr, const float* weight, 
 // Stage counts are sized so that two or three CTAs fit one SM: the co-resident CTAs hide each other's TMA round trips.
 extern "C" int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int* nbr, const float* weight, int n_out, int K,
                                          int cin, int cout, const int* kmap, const float* scale, const float* shift,
-                                         int relu, float* out, cudaStream_t stream) {
+                                         int relu, float* out, const int* n_dev, cudaStream_t stream) {
     if (n_out < 0 || n_in < 0 || K <= 0 || cin <= 0 || cout <= 0 || !weight || !out) return CRB3D_ERR_ARG;
     if (n_out == 0) return CRB3D_OK;
     if (!feat || !nbr || n_in == 0) return CRB3D_ERR_ARG;
     if (K > MAX_K || (cin != 16 && cin != 32 && cin != 64)) return CRB3D_ERR_UNSUPPORTED;
-#define TC_ARGS feat, n_in, nbr, weight, n_out, K, cin, kmap, scale, shift, relu, out, stream
+#define TC_ARGS feat, n_in, nbr, weight, n_out, K, cin, kmap, scale, shift, relu, out, n_dev, stream
     const int nkb = (cin + 31) / 32;
     if (nkb == 1) {                                        // stage = 16 KB + C_out*128 B
         if (cout == 16) return launch_tc<1, 16, 4, 2>(TC_ARGS);

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) vox_insert(const float* __restrict__ pts,
                                                   int* __restrict__ mins, int* __restrict__ pt_slot) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
+    if (p >= frame_off[P.batch_size]) { pt_slot[p] = -1; return; }   // rows of a capacity-sized buffer beyond the last frame
     const float* q = pts + p * P.pt_stride + P.xyz_col;
     int c[3];
     bool ok = true;

@@ -56,18 +56,21 @@ int crb3d_point_to_voxel_cpu(const float* pts, int64_t n, int stride, int n_feat
  * Neighbour table nbr[k][o] = input row feeding output row o through kernel offset k = (kz*KY+ky)*KX+kx, or -1.
  * shape / ksize / stride / pad / dilation arguments are HOST int[3] in (z,y,x) order. */
 int crb3d_subm_rulebook_workspace_bytes(int n, size_t* bytes);
-int crb3d_subm_rulebook(const int* coords, int n, const int* spatial_shape3, const int* ksize3, const int* dilation3,
-                        int* nbr, void* ws, size_t ws_bytes, cudaStream_t stream);
+/* n_dev / n_in_dev / n_out_dev style arguments (all nullable): DEVICE-side row counts. When given, the host-side n is only
+ * the capacity / row stride of the buffers, rows beyond the device count are neither read nor written, and a whole step
+ * can be recorded into one CUDA graph without reading any count back to the host. */
+int crb3d_subm_rulebook(const int* coords, int n, const int* n_dev, const int* spatial_shape3, const int* ksize3,
+                        const int* dilation3, int* nbr, void* ws, size_t ws_bytes, cudaStream_t stream);
 int crb3d_conv_out_shape(const int* in_shape3, const int* ksize3, const int* stride3, const int* pad3,
                          const int* dilation3, int* out_shape3);
 int crb3d_sparse_rulebook_workspace_bytes(int batch_size, const int* out_shape3, size_t* bytes);
 /* phase 1: active output coords in ascending linear (b,z,y,x) order; true count -> *n_out_dev (device int). */
-int crb3d_sparse_rulebook_coords(const int* coords_in, int n_in, int batch_size, const int* in_shape3,
+int crb3d_sparse_rulebook_coords(const int* coords_in, int n_in, const int* n_in_dev, int batch_size, const int* in_shape3,
                                  const int* out_shape3, const int* ksize3, const int* stride3, const int* pad3,
                                  const int* dilation3, int* coords_out, int cap_out, int* n_out_dev, void* ws,
                                  size_t ws_bytes, cudaStream_t stream);
 /* phase 2 (same ws, untouched since phase 1): nbr [K][n_out], nbr_t [K][n_in] (nullable). */
-int crb3d_sparse_rulebook_pairs(const int* coords_in, int n_in, int batch_size, const int* in_shape3,
+int crb3d_sparse_rulebook_pairs(const int* coords_in, int n_in, const int* n_in_dev, int batch_size, const int* in_shape3,
                                 const int* out_shape3, const int* ksize3, const int* stride3, const int* pad3,
                                 const int* dilation3, int n_out, int* nbr, int* nbr_t, void* ws, size_t ws_bytes,
                                 cudaStream_t stream);
@@ -85,13 +88,14 @@ int crb3d_rulebook_compact_pairs(const int* nbr, int K, int n_out, int pair_cap,
  * Input gradient = the same call with cin<->cout swapped, the transposed table and strides (1, cin, K*cin). */
 int crb3d_spconv_forward_f32(const float* feat, const int* nbr, const float* weight, int n_out, int K, int cin,
                              int cout, int64_t w_co_stride, int64_t w_k_stride, int64_t w_ci_stride, const int* kmap,
-                             const float* scale, const float* shift, int relu, float* out, cudaStream_t stream);
+                             const float* scale, const float* shift, int relu, float* out, const int* n_dev,
+                             cudaStream_t stream);
 /* tcgen05 path: TF32 inputs, fp32 accumulation in TMEM; feat (n_in, C_in) contiguous and 16-byte aligned (rows are
  * gathered by TMA); weight contiguous [C_out,K,C_in]; C_in in {16,32,64}, C_out in {16,32,64,128}, K <= 27, else
  * CRB3D_ERR_UNSUPPORTED (use the f32 entry point). */
 int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int* nbr, const float* weight, int n_out, int K, int cin,
                               int cout, const int* kmap, const float* scale, const float* shift, int relu, float* out,
-                              cudaStream_t stream);
+                              const int* n_dev, cudaStream_t stream);
 int crb3d_spconv_wgrad_workspace_bytes(int n_out, int K, int cin, int cout, size_t* bytes);
 int crb3d_spconv_wgrad_f32(const float* feat, const float* dout, const int* nbr, int n_out, int K, int cin, int cout,
                            int accumulate, float* dw, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -99,7 +103,7 @@ int crb3d_spconv_wgrad_f32(const float* feat, const float* dout, const int* nbr,
 /* ---- SparseConvTensor.dense() (height_compression.py:21-24) ------------------------------------------------
  * layout 0: (B,C,D,H,W); layout 1: (B,H,W,C*D) channels-last view of the BEV map. */
 int crb3d_sparse_to_dense(const float* feat, const int* coords, int n, int C, int B, int D, int H, int W, int layout,
-                          int zero_fill, float* dense, cudaStream_t stream);
+                          int zero_fill, float* dense, const int* n_dev, cudaStream_t stream);
 int crb3d_dense_to_sparse(const float* dense, const int* coords, int n, int C, int B, int D, int H, int W, int layout,
                           float* feat, cudaStream_t stream);
 

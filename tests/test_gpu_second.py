@@ -221,3 +221,37 @@ def test_cuda_graph_matches_eager(setup, cuda):
             model._graph = None
     for k in eager:
         assert torch.equal(eager[k], graphed[k]), k
+
+
+def test_full_graph_matches_eager(setup, cuda):
+    """The whole step recorded as ONE CUDA graph (capacity-sized static buffers, device-side counts) == the eager path with
+    host-visible counts, bit for bit - including a second, smaller batch replayed over the stale rows of the first one."""
+    from crb3d import synth
+    model, frames, pts, offs_t, anchors = setup
+    mx = max(len(f) for f in frames)
+    small = [synth.make_frame(7)[:9000], synth.make_frame(8)[:15000]]
+    offs2 = torch.from_numpy(np.cumsum([0] + [len(f) for f in small]).astype(np.int32)).to(cuda)
+    pts2 = torch.from_numpy(np.concatenate(small)).to(cuda)
+    keys = ("entropy", "num_boxes", "labels", "density", "boxes", "scores", "point_counts")
+    with torch.no_grad():
+        try:
+            model.prepare_inference(fold_bev_bn=True, spconv_tf32=True)
+            eager = []
+            for p, o, m in ((pts, offs_t, mx), (pts2, offs2, 15000)):
+                geom = model.geometry(p, o, 2)
+                eager.append({k: v.clone() for k, v in model.score_batch(p, o, 2, m, geom=geom).items()})
+            model.enable_full_graph(2, max_points_per_frame=mx + 100)
+            assert model._full_graph["kernels"] > 50
+            for rnd in range(2):
+                for (p, o, m), ref in zip(((pts, offs_t, mx), (pts2, offs2, 15000)), eager):
+                    out = model.score_batch(p, o, 2, m)           # routed to the graph
+                    assert "counts" in out
+                    assert bool((out["counts"].cpu().numpy() <= np.asarray(model._full_graph["caps"])).all())
+                    for k in keys:
+                        assert torch.equal(out[k], ref[k]), (rnd, k)
+        finally:
+            model._full_graph = None
+            model.backbone_2d._plan = None
+            model.dense_head._plan = None
+            from crb3d import ops
+            ops.SPCONV_TF32 = False
