@@ -456,24 +456,41 @@ class SECONDNet(nn.Module):
                            xyz_col=0, feat_col=0, n_feat=d["n_feat"], sync=False)
         feat, coords, n_dev = vox["mean"], vox["coords"], vox["n_dev"]
         shape = list(self.backbone_3d.sparse_shape)
-        books, counts, caps = {}, [n_dev], [coords.shape[0]]
-        for conv, bn, relu in self._sparse_layers():
-            if conv.subm:
-                key = (conv.indice_key, tuple(conv.kernel_size))
-                if key not in books:
-                    books[key] = ops.subm_rulebook(coords, shape, conv.kernel_size, conv.dilation, n_dev=n_dev)
-                nbr = books[key]
-            else:
-                cap_out = int(min(B * np.prod(ops.conv_out_shape(shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)),
-                                  g["growth"][len(caps) - 1] * coords.shape[0]))
-                coords, shape, nbr, n_dev = ops.sparse_rulebook_static(coords, n_dev, B, shape, conv.kernel_size, conv.stride,
-                                                                       conv.padding, cap_out, conv.dilation)
-                counts.append(n_dev)
-                caps.append(cap_out)
+        # geometry (8 rulebooks: dozens of small latency-bound kernels) runs on a forked branch of the graph, concurrently
+        # with the sparse convs of the earlier layers; each conv waits only for the event of ITS rulebook
+        main = torch.cuda.current_stream(g["points"].device)
+        side = g.setdefault("side", torch.cuda.Stream(g["points"].device))
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        books, counts, caps, plan = {}, [n_dev], [coords.shape[0]], []
+        with torch.cuda.stream(side):
+            for conv, bn, relu in self._sparse_layers():
+                if conv.subm:
+                    key = (conv.indice_key, tuple(conv.kernel_size))
+                    if key not in books:
+                        nbr = ops.subm_rulebook(coords, shape, conv.kernel_size, conv.dilation, n_dev=n_dev)
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        books[key] = (nbr, ev)
+                    nbr, ev = books[key]
+                else:
+                    cap_out = int(min(B * np.prod(ops.conv_out_shape(shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)),
+                                      g["growth"][len(caps) - 1] * coords.shape[0]))
+                    coords, shape, nbr, n_dev = ops.sparse_rulebook_static(coords, n_dev, B, shape, conv.kernel_size, conv.stride,
+                                                                           conv.padding, cap_out, conv.dilation)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    counts.append(n_dev)
+                    caps.append(cap_out)
+                plan.append((conv, bn, relu, nbr, n_dev, ev))
+        for conv, bn, relu, nbr, nd, ev in plan:
+            main.wait_event(ev)
             scale, shift = spconv.SparseSequential._bn_affine(bn) if bn is not None else (None, None)
             if conv.bias is not None:
                 shift = conv.bias if shift is None else shift + scale * conv.bias
-            feat = ops.spconv_forward(feat, nbr, conv.weight, scale=scale, shift=shift, relu=relu, n_dev=n_dev)
+            feat = ops.spconv_forward(feat, nbr, conv.weight, scale=scale, shift=shift, relu=relu, n_dev=nd)
+        n_dev = plan[-1][4]
         ops.sparse_to_dense(feat, coords, B, shape, channels_last_bev=True, out=g["spatial"], n_dev=n_dev)
         out = self.dense_and_post(g["spatial"].permute(0, 3, 1, 2), g["points"], g["offsets"][:-1], g["offsets"][1:], B,
                                   g["max_pts"])
