@@ -40,12 +40,25 @@ def build(force=False, verbose=True):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
 
+    # headers are shared: a source is recompiled when it, any header or the flags changed (per-object stamp files)
+    hh = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cuh", ".h")):
+            hh.update(open(os.path.join(CSRC, f), "rb").read())
+    hh.update(" ".join(ARCH + FLAGS).encode())
+    hdr_dig = hh.hexdigest()
+
     def compile_one(src):
         obj = os.path.join(objdir, src[:-3] + ".o")
+        d = hashlib.sha256(open(os.path.join(CSRC, src), "rb").read() + hdr_dig.encode()).hexdigest()
+        st = obj + ".digest"
+        if not force and os.path.exists(obj) and os.path.exists(st) and open(st).read() == d:
+            return obj
         cmd = [NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        open(st, "w").write(d)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:

@@ -110,33 +110,37 @@ __global__ void __launch_bounds__(192, 1) bev_conv3x3_tc(const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(128, N);
-            int sb = 0;
-            for (int kc = 0; kc < n_chunks; ++kc) {
-                const int buf = kc & 1;
-                mbar_wait(&full_a[buf], (kc >> 1) & 1);
-                for (int tap = 0; tap < 9; ++tap, ++sb) {
-                    const int stage = sb % NSTAGE_B;
-                    mbar_wait(&full_b[stage], (sb / NSTAGE_B) & 1);
-                    tc_fence_after();
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    const int ku = g.ku_is_ky ? ky : kx, kv = g.ku_is_ky ? kx : ky;
-                    const uint32_t a_off = (uint32_t)(kv * PU + ku) * 16;
-                    const uint32_t b_base = b_smem + stage * STAGE_B;
+        // whole warp, converged: only the tcgen05 instructions are predicated on one elected lane (see elect_one)
+        const uint32_t idesc = idesc_tf32(128, N);
+        const uint64_t desc_a0 = desc_nosw(a_smem, SLAB_A, PU * 16), desc_b0 = desc_nosw(b_smem, SLAB_B, 128);
+        int sb = 0;
+        for (int kc = 0; kc < n_chunks; ++kc) {
+            const int buf = kc & 1;
+            mbar_wait(&full_a[buf], (kc >> 1) & 1);
+            for (int tap = 0; tap < 9; ++tap, ++sb) {
+                const int stage = sb % NSTAGE_B;
+                mbar_wait(&full_b[stage], (sb / NSTAGE_B) & 1);
+                tc_fence_after();
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const int ku = g.ku_is_ky ? ky : kx, kv = g.ku_is_ky ? kx : ky;
+                // descriptors differ from the base ones only in the 14-bit start-address field (bytes >> 4)
+                const uint64_t da = desc_a0 + (uint64_t)((buf * CHUNK_A + (kv * PU + ku) * 16) >> 4);
+                const uint64_t db = desc_b0 + (uint64_t)((stage * STAGE_B) >> 4);
+                const uint32_t first = (kc > 0 || tap > 0) ? 1u : 0u;
+                if (elect_one()) {
 #pragma unroll
                     for (int t = 0; t < NT; ++t) {
-                        const uint32_t a_base = a_smem + buf * CHUNK_A + t * TILE_A + a_off;
 #pragma unroll
                         for (int j = 0; j < KC / 8; ++j)
-                            umma_tf32(tmem_base + t * N, desc_nosw(a_base + j * 2 * SLAB_A, SLAB_A, PU * 16),
-                                      desc_nosw(b_base + j * 2 * SLAB_B, SLAB_B, 128), idesc, (kc > 0 || tap > 0 || j > 0) ? 1u : 0u);
+                            umma_tf32(tmem_base + t * N, da + (uint64_t)((t * TILE_A + j * 2 * SLAB_A) >> 4),
+                                      db + (uint64_t)((j * 2 * SLAB_B) >> 4), idesc, (j > 0) ? 1u : first);
                     }
                     umma_commit(&empty_b[stage]);
+                    if (tap == 8) umma_commit(&empty_a[buf]);
+                    if (tap == 8 && kc == n_chunks - 1) umma_commit(&acc_bar);
                 }
-                umma_commit(&empty_a[buf]);
+                __syncwarp();
             }
-            umma_commit(&acc_bar);
         }
     } else {
         // ================================ epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =========================

@@ -15,7 +15,10 @@
 //       offsets into one TMEM tile, tcgen05.commit -> empty[stage] (and -> acc_full at the end).
 //   warps 2-5 (epilogue): tcgen05.ld 32 lanes x 32 columns, optional scale/shift/ReLU, one store per output row.
 // The output is written once, there are no atomics and the summation order is fixed (k ascending). No LSU gather at
-// all: an earlier cp.async version spent ~3000 cycles per stage just ISSUING 16-byte copies (tools/trace_spconv.py).
+// all: an earlier cp.async version spent ~3000 cycles per stage just ISSUING 16-byte copies (tools/trace_spconv.py), and
+// two later LSU variants (one thread per half row; cooperative 2-8 rows per LDGSTS) measured 65 us / 89 us on conv3.1
+// against 65 us for this TMA producer (profiles/r01_spconv_variants.txt) - the stage time is set by the latency of the
+// scattered 256-byte row fetches, not by who issues them.
 #include "common.cuh"
 #include <cuda.h>
 
@@ -188,27 +191,34 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
             }
             if (trace) trace[it * 4 + 1] = clock64();
         }
-    } else if (warp == PW && lane == 0) {
+    } else if (warp == PW) {
         // ================================ MMA issuer ================================
+        // the whole warp runs the loop converged and only the tcgen05 instructions are predicated on one elected lane:
+        // under `if (lane == 0)` every descriptor is a per-thread value that ptxas moves to the uniform register file
+        // before each UTCHMMA (issue + commit of a stage: 800 -> 500 cycles in tools/trace_spconv.py)
         const uint32_t idesc = make_idesc_tf32(TILE_M, COUT);
+        const uint64_t desc0 = make_desc_sw128(smem_base);
         for (int it = 0; it < n_act; ++it) {
             const int stage = it % STAGES;
             mbar_wait(&full_bar[stage], (it / STAGES) & 1);
-            long long* trace = (g_tc_trace && blockIdx.x == gridDim.x / 2) ? g_tc_trace : nullptr;
+            long long* trace = (g_tc_trace && blockIdx.x == gridDim.x / 2 && lane == 0) ? g_tc_trace : nullptr;
             if (trace) trace[it * 4 + 2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t a_base = smem_base + stage * STAGE_BYTES, b_base = a_base + A_BYTES;
+            const uint64_t da = desc0 + (uint64_t)((stage * STAGE_BYTES) >> 4), db = da + (uint64_t)(A_BYTES >> 4);
+            uint32_t elected;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+            if (elected) {
 #pragma unroll
-            for (int kb = 0; kb < NKB; ++kb) {
+                for (int kb = 0; kb < NKB; ++kb) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {  // 4 x (K = 8 floats = 32 bytes) per 128-byte swizzle row
-                    const uint64_t ad = make_desc_sw128(a_base + kb * (TILE_M * 128) + j * 32);
-                    const uint64_t bd = make_desc_sw128(b_base + kb * (COUT * 128) + j * 32);
-                    umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || kb > 0 || j > 0) ? 1u : 0u);
+                    for (int j = 0; j < 4; ++j)   // 4 x (K = 8 floats = 32 bytes) per 128-byte swizzle row
+                        umma_tf32(tmem_base, da + (uint64_t)((kb * (TILE_M * 128) + j * 32) >> 4),
+                                  db + (uint64_t)((kb * (COUT * 128) + j * 32) >> 4), idesc, (it > 0 || kb > 0 || j > 0) ? 1u : 0u);
                 }
+                umma_commit(&empty_bar[stage]);                   // frees the stage when these MMAs retire
+                if (it == n_act - 1) umma_commit(&acc_bar);       // accumulator complete
             }
-            umma_commit(&empty_bar[stage]);                   // frees the stage when these MMAs retire
-            if (it == n_act - 1) umma_commit(&acc_bar);       // accumulator complete
+            __syncwarp();
             if (trace) trace[it * 4 + 3] = clock64();
         }
     }

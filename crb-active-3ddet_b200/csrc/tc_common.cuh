@@ -73,6 +73,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
         "r"(accumulate));
 }
+// one lane of the (converged) warp; the MMA-issuing warps run their loops warp-uniformly and predicate only the
+// tcgen05 instructions on this, so that ptxas keeps descriptors / addresses in UNIFORM registers - a loop under
+// `if (lane == 0)` makes every operand a per-thread value that is moved to the uniform file (R2UR + stalls) before each
+// UTCHMMA, ~100 issue cycles per 64-cycle MMA (measured: 54 % tensor-pipe utilisation in bev_conv3x3_tc)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)));
 }
