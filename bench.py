@@ -142,7 +142,12 @@ def run_reference(args, rank, world):
     # same head-bias calibration as the GPU arm needs a forward; use the CPU oracle logits of one frame
     anchors = head_ops.anchors_tensor(model.dense_head.spec)
     frames = [synth.make_frame(i) for i in range(max(args.steps + args.warmup, 1))]
-    sd = model.state_dict()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    second_ref.CALIBRATE_BN = True      # CPU twin of second.calibrate_batchnorm, on the first batch of the GPU arm
+    try:
+        second_ref.score_frames(sd, model.cfg, [synth.make_frame(i) for i in range(args.batch)], anchors)
+    finally:
+        second_ref.CALIBRATE_BN = False
     _calibrate_cpu(sd, model, frames[0], anchors)
     for i in range(args.warmup):
         second_ref.score_frames(sd, model.cfg, [frames[i]], anchors)
@@ -153,7 +158,8 @@ def run_reference(args, rank, world):
     fps = args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.batch, args.gpus),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator and weight calibration as the own arm, done on the CPU)",
+            "config": workload_config(args.batch, args.gpus),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d steps x 1 frame (batch=1) of the same synthetic KITTI frames, torch threads=%d" % (args.steps, cores)},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -190,6 +196,7 @@ def run_own(args, rank, world, local_rank):
     ps = scorer.PoolScorer(model, device, args.batch)
     staged = [ps.stage_host(b) for b in batches]
     resident = [ps.to_device(s) for s in staged]
+    second.calibrate_batchnorm(model, resident[0][0], resident[0][1], args.batch)      # see the docstring: random init collapses
     second.calibrate_head_bias(model, resident[0][0], resident[0][1], args.batch, target_fraction=0.004)
     full_graph = not args.no_graph and not args.half_graph
     if full_graph:          # the WHOLE step (voxelize .. entropy) as one CUDA graph, every count device-side
@@ -350,7 +357,9 @@ def run_own(args, rank, world, local_rank):
             "dtype": ("f32 storage; tensor-core layers multiply in TF32 with fp32 accumulation (sparse convs, BEV convs, deblock/head "
                       "GEMMs; cuDNN TF32 where it is used is the reference's PyTorch default); --exact-fp32 switches the sparse "
                       "convs to fp32 FFMA") if not args.exact_fp32 else "f32 (sparse convs fp32 FFMA; BEV stack TF32)",
-            "data": "synthetic", "config": workload_config(args.batch, world),
+            "data": "synthetic (LiDAR-like clouds of SURVEY 8d; random-init SECOND weights with BatchNorm statistics taken from one "
+                    "synthetic batch and the class-head bias calibrated so that ~1 % of the anchors pass SCORE_THRESH)",
+            "config": workload_config(args.batch, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "roofline_secondary": roofline2}
     line["config"]["graph"] = ("whole step = one CUDA graph (device-side counts); static capacities exceeded: %s" % overflow) if full_graph \

@@ -88,7 +88,7 @@ def anchor_head_scores_topk(cls_preds, n_class, batch_size, thresh, k):
     score = torch.empty((B * A,), dtype=torch.float32, device=dev)
     label = torch.empty((B * A,), dtype=torch.int32, device=dev)
     cand = torch.empty((B, A), dtype=torch.int64, device=dev)
-    cand_count = torch.empty((B,), dtype=torch.int32, device=dev)
+    cand_count = torch.empty((B * 2049,), dtype=torch.int32, device=dev)   # counts + 2048-bin score histogram per frame
     top_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
     top_idx = torch.empty((B, k), dtype=torch.int64, device=dev)
     counts = torch.empty((B,), dtype=torch.int32, device=dev)

@@ -578,6 +578,35 @@ class SECONDNet(nn.Module):
                                    max_pts_per_frame)
 
 
+def calibrate_batchnorm(model, points, frame_offsets, batch_size):
+    """Synthetic weights only: sets every BatchNorm's running statistics to the statistics of one batch (one train-mode
+    forward with momentum 1). With the default init (running_mean 0, running_var 1) the activations of the 24 randomly
+    initialised layers decay geometrically (rms 1e-1 after conv1, 1e-10 at the head input on KITTI-shaped clouds), every
+    class logit equals its bias and all 211 200 anchors tie at one score - a degenerate workload for top-k and NMS. A
+    trained checkpoint carries real statistics; this gives the random model the same property."""
+    bns = [m for m in model.modules() if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d))]
+    old = [m.momentum for m in bns]
+    was_training = model.training
+    plan2d, planh = getattr(model.backbone_2d, "_plan", None), getattr(model.dense_head, "_plan", None)
+    model.backbone_2d._plan = None
+    model.dense_head._plan = None
+    try:
+        model.train()
+        for m in bns:
+            m.momentum = 1.0
+        with torch.no_grad():
+            model.forward_features(points, frame_offsets, batch_size)
+    finally:
+        for m, mo in zip(bns, old):
+            m.momentum = mo
+        model.train(was_training)
+    if plan2d is not None:
+        model.backbone_2d.build_inference_plan()
+    if planh is not None:
+        model.dense_head.build_inference_plan()
+    return model
+
+
 def calibrate_head_bias(model, points, frame_offsets, batch_size, target_fraction=0.03):
     """Synthetic weights only: the default conv_cls init (bias -log(99), anchor_head_single.py:37-38) yields no box
     above SCORE_THRESH, and with random features one class's logits dominate every anchor. Each class's logits are

@@ -9,6 +9,7 @@
 // Anchor layout (anchor_generator.py:18-62 + torch.cat(dim=-3) in generate_predicted_boxes): anchor index
 // a = ((y*nx + x)*n_class_sets + set)*n_rot + rot ; logits / box codes / dir bins are channels-last per location.
 #include "common.cuh"
+#include <string.h>
 
 #define CRB3D_MAX_ANCHOR_TYPES 16
 
@@ -47,10 +48,13 @@ __global__ void __launch_bounds__(256) head_scores_kernel(const float* __restric
 // launches); here the score pass itself appends the few thousand candidates as 64-bit keys (score bits << 32 | ~index:
 // descending key order = descending score, ties by ascending anchor index), and one CTA per frame selects the K largest
 // (only when more than K pass the threshold: MSD radix select, 11-bit digits) and bitonic-sorts them in shared memory.
+constexpr int TOPK_BINS = 2048;
+
 __global__ void __launch_bounds__(256) head_scores_cand_kernel(const float* __restrict__ cls, int64_t n_anchor_total, int n_class,
                                                                int64_t n_per_frame, float thresh, float* __restrict__ score,
                                                                int* __restrict__ label, unsigned long long* __restrict__ cand,
-                                                               int* __restrict__ cand_count) {
+                                                               int* __restrict__ cand_count, int* __restrict__ hist,
+                                                               unsigned int thresh_bits, int hshift) {
     // candidates are appended with ONE global atomic per (block, frame): a per-candidate atomicAdd on the frame counter
     // serialises at its L2 slice (measured 530 us for 4 x 60 k candidates)
     __shared__ int cnt[2], base[2];
@@ -79,6 +83,9 @@ __global__ void __launch_bounds__(256) head_scores_cand_kernel(const float* __re
             slot = f - f0;
             const unsigned int li = (unsigned int)(a - (int64_t)f * n_per_frame);
             key = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - li);
+            // coarse score histogram (monotone bins of the float bits above the threshold): lets the top-k kernel find its
+            // cut with ONE pass over the candidates instead of a multi-pass radix select
+            atomicAdd(&hist[(size_t)f * TOPK_BINS + min((int)((__float_as_uint(sc) - thresh_bits) >> hshift), TOPK_BINS - 1)], 1);
             if (n_per_frame < (int64_t)blockDim.x) {   // tiny frames: a block may span many of them - append directly
                 cand[(size_t)f * n_per_frame + atomicAdd(&cand_count[f], 1)] = key;
             } else {
@@ -99,9 +106,10 @@ constexpr int TOPK_THREADS = 1024;
 __global__ void __launch_bounds__(TOPK_THREADS) topk_sort_kernel(const unsigned long long* __restrict__ cand,
                                                                  const int* __restrict__ cand_count, int64_t n_per_frame, int K,
                                                                  float* __restrict__ top_score, long long* __restrict__ top_idx,
-                                                                 int* __restrict__ counts) {
+                                                                 int* __restrict__ counts, const int* __restrict__ ghist,
+                                                                 unsigned int thresh_bits, int hshift) {
     __shared__ unsigned long long keys[TOPK_MAX];
-    __shared__ unsigned int hist[2048];
+    __shared__ unsigned int hist[2048];               // generic path: digit histogram; fast path: boundary list (u64 x 1024)
     __shared__ int scan_s[33];
     __shared__ int d_s, need_s, cnt_s, nsel;
     const int f = blockIdx.x, tid = threadIdx.x;
@@ -112,9 +120,67 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_sort_kernel(const unsigned 
     for (int t = tid; t < TOPK_MAX; t += TOPK_THREADS) keys[t] = 0ull;
     if (tid == 0) nsel = 0;
     __syncthreads();
+    bool done_fast = false;
     if (nc <= K) {
         for (int t = tid; t < nc; t += TOPK_THREADS) keys[t] = src[t];
+        done_fast = true;
     } else {
+        // fast path: the score histogram filled by the score pass gives the boundary bin b (bins above it hold fewer
+        // than K candidates, together with b at least K); ONE pass over the candidates takes every key above b and
+        // collects the keys of b into a small list whose `need` largest complete the selection
+        const int* gh = ghist + (size_t)f * TOPK_BINS;
+        const int h0 = gh[2 * tid], h1 = gh[2 * tid + 1];
+        int total;
+        const int ex = block_excl_scan(h0 + h1, scan_s, &total);
+        const int above = total - ex - (h0 + h1);
+        if (above < K && above + h1 >= K) { d_s = 2 * tid + 1; need_s = K - above; cnt_s = h1; }
+        else if (above + h1 < K && above + h1 + h0 >= K) { d_s = 2 * tid; need_s = K - above - h1; cnt_s = h0; }
+        __syncthreads();
+        const int bbin = d_s, need = need_s, cnt_b = cnt_s;
+        constexpr int BCAP = 1024;
+        if (cnt_b <= BCAP) {
+            unsigned long long* bl = reinterpret_cast<unsigned long long*>(hist);
+            __shared__ int nb;
+            if (tid == 0) nb = 0;
+            for (int t = tid; t < BCAP; t += TOPK_THREADS) bl[t] = 0ull;
+            __syncthreads();
+            for (int t0 = 0; t0 < nc; t0 += 4 * TOPK_THREADS) {      // 4 independent loads in flight per thread
+                unsigned long long kk[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int t = t0 + u * TOPK_THREADS + tid; kk[u] = t < nc ? src[t] : 0ull; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (t0 + u * TOPK_THREADS + tid >= nc) continue;
+                    const int bin = min((int)(((unsigned int)(kk[u] >> 32) - thresh_bits) >> hshift), TOPK_BINS - 1);
+                    if (bin > bbin) { const int sl = atomicAdd(&nsel, 1); if (sl < TOPK_MAX) keys[sl] = kk[u]; }
+                    else if (bin == bbin) { const int sl = atomicAdd(&nb, 1); if (sl < BCAP) bl[sl] = kk[u]; }
+                }
+            }
+            __syncthreads();
+            int BP = 2;
+            while (BP < cnt_b) BP <<= 1;
+            for (int k = 2; k <= BP; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < BP; t += TOPK_THREADS) {
+                        const int u = t ^ j;
+                        if (u > t) {
+                            const unsigned long long a = bl[t], b = bl[u];
+                            if ((a < b) == ((t & k) == 0)) { bl[t] = b; bl[u] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            const int base = nsel;                     // == K - need
+            for (int t = tid; t < need; t += TOPK_THREADS) if (base + t < TOPK_MAX) keys[base + t] = bl[t];
+            done_fast = true;
+        }
+        __syncthreads();
+    }
+    if (!done_fast) {
+        if (tid == 0) nsel = 0;
+        for (int t = tid; t < TOPK_MAX; t += TOPK_THREADS) keys[t] = 0ull;
+        __syncthreads();
         // MSD radix select of the K largest keys (keys are unique): fix 11 (last pass: 9) bits per pass
         // bits shared by ALL keys are fixed up front (scores in [thresh, 1) share their exponent bits: without this the
         // first passes would pile every key into one or two histogram bins)
@@ -254,7 +320,7 @@ extern "C" int crb3d_anchor_head_scores(const float* cls_preds, int64_t n_anchor
 }
 
 // Scores + labels of every anchor AND the sorted top-K (K <= 4096) of the anchors with score >= thresh, per frame.
-// cand: (B, n_per_frame) uint64 scratch; cand_count: (B) int scratch (zeroed here); top_score/top_idx: (B, K), valid prefix
+// cand: (B, n_per_frame) uint64 scratch; cand_count: B * 2049 int scratch (zeroed here: counts + score histograms); top_score/top_idx: (B, K), valid prefix
 // = counts[b] = min(#candidates, K), the rest is 0.
 extern "C" int crb3d_anchor_head_scores_topk(const float* cls_preds, int B, int64_t n_per_frame, int n_class, float thresh, int K,
                                              float* score, int* label, unsigned long long* cand, int* cand_count,
@@ -264,10 +330,16 @@ extern "C" int crb3d_anchor_head_scores_topk(const float* cls_preds, int B, int6
         return CRB3D_ERR_ARG;
     if (K > TOPK_MAX || n_per_frame >= 0xFFFFFFFFll) return CRB3D_ERR_UNSUPPORTED;
     if (B == 0) return CRB3D_OK;
-    CRB3D_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int) * B, stream));
+    // cand_count scratch layout: [B] candidate counts, then [B][TOPK_BINS] score histograms
+    CRB3D_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)B * (1 + TOPK_BINS), stream));
+    int* hist = cand_count + B;
+    unsigned int tb, one;
+    { float t = thresh > 0.f ? thresh : 0.f, o = 1.0f; memcpy(&tb, &t, 4); memcpy(&one, &o, 4); }
+    int hshift = 0;
+    while (((one - tb) >> hshift) >= (unsigned int)TOPK_BINS) ++hshift;
     head_scores_cand_kernel<<<(unsigned)crb3d_divup((int64_t)B * n_per_frame, 256), 256, 0, stream>>>(
-        cls_preds, (int64_t)B * n_per_frame, n_class, n_per_frame, thresh, score, label, cand, cand_count);
-    topk_sort_kernel<<<B, TOPK_THREADS, 0, stream>>>(cand, cand_count, n_per_frame, K, top_score, top_idx, counts);
+        cls_preds, (int64_t)B * n_per_frame, n_class, n_per_frame, thresh, score, label, cand, cand_count, hist, tb, hshift);
+    topk_sort_kernel<<<B, TOPK_THREADS, 0, stream>>>(cand, cand_count, n_per_frame, K, top_score, top_idx, counts, hist, tb, hshift);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }

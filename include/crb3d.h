@@ -190,7 +190,7 @@ int crb3d_anchor_head_scores(const float* cls_preds, int64_t n_anchor_total, int
                              cudaStream_t stream);
 /* scores + labels of every anchor and, per frame, the anchors with score >= thresh sorted by descending score (ties:
  * ascending index) cut at K <= 4096 - the front half of class_agnostic_nms (model_nms_utils.py:6-25) without a full top-k.
- * cand (B, n_per_frame) uint64 and cand_count (B) are scratch; counts[b] = valid prefix of top_score/top_idx (B, K). */
+ * cand (B, n_per_frame) uint64 and cand_count (B * 2049 ints) are scratch; counts[b] = valid prefix of top_score/top_idx (B, K). */
 int crb3d_anchor_head_scores_topk(const float* cls_preds, int B, int64_t n_per_frame, int n_class, float thresh, int K,
                                   float* score, int* label, unsigned long long* cand, int* cand_count, float* top_score,
                                   long long* top_idx, int* counts, cudaStream_t stream);

@@ -31,9 +31,25 @@ BACKBONE_LAYERS = [
 ]
 
 
+# when True, every BatchNorm first overwrites its running statistics in `sd` with the statistics of its input (the CPU twin
+# of crb3d.second.calibrate_batchnorm: one train-mode forward with momentum 1), then normalises with them
+CALIBRATE_BN = False
+
+
 def _bn_eval(x, sd, prefix, eps=1e-3):
+    if CALIBRATE_BN:
+        sd[prefix + ".running_mean"] = x.mean(0)
+        sd[prefix + ".running_var"] = x.var(0, unbiased=True)
     w, b, rm, rv = (sd[prefix + s].float() for s in (".weight", ".bias", ".running_mean", ".running_var"))
     return (x - rm) / torch.sqrt(rv + eps) * w + b
+
+
+def _bn2d(x, sd, prefix):
+    if CALIBRATE_BN:
+        sd[prefix + ".running_mean"] = x.mean((0, 2, 3))
+        sd[prefix + ".running_var"] = x.var((0, 2, 3), unbiased=True)
+    return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"], sd[prefix + ".bias"],
+                        False, 0.0, 1e-3)
 
 
 def backbone3d(sd, feats, coords, batch_size, sparse_shape, collect=None):
@@ -63,15 +79,14 @@ def bev_head(sd, spatial, cfg):
     for i, (n_layers, stride) in enumerate(zip(cfg["layer_nums"], cfg["layer_strides"])):
         p = "backbone_2d.blocks.%d" % i
         x = F.conv2d(F.pad(x, (1, 1, 1, 1)), sd[p + ".1.weight"].float(), stride=stride)
-        x = torch.relu(F.batch_norm(x, sd[p + ".2.running_mean"], sd[p + ".2.running_var"], sd[p + ".2.weight"], sd[p + ".2.bias"], False, 0.0, 1e-3))
+        x = torch.relu(_bn2d(x, sd, p + ".2"))
         for k in range(n_layers):
             j = 4 + 3 * k
             x = F.conv2d(x, sd["%s.%d.weight" % (p, j)].float(), padding=1)
-            x = torch.relu(F.batch_norm(x, sd["%s.%d.running_mean" % (p, j + 1)], sd["%s.%d.running_var" % (p, j + 1)],
-                                        sd["%s.%d.weight" % (p, j + 1)], sd["%s.%d.bias" % (p, j + 1)], False, 0.0, 1e-3))
+            x = torch.relu(_bn2d(x, sd, "%s.%d" % (p, j + 1)))
         d = "backbone_2d.deblocks.%d" % i
         u = F.conv_transpose2d(x, sd[d + ".0.weight"].float(), stride=cfg["upsample_strides"][i])
-        ups.append(torch.relu(F.batch_norm(u, sd[d + ".1.running_mean"], sd[d + ".1.running_var"], sd[d + ".1.weight"], sd[d + ".1.bias"], False, 0.0, 1e-3)))
+        ups.append(torch.relu(_bn2d(u, sd, d + ".1")))
     x = torch.cat(ups, 1)
     B = x.shape[0]
     cls = F.conv2d(x, sd["dense_head.conv_cls.weight"], sd["dense_head.conv_cls.bias"]).permute(0, 2, 3, 1).reshape(B, -1, len(cfg["class_names"]))
@@ -102,7 +117,8 @@ def score_frames(sd, cfg, frames, anchors, collect=None, threads=None):
     if threads:
         torch.set_num_threads(threads)
     d = cfg["data"]
-    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    if not CALIBRATE_BN:      # (calibration writes the new statistics into the caller's dict)
+        sd = {k: v.detach().cpu() for k, v in sd.items()}
     B = len(frames)
     with torch.no_grad():
         feats, coords, _, _ = voxel.voxelize_batch(frames, d["pc_range"], d["voxel_size"], d["max_pts"], d["max_voxels_test"])

@@ -130,7 +130,8 @@ def test_bev_conv3x3_halo_tile(cuda, B, H, W, cin, cout):
 
 
 @pytest.mark.parametrize("B,A,thr,k,shift", [(4, 211200, 0.1, 4096, 0.0), (2, 5000, 0.5, 4096, 4.0), (3, 30000, 0.2, 512, 0.0),
-                                             (1, 100, 0.9, 64, 0.0), (2, 70000, 0.6, 4096, 0.0), (2, 64, 0.0, 4096, 0.0)])
+                                             (1, 100, 0.9, 64, 0.0), (2, 70000, 0.6, 4096, 0.0), (2, 64, 0.0, 4096, 0.0),
+                                             (2, 9000, 0.5, 4096, 30.0), (4, 211200, 0.1, 4096, 3.0)])
 def test_head_scores_topk(cuda, B, A, thr, k, shift):
     """Fused score pass + candidate top-k == (score >= thr) then sort by (score desc, anchor index asc), cut at k - both
     the few-candidates path and the radix-select path (more than k candidates); duplicates in the scores included."""
