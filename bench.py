@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the whole-step CUDA graph")
     ap.add_argument("--half-graph", action="store_true", help="round-1 mode: only the dense half in a CUDA graph, geometry pipelined on a side stream")
+    ap.add_argument("--slots", type=int, default=3, help="independent copies of the whole-step graph replayed on alternating streams")
     ap.add_argument("--no-pipeline", action="store_true", help="(with --half-graph/--no-graph) one batch at a time on one stream")
     ap.add_argument("--exact-fp32", action="store_true", help="sparse convs on the exact-fp32 SIMT kernel instead of tcgen05 TF32")
     return ap.parse_args()
@@ -200,7 +201,8 @@ def run_own(args, rank, world, local_rank):
     second.calibrate_head_bias(model, resident[0][0], resident[0][1], args.batch, target_fraction=0.004)
     full_graph = not args.no_graph and not args.half_graph
     if full_graph:          # the WHOLE step (voxelize .. entropy) as one CUDA graph, every count device-side
-        model.enable_full_graph(args.batch, max_points_per_frame=max(s[2] for s in staged) + 1024)
+        model.enable_full_graph(args.batch, max_points_per_frame=max(s[2] for s in staged) + 1024, slots=max(1, args.slots))
+        slot_streams = [torch.cuda.Stream(device) for _ in range(max(1, args.slots))]
     elif not args.no_graph:  # BEV backbone + head + post-processing (static shapes) as one CUDA graph
         model.enable_cuda_graph(args.batch, max_points_per_frame=max(s[2] for s in staged) + 1024)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
@@ -245,7 +247,18 @@ def run_own(args, rank, world, local_rank):
 
     barrier()
     ev0.record()
-    if serial:
+    if full_graph:      # consecutive batches alternate between the graph copies / streams; every step still flushes L2
+        main = torch.cuda.current_stream(device)
+        for st in slot_streams:
+            st.wait_stream(main)
+        for i in range(args.steps):
+            sl = i % len(slot_streams)
+            with torch.cuda.stream(slot_streams[sl]):
+                rec = model.full_graph_replay(resident[i % nb][0], resident[i % nb][1], slot=sl)
+                l2_flush()
+        for st in slot_streams:
+            main.wait_stream(st)
+    elif serial:
         for i in range(args.steps):
             rec = ps.score_device(resident[i % nb])
             l2_flush()
@@ -271,8 +284,13 @@ def run_own(args, rank, world, local_rank):
     e2e_t0 = time.perf_counter()
     outs = []
     if full_graph:      # H2D of the points into the static buffers, one graph launch, D2H of the record - all asynchronous
+        main = torch.cuda.current_stream(device)
+        for st in slot_streams:
+            st.wait_stream(main)
         for i in range(args.steps):
-            outs.append(ps.fetch_async(model.full_graph_replay(staged[i % nb][0], staged[i % nb][1])))
+            sl = i % len(slot_streams)
+            with torch.cuda.stream(slot_streams[sl]):
+                outs.append(ps.fetch_async(model.full_graph_replay(staged[i % nb][0], staged[i % nb][1], slot=sl)))
         torch.cuda.synchronize(device)
         out = {k: v.numpy() for k, v in outs[-1].items() if k != "counts"}
     elif args.no_pipeline:
@@ -362,7 +380,8 @@ def run_own(args, rank, world, local_rank):
             "config": workload_config(args.batch, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "roofline_secondary": roofline2}
-    line["config"]["graph"] = ("whole step = one CUDA graph (device-side counts); static capacities exceeded: %s" % overflow) if full_graph \
+    line["config"]["graph"] = ("whole step = one CUDA graph (device-side counts), %d copies replayed on alternating streams; static "
+                               "capacities exceeded: %s" % (max(1, args.slots), overflow)) if full_graph \
         else ("dense half in a CUDA graph" if not args.no_graph else "eager")
 
     if world == 1 and not args.no_cpu_baseline:

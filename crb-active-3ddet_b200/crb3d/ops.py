@@ -46,12 +46,13 @@ def _i32c(t):
 
 
 _WS = {}
+WS_TAG = None   # extra key: every captured copy of the whole-step graph owns its scratch (copies replay concurrently)
 
 
 def _ws(nbytes, device):
-    """Grow-only scratch buffer per (device, stream) from torch's caching allocator."""
+    """Grow-only scratch buffer per (device, stream, WS_TAG) from torch's caching allocator."""
     key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream)
+           torch.cuda.current_stream(device).cuda_stream, WS_TAG)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

@@ -452,6 +452,7 @@ class SECONDNet(nn.Module):
         are reported in `counts` (true values) next to `caps`; the caller re-scores such a batch on the dynamic path."""
         B = g["B"]
         d = self.cfg["data"]
+        ops.WS_TAG = id(g)       # scratch buffers private to this graph copy (see ops._ws); reset by the caller
         vox = ops.voxelize(g["points"], g["offsets"], B, d["pc_range"], d["voxel_size"], d["max_pts"], d["max_voxels_test"],
                            xyz_col=0, feat_col=0, n_feat=d["n_feat"], sync=False)
         feat, coords, n_dev = vox["mean"], vox["coords"], vox["n_dev"]
@@ -499,10 +500,21 @@ class SECONDNet(nn.Module):
         return out
 
     @torch.no_grad()
-    def enable_full_graph(self, batch_size, max_points_per_frame=32768, growth=(2.0, 1.0, 1.0, 1.0)):
+    def enable_full_graph(self, batch_size, max_points_per_frame=32768, growth=(2.0, 1.0, 1.0, 1.0), slots=1):
         """Captures the WHOLE scoring step (_static_step) for a fixed batch size into one CUDA graph: every count stays on
         the device, so one replay replaces ~250 kernel launches and 5 host synchronisations (the eager step is host-bound).
-        growth[i]: capacity of the i-th strided conv's output rows relative to its input capacity."""
+        growth[i]: capacity of the i-th strided conv's output rows relative to its input capacity.
+        slots > 1 captures that many independent copies (own static buffers): replayed on different streams, consecutive
+        batches overlap - the narrow tail of one step (greedy NMS pass, top-k sort, small rulebook kernels, ~10 % of the
+        step on a handful of SMs) runs under the wide kernels of the next one."""
+        if slots > 1:
+            copies = []
+            for _ in range(slots):
+                self.enable_full_graph(batch_size, max_points_per_frame, growth, slots=1)
+                copies.append(self._full_graph)
+            self._full_graphs = copies
+            self._full_graph = copies[0]
+            return self
         dev = next(self.parameters()).device
         d = self.cfg["data"]
         C, (D, H, W) = self.backbone_3d.num_point_features, self.bev_shape()
@@ -512,26 +524,30 @@ class SECONDNet(nn.Module):
         g["offsets"] = torch.zeros((batch_size + 1,), dtype=torch.int32, device=dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):          # warm-up outside capture (cuDNN autotune, workspace allocations)
-            for _ in range(3):
-                self._static_step(g)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        from . import _lib
-        k0 = _lib.LAUNCHES["kernels"]
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            g["out"] = self._static_step(g)
+        try:
+            with torch.cuda.stream(side):          # warm-up outside capture (cuDNN autotune, workspace allocations)
+                for _ in range(3):
+                    self._static_step(g)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            from . import _lib
+            k0 = _lib.LAUNCHES["kernels"]
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g["out"] = self._static_step(g)
+        finally:
+            ops.WS_TAG = None
         g["kernels"] = _lib.LAUNCHES["kernels"] - k0      # kernels of libcrb3d_sm100 recorded in the graph (per replay)
         g["graph"] = graph
         self._full_graph = g
+        self._full_graphs = [g]
         return self
 
-    def full_graph_replay(self, points, frame_offsets):
-        """Copies one batch into the static buffers and replays the whole-step graph. Returns the static output dict
-        (consume or copy it on the same stream before the next call); out["counts"] vs self._full_graph["caps"] tells
-        whether a capacity was exceeded."""
-        g = self._full_graph
+    def full_graph_replay(self, points, frame_offsets, slot=0):
+        """Copies one batch (device or pinned host tensors) into the static buffers of graph copy `slot` and replays it on
+        the current stream. Returns the static output dict (consume or copy it on the same stream before the next replay
+        of that slot); out["counts"] vs self._full_graph["caps"] tells whether a capacity was exceeded."""
+        g = self._full_graphs[slot]
         n = points.shape[0]
         if n > g["cap"] or frame_offsets.numel() != g["B"] + 1:
             raise ValueError("batch does not fit the captured graph")

@@ -249,8 +249,23 @@ def test_full_graph_matches_eager(setup, cuda):
                     assert bool((out["counts"].cpu().numpy() <= np.asarray(model._full_graph["caps"])).all())
                     for k in keys:
                         assert torch.equal(out[k], ref[k]), (rnd, k)
+            # two independent graph copies replayed CONCURRENTLY on two streams (own static buffers and scratch)
+            model.enable_full_graph(2, max_points_per_frame=mx + 100, slots=2)
+            streams = [torch.cuda.Stream(cuda), torch.cuda.Stream(cuda)]
+            torch.cuda.synchronize()
+            for rnd in range(3):
+                outs = []
+                for sl, (p, o) in enumerate(((pts, offs_t), (pts2, offs2))):
+                    with torch.cuda.stream(streams[sl]):
+                        r = model.full_graph_replay(p, o, slot=sl)
+                        outs.append({k: r[k].clone() for k in keys})
+                torch.cuda.synchronize()
+                for out, ref in zip(outs, eager):
+                    for k in keys:
+                        assert torch.equal(out[k], ref[k]), ("concurrent", rnd, k)
         finally:
             model._full_graph = None
+            model._full_graphs = None
             model.backbone_2d._plan = None
             model.dense_head._plan = None
             from crb3d import ops
