@@ -4,28 +4,28 @@
 //   pcdet/models/backbones_3d/spconv_backbone.py:77-117   (C_in >= 16 layers of VoxelBackBone8x)
 // Same contract as csrc/spconv_simt.cu:  out[o,:] = sum_k in[nbr[k][o],:] @ W[:,k,:]^T, W = [C_out, K, C_in].
 //
-// One CTA owns 128 consecutive output rows (the UMMA M). Six warps, mbarrier pipelined:
-//   warp 0 (producer): for every kernel offset k that has a neighbour in the tile, lane g gathers tile rows 4g..4g+3
-//       with ONE `cp.async.bulk.tensor.2d ... tile::gather4` per 32-channel block - the four row coordinates come
-//       straight from the neighbour table, an absent neighbour (-1) is out of bounds and is zero-filled by the TMA
-//       unit, the 128-byte swizzle of the UMMA K-major layout is applied by the hardware. The C_out x C_in weight
-//       slice is one 3-D TMA box. A 4-row group that has no neighbour now and had none when the stage was last used is
-//       skipped (the buffers start out zeroed), so ~85 % of the padded rows cost nothing.
-//   warp 1 (one lane): waits full[stage], issues C_in/8 tcgen05.mma (M=128, N=C_out, K=8, kind::tf32) accumulating ALL
-//       offsets into one TMEM tile, tcgen05.commit -> empty[stage] (and -> acc_full at the end).
-//   warps 2-5 (epilogue): tcgen05.ld 32 lanes x 32 columns, optional scale/shift/ReLU, one store per output row.
-// The output is written once, there are no atomics and the summation order is fixed (k ascending). No LSU gather at
-// all: an earlier cp.async version spent ~3000 cycles per stage just ISSUING 16-byte copies (tools/trace_spconv.py), and
-// two later LSU variants (one thread per half row; cooperative 2-8 rows per LDGSTS) measured 65 us / 89 us on conv3.1
-// against 65 us for this TMA producer (profiles/r01_spconv_variants.txt) - the stage time is set by the latency of the
-// scattered 256-byte row fetches, not by who issues them.
+// One CTA owns 128 consecutive output rows (the UMMA M). Nine warps, mbarrier pipelined:
+//   warps 0-7 (producers): threads 0..127 own one tile row each. For every kernel offset k that has a neighbour in the
+//       tile the owner reads its row's neighbour index from the table (prefetched one stage ahead) and appends the row to
+//       a shared-memory work list; all 256 producer threads then walk the list, one 16-byte cp.async per (row, chunk)
+//       into the 128B-swizzled K-major stage (`cp.async.mbarrier.arrive.noinc` signals full[stage]). A row without a
+//       neighbour costs nothing unless the stage's previous tenant left data there (one dirty bit per stage slot in the
+//       owner's register), in which case it is re-zeroed. One thread issues the C_out x C_in weight slice as a 3-D TMA box.
+//   warp 8 (converged, tcgen05 predicated on one elected lane): waits full[stage], issues C_in/8 tcgen05.mma (M=128,
+//       N=C_out, K=8, kind::tf32) accumulating ALL offsets into one TMEM tile, tcgen05.commit -> empty[stage].
+//   warps 0-3 again (epilogue): tcgen05.ld 32 lanes x 32 columns, optional scale/shift/ReLU, one store per output row.
+// The output is written once, there are no atomics and the summation order is fixed (k ascending). History of the row
+// path: one-warp cp.async (3000 cycles/stage of issue) -> TMA tile::gather4 (1400-2100 cycles/stage of issue + ~1500 in
+// the TMA unit, tools/trace_spconv.py) -> one thread per half row (half-empty sectors) -> per-warp cooperative loop
+// (serial latency) -> list-driven LSU gather -> two list-driven producer groups alternating over the stages (this file;
+// 553 -> 435 us over the 11 tensor-core layers of a batch-4 step, profiles/r01_spconv_variants.txt).
 #include "common.cuh"
 #include <cuda.h>
 
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int PW = 4;            // producer warps (also the epilogue warps)
+constexpr int PW = 8;            // producer warps; threads 0..127 additionally own one tile row each (warps 0..3 = epilogue)
 constexpr int THREADS = (PW + 1) * 32;
 constexpr int MAX_K = 27;
 
@@ -46,6 +46,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity));
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    // .ca: the copy goes through L1, which merges the 16 lanes that read one 256-byte row into two line requests; with .cg
+    // every 16-byte chunk is its own L2 request and the stage time is set by the request rate (~3 cycles per chunk per SM)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+// arrive on `bar` once all cp.async issued so far by this thread have completed (does not bump the pending count)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)));
 }
 
 // K-major, 128B-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
@@ -73,8 +86,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // NKB = ceil(C_in / 32) k-blocks (one 128-byte swizzle row holds 32 floats; C_in = 16 is zero-padded by the TMA unit).
+// STAGES must be even: stage slot it % STAGES is always written by producer group it % 2 (its dirty bits live there).
 template <int NKB, int COUT, int STAGES, int MIN_CTAS>
-__global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_constant__ CUtensorMap fmap,
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* __restrict__ feat, int cin,
                                                                    const __grid_constant__ CUtensorMap wmap,
                                                                    const int* __restrict__ nbr, int n_out, int K,
                                                                    const int* __restrict__ kmap, const float* __restrict__ scale,
@@ -89,8 +103,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
     constexpr int TMEM_COLS = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(16) int rows[MAX_K][TILE_M];
     __shared__ int act[MAX_K];
+    __shared__ int act_flag[MAX_K];
+    __shared__ unsigned int list_v[2][2][TILE_M], list_z[2][2][TILE_M];   // [group][double buffer][entries]: per-stage work lists
+    __shared__ int cnt_v[2][4], cnt_z[2][4];
     __shared__ int n_act_s;
     __shared__ uint64_t full_bar[STAGES];
     __shared__ uint64_t empty_bar[STAGES];
@@ -100,11 +116,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * TILE_M;
 
-    // ---- setup: barriers, TMEM, zeroed stages, neighbour rows of this tile for every offset
+    // ---- setup: barriers, TMEM, zeroed stages, which offsets have a neighbour in this tile
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], PW);  // one arrive.expect_tx per producer warp; the TMA unit completes the byte count
-            mbar_init(&empty_bar[s], 1);  // tcgen05.commit
+            mbar_init(&full_bar[s], TILE_M + 1);     // one arrival per producer thread + the weight box's expect_tx arrive
+            mbar_init(&empty_bar[s], 1);           // tcgen05.commit
         }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
@@ -117,62 +133,74 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
         float4* z = reinterpret_cast<float4*>(smem);
         for (int t = tid; t < STAGES * STAGE_BYTES / 16; t += THREADS) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int t = tid; t < K * TILE_M; t += THREADS) {
-        const int k = t / TILE_M, r = t - k * TILE_M;
-        const int o = row0 + r;
-        rows[k][r] = (o < nv) ? __ldg(&nbr[(size_t)k * n_out + o]) : -1;
+    if (warp < PW) {   // warp w scans offsets w, w + PW, ...: 128 table cells = one int4 per lane
+        for (int k = warp; k < K; k += PW) {
+            const int o = row0 + lane * 4;
+            int4 v = make_int4(-1, -1, -1, -1);
+            if (o + 3 < nv && ((((size_t)k * n_out + o) & 3) == 0)) v = __ldg(reinterpret_cast<const int4*>(nbr + (size_t)k * n_out + o));
+            else {
+                if (o < nv) v.x = __ldg(&nbr[(size_t)k * n_out + o]);
+                if (o + 1 < nv) v.y = __ldg(&nbr[(size_t)k * n_out + o + 1]);
+                if (o + 2 < nv) v.z = __ldg(&nbr[(size_t)k * n_out + o + 2]);
+                if (o + 3 < nv) v.w = __ldg(&nbr[(size_t)k * n_out + o + 3]);
+            }
+            const bool any = (v.x & v.y & v.z & v.w) >= 0;  // some entry is non-negative <=> the AND has a clear sign bit
+            const bool warp_any = __any_sync(0xffffffffu, any);
+            if (lane == 0) act_flag[k] = warp_any ? 1 : 0;
+        }
     }
-    asm volatile("fence.proxy.async.shared::cta;");  // the zero fill (generic proxy) precedes TMA writes / MMA reads
+    asm volatile("fence.proxy.async.shared::cta;");  // the zero fill (generic proxy) precedes the tensor core's reads
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = tmem_base_s;
-    // active offsets (warp 0 builds the compact list in ascending k: fixed summation order)
-    if (warp == 0) {
+    if (tid == 0) {   // compact list in ascending k: fixed summation order
+        for (int u = 0; u < 4; ++u) { cnt_v[0][u] = cnt_v[1][u] = 0; cnt_z[0][u] = cnt_z[1][u] = 0; }
         int n = 0;
-        for (int k = 0; k < K; ++k) {
-            const int4 v = reinterpret_cast<const int4*>(rows[k])[lane];
-            const bool any = (v.x & v.y & v.z & v.w) >= 0;  // some entry is non-negative <=> the AND has a clear sign bit
-            if (__any_sync(0xffffffffu, any)) { if (lane == 0) act[n] = k; ++n; }
-        }
-        if (lane == 0) n_act_s = n;
+        for (int k = 0; k < K; ++k)
+            if (act_flag[k]) act[n++] = k;
+        n_act_s = n;
     }
     __syncthreads();
     const int n_act = n_act_s;
     const uint32_t smem_base = smem_u32(smem);
 
     if (warp < PW) {
-        // ================================ producer warps: TMA gather4 + weight box ================================
-        // warp w, lane l < 32/PW owns the 4-row group g = l*PW + w (the per-thread TMA issue cost is spread over PW warps)
-        const int g = lane * PW + warp;
-        const bool owner = lane < 32 / PW;
-        for (int it = 0; it < n_act; ++it) {
-            const int stage = it % STAGES;
+        // ================================ producers: LSU gather (cp.async), no TMA on the row path =====================
+        // Threads 0..127 own one tile row each: per offset they read THEIR neighbour index straight from the table
+        // (prefetched one stage ahead) and append (row, source) to a shared-memory list when the row has a neighbour, or
+        // the row to a second list when it has none now but the stage's previous tenant left data there (one dirty bit
+        // per stage slot in the owner's register; the buffers start out zeroed). After one named barrier ALL 256 producer
+        // threads walk the lists: item i = (list entry i / chunks-per-row, 16-byte chunk i % chunks-per-row), one
+        // cp.async each (src-size 0 = zero fill for the second list). Consecutive lanes move consecutive chunks of a row,
+        // so every 32-byte sector that is fetched is used, the iterations are independent, and only the ~15-30 % of the
+        // (offset, row) slots that are occupied cost anything. Measured alternatives (profiles/r01_spconv_variants.txt):
+        // TMA tile::gather4 is bound by the TMA unit (~80 cycles per 4-row gather), one thread per half row issues
+        // half-empty sectors, a per-warp cooperative loop is bound by its own serial instruction latency.
+        // TWO producer groups (warps 0-3 / 4-7) alternate over the stages: `cp.async.mbarrier.arrive.noinc` holds the
+        // issuing thread until its copies have landed (measured: ~1500 cycles per stage), so one group would serialise
+        // issue and landing; with two, group g issues stage it+1 while group 1-g waits for stage it.
+        constexpr int NG = 2, GT = TILE_M;                // groups, threads per group (one row per thread)
+        const int grp = warp >> 2, gtid = tid & (GT - 1);
+        const int r = gtid;                               // tile row owned by this thread within its group
+        const int o = row0 + r;
+        const int cpr = cin >> 2;                         // 16-byte chunks per row (4, 8 or 16)
+        const int cshift = cpr == 16 ? 4 : (cpr == 8 ? 3 : 2);
+        uint32_t dirty = 0u;
+        int src_next = (grp < n_act && o < nv) ? __ldg(&nbr[(size_t)act[grp] * n_out + o]) : -1;
+        for (int it = grp, li = 0; it < n_act; it += NG, ++li) {
+            const int stage = it % STAGES, lb = li & 1;
+            const int src = src_next;
+            if (it + NG < n_act) src_next = (o < nv) ? __ldg(&nbr[(size_t)act[it + NG] * n_out + o]) : -1;
+            if (gtid == 0) { cnt_v[grp][(li + 2) & 3] = 0; cnt_z[grp][(li + 2) & 3] = 0; }
             if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1);
-            long long* trace = (g_tc_trace && blockIdx.x == gridDim.x / 2 && tid == 0) ? g_tc_trace + 128 : nullptr;
+            long long* trace = (g_tc_trace && blockIdx.x == gridDim.x / 2 && gtid == 0) ? g_tc_trace + 128 : nullptr;
             if (trace) trace[it * 4 + 0] = clock64();
-            const int k = act[it];
             const uint32_t a_base = smem_base + stage * STAGE_BYTES, b_base = a_base + A_BYTES;
-            const uint32_t bar = smem_u32(&full_bar[stage]);
-            int4 cur = make_int4(-1, -1, -1, -1);
-            bool need = false;
-            if (owner) {
-                cur = reinterpret_cast<const int4*>(rows[k])[g];
-                need = (cur.x & cur.y & cur.z & cur.w) >= 0;
-                if (!need && it >= STAGES) {  // stale data from the stage's previous tenant must be cleared
-                    const int4 prev = reinterpret_cast<const int4*>(rows[act[it - STAGES]])[g];
-                    need = (prev.x & prev.y & prev.z & prev.w) >= 0;
-                }
-            }
-            const unsigned int m = __ballot_sync(0xffffffffu, need);
-            if (lane == 0) {
-                uint32_t bytes = (uint32_t)__popc(m) * (uint32_t)(NKB * 512);
-                if (warp == 0) bytes += (uint32_t)B_BYTES;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes));
-            }
-            __syncwarp();
-            if (warp == PW - 1 && lane == 31) {   // an otherwise idle lane fetches the weight slice
-                const int kw = kmap ? kmap[k] : k;
+            if (gtid == GT - 1) {   // one thread of the group fetches the weight slice: one 3-D TMA box per k-block
+                const int kw = kmap ? kmap[act[it]] : act[it];
+                const uint32_t bar = smem_u32(&full_bar[stage]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)B_BYTES));
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb)
                     asm volatile(
@@ -180,22 +208,47 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
                         ::"r"(b_base + kb * (COUT * 128)), "l"(reinterpret_cast<uint64_t>(&wmap)), "r"(kb * 32), "r"(kw), "r"(0),
                         "r"(bar) : "memory");
             }
-            if (need) {
-#pragma unroll
-                for (int kb = 0; kb < NKB; ++kb)
-                    asm volatile(
-                        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
-                        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                        ::"r"(a_base + kb * (TILE_M * 128) + g * 512), "l"(reinterpret_cast<uint64_t>(&fmap)), "r"(kb * 32),
-                        "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w), "r"(bar) : "memory");
+            {
+                const bool valid = src >= 0;
+                const bool stale = !valid && (dirty & (1u << stage));
+                const unsigned int mv = __ballot_sync(0xffffffffu, valid), mz = __ballot_sync(0xffffffffu, stale);
+                if (valid) dirty |= 1u << stage; else dirty &= ~(1u << stage);
+                int bv = 0, bz = 0;
+                if (lane == 0) {
+                    if (mv) bv = atomicAdd(&cnt_v[grp][li & 3], __popc(mv));
+                    if (mz) bz = atomicAdd(&cnt_z[grp][li & 3], __popc(mz));
+                }
+                bv = __shfl_sync(0xffffffffu, bv, 0);
+                bz = __shfl_sync(0xffffffffu, bz, 0);
+                const unsigned int lt = (1u << lane) - 1u;
+                if (valid) list_v[grp][lb][bv + __popc(mv & lt)] = ((unsigned int)r << 25) | (unsigned int)src;
+                if (stale) list_z[grp][lb][bz + __popc(mz & lt)] = (unsigned int)r;
             }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GT));   // this group's lists are complete
+            if (trace) trace[it * 4 + 2] = clock64();
+            const int n_v = cnt_v[grp][li & 3] << cshift, n_z = cnt_z[grp][li & 3] << cshift;
+            for (int i = gtid; i < n_v; i += GT) {
+                const unsigned int e = list_v[grp][lb][i >> cshift];
+                const int row = (int)(e >> 25), c16 = i & (cpr - 1);
+                cp_async16(a_base + (row >> 3) * 1024 + (row & 7) * 128 + (c16 >> 3) * (TILE_M * 128) + (((c16 & 7) ^ (row & 7)) << 4),
+                           feat + (size_t)(e & 0x1FFFFFFu) * cin + c16 * 4);
+            }
+            if (n_z > 0) {   // stale rows: plain 16-byte zero stores (the LDGSTS path is the scarce resource) + proxy fence
+                for (int i = gtid; i < n_z; i += GT) {
+                    const int row = (int)list_z[grp][lb][i >> cshift], c16 = i & (cpr - 1);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(a_base + (row >> 3) * 1024 + (row & 7) * 128 + (c16 >> 3) * (TILE_M * 128) + (((c16 & 7) ^ (row & 7)) << 4)), "f"(0.0f));
+                }
+                asm volatile("fence.proxy.async.shared::cta;");
+            }
+            if (trace) trace[it * 4 + 3] = clock64();
+            cp_async_arrive(&full_bar[stage]);            // arrives when this thread's copies (if any) have landed
             if (trace) trace[it * 4 + 1] = clock64();
         }
     } else if (warp == PW) {
         // ================================ MMA issuer ================================
         // the whole warp runs the loop converged and only the tcgen05 instructions are predicated on one elected lane:
         // under `if (lane == 0)` every descriptor is a per-thread value that ptxas moves to the uniform register file
-        // before each UTCHMMA (issue + commit of a stage: 800 -> 500 cycles in tools/trace_spconv.py)
+        // before each UTCHMMA (~100 issue cycles per MMA, 800 cycles per stage in tools/trace_spconv.py)
         const uint32_t idesc = make_idesc_tf32(TILE_M, COUT);
         const uint64_t desc0 = make_desc_sw128(smem_base);
         for (int it = 0; it < n_act; ++it) {
@@ -203,6 +256,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const __grid_
             mbar_wait(&full_bar[stage], (it / STAGES) & 1);
             long long* trace = (g_tc_trace && blockIdx.x == gridDim.x / 2 && lane == 0) ? g_tc_trace : nullptr;
             if (trace) trace[it * 4 + 2] = clock64();
+            asm volatile("fence.proxy.async.shared::cta;");   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint64_t da = desc0 + (uint64_t)((stage * STAGE_BYTES) >> 4), db = da + (uint64_t)(A_BYTES >> 4);
             uint32_t elected;
@@ -309,29 +363,12 @@ int make_weight_map(const float* weight, int K, int cin, int cout, CUtensorMap* 
     return r == CUDA_SUCCESS ? CRB3D_OK : CRB3D_ERR_CUDA;
 }
 
-// 2-D view {ci, row} of the (n_in, C_in) feature matrix for tile::gather4: box {32, 1} (four rows are named per
-// instruction), 128-byte swizzle, out-of-bounds rows / columns read as zero (verified by tools/probe/gather4_probe.cu)
-int make_feature_map(const float* feat, int n_in, int cin, CUtensorMap* map) {
-    EncodeTiledFn enc = get_encode_fn();
-    if (!enc) return CRB3D_ERR_CUDA;
-    cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)n_in};
-    cuuint64_t strides[1] = {(cuuint64_t)cin * 4};
-    cuuint32_t box[2] = {32, 1};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(feat), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? CRB3D_OK : CRB3D_ERR_CUDA;
-}
-
 template <int NKB, int COUT, int STAGES, int MIN_CTAS>
 int launch_tc(const float* feat, int n_in, const int* nbr, const float* weight, int n_out, int K, int cin, const int* kmap,
               const float* scale, const float* shift, int relu, float* out, const int* n_dev, cudaStream_t stream) {
     constexpr size_t smem = (size_t)STAGES * (NKB * TILE_M * 128 + NKB * COUT * 128) + 1024;
-    CUtensorMap wmap, fmap;
+    CUtensorMap wmap;
     int rc = make_weight_map(weight, K, cin, COUT, &wmap);
-    if (rc) return rc;
-    rc = make_feature_map(feat, n_in, cin, &fmap);
     if (rc) return rc;
     auto kern = spconv_fwd_tc<NKB, COUT, STAGES, MIN_CTAS>;
     static bool attr_set = false;  // per instantiation; the attribute is per function (single-GPU processes)
@@ -339,7 +376,7 @@ int launch_tc(const float* feat, int n_in, const int* nbr, const float* weight, 
         CRB3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    kern<<<(unsigned)crb3d_divup(n_out, TILE_M), THREADS, smem, stream>>>(fmap, wmap, nbr, n_out, K, kmap, scale, shift, relu, out, n_dev);
+    kern<<<(unsigned)crb3d_divup(n_out, TILE_M), THREADS, smem, stream>>>(feat, cin, wmap, nbr, n_out, K, kmap, scale, shift, relu, out, n_dev);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -356,19 +393,19 @@ extern "C" int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int*
     if (n_out < 0 || n_in < 0 || K <= 0 || cin <= 0 || cout <= 0 || !weight || !out) return CRB3D_ERR_ARG;
     if (n_out == 0) return CRB3D_OK;
     if (!feat || !nbr || n_in == 0) return CRB3D_ERR_ARG;
-    if (K > MAX_K || (cin != 16 && cin != 32 && cin != 64)) return CRB3D_ERR_UNSUPPORTED;
+    if (K > MAX_K || (cin != 16 && cin != 32 && cin != 64) || n_in >= (1 << 25)) return CRB3D_ERR_UNSUPPORTED;
 #define TC_ARGS feat, n_in, nbr, weight, n_out, K, cin, kmap, scale, shift, relu, out, n_dev, stream
     const int nkb = (cin + 31) / 32;
     if (nkb == 1) {                                        // stage = 16 KB + C_out*128 B
         if (cout == 16) return launch_tc<1, 16, 4, 2>(TC_ARGS);
         if (cout == 32) return launch_tc<1, 32, 4, 2>(TC_ARGS);
         if (cout == 64) return launch_tc<1, 64, 4, 2>(TC_ARGS);
-        if (cout == 128) return launch_tc<1, 128, 3, 2>(TC_ARGS);
+        if (cout == 128) return launch_tc<1, 128, 2, 2>(TC_ARGS);
     } else if (nkb == 2) {                                 // stage = 32 KB + C_out*256 B
         if (cout == 16) return launch_tc<2, 16, 2, 2>(TC_ARGS);
         if (cout == 32) return launch_tc<2, 32, 2, 2>(TC_ARGS);
         if (cout == 64) return launch_tc<2, 64, 2, 2>(TC_ARGS);
-        if (cout == 128) return launch_tc<2, 128, 3, 1>(TC_ARGS);
+        if (cout == 128) return launch_tc<2, 128, 2, 1>(TC_ARGS);
     }
 #undef TC_ARGS
     return CRB3D_ERR_UNSUPPORTED;

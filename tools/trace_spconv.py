@@ -28,8 +28,8 @@ for key, cin, cout in (("subm3", 64, 64), ("subm1", 16, 16)):
     a, b = t[:128].reshape(32, 4), t[128:].reshape(32, 4)
     t0 = b[0, 0]
     print(key, cin, cout, "rows", d.nbr.shape[1])
-    print(" it | producer: stage free   TMA issued | mma: stage full   issued+committed")
+    print(" it | producer: stage free  lists+barrier  copies issued  arrive returned | mma: stage full   issued+committed")
     for it in range(27):
         if b[it, 0] == 0:
             break
-        print("%3d | %10d %12d | %10d %12d" % (it, b[it, 0] - t0, b[it, 1] - t0, a[it, 2] - t0, a[it, 3] - t0))
+        print("%3d | %10d %10d %10d %12d | %10d %12d" % (it, b[it, 0] - t0, b[it, 2] - t0, b[it, 3] - t0, b[it, 1] - t0, a[it, 2] - t0, a[it, 3] - t0))
