@@ -270,3 +270,35 @@ def test_full_graph_matches_eager(setup, cuda):
             model.dense_head._plan = None
             from crb3d import ops
             ops.SPCONV_TF32 = False
+
+
+def test_waymo_shaped_batch_graph_matches_eager(cuda):
+    """BASELINE configs[4] shapes (Waymo-synthetic: ~160 k points x 5 features per frame, 1504 x 1504 x 40 grid, 188 x 188 BEV
+    map - not a multiple of the 8 x 16 conv tile, batch 2): the whole-step graph equals the eager path bit for bit, the
+    static capacities hold, and boxes come out."""
+    from crb3d import second, synth
+    torch.manual_seed(0)
+    model = second.SECONDNet(second.WAYMO_SECOND_CFG).eval().to_device(cuda)
+    frames = [synth.make_frame(i, synth.WAYMO) for i in range(2)]
+    offs = torch.from_numpy(np.cumsum([0] + [len(f) for f in frames]).astype(np.int32)).to(cuda)
+    pts = torch.from_numpy(np.concatenate(frames)).to(cuda)
+    assert pts.shape[1] == 5 and pts.shape[0] > 250000
+    mx = max(len(f) for f in frames)
+    with torch.no_grad():
+        second.calibrate_batchnorm(model, pts, offs, 2)
+        model.prepare_inference(fold_bev_bn=True, spconv_tf32=True)
+        second.calibrate_head_bias(model, pts, offs, 2, target_fraction=0.004)
+        try:
+            geom = model.geometry(pts, offs, 2)
+            eager = {k: v.clone() for k, v in model.score_batch(pts, offs, 2, mx, geom=geom).items()}
+            model.enable_full_graph(2, max_points_per_frame=mx + 100)
+            out = model.score_batch(pts, offs, 2, mx)
+            assert bool((out["counts"].cpu().numpy() <= np.asarray(model._full_graph["caps"])).all())
+            for k in ("entropy", "num_boxes", "labels", "density", "boxes", "scores"):
+                assert torch.equal(out[k], eager[k]), k
+            assert int(out["num_boxes"].min()) > 5
+        finally:
+            from crb3d import ops
+            model._full_graph = None
+            model._full_graphs = None
+            ops.SPCONV_TF32 = False
