@@ -302,3 +302,34 @@ def test_waymo_shaped_batch_graph_matches_eager(cuda):
             model._full_graph = None
             model._full_graphs = None
             ops.SPCONV_TF32 = False
+
+
+def test_pool_scoring_graph_overflow_fallback_and_partial_batch(setup, cuda):
+    """PoolScorer over a 5-frame pool at batch 2 (the last batch is partial -> eager path) with the whole-step graph enabled,
+    once with generous capacities and once with capacities that are too small on purpose (every full batch overflows and
+    must be re-scored on the dynamic path): both equal the plain eager scoring of every frame."""
+    from crb3d import scorer, synth, ops
+    model, frames, pts, offs_t, anchors = setup
+    pool = [synth.make_frame(30 + i)[:: 2 + (i % 2)] for i in range(5)]
+    with torch.no_grad():
+        try:
+            model.prepare_inference(fold_bev_bn=True, spconv_tf32=True)
+            ps = scorer.PoolScorer(model, cuda, batch_size=2)
+            ref = ps.score_pool(pool)                                 # eager (no graph yet)
+            host_ref = ps.score_host(ps.stage_host(pool[:2]))
+            for growth in ((2.0, 1.0, 1.0, 1.0), (0.2, 0.2, 0.2, 0.2)):
+                model.enable_full_graph(2, max_points_per_frame=max(len(f) for f in pool) + 64, growth=growth)
+                got = ps.score_pool(pool)
+                assert sorted(got) == sorted(ref) == list(range(5))
+                for i in range(5):
+                    assert got[i]["entropy"] == ref[i]["entropy"], (growth, i)
+                    assert np.array_equal(got[i]["labels"], ref[i]["labels"]) and np.array_equal(got[i]["density"], ref[i]["density"])
+                host = ps.score_host(ps.stage_host(pool[:2]))
+                for k in host_ref:
+                    assert np.array_equal(host[k], host_ref[k]), (growth, k)
+        finally:
+            model._full_graph = None
+            model._full_graphs = None
+            model.backbone_2d._plan = None
+            model.dense_head._plan = None
+            ops.SPCONV_TF32 = False
