@@ -386,7 +386,8 @@ int launch_tc(const float* feat, int n_in, const int* nbr, const float* weight, 
 // TF32 tensor-core forward. feat: (n_in, C_in) contiguous; weight: contiguous [C_out, K, C_in] (for the input gradient
 // pass the transposed weight [C_in, K, C_out] and the transposed table). Supported: C_in in {16, 32, 64}, C_out in
 // {16, 32, 64, 128}, K <= 27; anything else returns CRB3D_ERR_UNSUPPORTED (callers use crb3d_spconv_forward_f32).
-// Stage counts are sized so that two or three CTAs fit one SM: the co-resident CTAs hide each other's TMA round trips.
+// Stage counts are sized so that two (C_in = 64) or three (C_in <= 32) CTAs fit one SM: the gather is latency-bound and
+// the co-resident CTAs hide each other's round trips (profiles/r01_spconv_variants.txt, variant G).
 extern "C" int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int* nbr, const float* weight, int n_out, int K,
                                          int cin, int cout, const int* kmap, const float* scale, const float* shift,
                                          int relu, float* out, const int* n_dev, cudaStream_t stream) {
@@ -397,9 +398,9 @@ extern "C" int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int*
 #define TC_ARGS feat, n_in, nbr, weight, n_out, K, cin, kmap, scale, shift, relu, out, n_dev, stream
     const int nkb = (cin + 31) / 32;
     if (nkb == 1) {                                        // stage = 16 KB + C_out*128 B
-        if (cout == 16) return launch_tc<1, 16, 4, 2>(TC_ARGS);
-        if (cout == 32) return launch_tc<1, 32, 4, 2>(TC_ARGS);
-        if (cout == 64) return launch_tc<1, 64, 4, 2>(TC_ARGS);
+        if (cout == 16) return launch_tc<1, 16, 2, 3>(TC_ARGS);
+        if (cout == 32) return launch_tc<1, 32, 2, 3>(TC_ARGS);
+        if (cout == 64) return launch_tc<1, 64, 2, 3>(TC_ARGS);
         if (cout == 128) return launch_tc<1, 128, 2, 2>(TC_ARGS);
     } else if (nkb == 2) {                                 // stage = 32 KB + C_out*256 B
         if (cout == 16) return launch_tc<2, 16, 2, 2>(TC_ARGS);
