@@ -405,6 +405,9 @@ extern "C" int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int*
     } else if (nkb == 2) {                                 // stage = 32 KB + C_out*256 B
         if (cout == 16) return launch_tc<2, 16, 2, 2>(TC_ARGS);
         if (cout == 32) return launch_tc<2, 32, 2, 2>(TC_ARGS);
+        // fewer tiles than SMs: one CTA per SM anyway, so spend the shared memory on four stages (each producer group then
+        // runs two stages ahead of the tensor core instead of waiting for its previous stage's MMAs)
+        if (cout == 64 && crb3d_divup(n_out, TILE_M) <= CRB3D_NUM_SMS) return launch_tc<2, 64, 4, 1>(TC_ARGS);
         if (cout == 64) return launch_tc<2, 64, 2, 2>(TC_ARGS);
         if (cout == 128) return launch_tc<2, 128, 2, 1>(TC_ARGS);
     }
