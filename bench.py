@@ -283,15 +283,8 @@ def run_own(args, rank, world, local_rank):
     barrier()
     e2e_t0 = time.perf_counter()
     outs = []
-    if full_graph:      # H2D of the points into the static buffers, one graph launch, D2H of the record - all asynchronous
-        main = torch.cuda.current_stream(device)
-        for st in slot_streams:
-            st.wait_stream(main)
-        for i in range(args.steps):
-            sl = i % len(slot_streams)
-            with torch.cuda.stream(slot_streams[sl]):
-                outs.append(ps.fetch_async(model.full_graph_replay(staged[i % nb][0], staged[i % nb][1], slot=sl)))
-        torch.cuda.synchronize(device)
+    if full_graph:      # the public throughput call: H2D into the static buffers, graph launch, D2H of the record, per batch
+        outs = ps.score_host_stream([staged[i % nb] for i in range(args.steps)])
         out = {k: v.numpy() for k, v in outs[-1].items() if k != "counts"}
     elif args.no_pipeline:
         for i in range(args.steps):

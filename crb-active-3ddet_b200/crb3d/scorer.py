@@ -60,6 +60,30 @@ class PoolScorer(object):
         torch.cuda.current_stream(self.device).synchronize()
         return {k: v.numpy() for k, v in out.items()}
 
+    def score_host_stream(self, staged_batches):
+        """Throughput form of score_host for a sequence of staged (pinned) batches: consecutive batches alternate over
+        the captured copies of the whole-step graph, each on its own stream - H2D of the points into that copy's static
+        buffers, one graph launch, D2H of the record into pinned memory - so the narrow tail of one batch runs under the
+        wide kernels of the next. Returns the list of pinned host records (dict of tensors, plus "counts") after one final
+        synchronisation; a batch whose counts exceed the static capacities must be re-scored with score_host."""
+        graphs = getattr(self.model, "_full_graphs", None)
+        if not graphs:
+            return [dict((k, torch.from_numpy(v)) for k, v in self.score_host(b).items()) for b in staged_batches]
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_slot_streams", None) is None or len(self._slot_streams) != len(graphs):
+            self._slot_streams = [torch.cuda.Stream(self.device) for _ in graphs]
+        for st in self._slot_streams:
+            st.wait_stream(main)
+        outs = []
+        for i, b in enumerate(staged_batches):
+            sl = i % len(graphs)
+            with torch.cuda.stream(self._slot_streams[sl]):
+                outs.append(self.fetch_async(self.model.full_graph_replay(b[0], b[1], slot=sl)))
+        for st in self._slot_streams:
+            main.wait_stream(st)
+        main.synchronize()
+        return outs
+
     def fetch_async(self, rec):
         """Queues the D2H copy of the record fields into pinned host tensors on the current stream (no sync)."""
         out = {}
@@ -132,26 +156,48 @@ class PoolScorer(object):
 
     def score_pool(self, frames, frame_ids=None):
         """Scores this rank's shard of `frames` (all ranks pass the same list) and all-gathers the records.
-        Returns a dict frame_id -> dict(entropy, labels (n,), density (n,)) identical on every rank."""
+        Returns a dict frame_id -> dict(entropy, labels (n,), density (n,)) identical on every rank.
+        Full batches go through the captured whole-step graphs when they are enabled (score_host_stream: consecutive
+        batches overlap on alternating graph copies); a partial last batch, a batch that does not fit the static buffers
+        or one whose row counts exceeded a static capacity is scored on the eager path (score_host)."""
         world, rank = _world_rank()
         ids = list(range(len(frames))) if frame_ids is None else list(frame_ids)
         mine = shard_indices(len(frames), rank, world)
-        recs, checks = [], []
+        sels = [mine[s:s + self.batch_size] for s in range(0, len(mine), self.batch_size)]
+        staged = [self.stage_host([frames[i] for i in sel]) for sel in sels]
         fg = getattr(self.model, "_full_graph", None)
-        for s in range(0, len(mine), self.batch_size):
-            sel = mine[s:s + self.batch_size]
-            dev = self.to_device(self.stage_host([frames[i] for i in sel]))
-            r = self.score_device(dev)
-            recs.append(self.record_tensor(r, sel))
-            if "counts" in r:                      # whole-step graph: remember the device-side counts of this batch
-                checks.append((len(recs) - 1, sel, dev, r["counts"].clone()))
-        for i, sel, dev, counts in checks:         # a static capacity was exceeded: re-score on the dynamic path
-            if not bool((counts.cpu().numpy() <= np.asarray(fg["caps"])).all()):
-                geom = self.model.geometry(dev[0], dev[1], dev[1].numel() - 1)
-                recs[i] = self.record_tensor(self.model.score_batch(dev[0], dev[1], dev[1].numel() - 1, dev[2], geom=geom), sel)
-        local = torch.cat(recs) if recs else torch.zeros((0, 3 + 2 * self.P), device=self.device)
+        fits = [fg is not None and fg["B"] == len(sel) and st[0].shape[0] <= fg["cap"] and st[2] <= fg["max_pts"]
+                for sel, st in zip(sels, staged)]
+        host = [None] * len(sels)
+        fast = [i for i, f in enumerate(fits) if f]
+        if fast:
+            caps = np.asarray(fg["caps"])
+            for i, o in zip(fast, self.score_host_stream([staged[i] for i in fast])):
+                if bool((o["counts"].numpy() <= caps).all()):
+                    host[i] = {k: o[k].numpy() for k in RECORD_FIELDS}
+        for i in range(len(sels)):
+            if host[i] is None:
+                host[i] = self._score_host_eager(staged[i])
+        rows = np.zeros((len(mine), 3 + 2 * self.P), dtype=np.float32)
+        r = 0
+        for sel, h in zip(sels, host):
+            for j, fi in enumerate(sel):
+                rows[r, 0], rows[r, 1], rows[r, 2] = fi, h["num_boxes"][j], h["entropy"][j]
+                rows[r, 3:3 + self.P] = h["labels"][j]
+                rows[r, 3 + self.P:] = h["density"][j]
+                r += 1
+        local = torch.from_numpy(rows).to(self.device)
         out = gather_records(local, len(frames), self.P, self.device)
         return {ids[k]: v for k, v in out.items()}
+
+    def _score_host_eager(self, staged):
+        """score_host on the dynamic path (host-visible counts), regardless of captured graphs."""
+        dev = self.to_device(staged)
+        geom = self.model.geometry(dev[0], dev[1], dev[1].numel() - 1)
+        rec = self.model.score_batch(dev[0], dev[1], dev[1].numel() - 1, dev[2], geom=geom)
+        out = {k: rec[k].to("cpu", non_blocking=True) for k in RECORD_FIELDS}
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: v.numpy() for k, v in out.items()}
 
 
 def _world_rank():
