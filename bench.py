@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the whole-step CUDA graph")
     ap.add_argument("--half-graph", action="store_true", help="round-1 mode: only the dense half in a CUDA graph, geometry pipelined on a side stream")
-    ap.add_argument("--slots", type=int, default=3, help="independent copies of the whole-step graph replayed on alternating streams")
+    ap.add_argument("--slots", type=int, default=4, help="independent copies of the whole-step graph replayed on alternating streams")
     ap.add_argument("--no-pipeline", action="store_true", help="(with --half-graph/--no-graph) one batch at a time on one stream")
     ap.add_argument("--exact-fp32", action="store_true", help="sparse convs on the exact-fp32 SIMT kernel instead of tcgen05 TF32")
     return ap.parse_args()
