@@ -58,3 +58,32 @@ def install():
     for alias, real in ALIASES.items():
         sys.modules[alias] = importlib.import_module(real)
     return sorted(ALIASES)
+
+
+def accelerate_bev_backbone(module):
+    """Gives an instance of the reference's `BaseBEVBackbone` (pcdet/models/backbones_2d/base_bev_backbone.py:7-112; same
+    `blocks` / `deblocks` structure and parameter names as crb3d.second.BaseBEVBackbone) the tensor-core inference plan of
+    this library: in eval mode without autograd `forward(data_dict)` runs the folded-BatchNorm plan (3x3 convs on
+    crb3d_bev_conv3x3_tf32, deblocks on crb3d_bev_gemm_tf32 writing their slice of the concatenated map); training and
+    autograd keep the module's own forward. Call again (or `module.build_inference_plan()`) after loading a checkpoint."""
+    import types
+
+    import torch
+
+    from .second import BaseBEVBackbone as Ours
+    original_forward = module.forward
+    module._fold = Ours._fold
+    module._tc_conv_pays = Ours._tc_conv_pays
+    module.build_inference_plan = types.MethodType(Ours.build_inference_plan, module)
+    module.forward_inference = types.MethodType(Ours.forward_inference, module)
+
+    def forward(self, data_dict):
+        x = data_dict["spatial_features"]
+        if not self.training and not torch.is_grad_enabled() and getattr(self, "_plan", None) is not None and x.is_cuda:
+            data_dict["spatial_features_2d"] = self.forward_inference(x)
+            return data_dict
+        return original_forward(data_dict)
+
+    module.forward = types.MethodType(forward, module)
+    module.build_inference_plan()
+    return module

@@ -152,3 +152,25 @@ def test_head_scores_topk(cuda, B, A, thr, k, shift):
         assert np.array_equal(ti[b, :n].cpu().numpy(), order)
         assert np.array_equal(ts[b, :n].cpu().numpy(), sc[b][order])
         assert float(ts[b, n:].abs().sum()) == 0
+
+
+def test_dropin_accelerate_bev_backbone(cuda):
+    """crb3d.dropin.accelerate_bev_backbone on a module with the reference's BaseBEVBackbone structure (plain nn.Module with
+    `blocks` / `deblocks`, NCHW-contiguous input like the reference's HeightCompression output)."""
+    from crb3d import dropin, second
+    _fp32_reference_mode()
+    torch.manual_seed(3)
+    ref_like = second.BaseBEVBackbone(second.KITTI_SECOND_CFG, 256).eval().to(cuda)     # same structure / parameter names
+    with torch.no_grad():
+        for m in ref_like.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_var.uniform_(0.5, 1.5)
+                m.running_mean.normal_(0, 0.1)
+        x = torch.randn(4, 256, 200, 176, device=cuda)                                  # NCHW contiguous
+        ref = torch.nn.Module.__call__(ref_like, dict(spatial_features=x))["spatial_features_2d"].clone()
+        torch.backends.cudnn.allow_tf32 = True
+        dropin.accelerate_bev_backbone(ref_like)
+        out = ref_like(dict(spatial_features=x))["spatial_features_2d"]
+    assert tuple(out.shape) == tuple(ref.shape) == (4, 512, 200, 176)
+    err = (out.double() - ref.double()).pow(2).mean().sqrt()
+    assert float(err) <= 2e-3 * float(ref.double().pow(2).mean().sqrt())
