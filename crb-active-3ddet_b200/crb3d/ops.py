@@ -214,7 +214,7 @@ def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transp
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(feat.device))
-    use_tc = ((SPCONV_TF32 if tf32 is None else tf32) and K <= 27 and cin in (16, 32, 64) and cout in (16, 32, 64, 128)
+    use_tc = ((SPCONV_TF32 if tf32 is None else tf32) and K <= 27 and cin in (4, 8, 16, 32, 64) and cout in (16, 32, 64, 128)
               and feat.shape[0] > 0)
     if use_tc:
         # tcgen05 path wants K-major weight rows [C_out', K, C_in']: the forward layout as is, its transpose for dX

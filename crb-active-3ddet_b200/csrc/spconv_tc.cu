@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
         const int grp = warp >> 2, gtid = tid & (GT - 1);
         const int r = gtid;                               // tile row owned by this thread within its group
         const int o = row0 + r;
-        const int cpr = cin >> 2;                         // 16-byte chunks per row (4, 8 or 16)
-        const int cshift = cpr == 16 ? 4 : (cpr == 8 ? 3 : 2);
+        const int cpr = cin >> 2;                         // 16-byte chunks per row (1, 2, 4, 8 or 16)
+        const int cshift = 31 - __clz(cpr);
         uint32_t dirty = 0u;
         int src_next = (grp < n_act && o < nv) ? __ldg(&nbr[(size_t)act[grp] * n_out + o]) : -1;
         for (int it = grp, li = 0; it < n_act; it += NG, ++li) {
@@ -394,7 +394,9 @@ extern "C" int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int*
     if (n_out < 0 || n_in < 0 || K <= 0 || cin <= 0 || cout <= 0 || !weight || !out) return CRB3D_ERR_ARG;
     if (n_out == 0) return CRB3D_OK;
     if (!feat || !nbr || n_in == 0) return CRB3D_ERR_ARG;
-    if (K > MAX_K || (cin != 16 && cin != 32 && cin != 64) || n_in >= (1 << 25)) return CRB3D_ERR_UNSUPPORTED;
+    // C_in = 4 / 8 (the first layer: raw voxel features) ride on the 32-channel path: the TMA weight box and the untouched
+    // tail of every 128-byte stage row are zero
+    if (K > MAX_K || (cin != 4 && cin != 8 && cin != 16 && cin != 32 && cin != 64) || n_in >= (1 << 25)) return CRB3D_ERR_UNSUPPORTED;
 #define TC_ARGS feat, n_in, nbr, weight, n_out, K, cin, kmap, scale, shift, relu, out, n_dev, stream
     const int nkb = (cin + 31) / 32;
     if (nkb == 1) {                                        // stage = 16 KB + C_out*128 B

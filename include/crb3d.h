@@ -91,7 +91,7 @@ int crb3d_spconv_forward_f32(const float* feat, const int* nbr, const float* wei
                              const float* scale, const float* shift, int relu, float* out, const int* n_dev,
                              cudaStream_t stream);
 /* tcgen05 path: TF32 inputs, fp32 accumulation in TMEM; feat (n_in, C_in) contiguous and 16-byte aligned (rows are
- * gathered by TMA); weight contiguous [C_out,K,C_in]; C_in in {16,32,64}, C_out in {16,32,64,128}, K <= 27, else
+ * gathered with cp.async); weight contiguous [C_out,K,C_in]; C_in in {4,8,16,32,64}, C_out in {16,32,64,128}, K <= 27, else
  * CRB3D_ERR_UNSUPPORTED (use the f32 entry point). */
 int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int* nbr, const float* weight, int n_out, int K, int cin,
                               int cout, const int* kmap, const float* scale, const float* shift, int relu, float* out,

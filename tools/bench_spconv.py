@@ -44,7 +44,7 @@ for name, key, cin, cout in layers:
     alg = 4 * (pairs * cin + n_out * cout + K * cin * cout) + 8 * pairs
     res = []
     for tf32 in (True, False):
-        if tf32 and cin < 16:
+        if tf32 and cin < 4:
             res.append(float("nan"))
             continue
         for _ in range(3):
