@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
         const int o = row0 + r;
         const int cpr = cin >> 2;                         // 16-byte chunks per row (1, 2, 4, 8 or 16)
         const int cshift = 31 - __clz(cpr);
+        long long* const trace_base = (blockIdx.x == gridDim.x / 2 && gtid == 0) ? g_tc_trace : nullptr;   // read once
         uint32_t dirty = 0u;
         int src_next = (grp < n_act && o < nv) ? __ldg(&nbr[(size_t)act[grp] * n_out + o]) : -1;
         for (int it = grp, li = 0; it < n_act; it += NG, ++li) {
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
             if (it + NG < n_act) src_next = (o < nv) ? __ldg(&nbr[(size_t)act[it + NG] * n_out + o]) : -1;
             if (gtid == 0) { cnt_v[grp][(li + 2) & 3] = 0; cnt_z[grp][(li + 2) & 3] = 0; }
             if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1);
-            long long* trace = (g_tc_trace && blockIdx.x == gridDim.x / 2 && gtid == 0) ? g_tc_trace + 128 : nullptr;
+            long long* trace = (trace_base && it < 32) ? trace_base + 128 : nullptr;
             if (trace) trace[it * 4 + 0] = clock64();
             const uint32_t a_base = smem_base + stage * STAGE_BYTES, b_base = a_base + A_BYTES;
             if (gtid == GT - 1) {   // one thread of the group fetches the weight slice: one 3-D TMA box per k-block
@@ -251,10 +252,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
         // before each UTCHMMA (~100 issue cycles per MMA, 800 cycles per stage in tools/trace_spconv.py)
         const uint32_t idesc = make_idesc_tf32(TILE_M, COUT);
         const uint64_t desc0 = make_desc_sw128(smem_base);
+        long long* const trace_mma = (blockIdx.x == gridDim.x / 2 && lane == 0) ? g_tc_trace : nullptr;
         for (int it = 0; it < n_act; ++it) {
             const int stage = it % STAGES;
             mbar_wait(&full_bar[stage], (it / STAGES) & 1);
-            long long* trace = (g_tc_trace && blockIdx.x == gridDim.x / 2 && lane == 0) ? g_tc_trace : nullptr;
+            long long* trace = (trace_mma && it < 32) ? trace_mma : nullptr;
             if (trace) trace[it * 4 + 2] = clock64();
             asm volatile("fence.proxy.async.shared::cta;");   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
             asm volatile("tcgen05.fence::after_thread_sync;");

@@ -132,3 +132,28 @@ def test_second_gradient_embedding_is_conv_cls_weight_grad(cuda):
     loss.backward()
     ref = w.grad.reshape(-1)
     assert float((emb - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
+def test_coreset_furthest_first_and_badge_kmeanspp(cuda):
+    """crb3d.strategies against a numpy restatement of coreset_sampling.py:31-52 (mean-initialised greedy k-centre) and
+    sklearn.cluster.kmeans_plusplus (badge_sampling.py:190-196)."""
+    from sklearn.cluster import kmeans_plusplus
+    from crb3d import strategies
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(400, 64)).astype(np.float32) * rng.uniform(0.5, 3.0, size=(400, 1)).astype(np.float32)
+    Xs = rng.normal(size=(50, 64)).astype(np.float32)
+
+    def sq(a, b):
+        d = (a.astype(np.float64) ** 2).sum(1)[:, None] + (b.astype(np.float64) ** 2).sum(1)[None, :] - 2.0 * a.astype(np.float64) @ b.astype(np.float64).T
+        return np.clip(d, 0, None)
+    min_dist = sq(X, Xs).mean(1)
+    ref = []
+    for i in range(30):
+        j = int(np.argmax(min_dist))
+        ref.append(j)
+        min_dist = np.minimum(min_dist, sq(X, X[j:j + 1])[:, 0])
+    got = strategies.furthest_first(torch.from_numpy(X).to(cuda), torch.from_numpy(Xs).to(cuda), 30).cpu().numpy()
+    assert np.array_equal(got, np.asarray(ref))
+    _, idx = kmeans_plusplus(X, 25, random_state=0)
+    assert np.array_equal(strategies.kmeans_pp_select(torch.from_numpy(X).to(cuda), 25), idx)
