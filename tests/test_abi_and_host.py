@@ -209,3 +209,26 @@ def test_reference_wrappers_import_unmodified_on_dropin():
     for fn in ("boxes_iou3d_gpu", "nms_gpu", "nms_normal_gpu", "boxes_iou_bev"):
         assert callable(getattr(iou_utils, fn))
     assert callable(roi_utils.points_in_boxes_gpu) and callable(roi_utils.RoIAwarePool3d)
+
+
+def test_furthest_first_host_logic_cpu():
+    """crb3d.strategies.furthest_first is plain tensor code: on CPU tensors it must reproduce the reference loop
+    (coreset_sampling.py:31-52: mean-initialised distances, arg-max, element-wise min) restated in numpy."""
+    import numpy as np
+    import torch
+    from crb3d import strategies
+    rng = np.random.default_rng(11)
+    X = (rng.normal(size=(120, 16)) * rng.uniform(0.5, 3.0, size=(120, 1))).astype(np.float32)
+    Xs = rng.normal(size=(20, 16)).astype(np.float32)
+
+    def sq(a, b):
+        a, b = a.astype(np.float64), b.astype(np.float64)
+        return np.clip((a ** 2).sum(1)[:, None] + (b ** 2).sum(1)[None, :] - 2.0 * a @ b.T, 0, None)
+    md = sq(X, Xs).mean(1)
+    ref = []
+    for _ in range(12):
+        j = int(np.argmax(md))
+        ref.append(j)
+        md = np.minimum(md, sq(X, X[j:j + 1])[:, 0])
+    got = strategies.furthest_first(torch.from_numpy(X), torch.from_numpy(Xs), 12).numpy()
+    assert np.array_equal(got, np.asarray(ref))
