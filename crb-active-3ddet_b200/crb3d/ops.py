@@ -3,6 +3,7 @@ every function here launches hand-written sm_100a kernels from libcrb3d_sm100.so
 There is no CPU path: CPU tensors are rejected (except for the two explicit *_cpu host ops).
 """
 import ctypes
+import os
 from ctypes import c_size_t, byref
 
 import numpy as np
@@ -297,6 +298,9 @@ def pack_conv3x3_weight(weight):
     return w.permute(0, 2, 3, 4, 1, 5).contiguous()
 
 
+CONV_VARIANT = int(os.environ.get("CRB3D_CONV_VARIANT", "0"))   # kernel experiments, see bev_conv_tc.cu
+
+
 def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None, round_out=False):
     """3x3 / stride 1 / pad 1 conv (+bias, ReLU) on the tensor cores. x_nhwc: (B, H, W, C_in) contiguous fp32 CUDA;
     wpack: pack_conv3x3_weight(...). Returns (B, H, W, C_out) contiguous."""
@@ -313,7 +317,7 @@ def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None, round_out=False):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(x_nhwc.device))
     _lib.call("crb3d_bev_conv3x3_tf32", _p(x_nhwc), B, H, W, cin, _p(wpack), cout, _p(_f32c(bias)) if bias is not None else None,
-              int(bool(relu)) | (2 if round_out else 0), _p(out), _stream(x_nhwc.device))
+              int(bool(relu)) | (2 if round_out else 0) | (CONV_VARIANT << 8), _p(out), _stream(x_nhwc.device))
     if timed:
         e1.record(torch.cuda.current_stream(x_nhwc.device))
         prof["conv2d"].append((e0, e1, 2.0 * 9 * cin * cout * B * H * W))

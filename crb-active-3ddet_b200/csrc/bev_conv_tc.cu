@@ -28,18 +28,21 @@ using namespace tc;
 
 constexpr int TU = 8, TV = 16;                 // output tile: 8 pixels along u (fast), 16 along v
 constexpr int PU = TU + 2, PV = TV + 2;        // halo tile
-constexpr int KC = 16;                         // input channels per chunk = 4 slabs of 4 floats = 2 MMAs (K = 8)
+constexpr int KC = 16;                         // input channels per chunk = one 64-byte swizzle row = 2 MMAs (K = 8)
 constexpr int NT = 4;                          // output tiles per CTA
 constexpr int N = 128;                         // output channels per CTA
-constexpr int SLAB_A = PU * PV * 16;           // 2880 B
-constexpr int TILE_A = (KC / 4) * SLAB_A;      // 11520 B per (tile, chunk)
-constexpr int CHUNK_A = NT * TILE_A;           // 46080 B
+constexpr int TILE_A_BYTES = PU * PV * KC * 4; // 11520 B land per (tile, chunk)
+constexpr int TILE_A = 12288;                  // ... in a slot padded to the 1024 B alignment of the swizzle pattern
+constexpr int CHUNK_A = NT * TILE_A;           // 49152 B
+constexpr int NSTAGE_A = 3;
 constexpr int SLAB_B = N * 16;                 // 2048 B
 constexpr int STAGE_B = (KC / 4) * SLAB_B;     // 8192 B per (tap, chunk)
 constexpr int NSTAGE_B = 6;
-constexpr int SMEM_BYTES = 2 * CHUNK_A + NSTAGE_B * STAGE_B;   // 141312
+constexpr int SMEM_BYTES = NSTAGE_A * CHUNK_A + NSTAGE_B * STAGE_B;   // 196608
 constexpr int PITCH = N + 4;                   // staging row pitch (floats)
-static_assert(SMEM_BYTES >= 128 * PITCH * 4, "staging must fit in the pipeline buffers");
+constexpr int EPI_WARPS = 8;                   // two warps per TMEM lane quarter, two tiles each
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+static_assert(SMEM_BYTES >= EPI_WARPS * 32 * PITCH * 4, "staging must fit in the pipeline buffers");
 
 struct ConvGeom {
     int U, V, B;                 // extent of the fast / slow tile dimension and the batch
@@ -48,83 +51,118 @@ struct ConvGeom {
     int ku_is_ky;                // 1: u = y (tap row offset moves along u); 0: u = x
 };
 
-__global__ void __launch_bounds__(192, 1) bev_conv3x3_tc(const __grid_constant__ CUtensorMap amap,
-                                                          const float* __restrict__ wpack, int n_chunks,
-                                                          const float* __restrict__ bias, int relu, float* __restrict__ out,
-                                                          const __grid_constant__ ConvGeom g) {
+// 64B swizzle K-major descriptor: rows of 64 bytes (16 channels of one pixel), 8-row groups `sbo` bytes apart. The
+// swizzle is a function of the absolute shared-memory address (16-byte chunk index ^= address bits 7-8), the same the
+// TMA unit applied when it wrote the tile, so the start address may sit on ANY row (measured: parity holds for all taps).
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t smem_addr, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+           (4ull << 61);
+}
+
+__device__ long long g_conv_trace[1024 * 16];    // experiment bit 2: per-CTA phase stamps (tools/bench_bev.py trace)
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// tcgen05.ld split into issue and wait, so that the next 32 accumulator columns are in flight while the previous 32
+// are converted; the wait names the registers as in/out operands to keep their uses behind it
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
+}
+
+__global__ void __launch_bounds__(THREADS, 1) bev_conv3x3_tc(const __grid_constant__ CUtensorMap amap,
+                                                              const float* __restrict__ wpack, int n_chunks,
+                                                              const float* __restrict__ bias, int relu, float* __restrict__ out,
+                                                              const __grid_constant__ ConvGeom g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full_a[2], empty_a[2], full_b[NSTAGE_B], empty_b[NSTAGE_B], acc_bar;
+    __shared__ uint64_t full_a[NSTAGE_A], empty_a[NSTAGE_A], full_b[NSTAGE_B], empty_b[NSTAGE_B], acc_bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias_s[N];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool tracing = ((relu >> 8) & 2) && blockIdx.x < 1024;
+    long long* tr = g_conv_trace + blockIdx.x * 16;
+    if (tracing && tid == 0) { tr[0] = gtime(); uint32_t sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); tr[6] = sm; }
     const int tile0 = blockIdx.x * NT;
     const int nh = blockIdx.y;                                  // which 128 output channels
     const float* wsrc = wpack + (size_t)nh * 9 * n_chunks * (STAGE_B / 4);
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < NSTAGE_A; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
         for (int s = 0; s < NSTAGE_B; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         mbar_init(&acc_bar, 1);
         mbar_fence_init();
         tma_prefetch_desc(&amap);
     }
     if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+    if (warp == 3)
+        for (int i = lane; i < N; i += 32) bias_s[i] = bias ? __ldg(&bias[nh * N + i]) : 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t a_smem = smem_u32(smem), b_smem = a_smem + 2 * CHUNK_A;
+    if (tracing && tid == 0) tr[1] = gtime();
+    const uint32_t a_smem = smem_u32(smem), b_smem = a_smem + NSTAGE_A * CHUNK_A;
 
     if (warp == 0) {
+        // ================================ weight producer: one 8 KB slice per (chunk, tap), 6 deep ====================
         if (lane == 0) {
-            int tu0[NT], tv0[NT], tb[NT];
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                const int ti = tile0 + t;
-                if (ti < g.n_tiles) {
-                    const int per_img = g.tiles_u * g.tiles_v;
-                    tb[t] = ti / per_img;
-                    const int rem = ti - tb[t] * per_img;
-                    tv0[t] = (rem / g.tiles_u) * TV;
-                    tu0[t] = (rem % g.tiles_u) * TU;
-                } else { tb[t] = g.B; tu0[t] = 0; tv0[t] = 0; }   // fully out of bounds: the TMA unit writes zeros
-            }
             int sb = 0;
-            for (int kc = 0; kc < n_chunks; ++kc) {
-                const int buf = kc & 1;
-                if (kc >= 2) mbar_wait(&empty_a[buf], ((kc >> 1) - 1) & 1);
-                mbar_expect_tx(&full_a[buf], CHUNK_A);
-#pragma unroll
-                for (int t = 0; t < NT; ++t)
-                    tma_load_5d(a_smem + buf * CHUNK_A + t * TILE_A, &amap, 0, tu0[t] - 1, tv0[t] - 1, kc * (KC / 4), tb[t],
-                                &full_a[buf]);
+            for (int kc = 0; kc < n_chunks; ++kc)
                 for (int tap = 0; tap < 9; ++tap, ++sb) {
                     const int stage = sb % NSTAGE_B;
-                    if (sb >= NSTAGE_B) mbar_wait(&empty_b[stage], ((sb / NSTAGE_B) - 1) & 1);
+                    if (sb >= NSTAGE_B) {
+                        const long long t0 = tracing ? clock64() : 0;
+                        mbar_wait(&empty_b[stage], ((sb / NSTAGE_B) - 1) & 1);
+                        if (tracing) tr[7] += clock64() - t0;
+                    }
                     mbar_expect_tx(&full_b[stage], STAGE_B);
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                  ::"r"(b_smem + stage * STAGE_B), "l"(wsrc + ((size_t)tap * n_chunks + kc) * (STAGE_B / 4)),
                                    "r"(STAGE_B), "r"(smem_u32(&full_b[stage])) : "memory");
                 }
-            }
         }
+        __syncwarp();
     } else if (warp == 1) {
+        // ================================ MMA issuer ====================================================================
         // whole warp, converged: only the tcgen05 instructions are predicated on one elected lane (see elect_one)
         const uint32_t idesc = idesc_tf32(128, N);
-        const uint64_t desc_a0 = desc_nosw(a_smem, SLAB_A, PU * 16), desc_b0 = desc_nosw(b_smem, SLAB_B, 128);
+        const uint64_t desc_a0 = desc_sw64(a_smem, PU * 64), desc_b0 = desc_nosw(b_smem, SLAB_B, 128);
         int sb = 0;
         for (int kc = 0; kc < n_chunks; ++kc) {
-            const int buf = kc & 1;
-            mbar_wait(&full_a[buf], (kc >> 1) & 1);
+            const int abuf = kc % NSTAGE_A;
+            long long t0 = tracing ? clock64() : 0;
+            mbar_wait(&full_a[abuf], (kc / NSTAGE_A) & 1);
+            if (tracing && lane == 0) { tr[9] += clock64() - t0; if (kc == 0) tr[2] = gtime(); }
             for (int tap = 0; tap < 9; ++tap, ++sb) {
                 const int stage = sb % NSTAGE_B;
+                t0 = tracing ? clock64() : 0;
                 mbar_wait(&full_b[stage], (sb / NSTAGE_B) & 1);
+                if (tracing && lane == 0) tr[8] += clock64() - t0;
                 tc_fence_after();
                 const int ky = tap / 3, kx = tap - ky * 3;
                 const int ku = g.ku_is_ky ? ky : kx, kv = g.ku_is_ky ? kx : ky;
-                // descriptors differ from the base ones only in the 14-bit start-address field (bytes >> 4)
-                const uint64_t da = desc_a0 + (uint64_t)((buf * CHUNK_A + (kv * PU + ku) * 16) >> 4);
+                // descriptors differ from the base ones only in the 14-bit start-address field (bytes >> 4): the operand of
+                // tap (kv, ku) is the halo tile read from pixel row kv * PU + ku on
+                const uint64_t da = desc_a0 + (uint64_t)((abuf * CHUNK_A + (kv * PU + ku) * 64) >> 4);
                 const uint64_t db = desc_b0 + (uint64_t)((stage * STAGE_B) >> 4);
                 const uint32_t first = (kc > 0 || tap > 0) ? 1u : 0u;
                 if (elect_one()) {
@@ -132,72 +170,118 @@ __global__ void __launch_bounds__(192, 1) bev_conv3x3_tc(const __grid_constant__
                     for (int t = 0; t < NT; ++t) {
 #pragma unroll
                         for (int j = 0; j < KC / 8; ++j)
-                            umma_tf32(tmem_base + t * N, da + (uint64_t)((t * TILE_A + j * 2 * SLAB_A) >> 4),
+                            umma_tf32(tmem_base + t * N, da + (uint64_t)((t * TILE_A + j * 32) >> 4),
                                       db + (uint64_t)((j * 2 * SLAB_B) >> 4), idesc, (j > 0) ? 1u : first);
                     }
                     umma_commit(&empty_b[stage]);
-                    if (tap == 8) umma_commit(&empty_a[buf]);
+                    if (tap == 8) umma_commit(&empty_a[abuf]);
                     if (tap == 8 && kc == n_chunks - 1) umma_commit(&acc_bar);
                 }
                 __syncwarp();
             }
         }
+        if (tracing && lane == 0) tr[3] = gtime();
     } else {
-        // ================================ epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =========================
-        const int q = warp & 3;
-        mbar_wait(&acc_bar, 0);
-        tc_fence_after();
-        float* stage_f = reinterpret_cast<float*>(smem) + (size_t)q * 32 * PITCH;
-        const int r = q * 32 + lane;                 // tile row of this thread: r = v_local * 8 + u_local
-        const int vl = r >> 3, ul = r & 7;
-        const float* bias_n = bias ? bias + nh * N : nullptr;
-#pragma unroll 1
-        for (int t = 0; t < NT; ++t) {
-            const int ti = tile0 + t;
-            if (ti >= g.n_tiles) break;              // uniform per CTA
-            const int per_img = g.tiles_u * g.tiles_v;
-            const int b = ti / per_img, rem = ti - b * per_img;
-            const int v = (rem / g.tiles_u) * TV + vl, u = (rem % g.tiles_u) * TU + ul;
-            const long long orow = (u < g.U && v < g.V) ? (long long)b * g.sb + (long long)u * g.su + (long long)v * g.sv + nh * N : -1;
-#pragma unroll 1
-            for (int c0 = 0; c0 < N; c0 += 32) {
-                uint32_t vv[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * N + c0), vv);
+        if (warp == 2) {
+            // ============================ activation producer (one lane; its own thread so that the next chunks are requested
+            // as soon as their buffer drains, not after the weight slices in between) =====================================
+            if (lane == 0) {
+                int tu0[NT], tv0[NT], tb[NT];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 w;
-                    float* wp = reinterpret_cast<float*>(&w);
+                for (int t = 0; t < NT; ++t) {
+                    const int ti = tile0 + t;
+                    if (ti < g.n_tiles) {
+                        const int per_img = g.tiles_u * g.tiles_v;
+                        tb[t] = ti / per_img;
+                        const int rem = ti - tb[t] * per_img;
+                        tv0[t] = (rem / g.tiles_u) * TV;
+                        tu0[t] = (rem % g.tiles_u) * TU;
+                    } else { tb[t] = g.B; tu0[t] = 0; tv0[t] = 0; }   // fully out of bounds: the TMA unit writes zeros
+                }
+                for (int kc = 0; kc < n_chunks; ++kc) {
+                    const int abuf = kc % NSTAGE_A;
+                    if (kc >= NSTAGE_A) mbar_wait(&empty_a[abuf], ((kc / NSTAGE_A) - 1) & 1);
+                    mbar_expect_tx(&full_a[abuf], NT * TILE_A_BYTES);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float x = __uint_as_float(vv[j + e]);
-                        if (bias_n) x += __ldg(&bias_n[c0 + j + e]);
-                        if (relu & 1) x = fmaxf(x, 0.0f);
-                        if (relu & 2) x = tf32_rn(x);
-                        wp[e] = x;
-                    }
-                    *reinterpret_cast<float4*>(stage_f + (size_t)lane * PITCH + c0 + j) = w;
+                    for (int t = 0; t < NT; ++t)
+                        tma_load_4d(a_smem + abuf * CHUNK_A + t * TILE_A, &amap, kc * KC, tu0[t] - 1, tv0[t] - 1, tb[t], &full_a[abuf]);
                 }
             }
             __syncwarp();
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {        // one 512-byte pixel row per iteration, 16 bytes per lane
-                const long long orr = __shfl_sync(0xffffffffu, orow, rr);
-                if (orr >= 0)
-                    *reinterpret_cast<float4*>(out + orr + lane * 4) = *reinterpret_cast<const float4*>(stage_f + (size_t)rr * PITCH + lane * 4);
+        }
+        // ================================ epilogue (warps 2..9 -> TMEM lane quarters 2,3,0,1,2,3,0,1) =================
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        mbar_wait(&acc_bar, 0);
+        tc_fence_after();
+        if (tracing && tid == 64) tr[4] = gtime();
+        float* stage_f = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * PITCH;
+        const bool no_store = (relu >> 8) & 4;
+        const int do_relu = relu & 1, do_round = relu & 2;
+        const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
+#pragma unroll 1
+        for (int t = half * (NT / 2); t < (half + 1) * (NT / 2); ++t) {
+            const int ti = tile0 + t;
+            if (ti >= g.n_tiles) break;              // uniform per warp
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * N);
+            uint32_t va[32], vb[32];
+            auto convert = [&](const uint32_t* vv, int c0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bq = bias4[(c0 + j) >> 2];
+                    float4 w = make_float4(__uint_as_float(vv[j]) + bq.x, __uint_as_float(vv[j + 1]) + bq.y,
+                                           __uint_as_float(vv[j + 2]) + bq.z, __uint_as_float(vv[j + 3]) + bq.w);
+                    if (do_relu) { w.x = fmaxf(w.x, 0.0f); w.y = fmaxf(w.y, 0.0f); w.z = fmaxf(w.z, 0.0f); w.w = fmaxf(w.w, 0.0f); }
+                    if (do_round) { w.x = tf32_rn(w.x); w.y = tf32_rn(w.y); w.z = tf32_rn(w.z); w.w = tf32_rn(w.w); }
+                    *reinterpret_cast<float4*>(stage_f + (size_t)lane * PITCH + c0 + j) = w;
+                }
+            };
+            tmem_ld32_issue(taddr, va);
+            tmem_ld32_wait(va);
+            tmem_ld32_issue(taddr + 32, vb);
+            convert(va, 0);
+            tmem_ld32_wait(vb);
+            tmem_ld32_issue(taddr + 64, va);
+            convert(vb, 32);
+            tmem_ld32_wait(va);
+            tmem_ld32_issue(taddr + 96, vb);
+            convert(va, 64);
+            tmem_ld32_wait(vb);
+            convert(vb, 96);
+            __syncwarp();
+            // tile row r = q*32 + rr = v_local * 8 + u_local: one 512-byte pixel row per iteration, 16 bytes per lane
+            const int per_img = g.tiles_u * g.tiles_v;
+            const int b = ti / per_img, rem = ti - b * per_img;
+            const int tv = (rem / g.tiles_u) * TV + q * 4, tu = (rem % g.tiles_u) * TU;
+            float* obase = out + (long long)b * g.sb + nh * N + lane * 4;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+                const int v = tv + (rr >> 3), u = tu + (rr & 7);
+                if (u < g.U && v < g.V && !no_store)
+                    *reinterpret_cast<float4*>(obase + (long long)u * g.su + (long long)v * g.sv) =
+                        *reinterpret_cast<const float4*>(stage_f + (size_t)rr * PITCH + lane * 4);
             }
             __syncwarp();
         }
+        if (tracing && tid == 64) tr[10] = gtime();
     }
     tc_fence_before();
     __syncthreads();
+    if (tracing && tid == 0) tr[5] = gtime();
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace
 
-// in: (B, H, W, C_in) channels-last fp32; wpack: weights packed by crb3d.ops.pack_conv3x3_weight into
-// [C_out/128][tap = ky*3+kx][C_in/16][slab 4][128 co][4 ci]; bias: C_out or null; out: (B, H, W, C_out) channels-last.
-// relu: bit 0 = ReLU, bit 1 = round the stored values to TF32 (round-to-nearest). Supported: C_in % 16 == 0, C_out % 128 == 0. The 8-pixel tile edge runs along H when H % 8 == 0 (else along W).
+// debug: copies the phase stamps of the last variant-4 launch (16 int64 per CTA) to the host
+extern "C" int crb3d_bev_conv3x3_trace(long long* host_out, int n_ctas) {
+    if (!host_out || n_ctas <= 0 || n_ctas > 1024) return CRB3D_ERR_ARG;
+    CRB3D_CUDA(cudaMemcpyFromSymbol(host_out, g_conv_trace, sizeof(long long) * 16 * n_ctas));
+    long long* zero = new long long[16 * 1024]();
+    cudaMemcpyToSymbol(g_conv_trace, zero, sizeof(long long) * 16 * 1024);
+    delete[] zero;
+    return CRB3D_OK;
+}
+
 extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int cin, const float* wpack, int cout,
                                       const float* bias, int relu, float* out, cudaStream_t stream) {
     if (!in || !wpack || !out || B <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) return CRB3D_ERR_ARG;
@@ -218,10 +302,10 @@ extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int 
     CUtensorMap amap;
     {
         const uint64_t ysb = (uint64_t)W * cin * 4, xsb = (uint64_t)cin * 4;
-        const uint64_t dims[5] = {4, (uint64_t)g.U, (uint64_t)g.V, (uint64_t)cin / 4, (uint64_t)B};
-        const uint64_t strides[4] = {u_is_y ? ysb : xsb, u_is_y ? xsb : ysb, 16, (uint64_t)H * W * cin * 4};
-        const uint32_t box[5] = {4, PU, PV, KC / 4, 1};
-        int rc = make_map_f32(&amap, in, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)g.U, (uint64_t)g.V, (uint64_t)B};
+        const uint64_t strides[3] = {u_is_y ? ysb : xsb, u_is_y ? xsb : ysb, (uint64_t)H * W * cin * 4};
+        const uint32_t box[4] = {KC, PU, PV, 1};
+        int rc = make_map_f32(&amap, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
     }
     static bool attr_set = false;
@@ -229,7 +313,7 @@ extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int 
         CRB3D_CUDA(cudaFuncSetAttribute(bev_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024));
         attr_set = true;
     }
-    bev_conv3x3_tc<<<dim3((unsigned)crb3d_divup(g.n_tiles, NT), (unsigned)(cout / N)), 192, SMEM_BYTES + 1024, stream>>>(
+    bev_conv3x3_tc<<<dim3((unsigned)crb3d_divup(g.n_tiles, NT), (unsigned)(cout / N)), THREADS, SMEM_BYTES + 1024, stream>>>(
         amap, wpack, cin / KC, bias, relu, out, g);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;

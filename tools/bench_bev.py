@@ -86,6 +86,49 @@ def gemm_case(name, M, K, N, n_sub=1, up=0, in_hw=(0, 0), segs_w=None, ctot=None
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":      # kernel experiments of bev_conv_tc.cu (results of 2, 3 are wrong by design)
+        for v in (0, 4):
+            ops.CONV_VARIANT = v
+            print("variant", v, flush=True)
+            conv_case(1, 37, 29, 64, 256)
+            conv_case(4, 200, 176, 128, 128)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "trace":         # per-CTA phase breakdown of bev_conv3x3_tc (variants 4 / 5)
+        import ctypes
+        import numpy as np
+        from crb3d import _lib
+        lib = _lib.load()
+        lib.crb3d_bev_conv3x3_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(4, 200, 176, 128, generator=g).cuda()
+        wp = ops.pack_conv3x3_weight((torch.randn(128, 128, 3, 3, generator=g) / 30).cuda())
+        b = torch.randn(128, generator=g).cuda()
+        out = torch.empty(4, 200, 176, 128, device="cuda")
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        n = 275
+        buf = np.zeros((n, 16), dtype=np.int64)
+        for v in (2, 6):
+            ops.CONV_VARIANT = v
+            for _ in range(3):
+                ops.bev_conv3x3(x, wp, b, True, out=out)
+            torch.cuda.synchronize()
+            lib.crb3d_bev_conv3x3_trace(buf.ctypes.data, n)
+            flush.fill_(1)
+            ops.bev_conv3x3(x, wp, b, True, out=out)
+            torch.cuda.synchronize()
+            lib.crb3d_bev_conv3x3_trace(buf.ctypes.data, n)
+            t0 = buf[:, 0].min()
+            first = buf[:, 0] - t0 < 5000          # CTAs of the first wave
+            print("variant %d: kernel span %.1f us; %d first-wave CTAs" % (v, (buf[:, 5].max() - t0) / 1e3, int(first.sum())))
+            for name, sel in (("wave 1", first), ("wave 2", ~first)):
+                d = buf[sel]
+                print("  %s: start +%.1f us | setup %.2f | first data %.2f | main loop %.2f | drain %.2f | epilogue %.2f | total %.2f us"
+                      % (name, np.median(d[:, 0] - t0) / 1e3, np.median(d[:, 1] - d[:, 0]) / 1e3, np.median(d[:, 2] - d[:, 1]) / 1e3,
+                         np.median(d[:, 3] - d[:, 2]) / 1e3, np.median(d[:, 4] - d[:, 3]) / 1e3, np.median(d[:, 10] - d[:, 4]) / 1e3,
+                         np.median(d[:, 5] - d[:, 0]) / 1e3))
+                print("    waits (clk): producer on empty_b %d, mma on full_b %d, mma on full_a %d" %
+                      (np.median(d[:, 7]), np.median(d[:, 8]), np.median(d[:, 9])))
+        sys.exit(0)
     gemm_case("deconv1-contig", 4 * 200 * 176, 128, 256, ctot=256)
     gemm_case("deconv1", 4 * 200 * 176, 128, 256, ctot=512)
     gemm_case("deconv2", 4 * 100 * 88, 256, 256, n_sub=4, up=2, in_hw=(100, 88), ctot=512)
