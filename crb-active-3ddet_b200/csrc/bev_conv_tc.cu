@@ -270,6 +270,262 @@ __global__ void __launch_bounds__(THREADS, 1) bev_conv3x3_tc(const __grid_consta
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2, persistent, accumulators double-buffered in TMEM).
+// The phase trace of the kernel above shows where a 2-wave launch loses time: ~5 us until the first operands arrive and
+// ~8 us of epilogue per wave (the 148 x 256 KB store burst runs at the HBM write rate) with the tensor pipe idle, and a
+// B operand that is re-read from shared memory by every M128 MMA (128 B/clk, the whole shared-memory bandwidth). Here
+//   * two CTAs of a cluster issue ONE M256 x N128 x K8 MMA: each holds its own 128 pixels (A) and HALF of the weight
+//     slice (64 output channels, B) - shared-memory operand traffic per SM drops to 96 B/clk and the weight traffic
+//     from L2 per SM halves, which is what makes a 2-tile work item (instead of 4) affordable;
+//   * a work item is 2 tiles per CTA = 256 TMEM columns, so the other 256 columns take the next item while 8 epilogue
+//     warps drain this one: the stores are spread over the main loop of the next item, the operand pipeline never
+//     empties between items, and setup / first-data latency is paid once per CTA.
+// Both CTAs run the producers (TMA .cta_group::2 completes on the LEADER's barriers), the leader's warp 1 issues the
+// MMAs and multicasts the commits to both CTAs, the epilogue warps of both CTAs arrive on the leader's acc_empty.
+namespace pair {
+
+constexpr int IT = 2;                           // tiles per CTA per work item
+constexpr int ITEM_A = IT * TILE_A;             // 24576 B per (item, chunk)
+constexpr int NSA = 4;
+constexpr int HALF_B = STAGE_B / 2;             // 4096 B: 64 output channels x 16 input channels of one tap
+constexpr int NSB = 8;
+constexpr int EPW = 8;                          // epilogue warps: (tile, TMEM lane quarter)
+constexpr int SPITCH = 64 + 4;                  // staging row pitch (floats): 64-column halves
+constexpr int STAGING = EPW * 32 * SPITCH * 4;  // 69632 B
+constexpr int SMEM = NSA * ITEM_A + NSB * HALF_B + STAGING;   // 200704
+constexpr int NTHREADS = 32 * (3 + EPW);
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t leader_addr(const void* local) {        // the same variable in CTA 0 of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(local)));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void remote_arrive(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate));
+}
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {               // arrives on `bar` of BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap, int n_chunks,
+                    const float* __restrict__ bias, int relu, float* __restrict__ out, const __grid_constant__ ConvGeom g) {
+    extern __shared__ uint8_t smem_raw[];
+    // the dynamic window starts at the same offset in both CTAs; descriptors address both CTAs with one offset
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_a[NSA], empty_a[NSA], full_b[NSB], empty_b[NSB], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias_s[N];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    const int nh = blockIdx.y;
+    const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    const int n_items = (g.n_tiles + 2 * IT - 1) / (2 * IT);
+
+    if (tid == 0) {
+        for (int s = 0; s < NSA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < NSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * EPW); }
+        mbar_fence_init();
+        tma_prefetch_desc(&amap);
+        tma_prefetch_desc(&wmap);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    if (warp == 3)
+        for (int i = lane; i < N; i += 32) bias_s[i] = bias ? __ldg(&bias[nh * N + i]) : 0.0f;
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                          // the peer's barriers are initialised before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t a_smem = smem_u32(smem), b_smem = a_smem + NSA * ITEM_A;
+
+    if (warp == 0) {
+        // ================================ weight producer: this CTA's 64 output channels of every (chunk, tap) =========
+        if (lane == 0) {
+            int sb = 0;
+            const int row0 = nh * 9 * n_chunks * 2;
+            for (int item = cluster_id; item < n_items; item += n_clusters)
+                for (int kc = 0; kc < n_chunks; ++kc)
+                    for (int tap = 0; tap < 9; ++tap, ++sb) {
+                        const int stage = sb % NSB;
+                        if (sb >= NSB) mbar_wait(&empty_b[stage], ((sb / NSB) - 1) & 1);
+                        if (leader) mbar_expect_tx(&full_b[stage], 2 * HALF_B);
+                        tma2_load_2d(b_smem + stage * HALF_B, &wmap, 0, (row0 + (tap * n_chunks + kc) * 2 + (int)rank) * 4,
+                                     leader_addr(&full_b[stage]));
+                    }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA only) ===================================================
+        if (leader) {
+            const uint32_t idesc = idesc_tf32(256, N);
+            const uint64_t desc_a0 = desc_sw64(a_smem, PU * 64), desc_b0 = desc_nosw(b_smem, 64 * 16, 128);
+            int sb = 0, ca = 0, it = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
+                const int set = it & 1;
+                if (it >= 2) mbar_wait(&acc_empty[set], ((it >> 1) - 1) & 1);
+                tc_fence_after();
+                for (int kc = 0; kc < n_chunks; ++kc, ++ca) {
+                    const int abuf = ca % NSA;
+                    mbar_wait(&full_a[abuf], (ca / NSA) & 1);
+                    for (int tap = 0; tap < 9; ++tap, ++sb) {
+                        const int stage = sb % NSB;
+                        mbar_wait(&full_b[stage], (sb / NSB) & 1);
+                        tc_fence_after();
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const int ku = g.ku_is_ky ? ky : kx, kv = g.ku_is_ky ? kx : ky;
+                        const uint64_t da = desc_a0 + (uint64_t)((abuf * ITEM_A + (kv * PU + ku) * 64) >> 4);
+                        const uint64_t db = desc_b0 + (uint64_t)((stage * HALF_B) >> 4);
+                        const uint32_t first = (kc > 0 || tap > 0) ? 1u : 0u;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int t = 0; t < IT; ++t) {
+#pragma unroll
+                                for (int j = 0; j < KC / 8; ++j)
+                                    umma2_tf32(tmem_base + set * (IT * N) + t * N, da + (uint64_t)((t * TILE_A + j * 32) >> 4),
+                                               db + (uint64_t)((j * 2 * 64 * 16) >> 4), idesc, (j > 0) ? 1u : first);
+                            }
+                            umma2_commit(&empty_b[stage]);
+                            if (tap == 8) umma2_commit(&empty_a[abuf]);
+                            if (tap == 8 && kc == n_chunks - 1) umma2_commit(&acc_full[set]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ================================ activation producer: this CTA's two tiles of every item ========================
+        if (lane == 0) {
+            int ca = 0;
+            const int per_img = g.tiles_u * g.tiles_v;
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                int tu0[IT], tv0[IT], tb[IT];
+#pragma unroll
+                for (int t = 0; t < IT; ++t) {
+                    const int ti = (item * 2 + (int)rank) * IT + t;
+                    if (ti < g.n_tiles) {
+                        tb[t] = ti / per_img;
+                        const int rem = ti - tb[t] * per_img;
+                        tv0[t] = (rem / g.tiles_u) * TV;
+                        tu0[t] = (rem % g.tiles_u) * TU;
+                    } else { tb[t] = g.B; tu0[t] = 0; tv0[t] = 0; }   // fully out of bounds: the TMA unit writes zeros
+                }
+                for (int kc = 0; kc < n_chunks; ++kc, ++ca) {
+                    const int abuf = ca % NSA;
+                    if (ca >= NSA) mbar_wait(&empty_a[abuf], ((ca / NSA) - 1) & 1);
+                    if (leader) mbar_expect_tx(&full_a[abuf], 2 * IT * TILE_A_BYTES);
+                    const uint32_t bar = leader_addr(&full_a[abuf]);
+#pragma unroll
+                    for (int t = 0; t < IT; ++t)
+                        tma2_load_4d(a_smem + abuf * ITEM_A + t * TILE_A, &amap, kc * KC, tu0[t] - 1, tv0[t] - 1, tb[t], bar);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ epilogue: warp -> (tile = (warp-3)/4, TMEM lane quarter = warp%4) ==============
+        const int q = warp & 3, t = (warp - 3) >> 2;
+        float* stage_f = reinterpret_cast<float*>(smem + NSA * ITEM_A + NSB * HALF_B) + (size_t)(warp - 3) * 32 * SPITCH;
+        const int do_relu = relu & 1, do_round = relu & 2;
+        const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
+        const int per_img = g.tiles_u * g.tiles_v;
+        const uint32_t acc_empty_leader[2] = {leader_addr(&acc_empty[0]), leader_addr(&acc_empty[1])};
+        int it = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
+            const int set = it & 1;
+            mbar_wait(&acc_full[set], (it >> 1) & 1);
+            tc_fence_after();
+            const int ti = (item * 2 + (int)rank) * IT + t;
+            const bool live = ti < g.n_tiles;        // uniform per warp
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * (IT * N) + t * N);
+            const int b = live ? ti / per_img : 0, rem = ti - b * per_img;
+            const int tv = (rem / g.tiles_u) * TV + q * 4, tu = (rem % g.tiles_u) * TU;
+            float* obase = out + (long long)b * g.sb + nh * N + (lane & 15) * 4;
+            uint32_t va[32], vb[32];
+            auto convert = [&](const uint32_t* vv, int c0, int s0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bq = bias4[(c0 + j) >> 2];
+                    float4 w = make_float4(__uint_as_float(vv[j]) + bq.x, __uint_as_float(vv[j + 1]) + bq.y,
+                                           __uint_as_float(vv[j + 2]) + bq.z, __uint_as_float(vv[j + 3]) + bq.w);
+                    if (do_relu) { w.x = fmaxf(w.x, 0.0f); w.y = fmaxf(w.y, 0.0f); w.z = fmaxf(w.z, 0.0f); w.w = fmaxf(w.w, 0.0f); }
+                    if (do_round) { w.x = tf32_rn(w.x); w.y = tf32_rn(w.y); w.z = tf32_rn(w.z); w.w = tf32_rn(w.w); }
+                    *reinterpret_cast<float4*>(stage_f + (size_t)lane * SPITCH + s0 + j) = w;
+                }
+            };
+            auto store_half = [&](int c0) {          // 32 rows x 64 columns: two 256-byte row pieces per instruction
+                __syncwarp();
+#pragma unroll 8
+                for (int r2 = 0; r2 < 32; r2 += 2) {
+                    const int rr = r2 + (lane >> 4);
+                    const int v = tv + (rr >> 3), u = tu + (rr & 7);
+                    if (live && u < g.U && v < g.V)
+                        *reinterpret_cast<float4*>(obase + (long long)u * g.su + (long long)v * g.sv + c0) =
+                            *reinterpret_cast<const float4*>(stage_f + (size_t)rr * SPITCH + (lane & 15) * 4);
+                }
+                __syncwarp();
+            };
+            tmem_ld32_issue(taddr, va);
+            tmem_ld32_wait(va);
+            tmem_ld32_issue(taddr + 32, vb);
+            convert(va, 0, 0);
+            tmem_ld32_wait(vb);
+            tmem_ld32_issue(taddr + 64, va);
+            convert(vb, 32, 32);
+            store_half(0);
+            tmem_ld32_wait(va);
+            tmem_ld32_issue(taddr + 96, vb);
+            convert(va, 64, 0);
+            tmem_ld32_wait(vb);
+            // every column of this warp's accumulator slice is in registers: hand the TMEM set back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) remote_arrive(acc_empty_leader[set]);
+            convert(vb, 96, 32);
+            store_half(64);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                          // the peer may still read this CTA's shared memory / signal its barriers
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+}
+
+}  // namespace pair
+
 }  // namespace
 
 // debug: copies the phase stamps of the last variant-4 launch (16 int64 per CTA) to the host
@@ -311,7 +567,27 @@ extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int 
     static bool attr_set = false;
     if (!attr_set) {
         CRB3D_CUDA(cudaFuncSetAttribute(bev_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024));
+        CRB3D_CUDA(cudaFuncSetAttribute(pair::bev_conv3x3_pair_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM + 1024));
         attr_set = true;
+    }
+    if ((relu >> 8) & 1) {
+        // CTA-pair kernel; wpack is the SPLIT layout [C_out/128][tap][C_in/16][half][4 slabs][64 co][4 ci]
+        CUtensorMap wmap;
+        const uint64_t wrows = (uint64_t)(cout / N) * 9 * (cin / KC) * 2 * 4;
+        const uint64_t wdims[2] = {256, wrows};
+        const uint64_t wstr[1] = {1024};
+        const uint32_t wbox[2] = {256, 4};
+        int rc = make_map_f32(&wmap, wpack, 2, wdims, wstr, wbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        const int ny = cout / N;
+        const int n_items = (int)crb3d_divup(g.n_tiles, 2 * pair::IT);
+        int n_clusters = CRB3D_NUM_SMS / 2 / ny;
+        if (n_clusters < 1) n_clusters = 1;
+        if (n_clusters > n_items) n_clusters = n_items;
+        pair::bev_conv3x3_pair_tc<<<dim3((unsigned)(2 * n_clusters), (unsigned)ny), pair::NTHREADS, pair::SMEM + 1024, stream>>>(
+            amap, wmap, cin / KC, bias, relu, out, g);
+        CRB3D_CHECK_LAUNCH();
+        return CRB3D_OK;
     }
     bev_conv3x3_tc<<<dim3((unsigned)crb3d_divup(g.n_tiles, NT), (unsigned)(cout / N)), THREADS, SMEM_BYTES + 1024, stream>>>(
         amap, wpack, cin / KC, bias, relu, out, g);

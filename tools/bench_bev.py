@@ -87,11 +87,14 @@ def gemm_case(name, M, K, N, n_sub=1, up=0, in_hw=(0, 0), segs_w=None, ctot=None
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "variants":      # kernel experiments of bev_conv_tc.cu (results of 2, 3 are wrong by design)
-        for v in (0, 4):
+        for v in (0, 1):
             ops.CONV_VARIANT = v
             print("variant", v, flush=True)
+            conv_case(1, 16, 16, 16, 128)
+            conv_case(2, 24, 40, 32, 128)
             conv_case(1, 37, 29, 64, 256)
             conv_case(4, 200, 176, 128, 128)
+            conv_case(4, 100, 88, 256, 256)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "trace":         # per-CTA phase breakdown of bev_conv3x3_tc (variants 4 / 5)
         import ctypes
