@@ -289,16 +289,16 @@ def bev_gemm(a, weight, bias, relu, segs, n_sub=1, up=0, in_hw=(0, 0), round_out
               _stream(a.device))
 
 
-CONV_VARIANT = int(os.environ.get("CRB3D_CONV_VARIANT", "0"))   # bit 0: CTA-pair kernel (see bev_conv_tc.cu)
+CONV_VARIANT = int(os.environ.get("CRB3D_CONV_VARIANT", "0"))   # bit 0: single-CTA kernel, bits 1-2: its experiments (bev_conv_tc.cu)
 
 
 def pack_conv3x3_weight(weight, split=None):
     """(C_out, C_in, 3, 3) conv weight -> the slab layout of csrc/bev_conv_tc.cu:
-    [C_out/128][tap = ky*3+kx][C_in/16][4 slabs][128 co][4 ci] (contiguous fp32); split=True: the CTA-pair layout
-    [C_out/128][tap][C_in/16][half][4 slabs][64 co][4 ci] (each CTA of a pair holds 64 output channels)."""
+    [C_out/128][tap = ky*3+kx][C_in/16][half][4 slabs][64 co][4 ci] (contiguous fp32; each CTA of a pair holds 64 output
+    channels of a slice); split=False: [C_out/128][tap][C_in/16][4 slabs][128 co][4 ci] of the single-CTA kernel."""
     cout, cin = weight.shape[0], weight.shape[1]
     assert tuple(weight.shape[2:]) == (3, 3) and cout % 128 == 0 and cin % 16 == 0
-    split = bool(CONV_VARIANT & 1) if split is None else split
+    split = not (CONV_VARIANT & 1) if split is None else split
     w = round_tf32(weight.detach().float()).permute(0, 2, 3, 1)             # (cout, ky, kx, cin)
     if split:
         w = w.reshape(cout // 128, 2, 64, 9, cin // 16, 4, 4)                # nh, half, co, tap, chunk, slab, ci
@@ -314,7 +314,7 @@ def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None, round_out=False):
     assert x_nhwc.dtype == torch.float32 and x_nhwc.is_contiguous() and wpack.is_contiguous()
     B, H, W, cin = x_nhwc.shape
     cout = wpack.shape[0] * 128
-    assert wpack.shape[2] * 16 == cin and (wpack.dim() == 7) == bool(CONV_VARIANT & 1)
+    assert wpack.shape[2] * 16 == cin and (wpack.dim() == 7) == (not (CONV_VARIANT & 1))
     if out is None:
         out = torch.empty((B, H, W, cout), dtype=torch.float32, device=x_nhwc.device)
     prof = PROFILE

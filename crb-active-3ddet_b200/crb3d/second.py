@@ -195,15 +195,16 @@ class BaseBEVBackbone(nn.Module):
 
     @staticmethod
     def _tc_conv_pays(B, H, W, cout, cin=128):
-        """The halo-tile kernel runs one CTA (4 tiles of 128 pixels x 128 channels) per SM: use it when its CTA count
-        fills whole waves of the 148 SMs, otherwise cuDNN's finer tiles win (BEV_CONV_TC = True/False overrides)."""
+        """The halo-tile kernel is persistent: 74 CTA pairs take work items of 4 tiles (128 pixels x 128 channels each) in
+        turn. Use it when the items fill whole rounds of the 74 pairs, otherwise cuDNN's finer tiles win
+        (BEV_CONV_TC = True/False overrides)."""
         if BEV_CONV_TC != "auto":
             return bool(BEV_CONV_TC)
-        if cin > 128:      # measured on B200 (tools/bench_bev.py): cuDNN's 256-channel kernels reach 650-690 TF/s, ours ~490
+        if cout > 128:     # measured on B200 (tools/bench_bev.py, 256->256 at 100x88): cuDNN 60 us / 690 TF/s, ours 83 us
             return False
         u, v = (H, W) if H % 8 == 0 or W % 8 != 0 else (W, H)
-        ctas = -(-(B * -(-u // 8) * -(-v // 16)) // 4) * (cout // 128)
-        return ctas / (-(-ctas // 148) * 148.0) >= 0.8
+        items = -(-(B * -(-u // 8) * -(-v // 16)) // 4)
+        return items / (-(-items // 74) * 74.0) >= 0.8
 
     def forward_inference(self, x):
         B = x.shape[0]

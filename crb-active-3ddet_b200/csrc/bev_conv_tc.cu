@@ -570,8 +570,8 @@ extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int 
         CRB3D_CUDA(cudaFuncSetAttribute(pair::bev_conv3x3_pair_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM + 1024));
         attr_set = true;
     }
-    if ((relu >> 8) & 1) {
-        // CTA-pair kernel; wpack is the SPLIT layout [C_out/128][tap][C_in/16][half][4 slabs][64 co][4 ci]
+    if (!((relu >> 8) & 1)) {
+        // CTA-pair kernel (default); wpack is the SPLIT layout [C_out/128][tap][C_in/16][half][4 slabs][64 co][4 ci]
         CUtensorMap wmap;
         const uint64_t wrows = (uint64_t)(cout / N) * 9 * (cin / KC) * 2 * 4;
         const uint64_t wdims[2] = {256, wrows};

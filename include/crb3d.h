@@ -177,8 +177,10 @@ int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long lda, const
 
 /* ---- 3x3 / stride 1 / pad 1 BEV convolution on tcgen05 (halo-tile implicit GEMM, TF32 in, fp32 accumulate) with
  *      the folded BatchNorm shift + ReLU fused (base_bev_backbone.py:33-50,96-99).
- *      in: (B,H,W,C_in) channels-last; wpack: [C_out/128][ky*3+kx][C_in/16][4][128][4] (crb3d.ops.pack_conv3x3_weight);
- *      bias: C_out or null; out: (B,H,W,C_out) channels-last. Supported: C_in % 16 == 0, C_out % 128 == 0. */
+ *      in: (B,H,W,C_in) channels-last; wpack: [C_out/128][ky*3+kx][C_in/16][2][4][64][4] (crb3d.ops.pack_conv3x3_weight:
+ *      each CTA of a cta_group::2 pair holds 64 output channels of a slice); bias: C_out or null; out: (B,H,W,C_out)
+ *      channels-last. relu: bit 0 ReLU, bit 1 round the stored values to TF32, bit 8 single-CTA kernel (wpack then
+ *      [C_out/128][ky*3+kx][C_in/16][4][128][4]). Supported: C_in % 16 == 0, C_out % 128 == 0. */
 int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int cin, const float* wpack, int cout, const float* bias,
                            int relu, float* out, cudaStream_t stream);
 
