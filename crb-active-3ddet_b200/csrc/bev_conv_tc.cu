@@ -290,11 +290,12 @@ constexpr int IT = 2;                           // tiles per CTA per work item
 constexpr int ITEM_A = IT * TILE_A;             // 24576 B per (item, chunk)
 constexpr int NSA = 4;
 constexpr int HALF_B = STAGE_B / 2;             // 4096 B: 64 output channels x 16 input channels of one tap
-constexpr int NSB = 8;
+constexpr int ROW_B = 3 * HALF_B;               // a weight stage = the three taps of one kernel row: 12 MMAs per barrier round trip
+constexpr int NSB = 4;
 constexpr int EPW = 8;                          // epilogue warps: (tile, TMEM lane quarter)
 constexpr int SPITCH = 64 + 4;                  // staging row pitch (floats): 64-column halves
 constexpr int STAGING = EPW * 32 * SPITCH * 4;  // 69632 B
-constexpr int SMEM = NSA * ITEM_A + NSB * HALF_B + STAGING;   // 200704
+constexpr int SMEM = NSA * ITEM_A + NSB * ROW_B + STAGING;   // 217088
 constexpr int NTHREADS = 32 * (3 + EPW);
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -349,6 +350,9 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
     const int nh = blockIdx.y;
     const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
     const int n_items = (g.n_tiles + 2 * IT - 1) / (2 * IT);
+    const bool tracing = ((relu >> 8) & 2) && blockIdx.x < 1024 && blockIdx.y == 0;
+    long long* tr = g_conv_trace + blockIdx.x * 16;
+    if (tracing && tid == 0) { tr[0] = gtime(); uint32_t sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); tr[6] = sm; }
 
     if (tid == 0) {
         for (int s = 0; s < NSA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
@@ -369,22 +373,32 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
     cluster_sync_all();                          // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    if (tracing && tid == 0) tr[1] = gtime();
     const uint32_t a_smem = smem_u32(smem), b_smem = a_smem + NSA * ITEM_A;
 
     if (warp == 0) {
         // ================================ weight producer: this CTA's 64 output channels of every (chunk, tap) =========
         if (lane == 0) {
             int sb = 0;
+            long long w_empty = 0;
             const int row0 = nh * 9 * n_chunks * 2;
             for (int item = cluster_id; item < n_items; item += n_clusters)
                 for (int kc = 0; kc < n_chunks; ++kc)
-                    for (int tap = 0; tap < 9; ++tap, ++sb) {
+                    for (int row = 0; row < 3; ++row, ++sb) {
                         const int stage = sb % NSB;
-                        if (sb >= NSB) mbar_wait(&empty_b[stage], ((sb / NSB) - 1) & 1);
-                        if (leader) mbar_expect_tx(&full_b[stage], 2 * HALF_B);
-                        tma2_load_2d(b_smem + stage * HALF_B, &wmap, 0, (row0 + (tap * n_chunks + kc) * 2 + (int)rank) * 4,
-                                     leader_addr(&full_b[stage]));
+                        if (sb >= NSB) {
+                            const long long t0 = tracing ? clock64() : 0;
+                            mbar_wait(&empty_b[stage], ((sb / NSB) - 1) & 1);
+                            if (tracing) w_empty += clock64() - t0;
+                        }
+                        if (leader) mbar_expect_tx(&full_b[stage], 2 * ROW_B);
+                        const uint32_t bar = leader_addr(&full_b[stage]);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            tma2_load_2d(b_smem + stage * ROW_B + k * HALF_B, &wmap, 0,
+                                         (row0 + ((row * 3 + k) * n_chunks + kc) * 2 + (int)rank) * 4, bar);
                     }
+            if (tracing) tr[7] = w_empty;
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -393,38 +407,50 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
             const uint32_t idesc = idesc_tf32(256, N);
             const uint64_t desc_a0 = desc_sw64(a_smem, PU * 64), desc_b0 = desc_nosw(b_smem, 64 * 16, 128);
             int sb = 0, ca = 0, it = 0;
+            const long long tloop = tracing ? clock64() : 0;
+            long long w_a = 0, w_b = 0, w_acc = 0;
             for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
                 const int set = it & 1;
+                long long t0 = tracing ? clock64() : 0;
                 if (it >= 2) mbar_wait(&acc_empty[set], ((it >> 1) - 1) & 1);
+                if (tracing) w_acc += clock64() - t0;
                 tc_fence_after();
                 for (int kc = 0; kc < n_chunks; ++kc, ++ca) {
                     const int abuf = ca % NSA;
+                    t0 = tracing ? clock64() : 0;
                     mbar_wait(&full_a[abuf], (ca / NSA) & 1);
-                    for (int tap = 0; tap < 9; ++tap, ++sb) {
+                    if (tracing) { w_a += clock64() - t0; if (ca == 0 && lane == 0) tr[2] = gtime(); }
+                    for (int row = 0; row < 3; ++row, ++sb) {
                         const int stage = sb % NSB;
+                        t0 = tracing ? clock64() : 0;
                         mbar_wait(&full_b[stage], (sb / NSB) & 1);
+                        if (tracing) w_b += clock64() - t0;
                         tc_fence_after();
-                        const int ky = tap / 3, kx = tap - ky * 3;
-                        const int ku = g.ku_is_ky ? ky : kx, kv = g.ku_is_ky ? kx : ky;
-                        const uint64_t da = desc_a0 + (uint64_t)((abuf * ITEM_A + (kv * PU + ku) * 64) >> 4);
-                        const uint64_t db = desc_b0 + (uint64_t)((stage * HALF_B) >> 4);
-                        const uint32_t first = (kc > 0 || tap > 0) ? 1u : 0u;
                         if (elect_one()) {
 #pragma unroll
-                            for (int t = 0; t < IT; ++t) {
+                            for (int k = 0; k < 3; ++k) {
+                                // tap (ky, kx) = (row, k): the halo tile read from pixel row kv * PU + ku on
+                                const int ku = g.ku_is_ky ? row : k, kv = g.ku_is_ky ? k : row;
+                                const uint64_t da = desc_a0 + (uint64_t)((abuf * ITEM_A + (kv * PU + ku) * 64) >> 4);
+                                const uint64_t db = desc_b0 + (uint64_t)((stage * ROW_B + k * HALF_B) >> 4);
+                                const uint32_t first = (kc > 0 || row > 0 || k > 0) ? 1u : 0u;
 #pragma unroll
-                                for (int j = 0; j < KC / 8; ++j)
-                                    umma2_tf32(tmem_base + set * (IT * N) + t * N, da + (uint64_t)((t * TILE_A + j * 32) >> 4),
-                                               db + (uint64_t)((j * 2 * 64 * 16) >> 4), idesc, (j > 0) ? 1u : first);
+                                for (int t = 0; t < IT; ++t) {
+#pragma unroll
+                                    for (int j = 0; j < KC / 8; ++j)
+                                        umma2_tf32(tmem_base + set * (IT * N) + t * N, da + (uint64_t)((t * TILE_A + j * 32) >> 4),
+                                                   db + (uint64_t)((j * 2 * 64 * 16) >> 4), idesc, (j > 0) ? 1u : first);
+                                }
                             }
                             umma2_commit(&empty_b[stage]);
-                            if (tap == 8) umma2_commit(&empty_a[abuf]);
-                            if (tap == 8 && kc == n_chunks - 1) umma2_commit(&acc_full[set]);
+                            if (row == 2) umma2_commit(&empty_a[abuf]);
+                            if (row == 2 && kc == n_chunks - 1) umma2_commit(&acc_full[set]);
                         }
                         __syncwarp();
                     }
                 }
             }
+            if (tracing && lane == 0) { tr[3] = gtime(); tr[13] = clock64() - tloop; tr[14] = it; tr[9] = w_a; tr[8] = w_b; tr[11] = w_acc; }
         }
     } else if (warp == 2) {
         // ================================ activation producer: this CTA's two tiles of every item ========================
@@ -458,15 +484,18 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
     } else {
         // ================================ epilogue: warp -> (tile = (warp-3)/4, TMEM lane quarter = warp%4) ==============
         const int q = warp & 3, t = (warp - 3) >> 2;
-        float* stage_f = reinterpret_cast<float*>(smem + NSA * ITEM_A + NSB * HALF_B) + (size_t)(warp - 3) * 32 * SPITCH;
+        float* stage_f = reinterpret_cast<float*>(smem + NSA * ITEM_A + NSB * ROW_B) + (size_t)(warp - 3) * 32 * SPITCH;
         const int do_relu = relu & 1, do_round = relu & 2;
         const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
         const int per_img = g.tiles_u * g.tiles_v;
         const uint32_t acc_empty_leader[2] = {leader_addr(&acc_empty[0]), leader_addr(&acc_empty[1])};
         int it = 0;
+        long long w_full = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
             const int set = it & 1;
+            const long long t0 = tracing ? clock64() : 0;
             mbar_wait(&acc_full[set], (it >> 1) & 1);
+            if (tracing) w_full += clock64() - t0;
             tc_fence_after();
             const int ti = (item * 2 + (int)rank) * IT + t;
             const bool live = ti < g.n_tiles;        // uniform per warp
@@ -517,10 +546,12 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
             convert(vb, 96, 32);
             store_half(64);
         }
+        if (tracing && warp == 3 && lane == 0) { tr[10] = gtime(); tr[12] = w_full; }
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                          // the peer may still read this CTA's shared memory / signal its barriers
+    if (tracing && tid == 0) tr[5] = gtime();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
 }
 

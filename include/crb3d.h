@@ -183,6 +183,8 @@ int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long lda, const
  *      [C_out/128][ky*3+kx][C_in/16][4][128][4]). Supported: C_in % 16 == 0, C_out % 128 == 0. */
 int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int cin, const float* wpack, int cout, const float* bias,
                            int relu, float* out, cudaStream_t stream);
+/* debug: per-CTA phase stamps (16 int64 per CTA) of the last launch made with relu bit 9 set (tools/bench_bev.py trace). */
+int crb3d_bev_conv3x3_trace(long long* host_out, int n_ctas);
 
 /* ---- anchor-head post-processing (anchor_head_template.py:238-285, box_coder_utils.py:45-77,
  *      detector3d_template.py:281-311): max-class sigmoid score + 1-based label for every anchor, and lazy

@@ -97,7 +97,7 @@ if __name__ == "__main__":
             conv_case(4, 100, 88, 256, 256)
             conv_case(8, 200, 176, 128, 128, check=False)
         sys.exit(0)
-    if len(sys.argv) > 1 and sys.argv[1] == "trace":         # per-CTA phase breakdown of bev_conv3x3_tc (variants 4 / 5)
+    if len(sys.argv) > 1 and sys.argv[1] == "trace":         # per-CTA phase breakdown of the conv kernels (experiment bit 1)
         import ctypes
         import numpy as np
         from crb3d import _lib
@@ -105,14 +105,15 @@ if __name__ == "__main__":
         lib.crb3d_bev_conv3x3_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
         g = torch.Generator().manual_seed(1)
         x = torch.randn(4, 200, 176, 128, generator=g).cuda()
-        wp = ops.pack_conv3x3_weight((torch.randn(128, 128, 3, 3, generator=g) / 30).cuda(), split=False)
+        w = (torch.randn(128, 128, 3, 3, generator=g) / 30).cuda()
         b = torch.randn(128, generator=g).cuda()
         out = torch.empty(4, 200, 176, 128, device="cuda")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-        n = 275
-        buf = np.zeros((n, 16), dtype=np.int64)
-        for v in (3, 7):
+        buf = np.zeros((296, 16), dtype=np.int64)
+        for v in (2, 3):
             ops.CONV_VARIANT = v
+            wp = ops.pack_conv3x3_weight(w)
+            n = 148 if v == 2 else 275
             for _ in range(3):
                 ops.bev_conv3x3(x, wp, b, True, out=out)
             torch.cuda.synchronize()
@@ -121,17 +122,30 @@ if __name__ == "__main__":
             ops.bev_conv3x3(x, wp, b, True, out=out)
             torch.cuda.synchronize()
             lib.crb3d_bev_conv3x3_trace(buf.ctypes.data, n)
-            t0 = buf[:, 0].min()
-            first = buf[:, 0] - t0 < 5000          # CTAs of the first wave
-            print("variant %d: kernel span %.1f us; %d first-wave CTAs" % (v, (buf[:, 5].max() - t0) / 1e3, int(first.sum())))
-            for name, sel in (("wave 1", first), ("wave 2", ~first)):
-                d = buf[sel]
-                print("  %s: start +%.1f us | setup %.2f | first data %.2f | main loop %.2f | drain %.2f | epilogue %.2f | total %.2f us"
-                      % (name, np.median(d[:, 0] - t0) / 1e3, np.median(d[:, 1] - d[:, 0]) / 1e3, np.median(d[:, 2] - d[:, 1]) / 1e3,
-                         np.median(d[:, 3] - d[:, 2]) / 1e3, np.median(d[:, 4] - d[:, 3]) / 1e3, np.median(d[:, 10] - d[:, 4]) / 1e3,
-                         np.median(d[:, 5] - d[:, 0]) / 1e3))
-                print("    waits (clk): producer on empty_b %d, mma on full_b %d, mma on full_a %d" %
-                      (np.median(d[:, 7]), np.median(d[:, 8]), np.median(d[:, 9])))
+            d = buf[:n]
+            t0 = d[:, 0].min()
+            print("variant %d (%s): kernel span %.1f us" % (v, "CTA pair" if v == 2 else "single CTA", (max(d[:, 5].max(), d[:, 10].max()) - t0) / 1e3))
+            if v == 2:
+                ld = d[0::2]            # leaders
+                mhz = np.median(ld[:, 13] / np.maximum(ld[:, 3] - ld[:, 2], 1)) * 1e3
+                print("  leaders: setup %.2f | first data %.2f | mma loop %.2f (%.0f clk at ~%.0f MHz, %d..%d items) | last epilogue ends +%.2f | exit +%.2f us"
+                      % (np.median(ld[:, 1] - ld[:, 0]) / 1e3, np.median(ld[:, 2] - ld[:, 1]) / 1e3, np.median(ld[:, 3] - ld[:, 2]) / 1e3,
+                         np.median(ld[:, 13]), mhz, ld[:, 14].min(), ld[:, 14].max(), np.median(ld[:, 10] - ld[:, 3]) / 1e3,
+                         np.median(ld[:, 5] - ld[:, 3]) / 1e3))
+                for items in sorted(set(ld[:, 14])):
+                    sel = ld[ld[:, 14] == items]
+                    print("    %d leaders with %d items: mma loop %.2f us = %.0f clk/item; waits (clk) full_a %d full_b %d acc_empty %d; B producer on empty_b %d; epilogue warp on acc_full %d"
+                          % (len(sel), items, np.median(sel[:, 3] - sel[:, 2]) / 1e3, np.median(sel[:, 13]) / items, np.median(sel[:, 9]),
+                             np.median(sel[:, 8]), np.median(sel[:, 11]), np.median(sel[:, 7]), np.median(sel[:, 12])))
+            else:
+                first = d[:, 0] - t0 < 5000          # CTAs of the first wave
+                for name, sel in (("wave 1", first), ("wave 2", ~first)):
+                    e = d[sel]
+                    print("  %s: start +%.1f us | setup %.2f | first data %.2f | main loop %.2f | drain %.2f | epilogue %.2f us"
+                          % (name, np.median(e[:, 0] - t0) / 1e3, np.median(e[:, 1] - e[:, 0]) / 1e3, np.median(e[:, 2] - e[:, 1]) / 1e3,
+                             np.median(e[:, 3] - e[:, 2]) / 1e3, np.median(e[:, 4] - e[:, 3]) / 1e3, np.median(e[:, 10] - e[:, 4]) / 1e3))
+                    print("    waits (clk): producer on empty_b %d, mma on full_b %d, mma on full_a %d" %
+                          (np.median(e[:, 7]), np.median(e[:, 8]), np.median(e[:, 9])))
         sys.exit(0)
     gemm_case("deconv1-contig", 4 * 200 * 176, 128, 256, ctot=256)
     gemm_case("deconv1", 4 * 200 * 176, 128, 256, ctot=512)

@@ -20,7 +20,7 @@ def launches(path, steps):
         return v / 1000 if r["Metric Unit"] == "ns" else (v * 1000 if r["Metric Unit"] == "ms" else v)
 
     def nm(r):
-        n = r["Kernel Name"].replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+        n = r["Kernel Name"].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("pair::", "")
         return re.sub(r"\(.*", "", n).replace("void ", "")[:72]
 
     idx = [i for i, r in enumerate(rows) if nm(r).startswith("vox_insert")]
