@@ -57,6 +57,7 @@ SIGNATURES = {
     "crb3d_three_interpolate_grad_stack": [c_int, c_int, P, P, P, P, P],
     "crb3d_bev_gemm_tf32": [P, c_int64, c_int, c_int64, P, c_int, c_int, P, c_int, c_int, P, P, P, P, c_int, c_int, c_int, P],
     "crb3d_bev_conv3x3_tf32": [P, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, P],
+    "crb3d_bev_conv3x3_trace": [P, c_int],
     "crb3d_anchor_head_scores": [P, c_int64, c_int, P, P, P],
     "crb3d_anchor_head_scores_topk": [P, c_int, c_int64, c_int, c_float, c_int, P, P, P, P, P, P, P, P],
     "crb3d_anchor_decode_select": [P, P, P, c_int, c_int, c_int64, P, P, P],
