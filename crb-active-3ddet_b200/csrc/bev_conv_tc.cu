@@ -9,17 +9,17 @@
 // Why not im2col-style loads: at TF32 a 128 x 128 x 32 k-block needs 32 KB of operands per 270 tensor-pipe cycles,
 // ~120 B/clk/SM against an L2 feed of ~42 B/clk/SM - the nine shifted copies of the activation tile alone would make
 // the kernel L2-bound at a third of the tensor peak. Instead:
-//   * the (8+2) x (16+2) input halo of a 128-pixel output tile is loaded ONCE per 16-channel chunk, by one 5-D TMA box
-//     whose out-of-bounds rows/columns are zero-filled by the TMA unit (that IS the conv padding), into the NO-SWIZZLE
-//     K-major layout [4-channel slab][v][u][4 floats]: every pixel row is 16 bytes, so the operand of tap (kv,ku) is the
-//     same tile read through a descriptor whose start address is advanced by (kv*10 + ku)*16 bytes (SBO = one v step,
-//     LBO = one slab). Activation traffic drops 9 x 128 / 180 = 6.4x;
-//   * a CTA owns FOUR output tiles (4 x 128 TMEM columns = the whole TMEM), so each 8 KB weight slice (one tap, 16 input
-//     channels, 128 output channels - pre-packed on the host into the same slab layout, fetched with one bulk copy) feeds
-//     eight M128 x N128 x K8 MMAs: weight traffic per flop drops 4x. Total operand feed ~24 B/clk/SM.
-// Warp roles: warp 0 / one lane = TMA producer (activation chunks double-buffered, weight slices 6 deep), warp 1 / one
-// lane = MMA issuer, warps 2-5 = epilogue (tcgen05.ld, bias/ReLU, 512-byte pixel rows staged in the drained pipeline
-// buffers and stored as whole lines).
+//   * the (8+2) x (16+2) input halo of a 128-pixel output tile is loaded ONCE per 16-channel chunk, by one 4-D TMA box
+//     whose out-of-bounds rows/columns are zero-filled by the TMA unit (that IS the conv padding), as 64-byte pixel
+//     rows with the 64B swizzle (full 32-byte sectors from L2). The swizzle is a function of the absolute shared-memory
+//     address, so the operand of tap (kv,ku) is the same tile read through a descriptor whose start address is advanced
+//     by (kv*10 + ku)*64 bytes (SBO = one v step). Activation traffic drops 9 x 128 / 180 = 6.4x;
+//   * every weight slice (one tap, 16 input channels, 128 output channels, pre-packed on the host into the no-swizzle
+//     slab layout) feeds the MMAs of several tiles.
+// Two kernels: bev_conv3x3_pair_tc (default, further down: CTA pairs with cta_group::2 MMAs, persistent, accumulators
+// double-buffered in TMEM) and its single-CTA predecessor bev_conv3x3_tc (flag bit 8; 4 tiles per CTA = the whole TMEM,
+// warp 0 = weight producer, warp 1 = MMA issuer, warp 2 lane 0 = activation producer, warps 2-9 = epilogue staged in the
+// drained pipeline buffers). profiles/r01_conv_pair_ncu.txt holds the measurements behind both designs.
 #include "tc_common.cuh"
 
 namespace {
