@@ -129,6 +129,23 @@ def test_bev_conv3x3_halo_tile(cuda, B, H, W, cin, cout):
     _check(lin, torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), None, padding=1).permute(0, 2, 3, 1), "conv3x3 linear")
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 24, 40, 32, 128), (1, 37, 29, 64, 256), (5, 9, 7, 16, 128)])
+def test_bev_conv3x3_single_cta_kernel(cuda, B, H, W, cin, cout, monkeypatch):
+    """The single-CTA predecessor of the CTA-pair kernel (flag bit 8, unsplit weight layout) stays a valid comparison arm."""
+    from crb3d import ops
+    _fp32_reference_mode()
+    monkeypatch.setattr(ops, "CONV_VARIANT", 1)
+    g = torch.Generator(device="cpu").manual_seed(H * W + cin + 1)
+    x = torch.randn(B, H, W, cin, generator=g).to(cuda)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * np.sqrt(cin))).to(cuda)
+    b = torch.randn(cout, generator=g).to(cuda)
+    wp = ops.pack_conv3x3_weight(w)
+    assert wp.dim() == 6
+    out = ops.bev_conv3x3(x, wp, b, True)
+    ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=1)).permute(0, 2, 3, 1)
+    _check(out, ref, "conv3x3 single-CTA")
+
+
 @pytest.mark.parametrize("B,A,thr,k,shift", [(4, 211200, 0.1, 4096, 0.0), (2, 5000, 0.5, 4096, 4.0), (3, 30000, 0.2, 512, 0.0),
                                              (1, 100, 0.9, 64, 0.0), (2, 70000, 0.6, 4096, 0.0), (2, 64, 0.0, 4096, 0.0),
                                              (2, 9000, 0.5, 4096, 30.0), (4, 211200, 0.1, 4096, 3.0)])
