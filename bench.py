@@ -345,13 +345,13 @@ def run_own(args, rank, world, local_rank):
                "launches_per_step": len(pair_records[0]), "algorithmic_bytes_per_step": alg_bytes / max(args.steps, 1),
                "kernel_ms_per_step": conv_total_ms / max(args.steps, 1),
                "share_of_step": conv_total_ms / max(args.steps, 1) / step_ms_avg}
-    # (b) bev_conv3x3_tc, tensor bound: 2*9*C_in*C_out*pixels flops / time; TF32 peak = half the measured bf16 rate
+    # (b) bev_conv3x3_pair_tc, tensor bound: 2*9*C_in*C_out*pixels flops / time; TF32 peak = half the measured bf16 rate
     c2 = prof_records["conv2d"]
     c2_ms = sum(a.elapsed_time(b) for a, b, _ in c2)
     c2_flops = sum(f for _, _, f in c2)
     tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
     c2_ach = c2_flops / (c2_ms / 1e3) / 1e12 if c2_ms > 0 else 0.0
-    roof_c2 = {"kernel": "bev_conv3x3_tc (halo-tile tcgen05 TF32 conv, %d launches per step)" % (len(c2) // max(args.steps, 1)),
+    roof_c2 = {"kernel": "bev_conv3x3_pair_tc (halo-tile tcgen05 cta_group::2 TF32 conv, %d launches per step)" % (len(c2) // max(args.steps, 1)),
                "bound": "tensor", "achieved": c2_ach, "peak": tf32_peak,
                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 = half the bf16 rate; of measured)" if peaks
                                else "fallback 1400/2 TFLOP/s (of fallback)"),
