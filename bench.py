@@ -31,6 +31,15 @@ UNIT = "frames/s"
 N_DISTINCT_FRAMES = 16
 
 
+def progress(msg):
+    """Per-phase progress on stderr: the tail of a killed run shows where it stopped."""
+    sys.stderr.write("[bench rank %s %.1fs] %s\n" % (os.environ.get("RANK", "0"), time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,6 +200,8 @@ def run_own(args, rank, world, local_rank):
     _lib.load()  # fail loudly if the native library is missing
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    _lib.init_device(local_rank)
+    progress("building the model")
     model = build_model(device)
     model.prepare_inference(fold_bev_bn=True, spconv_tf32=not args.exact_fp32)
     frames, batches = make_batches(args.batch)
@@ -200,6 +211,7 @@ def run_own(args, rank, world, local_rank):
     second.calibrate_batchnorm(model, resident[0][0], resident[0][1], args.batch)      # see the docstring: random init collapses
     second.calibrate_head_bias(model, resident[0][0], resident[0][1], args.batch, target_fraction=0.004)
     full_graph = not args.no_graph and not args.half_graph
+    progress("calibrated; capturing graphs")
     if full_graph:          # the WHOLE step (voxelize .. entropy) as one CUDA graph, every count device-side
         model.enable_full_graph(args.batch, max_points_per_frame=max(s[2] for s in staged) + 1024, slots=max(1, args.slots))
         slot_streams = [torch.cuda.Stream(device) for _ in range(max(1, args.slots))]
@@ -218,6 +230,7 @@ def run_own(args, rank, world, local_rank):
         geom = model.geometry(dev_batch[0], dev_batch[1], dev_batch[1].numel() - 1)
         return model.score_batch(dev_batch[0], dev_batch[1], dev_batch[1].numel() - 1, dev_batch[2], geom=geom)
 
+    progress("graphs captured; counting pairs")
     pair_records = []
     for b in range(nb):
         ops.PROFILE = {"mode": "pairs", "records": []}
@@ -231,6 +244,7 @@ def run_own(args, rank, world, local_rank):
     else:  # warm the side stream's allocator pool too: same code path as the timed region
         for _ in ps.score_stream((resident[i % nb] for i in range(max(args.warmup, 3))), from_host=False):
             pass
+    progress("warm-up done")
     barrier()
 
     # ---- timed region 1: device-resident inputs ---------------------------------------------------------------
@@ -273,6 +287,7 @@ def run_own(args, rank, world, local_rank):
     barrier()
     launches = _lib.LAUNCHES["kernels"] - k0
     total_ms = ev0.elapsed_time(ev1)
+    progress("timed region 1 done (%.2f ms)" % total_ms)
     overflow = False
     if full_graph:
         overflow = not bool((rec["counts"].cpu().numpy() <= np.asarray(model._full_graph["caps"])).all())
@@ -296,6 +311,7 @@ def run_own(args, rank, world, local_rank):
         out = {k: v.numpy() for k, v in outs[-1].items()}
     torch.cuda.synchronize(device)
     e2e_ms = (time.perf_counter() - e2e_t0) * 1e3
+    progress("timed region 2 (e2e) done (%.2f ms)" % e2e_ms)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     h2d = int(np.mean([s[0].numel() * 4 + s[1].numel() * 4 for s in staged]))
@@ -309,6 +325,8 @@ def run_own(args, rank, world, local_rank):
         l2_flush()
     ops.PROFILE = None
     torch.cuda.synchronize(device)
+    _lib.raise_if_device_error()
+    progress("instrumented pass done")
 
     # max over ranks
     if world > 1:
@@ -415,9 +433,17 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that stops answering is reported after 2 minutes (default: 10), with the flight recorder's last collectives
+        os.environ.setdefault("TORCH_NCCL_TRACE_BUFFER_SIZE", "2000")
+        os.environ.setdefault("TORCH_NCCL_DUMP_ON_TIMEOUT", "1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=120))
     try:
         run_own(args, rank, world, local_rank)
+    except Exception:
+        from crb3d import _lib
+        progress("FAILED; device diagnostics record: %r" % (_lib.last_device_error(),))
+        raise
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -15,6 +15,10 @@ P = c_void_p  # every device/host buffer crosses as a raw address
 SIGNATURES = {
     "crb3d_version": [],
     "crb3d_strerror": [c_int],
+    "crb3d_diag_init": [],
+    "crb3d_last_device_error": [P],
+    "crb3d_diag_clear": [],
+    "crb3d_device_sm_count": [P],
     "crb3d_voxelize_workspace_bytes": [c_int64, c_int, c_int, POINTER(c_size_t)],
     "crb3d_voxelize": [P, c_int64, c_int, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, P, P, P, P, P, P,
                        c_size_t, P],
@@ -110,11 +114,42 @@ KERNELS_PER_CALL = {
     "crb3d_group_points_grad_stack": 1, "crb3d_farthest_point_sampling": 1, "crb3d_stack_farthest_point_sampling": 1,
     "crb3d_three_nn_stack": 1, "crb3d_three_interpolate_stack": 1, "crb3d_three_interpolate_grad_stack": 1,
     "crb3d_label_entropy": 1, "crb3d_label_entropy_ranges": 1, "crb3d_pairwise_sqdist_f64": 1,
-    "crb3d_bev_gemm_tf32": [P, c_int64, c_int, c_int64, P, c_int, c_int, P, c_int, c_int, P, P, P, P, c_int, c_int, c_int, P],
     "crb3d_anchor_head_scores": 1, "crb3d_anchor_head_scores_topk": 2, "crb3d_anchor_decode_select": 1, "crb3d_gather_rows_f32": 1, "crb3d_gather_rows_i32": 1,
     "crb3d_spconv_forward_tf32": 1, "crb3d_bev_gemm_tf32": 1, "crb3d_bev_conv3x3_tf32": 1,
 }
 LAUNCHES = {"kernels": 0, "calls": 0}
+
+
+KERNEL_NAMES = {1: "spconv_fwd_tc", 2: "bev_conv3x3_tc", 3: "bev_conv3x3_pair_tc", 4: "bev_gemm_tc", 5: "hash_insert",
+                6: "hash_find", 7: "bev_conv3x3_s2_tc", 8: "fc_gemm_tc"}
+SITE_NAMES = {1: "full_a", 2: "empty_a", 3: "full_b", 4: "empty_b", 5: "acc_full", 6: "acc_empty", 7: "acc_bar", 8: "full_bar",
+              9: "empty_bar", 10: "b_full"}
+_DIAG_DEVICES = set()
+
+
+def init_device(index):
+    """Registers the diagnostics record with every kernel module on CUDA device `index` (idempotent; outside capture)."""
+    if index in _DIAG_DEVICES:
+        return
+    import torch
+    with torch.cuda.device(index):
+        check(load().crb3d_diag_init(), "crb3d_diag_init")
+    _DIAG_DEVICES.add(index)
+
+
+def last_device_error():
+    """None, or a dict describing the bounded wait / probe that gave up (readable even after the CUDA context died)."""
+    out = (ctypes.c_uint * 12)()
+    if load().crb3d_last_device_error(out) == 0:
+        return None
+    return dict(kernel=KERNEL_NAMES.get(out[1], out[1]), site=SITE_NAMES.get(out[2], out[2]), parity=out[3],
+                block=(out[4], out[5]), thread=out[6], extra=out[7], waited_ms=((out[9] << 32) | out[8]) / 1e6, device=out[10])
+
+
+def raise_if_device_error(prefix=""):
+    e = last_device_error()
+    if e is not None:
+        raise RuntimeError("%scrb3d device error: %r" % (prefix, e))
 
 
 def call(name, *args):

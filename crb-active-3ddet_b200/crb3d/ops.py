@@ -29,7 +29,10 @@ def _p(t):
 
 
 def _stream(dev=None):
-    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    st = torch.cuda.current_stream(dev)
+    if st.device_index not in _lib._DIAG_DEVICES:   # first launch on this device: hook up the bounded-wait diagnostics
+        _lib.init_device(st.device_index)
+    return ctypes.c_void_p(st.cuda_stream)
 
 
 def _need_cuda(*ts):

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(THREADS, 1) bev_conv3x3_tc(const __grid_consta
                     const int stage = sb % NSTAGE_B;
                     if (sb >= NSTAGE_B) {
                         const long long t0 = tracing ? clock64() : 0;
-                        mbar_wait(&empty_b[stage], ((sb / NSTAGE_B) - 1) & 1);
+                        mbar_wait(&empty_b[stage], ((sb / NSTAGE_B) - 1) & 1, (CRB3D_K_BEV_CONV << 8) | 4);
                         if (tracing) tr[7] += clock64() - t0;
                     }
                     mbar_expect_tx(&full_b[stage], STAGE_B);
@@ -150,12 +150,12 @@ __global__ void __launch_bounds__(THREADS, 1) bev_conv3x3_tc(const __grid_consta
         for (int kc = 0; kc < n_chunks; ++kc) {
             const int abuf = kc % NSTAGE_A;
             long long t0 = tracing ? clock64() : 0;
-            mbar_wait(&full_a[abuf], (kc / NSTAGE_A) & 1);
+            mbar_wait(&full_a[abuf], (kc / NSTAGE_A) & 1, (CRB3D_K_BEV_CONV << 8) | 1);
             if (tracing && lane == 0) { tr[9] += clock64() - t0; if (kc == 0) tr[2] = gtime(); }
             for (int tap = 0; tap < 9; ++tap, ++sb) {
                 const int stage = sb % NSTAGE_B;
                 t0 = tracing ? clock64() : 0;
-                mbar_wait(&full_b[stage], (sb / NSTAGE_B) & 1);
+                mbar_wait(&full_b[stage], (sb / NSTAGE_B) & 1, (CRB3D_K_BEV_CONV << 8) | 3);
                 if (tracing && lane == 0) tr[8] += clock64() - t0;
                 tc_fence_after();
                 const int ky = tap / 3, kx = tap - ky * 3;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) bev_conv3x3_tc(const __grid_consta
                 }
                 for (int kc = 0; kc < n_chunks; ++kc) {
                     const int abuf = kc % NSTAGE_A;
-                    if (kc >= NSTAGE_A) mbar_wait(&empty_a[abuf], ((kc / NSTAGE_A) - 1) & 1);
+                    if (kc >= NSTAGE_A) mbar_wait(&empty_a[abuf], ((kc / NSTAGE_A) - 1) & 1, (CRB3D_K_BEV_CONV << 8) | 2);
                     mbar_expect_tx(&full_a[abuf], NT * TILE_A_BYTES);
 #pragma unroll
                     for (int t = 0; t < NT; ++t)
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) bev_conv3x3_tc(const __grid_consta
         }
         // ================================ epilogue (warps 2..9 -> TMEM lane quarters 2,3,0,1,2,3,0,1) =================
         const int q = warp & 3, half = (warp - 2) >> 2;
-        mbar_wait(&acc_bar, 0);
+        mbar_wait(&acc_bar, 0, (CRB3D_K_BEV_CONV << 8) | 7);
         tc_fence_after();
         if (tracing && tid == 64) tr[4] = gtime();
         float* stage_f = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * PITCH;
@@ -388,7 +388,7 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
                         const int stage = sb % NSB;
                         if (sb >= NSB) {
                             const long long t0 = tracing ? clock64() : 0;
-                            mbar_wait(&empty_b[stage], ((sb / NSB) - 1) & 1);
+                            mbar_wait(&empty_b[stage], ((sb / NSB) - 1) & 1, (CRB3D_K_BEV_CONV_PAIR << 8) | 4);
                             if (tracing) w_empty += clock64() - t0;
                         }
                         if (leader) mbar_expect_tx(&full_b[stage], 2 * ROW_B);
@@ -412,18 +412,18 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
             for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
                 const int set = it & 1;
                 long long t0 = tracing ? clock64() : 0;
-                if (it >= 2) mbar_wait(&acc_empty[set], ((it >> 1) - 1) & 1);
+                if (it >= 2) mbar_wait(&acc_empty[set], ((it >> 1) - 1) & 1, (CRB3D_K_BEV_CONV_PAIR << 8) | 6);
                 if (tracing) w_acc += clock64() - t0;
                 tc_fence_after();
                 for (int kc = 0; kc < n_chunks; ++kc, ++ca) {
                     const int abuf = ca % NSA;
                     t0 = tracing ? clock64() : 0;
-                    mbar_wait(&full_a[abuf], (ca / NSA) & 1);
+                    mbar_wait(&full_a[abuf], (ca / NSA) & 1, (CRB3D_K_BEV_CONV_PAIR << 8) | 1);
                     if (tracing) { w_a += clock64() - t0; if (ca == 0 && lane == 0) tr[2] = gtime(); }
                     for (int row = 0; row < 3; ++row, ++sb) {
                         const int stage = sb % NSB;
                         t0 = tracing ? clock64() : 0;
-                        mbar_wait(&full_b[stage], (sb / NSB) & 1);
+                        mbar_wait(&full_b[stage], (sb / NSB) & 1, (CRB3D_K_BEV_CONV_PAIR << 8) | 3);
                         if (tracing) w_b += clock64() - t0;
                         tc_fence_after();
                         if (elect_one()) {
@@ -471,7 +471,7 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
                 }
                 for (int kc = 0; kc < n_chunks; ++kc, ++ca) {
                     const int abuf = ca % NSA;
-                    if (ca >= NSA) mbar_wait(&empty_a[abuf], ((ca / NSA) - 1) & 1);
+                    if (ca >= NSA) mbar_wait(&empty_a[abuf], ((ca / NSA) - 1) & 1, (CRB3D_K_BEV_CONV_PAIR << 8) | 2);
                     if (leader) mbar_expect_tx(&full_a[abuf], 2 * IT * TILE_A_BYTES);
                     const uint32_t bar = leader_addr(&full_a[abuf]);
 #pragma unroll
@@ -494,7 +494,7 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
         for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
             const int set = it & 1;
             const long long t0 = tracing ? clock64() : 0;
-            mbar_wait(&acc_full[set], (it >> 1) & 1);
+            mbar_wait(&acc_full[set], (it >> 1) & 1, (CRB3D_K_BEV_CONV_PAIR << 8) | 5);
             if (tracing) w_full += clock64() - t0;
             tc_fence_after();
             const int ti = (item * 2 + (int)rank) * IT + t;
@@ -595,11 +595,12 @@ extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int 
         int rc = make_map_f32(&amap, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[CRB3D_MAX_DEVICES] = {};   // the attribute is per function per device
+    const int dev = crb3d_current_device();
+    if (!attr_set[dev]) {
         CRB3D_CUDA(cudaFuncSetAttribute(bev_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024));
         CRB3D_CUDA(cudaFuncSetAttribute(pair::bev_conv3x3_pair_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM + 1024));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     if (!((relu >> 8) & 1)) {
         // CTA-pair kernel (default); wpack is the SPLIT layout [C_out/128][tap][C_in/16][half][4 slabs][64 co][4 ci]
@@ -612,7 +613,7 @@ extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int 
         if (rc) return rc;
         const int ny = cout / N;
         const int n_items = (int)crb3d_divup(g.n_tiles, 2 * pair::IT);
-        int n_clusters = CRB3D_NUM_SMS / 2 / ny;
+        int n_clusters = crb3d_num_sms() / 2 / ny;
         if (n_clusters < 1) n_clusters = 1;
         if (n_clusters > n_items) n_clusters = n_items;
         pair::bev_conv3x3_pair_tc<<<dim3((unsigned)(2 * n_clusters), (unsigned)ny), pair::NTHREADS, pair::SMEM + 1024, stream>>>(
@@ -625,3 +626,5 @@ extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int 
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
+
+CRB3D_DIAG_DEFINE_SETTER(bev_conv)

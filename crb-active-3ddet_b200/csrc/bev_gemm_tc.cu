@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
                 const int m0 = (rank + i * ctas_per_slice) * TILE_M;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int stage = it % STAGES;
-                    if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1);
+                    if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1, (CRB3D_K_BEV_GEMM << 8) | 9);
                     const uint32_t a_dst = ring_base + stage * STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     tma_load_2d(a_dst, &amap, kb * BK, m0, &full_bar[stage]);
@@ -131,15 +131,15 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
     } else if (warp == 1) {
         if (lane == 0 && my_tiles > 0) {
             const uint32_t idesc = idesc_tf32(TILE_M, N);
-            if (BRES) mbar_wait(&b_full, 0);
+            if (BRES) mbar_wait(&b_full, 0, (CRB3D_K_BEV_GEMM << 8) | 10);
             int it = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int acc = i & 1;
-                if (i >= 2) mbar_wait(&acc_empty[acc], ((i >> 1) - 1) & 1);   // the epilogue has drained this accumulator
+                if (i >= 2) mbar_wait(&acc_empty[acc], ((i >> 1) - 1) & 1, (CRB3D_K_BEV_GEMM << 8) | 6);   // the epilogue has drained this accumulator
                 tc_fence_after();
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int stage = it % STAGES;
-                    mbar_wait(&full_bar[stage], (it / STAGES) & 1);
+                    mbar_wait(&full_bar[stage], (it / STAGES) & 1, (CRB3D_K_BEV_GEMM << 8) | 8);
                     tc_fence_after();
                     const uint32_t a_base = ring_base + stage * STAGE_BYTES;
                     const uint32_t b_base = BRES ? bres_base + kb * C::B_BYTES : a_base + C::A_BYTES;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
                     } else orow = m;
                 }
                 rowoff[lane] = orow < 0 ? -1 : orow * stride;
-                mbar_wait(&acc_full[acc], (i >> 1) & 1);
+                mbar_wait(&acc_full[acc], (i >> 1) & 1, (CRB3D_K_BEV_GEMM << 8) | 5);
                 tc_fence_after();
 #pragma unroll 1
                 for (int c0 = h * 32; c0 < N; c0 += 64) {
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
             for (int i = 0; i < my_tiles; ++i) {
                 const int acc = i & 1;
                 const long long mrow0 = (long long)(rank + i * ctas_per_slice) * TILE_M + q * 32;   // first row of the quarter
-                mbar_wait(&acc_full[acc], (i >> 1) & 1);
+                mbar_wait(&acc_full[acc], (i >> 1) & 1, (CRB3D_K_BEV_GEMM << 8) | 5);
                 tc_fence_after();
 #pragma unroll 1
                 for (int c0 = h * 16; c0 < N; c0 += 32) {
@@ -293,13 +293,14 @@ int launch_gemm(const float* A, long long M, int K, long long lda, const float* 
                         (size_t)STAGES * (C::A_BYTES + (BRES ? 0 : C::B_BYTES));
     if (smem > 227 * 1024) return CRB3D_ERR_UNSUPPORTED;
     auto kern = bev_gemm_tc<N, STAGES, BRES, DENSE>;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    static size_t smem_set[CRB3D_MAX_DEVICES] = {};   // the attribute is per function per device
+    const int dev = crb3d_current_device();
+    if (smem > smem_set[dev]) {
         CRB3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        smem_set[dev] = smem;
     }
     const int n_tiles = (int)crb3d_divup(M, TILE_M);
-    int per_slice = CRB3D_NUM_SMS / n_slices;
+    int per_slice = crb3d_num_sms() / n_slices;
     if (per_slice < 1) per_slice = 1;
     if (per_slice > n_tiles) per_slice = n_tiles;
     kern<<<(unsigned)(n_slices * per_slice), 320, smem, stream>>>(amap, wmap, (int)M, K, per_slice, halves, bias, relu, out);
@@ -351,3 +352,5 @@ extern "C" int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long
     if (dense && N == 80) return launch_gemm<80, 6, false, true>(A, M, K, lda, W, n_sub, 1, bias, relu, o, stream);
     return CRB3D_ERR_UNSUPPORTED;
 }
+
+CRB3D_DIAG_DEFINE_SETTER(bev_gemm)

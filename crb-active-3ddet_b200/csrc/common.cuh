@@ -11,7 +11,73 @@
 #define CRB3D_ERR_WORKSPACE (-3)
 #define CRB3D_ERR_UNSUPPORTED (-4)
 
-#define CRB3D_NUM_SMS 148  // B200: 2 dies x 74 SMs
+#define CRB3D_ERR_DEVICE (-5)   // a kernel gave up on a bounded wait / probe (see crb3d_last_device_error)
+
+#define CRB3D_NUM_SMS 148  // B200: 2 dies x 74 SMs (default; launchers size grids with crb3d_num_sms())
+#define CRB3D_MAX_DEVICES 16
+
+// SM count of the current device (cudaDeviceGetAttribute, cached per device) and the current device's index
+int crb3d_num_sms();
+int crb3d_current_device();
+
+// ---------------------------------------------------------------------------------------------
+// Device-side diagnostics: every wait / probe loop in this library is BOUNDED. A kernel that exceeds its budget claims
+// the process-wide record (zero-copy pinned host memory, so it stays readable after the context dies), fills it in and
+// traps: a hang becomes a launch failure at the next synchronisation and crb3d_last_device_error() says where.
+// Without relocatable device code every translation unit owns a copy of the pointer; csrc/diag.cu sets all of them.
+// ---------------------------------------------------------------------------------------------
+struct Crb3dDiagRec {
+    unsigned int flag;      // 0 = clear, 1 = being written, 2 = complete
+    unsigned int kernel;    // CRB3D_K_* id
+    unsigned int site;      // barrier / loop id inside the kernel
+    unsigned int parity;    // mbarrier parity waited for (or probe count)
+    unsigned int block_x, block_y, thread;
+    unsigned int extra;     // iteration / stage / whatever the site documents
+    unsigned long long waited_ns;
+    unsigned int device;
+    unsigned int pad;
+};
+
+enum {
+    CRB3D_K_SPCONV_TC = 1, CRB3D_K_BEV_CONV = 2, CRB3D_K_BEV_CONV_PAIR = 3, CRB3D_K_BEV_GEMM = 4, CRB3D_K_HASH_INSERT = 5,
+    CRB3D_K_HASH_FIND = 6, CRB3D_K_BEV_CONV_S2 = 7, CRB3D_K_FC_GEMM = 8
+};
+
+#define CRB3D_WAIT_BUDGET_NS 4000000000ull   // 4 s: three orders of magnitude above the longest kernel of this library
+
+#ifdef __CUDACC__
+static __device__ Crb3dDiagRec* g_crb3d_diag = nullptr;   // per translation unit (set by CRB3D_DIAG_DEFINE_SETTER's function)
+static __device__ unsigned int g_crb3d_diag_device = 0;
+
+#define CRB3D_DIAG_DEFINE_SETTER(name)                                                                        \
+    extern "C" int crb3d_diag_set_##name(void* host_mapped, unsigned int device) {                            \
+        Crb3dDiagRec* p = (Crb3dDiagRec*)host_mapped;                                                         \
+        if (cudaMemcpyToSymbol(g_crb3d_diag, &p, sizeof(p)) != cudaSuccess) return CRB3D_ERR_CUDA;             \
+        if (cudaMemcpyToSymbol(g_crb3d_diag_device, &device, sizeof(device)) != cudaSuccess) return CRB3D_ERR_CUDA; \
+        return CRB3D_OK;                                                                                       \
+    }
+
+__device__ __forceinline__ unsigned long long crb3d_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// cold path: record + trap (never returns)
+static __device__ __noinline__ void crb3d_diag_fail(unsigned int kernel, unsigned int site, unsigned int parity, unsigned int extra,
+                                             unsigned long long waited_ns) {
+    Crb3dDiagRec* r = g_crb3d_diag;
+    if (r && atomicCAS_system(&r->flag, 0u, 1u) == 0u) {
+        r->kernel = kernel; r->site = site; r->parity = parity; r->extra = extra;
+        r->block_x = blockIdx.x; r->block_y = blockIdx.y; r->thread = threadIdx.x;
+        r->waited_ns = waited_ns; r->device = g_crb3d_diag_device;
+        __threadfence_system();
+        r->flag = 2u;
+        __threadfence_system();
+    }
+    __trap();
+}
+#endif
 
 #define CRB3D_CHECK_LAUNCH()                                   \
     do {                                                       \
@@ -67,9 +133,10 @@ __device__ __forceinline__ uint32_t hash_u64(unsigned long long k) {
 }
 
 // Returns the slot that holds `key`, inserting it if absent.
+// The probe sequence is bounded by the capacity: a full table (a caller sized it wrong) is a device error, not a hang.
 __device__ __forceinline__ uint32_t hash_insert(unsigned long long* keys, uint32_t cap_mask, unsigned long long key) {
     uint32_t s = hash_u64(key) & cap_mask;
-    while (true) {
+    for (uint32_t probes = 0; probes <= cap_mask; ++probes) {
         unsigned long long cur = keys[s];
         if (cur == key) return s;
         if (cur == CRB3D_EMPTY_KEY) {
@@ -78,18 +145,21 @@ __device__ __forceinline__ uint32_t hash_insert(unsigned long long* keys, uint32
         }
         s = (s + 1) & cap_mask;
     }
+    crb3d_diag_fail(CRB3D_K_HASH_INSERT, 0, cap_mask, (unsigned int)key, 0);
+    return 0;
 }
 
 // Returns slot or 0xFFFFFFFF when absent.
 __device__ __forceinline__ uint32_t hash_find(const unsigned long long* __restrict__ keys, uint32_t cap_mask,
                                               unsigned long long key) {
     uint32_t s = hash_u64(key) & cap_mask;
-    while (true) {
+    for (uint32_t probes = 0; probes <= cap_mask; ++probes) {
         unsigned long long cur = __ldg(&keys[s]);
         if (cur == key) return s;
         if (cur == CRB3D_EMPTY_KEY) return 0xFFFFFFFFu;
         s = (s + 1) & cap_mask;
     }
+    return 0xFFFFFFFFu;   // a table without an empty slot and without the key: absent
 }
 
 // ---------------------------------------------------------------------------------------------

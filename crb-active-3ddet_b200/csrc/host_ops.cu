@@ -14,6 +14,7 @@ extern "C" const char* crb3d_strerror(int code) {
         case CRB3D_ERR_CUDA: return "CUDA call or kernel launch failed";
         case CRB3D_ERR_WORKSPACE: return "workspace missing or too small";
         case CRB3D_ERR_UNSUPPORTED: return "shape not supported by this kernel";
+        case CRB3D_ERR_DEVICE: return "a kernel exceeded a bounded wait / probe (crb3d_last_device_error has the record)";
         default: return "unknown error";
     }
 }

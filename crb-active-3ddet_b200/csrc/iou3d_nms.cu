@@ -477,8 +477,8 @@ int launch_mask(const float* boxes, const int* counts, int B, int n, float thres
     else
         nms_mask_kernel<false><<<mg, MASK_THREADS, 0, stream>>>(n, thresh, boxes, w.rb, w.circ, w.maskT, w.rows_pad, counts, n, prefix, idx, m_dev, w.gq, cnt, w.gq_cap);
     if (w.gq) {
-        if (rotated) nms_eval_kernel<true><<<CRB3D_NUM_SMS * 4, 256, 0, stream>>>(w.gq, cnt, w.gq_cap, thresh, boxes, w.rb, idx, n, w.maskT, w.rows_pad);
-        else nms_eval_kernel<false><<<CRB3D_NUM_SMS * 4, 256, 0, stream>>>(w.gq, cnt, w.gq_cap, thresh, boxes, w.rb, idx, n, w.maskT, w.rows_pad);
+        if (rotated) nms_eval_kernel<true><<<crb3d_num_sms() * 4, 256, 0, stream>>>(w.gq, cnt, w.gq_cap, thresh, boxes, w.rb, idx, n, w.maskT, w.rows_pad);
+        else nms_eval_kernel<false><<<crb3d_num_sms() * 4, 256, 0, stream>>>(w.gq, cnt, w.gq_cap, thresh, boxes, w.rb, idx, n, w.maskT, w.rows_pad);
     }
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
@@ -500,7 +500,8 @@ int launch_reduce(const int* counts, int B, int n, int max_keep, long long* keep
     const bool stream_mode = 16 * (size_t)w.rows_pad + list <= 200 * 1024;
     const size_t smem = (stream_mode ? 16 * (size_t)w.rows_pad : 0) + list;
     if (smem > 200 * 1024) return CRB3D_ERR_UNSUPPORTED;
-    static size_t smem_set[2] = {0, 0};
+    static size_t smem_set_dev[CRB3D_MAX_DEVICES][2] = {};   // the attribute is per function per device
+    size_t* smem_set = smem_set_dev[crb3d_current_device()];
     if (smem > 40 * 1024 && smem > smem_set[stream_mode]) {
         if (stream_mode) CRB3D_CUDA(cudaFuncSetAttribute(nms_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else CRB3D_CUDA(cudaFuncSetAttribute(nms_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

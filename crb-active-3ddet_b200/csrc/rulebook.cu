@@ -318,3 +318,5 @@ extern "C" int crb3d_rulebook_compact_pairs(const int* nbr, int K, int n_out, in
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
+
+CRB3D_DIAG_DEFINE_SETTER(rulebook)

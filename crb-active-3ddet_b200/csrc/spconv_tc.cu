@@ -19,8 +19,7 @@
 // the TMA unit, tools/trace_spconv.py) -> one thread per half row (half-empty sectors) -> per-warp cooperative loop
 // (serial latency) -> list-driven LSU gather -> two list-driven producer groups alternating over the stages (this file;
 // 553 -> 435 us over the 11 tensor-core layers of a batch-4 step, profiles/r01_spconv_variants.txt).
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 
 namespace {
 
@@ -33,20 +32,9 @@ constexpr int MAX_K = 27;
 // MMA thread after full-wait / after issuing + committing); set through crb3d_debug_set_tc_trace, null in production
 __device__ long long* g_tc_trace = nullptr;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity));
-}
+using tc::smem_u32;
+using tc::mbar_init;
+using tc::mbar_wait;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     // .ca: the copy goes through L1, which merges the 16 lanes that read one 256-byte row into two line requests; with .cg
@@ -194,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
             const int src = src_next;
             if (it + NG < n_act) src_next = (o < nv) ? __ldg(&nbr[(size_t)act[it + NG] * n_out + o]) : -1;
             if (gtid == 0) { cnt_v[grp][(li + 2) & 3] = 0; cnt_z[grp][(li + 2) & 3] = 0; }
-            if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1);
+            if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1, (CRB3D_K_SPCONV_TC << 8) | 9, it);
             long long* trace = (trace_base && it < 32) ? trace_base + 128 : nullptr;
             if (trace) trace[it * 4 + 0] = clock64();
             const uint32_t a_base = smem_base + stage * STAGE_BYTES, b_base = a_base + A_BYTES;
@@ -255,7 +243,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
         long long* const trace_mma = (blockIdx.x == gridDim.x / 2 && lane == 0) ? g_tc_trace : nullptr;
         for (int it = 0; it < n_act; ++it) {
             const int stage = it % STAGES;
-            mbar_wait(&full_bar[stage], (it / STAGES) & 1);
+            mbar_wait(&full_bar[stage], (it / STAGES) & 1, (CRB3D_K_SPCONV_TC << 8) | 8, it);
             long long* trace = (trace_mma && it < 32) ? trace_mma : nullptr;
             if (trace) trace[it * 4 + 2] = clock64();
             asm volatile("fence.proxy.async.shared::cta;");   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
@@ -282,7 +270,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
     // ---- epilogue: TMEM -> registers -> global (warps 0..3; a warp may only touch TMEM lanes 32*(warp%4)..+31)
     if (warp < 4) {
         if (n_act > 0) {
-            mbar_wait(&acc_bar, 0);
+            mbar_wait(&acc_bar, 0, (CRB3D_K_SPCONV_TC << 8) | 7);
             asm volatile("tcgen05.fence::after_thread_sync;");
         }
         const int quarter = warp & 3;
@@ -335,25 +323,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess) return nullptr;
-        fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 // 3-D view {ci, k, co} of the contiguous [C_out, K, C_in] weight; box {32, 1, cout}, 128-byte swizzle, zero OOB fill
 int make_weight_map(const float* weight, int K, int cin, int cout, CUtensorMap* map) {
-    EncodeTiledFn enc = get_encode_fn();
+    tc::EncodeTiledFn enc = tc::get_encode_fn();
     if (!enc) return CRB3D_ERR_CUDA;
     cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)K, (cuuint64_t)cout};
     cuuint64_t strides[2] = {(cuuint64_t)cin * 4, (cuuint64_t)K * cin * 4};
@@ -373,10 +345,11 @@ int launch_tc(const float* feat, int n_in, const int* nbr, const float* weight, 
     int rc = make_weight_map(weight, K, cin, COUT, &wmap);
     if (rc) return rc;
     auto kern = spconv_fwd_tc<NKB, COUT, STAGES, MIN_CTAS>;
-    static bool attr_set = false;  // per instantiation; the attribute is per function (single-GPU processes)
-    if (!attr_set) {
+    static bool attr_set[CRB3D_MAX_DEVICES] = {};  // per instantiation and per device (the attribute is per function per device)
+    const int dev = crb3d_current_device();
+    if (!attr_set[dev]) {
         CRB3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     kern<<<(unsigned)crb3d_divup(n_out, TILE_M), THREADS, smem, stream>>>(feat, cin, wmap, nbr, n_out, K, kmap, scale, shift, relu, out, n_dev);
     CRB3D_CHECK_LAUNCH();
@@ -411,7 +384,7 @@ extern "C" int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int*
         if (cout == 32) return launch_tc<2, 32, 2, 2>(TC_ARGS);
         // fewer tiles than SMs: one CTA per SM anyway, so spend the shared memory on four stages (each producer group then
         // runs two stages ahead of the tensor core instead of waiting for its previous stage's MMAs)
-        if (cout == 64 && crb3d_divup(n_out, TILE_M) <= CRB3D_NUM_SMS) return launch_tc<2, 64, 4, 1>(TC_ARGS);
+        if (cout == 64 && crb3d_divup(n_out, TILE_M) <= crb3d_num_sms()) return launch_tc<2, 64, 4, 1>(TC_ARGS);
         if (cout == 64) return launch_tc<2, 64, 2, 2>(TC_ARGS);
         if (cout == 128) return launch_tc<2, 128, 2, 1>(TC_ARGS);
     }
@@ -423,3 +396,5 @@ extern "C" int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int*
 extern "C" int crb3d_debug_set_tc_trace(long long* buf) {
     return cudaMemcpyToSymbol(g_tc_trace, &buf, sizeof(buf)) == cudaSuccess ? CRB3D_OK : CRB3D_ERR_CUDA;
 }
+
+CRB3D_DIAG_DEFINE_SETTER(spconv_tc)

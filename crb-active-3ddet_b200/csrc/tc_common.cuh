@@ -12,14 +12,28 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;"); }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: `tag` = (CRB3D_K_* kernel id << 8) | site id. After CRB3D_WAIT_BUDGET_NS without the phase completing the
+// thread records (kernel, site, parity, extra, block, thread) in the host-visible diagnostics record and traps - a lost
+// arrival shows up as a launch failure with a location instead of a GPU that spins until a watchdog kills the process.
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity));
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0, uint32_t extra = 0) {
+    const uint32_t addr = smem_u32(bar);
+    if (mbar_try_wait(addr, parity)) return;
+    const unsigned long long t0 = crb3d_globaltimer();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(addr, parity)) {
+        if ((++spins & 255u) == 0u) {
+            const unsigned long long dt = crb3d_globaltimer() - t0;
+            if (dt > CRB3D_WAIT_BUDGET_NS) crb3d_diag_fail(tag >> 8, tag & 0xFFu, parity, extra, dt);
+        }
+    }
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes));

@@ -204,3 +204,5 @@ extern "C" int crb3d_voxelize(const float* points, int64_t n_points, int pt_stri
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
+
+CRB3D_DIAG_DEFINE_SETTER(voxelize)

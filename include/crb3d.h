@@ -25,9 +25,25 @@ typedef struct CUstream_st* cudaStream_t;
 #define CRB3D_ERR_CUDA (-2)        /* a CUDA call / launch failed */
 #define CRB3D_ERR_WORKSPACE (-3)   /* workspace missing or too small */
 #define CRB3D_ERR_UNSUPPORTED (-4) /* shape outside what the kernels cover */
+#define CRB3D_ERR_DEVICE (-5)      /* a kernel exceeded a bounded wait / probe: see crb3d_last_device_error */
 
 const char* crb3d_version(void);
 const char* crb3d_strerror(int code);
+
+/* ---- device-side diagnostics -----------------------------------------------------------------------------------
+ * No reference counterpart (the reference's native code never waits on the device; its host errors are
+ * fprintf + exit(-1), pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:14-26). Every mbarrier wait and hash probe of this library
+ * is bounded (4 s / table capacity). A kernel that runs out of budget writes {kernel id, site, parity, block, thread,
+ * waited ns} into one zero-copy pinned HOST record and traps, so a lost arrival surfaces as a launch failure with a
+ * location at the next synchronisation instead of a GPU that spins until a watchdog kills the process.
+ * crb3d_diag_init: once per device (current device), before the first kernel and outside stream capture; this is the one
+ *   call of the library that allocates (64 bytes of pinned host memory per process).
+ * crb3d_last_device_error: HOST out[12] = {flag, kernel, site, parity, block_x, block_y, thread, extra, ns_lo, ns_hi,
+ *   device, 0}; returns CRB3D_OK (nothing recorded) or CRB3D_ERR_DEVICE. Reads host memory only: valid after a trap. */
+int crb3d_diag_init(void);
+int crb3d_last_device_error(unsigned int* out12);
+int crb3d_diag_clear(void);
+int crb3d_device_sm_count(int* n);
 
 /* ---- voxelization + MeanVFE ---------------------------------------------------------------------------------
  * replaces spconv.utils.Point2VoxelCPU3d.point_to_voxel (pcdet/datasets/processor/data_processor.py:15-60,115-143)
