@@ -49,6 +49,21 @@ def _i32c(t):
     return t if (t.dtype == torch.int32 and t.is_contiguous()) else t.int().contiguous()
 
 
+def debug_mark(slot, value):
+    """Debug: queues a one-thread kernel that stores `value` in host-visible marker `slot` (see csrc/diag.cu)."""
+    lib = _lib.load()
+    lib.crb3d_debug_mark.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    _lib.check(lib.crb3d_debug_mark(int(slot), int(value), _stream()), "crb3d_debug_mark")
+
+
+def debug_read_markers(n=16):
+    lib = _lib.load()
+    out = (ctypes.c_int * n)()
+    lib.crb3d_debug_read_markers.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    _lib.check(lib.crb3d_debug_read_markers(out, n), "crb3d_debug_read_markers")
+    return list(out)
+
+
 _WS = {}
 WS_TAG = None   # extra key: every captured copy of the whole-step graph owns its scratch (copies replay concurrently)
 

@@ -9,6 +9,7 @@ Module and parameter names mirror the reference so its checkpoints load unchange
 the rulebook phase: max-class scores, top-k, lazy decode, batched rotated NMS, points-in-boxes density and the label
 entropy all stay on the device.
 """
+import os
 from functools import partial
 
 import numpy as np
@@ -48,8 +49,11 @@ WAYMO_SECOND_CFG = dict(
 )
 
 
+# debug: one-thread marker kernels between the stages of the whole-step graph (tools/stress_hang.py reads them after a hang)
+MARKERS = bool(int(os.environ.get("CRB3D_MARKERS", "0")))
+
 # tcgen05 halo-tile kernel for the 3x3 stride-1 BEV convs: "auto" (when its CTA count fills whole waves), True, False
-BEV_CONV_TC = "auto"
+BEV_CONV_TC = {"0": False, "1": True}.get(os.environ.get("CRB3D_BEV_CONV_TC", ""), "auto")
 
 
 def post_act_block(in_channels, out_channels, kernel_size, indice_key=None, stride=1, padding=0, conv_type="subm", norm_fn=None):
@@ -206,8 +210,10 @@ class BaseBEVBackbone(nn.Module):
         items = -(-(B * -(-u // 8) * -(-v // 16)) // 4)
         return items / (-(-items // 74) * 74.0) >= 0.8
 
-    def forward_inference(self, x):
+    def forward_inference(self, x, mark=None):
         B = x.shape[0]
+        mark = mark or (lambda stage: None)
+        li = 0
         gemm_ok = all(g is not None for _, _, g in self._plan)
         if gemm_ok:
             ctot = sum(g[0].shape[0] // (g[2] * g[2]) for _, _, g in self._plan)
@@ -222,6 +228,8 @@ class BaseBEVBackbone(nn.Module):
                 else:
                     xh = torch.cudnn_convolution_relu(xh.permute(0, 3, 1, 2), w, b, stride, pad, (1, 1), 1).permute(0, 2, 3, 1)
                     xh = xh if xh.is_contiguous() else xh.contiguous()
+                li += 1
+                mark(200 + li)
             if not gemm_ok:
                 ups.append(torch.relu_(torch.nn.functional.conv_transpose2d(xh.permute(0, 3, 1, 2), dw, db, stride=ds)))
                 continue
@@ -233,6 +241,7 @@ class BaseBEVBackbone(nn.Module):
             assert cat.shape[1] == h * st and cat.shape[2] == wd * st
             ops.bev_gemm(xh.view(B * h * wd, xh.shape[3]), gw, gb, True, [(cat.view(-1, ctot)[:, c0:], 0, cout, ctot)],
                          n_sub=st * st, up=2 if st == 2 else 0, in_hw=(h, wd), round_out=True)
+            mark(300 + li)
             c0 += cout
         if gemm_ok:
             return cat.permute(0, 3, 1, 2)
@@ -241,7 +250,7 @@ class BaseBEVBackbone(nn.Module):
     def forward(self, batch_dict):
         x = batch_dict["spatial_features"]
         if not self.training and not torch.is_grad_enabled() and getattr(self, "_plan", None) is not None:
-            batch_dict["spatial_features_2d"] = self.forward_inference(x)
+            batch_dict["spatial_features_2d"] = self.forward_inference(x, batch_dict.get("_mark"))
             return batch_dict
         ups = []
         for i in range(len(self.blocks)):
@@ -365,12 +374,16 @@ class SECONDNet(nn.Module):
         return bd
 
     @torch.no_grad()
-    def dense_and_post(self, spatial_features, points_xyz, pt_begin, pt_end, batch_size, max_pts_per_frame):
+    def dense_and_post(self, spatial_features, points_xyz, pt_begin, pt_end, batch_size, max_pts_per_frame, mark=None):
         """Static-shape half of the step: BEV backbone -> anchor head -> max-class score / top-k / lazy decode -> batched
         rotated NMS -> points-in-boxes density -> label entropy. No host synchronisation and no data-dependent shape, so
         the whole thing is capturable in one CUDA graph (enable_cuda_graph)."""
         cfg = self.cfg
-        bd = self.dense_head(self.backbone_2d(dict(spatial_features=spatial_features)))
+        mark = mark or (lambda stage: None)
+        bd = self.backbone_2d(dict(spatial_features=spatial_features, _mark=mark))
+        mark(40)
+        bd = self.dense_head(bd)
+        mark(41)
         B, A = batch_size, self.dense_head.num_anchors
         dev = spatial_features.device
         # class_agnostic_nms (model_nms_utils.py:6-25): score >= thresh, top-k(NMS_PRE_MAXSIZE) - valid entries are a prefix
@@ -384,9 +397,12 @@ class SECONDNet(nn.Module):
             score, label = score.view(B, A), label.view(B, A, 1)
             top_scores, top_idx = torch.topk(score, k, dim=1)
             counts = (top_scores >= cfg["score_thresh"]).sum(dim=1).int()
+        mark(42)
         boxes = head_ops.anchor_decode_select(bd["box_preds"], bd["dir_cls_preds"], top_idx, self.dense_head.spec, A)
         P = cfg["nms_post_maxsize"]
+        mark(43)
         keep, num = ops.nms_batched(boxes, counts, cfg["nms_thresh"], rotated=True, max_keep=P)
+        mark(44)
         final_boxes = head_ops.gather_rows(boxes, keep, num, 0.0)
         final_scores = head_ops.gather_rows(top_scores.unsqueeze(-1).contiguous(), keep, num, 0.0).squeeze(-1)
         anchor_of_kept = head_ops.gather_rows(top_idx.int().unsqueeze(-1).contiguous(), keep, num, 0).squeeze(-1)
@@ -454,9 +470,13 @@ class SECONDNet(nn.Module):
         B = g["B"]
         d = self.cfg["data"]
         ops.WS_TAG = id(g)       # scratch buffers private to this graph copy (see ops._ws); reset by the caller
+        mark = (lambda stage: ops.debug_mark(g.get("slot", 0) * 2, stage)) if MARKERS else (lambda stage: None)
+        mark_side = (lambda stage: ops.debug_mark(g.get("slot", 0) * 2 + 1, stage)) if MARKERS else (lambda stage: None)
+        mark(1)
         vox = ops.voxelize(g["points"], g["offsets"], B, d["pc_range"], d["voxel_size"], d["max_pts"], d["max_voxels_test"],
                            xyz_col=0, feat_col=0, n_feat=d["n_feat"], sync=False)
         feat, coords, n_dev = vox["mean"], vox["coords"], vox["n_dev"]
+        mark(2)
         shape = list(self.backbone_3d.sparse_shape)
         # geometry (8 rulebooks: dozens of small latency-bound kernels) runs on a forked branch of the graph, concurrently
         # with the sparse convs of the earlier layers; each conv waits only for the event of ITS rulebook
@@ -468,6 +488,7 @@ class SECONDNet(nn.Module):
         books, counts, caps, plan = {}, [n_dev], [coords.shape[0]], []
         with torch.cuda.stream(side):
             for conv, bn, relu in self._sparse_layers():
+                mark_side(100 + len(plan))    # before this layer's rulebook (its event is recorded after, so the branch stays joined)
                 if conv.subm:
                     key = (conv.indice_key, tuple(conv.kernel_size))
                     if key not in books:
@@ -486,16 +507,19 @@ class SECONDNet(nn.Module):
                     counts.append(n_dev)
                     caps.append(cap_out)
                 plan.append((conv, bn, relu, nbr, n_dev, ev))
-        for conv, bn, relu, nbr, nd, ev in plan:
+        for li, (conv, bn, relu, nbr, nd, ev) in enumerate(plan):
             main.wait_event(ev)
             scale, shift = spconv.SparseSequential._bn_affine(bn) if bn is not None else (None, None)
             if conv.bias is not None:
                 shift = conv.bias if shift is None else shift + scale * conv.bias
             feat = ops.spconv_forward(feat, nbr, conv.weight, scale=scale, shift=shift, relu=relu, n_dev=nd)
+            mark(10 + li)
         n_dev = plan[-1][4]
         ops.sparse_to_dense(feat, coords, B, shape, channels_last_bev=True, out=g["spatial"], n_dev=n_dev)
+        mark(30)
         out = self.dense_and_post(g["spatial"].permute(0, 3, 1, 2), g["points"], g["offsets"][:-1], g["offsets"][1:], B,
-                                  g["max_pts"])
+                                  g["max_pts"], mark=mark)
+        mark(99)
         out["counts"] = torch.cat(counts)
         g["caps"] = caps
         return out
@@ -510,16 +534,19 @@ class SECONDNet(nn.Module):
         step on a handful of SMs) runs under the wide kernels of the next one."""
         if slots > 1:
             copies = []
-            for _ in range(slots):
+            for i in range(slots):
+                self._next_slot = i
                 self.enable_full_graph(batch_size, max_points_per_frame, growth, slots=1)
                 copies.append(self._full_graph)
+            self._next_slot = 0
             self._full_graphs = copies
             self._full_graph = copies[0]
             return self
         dev = next(self.parameters()).device
         d = self.cfg["data"]
         C, (D, H, W) = self.backbone_3d.num_point_features, self.bev_shape()
-        g = dict(B=batch_size, cap=batch_size * max_points_per_frame, max_pts=max_points_per_frame, growth=list(growth))
+        g = dict(B=batch_size, cap=batch_size * max_points_per_frame, max_pts=max_points_per_frame, growth=list(growth),
+                 slot=getattr(self, "_next_slot", 0))
         g["spatial"] = torch.zeros((batch_size, H, W, C * D), device=dev)
         g["points"] = torch.zeros((g["cap"], d["n_feat"]), device=dev)
         g["offsets"] = torch.zeros((batch_size + 1,), dtype=torch.int32, device=dev)

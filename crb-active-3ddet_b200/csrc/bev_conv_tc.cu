@@ -362,6 +362,11 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
         tma_prefetch_desc(&amap);
         tma_prefetch_desc(&wmap);
     }
+    // Both CTAs of the pair must be running before the PAIR allocation touches the peer SM's tensor memory: round 1
+    // allocated first and synchronised the cluster afterwards, and about one launch in 10^4 (with other graph copies'
+    // kernels in flight) never came back from tcgen05.alloc - the only unbounded wait of this kernel (hang
+    // root cause; tools/stress_hang.py reproduces it within ~50 repetitions and is clean with this barrier).
+    cluster_sync_all();
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");

@@ -13,6 +13,10 @@ extern "C" int crb3d_diag_set_rulebook(void*, unsigned int);
 extern "C" int crb3d_diag_set_voxelize(void*, unsigned int);
 
 namespace {
+// debug markers (tools/stress_hang.py): 64 ints of zero-copy host memory behind the record; a one-thread kernel stores a
+// stage id into its slot, so that after a hang the host can read how far every concurrently replayed graph copy got
+__global__ void mark_kernel(volatile int* p, int v) { *p = v; __threadfence_system(); }
+constexpr int N_MARKERS = 64;
 Crb3dDiagRec* g_host_rec = nullptr;          // cudaHostAllocMapped | Portable: one per process
 bool g_dev_init[CRB3D_MAX_DEVICES] = {};
 int g_sms[CRB3D_MAX_DEVICES] = {};
@@ -41,8 +45,8 @@ extern "C" int crb3d_diag_init(void) {
     if (g_dev_init[d]) return CRB3D_OK;
     if (!g_host_rec) {
         void* p = nullptr;
-        CRB3D_CUDA(cudaHostAlloc(&p, sizeof(Crb3dDiagRec), cudaHostAllocMapped | cudaHostAllocPortable));
-        memset(p, 0, sizeof(Crb3dDiagRec));
+        CRB3D_CUDA(cudaHostAlloc(&p, sizeof(Crb3dDiagRec) + sizeof(int) * N_MARKERS, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(p, 0, sizeof(Crb3dDiagRec) + sizeof(int) * N_MARKERS);
         g_host_rec = (Crb3dDiagRec*)p;
     }
     void* dptr = nullptr;
@@ -80,5 +84,21 @@ extern "C" int crb3d_diag_clear(void) {
 extern "C" int crb3d_device_sm_count(int* n) {
     if (!n) return CRB3D_ERR_ARG;
     *n = crb3d_num_sms();
+    return CRB3D_OK;
+}
+
+// Debug (not in include/crb3d.h): queue a one-thread kernel on `stream` that stores `value` into host-visible marker `slot`.
+extern "C" int crb3d_debug_mark(int slot, int value, cudaStream_t stream) {
+    if (!g_host_rec || slot < 0 || slot >= N_MARKERS) return CRB3D_ERR_ARG;
+    void* dptr = nullptr;
+    CRB3D_CUDA(cudaHostGetDevicePointer(&dptr, g_host_rec, 0));
+    mark_kernel<<<1, 1, 0, stream>>>((volatile int*)((char*)dptr + sizeof(Crb3dDiagRec)) + slot, value);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+extern "C" int crb3d_debug_read_markers(int* out, int n) {
+    if (!g_host_rec || !out || n < 0 || n > N_MARKERS) return CRB3D_ERR_ARG;
+    const volatile int* m = (const volatile int*)((const char*)g_host_rec + sizeof(Crb3dDiagRec));
+    for (int i = 0; i < n; ++i) out[i] = m[i];
     return CRB3D_OK;
 }

@@ -27,12 +27,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
     const uint32_t addr = smem_u32(bar);
     if (mbar_try_wait(addr, parity)) return;
     const unsigned long long t0 = crb3d_globaltimer();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(addr, parity)) {
-        if ((++spins & 255u) == 0u) {
-            const unsigned long long dt = crb3d_globaltimer() - t0;
-            if (dt > CRB3D_WAIT_BUDGET_NS) crb3d_diag_fail(tag >> 8, tag & 0xFFu, parity, extra, dt);
-        }
+    while (!mbar_try_wait(addr, parity)) {   // try_wait itself suspends for a system-dependent time: check the clock every time
+        const unsigned long long dt = crb3d_globaltimer() - t0;
+        if (dt > CRB3D_WAIT_BUDGET_NS) crb3d_diag_fail(tag >> 8, tag & 0xFFu, parity, extra, dt);
     }
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
