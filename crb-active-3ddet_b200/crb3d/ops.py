@@ -209,7 +209,8 @@ def compact_pairs(nbr):
 
 
 # ----------------------------------------------------------------------------------------------- sparse conv
-def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transpose=False, kmap=None, tf32=None, n_dev=None):
+def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transpose=False, kmap=None, tf32=None, n_dev=None,
+                   round_out=False):
     """out[o] = sum_k feat[nbr[k][o]] @ W_k. weight: [C_out, (kz,ky,kx)|K, C_in] (spconv layout).
     transpose=True computes the input gradient: feat is dY (rows of the conv OUTPUT), nbr the transposed table."""
     _need_cuda(feat, nbr, weight)
@@ -242,7 +243,7 @@ def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transp
             w_tc = w_tc.permute(2, 1, 0).contiguous()
         _lib.call("crb3d_spconv_forward_tf32", _p(feat), feat.shape[0], _p(nbr), _p(w_tc), n_out, K, cin, cout, _p(kmap),
                   _p(_f32c(scale)) if scale is not None else None, _p(_f32c(shift)) if shift is not None else None,
-                  int(bool(relu)), _p(out), _p(n_dev), _stream(feat.device))
+                  int(bool(relu)) | (2 if round_out else 0), _p(out), _p(n_dev), _stream(feat.device))
     else:
         _lib.call("crb3d_spconv_forward_f32", _p(feat), _p(nbr), _p(weight), n_out, K, cin, cout, strides[0], strides[1],
                   strides[2], _p(kmap), _p(_f32c(scale)) if scale is not None else None,

@@ -56,6 +56,18 @@ MARKERS = bool(int(os.environ.get("CRB3D_MARKERS", "0")))
 BEV_CONV_TC = {"0": False, "1": True}.get(os.environ.get("CRB3D_BEV_CONV_TC", ""), "auto")
 
 
+def _tf32_weight(conv):
+    """The conv's weight rounded to TF32 (round to nearest) once per parameter version: the tensor core truncates fp32
+    operands, a systematic shrink of ~3e-4 per operand per layer (the BEV stack does the same in its inference plan)."""
+    w = conv.weight
+    key = (w._version, w.data_ptr())
+    c = getattr(conv, "_crb3d_w_tf32", None)
+    if c is None or c[0] != key:
+        c = (key, ops.round_tf32(w))
+        conv._crb3d_w_tf32 = c
+    return c[1]
+
+
 def post_act_block(in_channels, out_channels, kernel_size, indice_key=None, stride=1, padding=0, conv_type="subm", norm_fn=None):
     if conv_type == "subm":
         conv = spconv.SubMConv3d(in_channels, out_channels, kernel_size, bias=False, indice_key=indice_key)
@@ -512,7 +524,9 @@ class SECONDNet(nn.Module):
             scale, shift = spconv.SparseSequential._bn_affine(bn) if bn is not None else (None, None)
             if conv.bias is not None:
                 shift = conv.bias if shift is None else shift + scale * conv.bias
-            feat = ops.spconv_forward(feat, nbr, conv.weight, scale=scale, shift=shift, relu=relu, n_dev=nd)
+            tc = ops.SPCONV_TF32
+            feat = ops.spconv_forward(feat, nbr, _tf32_weight(conv) if tc else conv.weight, scale=scale, shift=shift, relu=relu,
+                                      n_dev=nd, round_out=tc)
             mark(10 + li)
         n_dev = plan[-1][4]
         ops.sparse_to_dense(feat, coords, B, shape, channels_last_bev=True, out=g["spatial"], n_dev=n_dev)

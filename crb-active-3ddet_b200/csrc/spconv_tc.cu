@@ -39,14 +39,14 @@ using tc::mbar_wait;
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     // .ca: the copy goes through L1, which merges the 16 lanes that read one 256-byte row into two line requests; with .cg
     // every 16-byte chunk is its own L2 request and the stage time is set by the request rate (~3 cycles per chunk per SM)
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 // arrive on `bar` once all cp.async issued so far by this thread have completed (does not bump the pending count)
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)));
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)));
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // K-major, 128B-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
@@ -142,12 +142,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = tmem_base_s;
-    if (tid == 0) {   // compact list in ascending k: fixed summation order
-        for (int u = 0; u < 4; ++u) { cnt_v[0][u] = cnt_v[1][u] = 0; cnt_z[0][u] = cnt_z[1][u] = 0; }
-        int n = 0;
-        for (int k = 0; k < K; ++k)
-            if (act_flag[k]) act[n++] = k;
-        n_act_s = n;
+    if (warp == 0) {   // compact list in ascending k (fixed summation order): one ballot
+        for (int u = lane; u < 8; u += 32) { cnt_v[u >> 2][u & 3] = 0; cnt_z[u >> 2][u & 3] = 0; }
+        const bool f = lane < K && act_flag[lane] != 0;
+        const unsigned int m = __ballot_sync(0xffffffffu, f);
+        if (f) act[__popc(m & ((1u << lane) - 1u))] = lane;
+        if (lane == 0) n_act_s = __popc(m);
     }
     __syncthreads();
     const int n_act = n_act_s;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
                 if (valid) list_v[grp][lb][bv + __popc(mv & lt)] = ((unsigned int)r << 25) | (unsigned int)src;
                 if (stale) list_z[grp][lb][bz + __popc(mz & lt)] = (unsigned int)r;
             }
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GT));   // this group's lists are complete
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GT) : "memory");   // this group's lists are complete
             if (trace) trace[it * 4 + 2] = clock64();
             const int n_v = cnt_v[grp][li & 3] << cshift, n_z = cnt_z[grp][li & 3] << cshift;
             for (int i = gtid; i < n_v; i += GT) {
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
                     const int row = (int)list_z[grp][lb][i >> cshift], c16 = i & (cpr - 1);
                     asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(a_base + (row >> 3) * 1024 + (row & 7) * 128 + (c16 >> 3) * (TILE_M * 128) + (((c16 & 7) ^ (row & 7)) << 4)), "f"(0.0f));
                 }
-                asm volatile("fence.proxy.async.shared::cta;");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
             if (trace) trace[it * 4 + 3] = clock64();
             cp_async_arrive(&full_bar[stage]);            // arrives when this thread's copies (if any) have landed
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
             mbar_wait(&full_bar[stage], (it / STAGES) & 1, (CRB3D_K_SPCONV_TC << 8) | 8, it);
             long long* trace = (trace_mma && it < 32) ? trace_mma : nullptr;
             if (trace) trace[it * 4 + 2] = clock64();
-            asm volatile("fence.proxy.async.shared::cta;");   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint64_t da = desc0 + (uint64_t)((stage * STAGE_BYTES) >> 4), db = da + (uint64_t)(A_BYTES >> 4);
             uint32_t elected;
@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
                         const int c = c0 + j + u;
                         if (scale) x = fmaf(x, __ldg(&scale[c]), shift ? __ldg(&shift[c]) : 0.0f);
                         else if (shift) x += __ldg(&shift[c]);
-                        if (relu) x = fmaxf(x, 0.0f);
+                        if (relu & 1) x = fmaxf(x, 0.0f);
+                        if (relu & 2) x = tc::tf32_rn(x);   // the next tensor-core layer then reads exactly what was stored
                         wp[u] = x;
                     }
                     *reinterpret_cast<float4*>(dst + j) = w;
@@ -361,6 +362,7 @@ int launch_tc(const float* feat, int n_in, const int* nbr, const float* weight, 
 // TF32 tensor-core forward. feat: (n_in, C_in) contiguous; weight: contiguous [C_out, K, C_in] (for the input gradient
 // pass the transposed weight [C_in, K, C_out] and the transposed table). Supported: C_in in {16, 32, 64}, C_out in
 // {16, 32, 64, 128}, K <= 27; anything else returns CRB3D_ERR_UNSUPPORTED (callers use crb3d_spconv_forward_f32).
+// relu: bit 0 = ReLU, bit 1 = round the stored values to TF32 (round-to-nearest; the tensor core truncates fp32 operands).
 // Stage counts are sized so that two (C_in = 64) or three (C_in <= 32) CTAs fit one SM: the gather is latency-bound and
 // the co-resident CTAs hide each other's round trips (profiles/r01_spconv_variants.txt, variant G).
 extern "C" int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int* nbr, const float* weight, int n_out, int K,

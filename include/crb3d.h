@@ -108,7 +108,8 @@ int crb3d_spconv_forward_f32(const float* feat, const int* nbr, const float* wei
                              cudaStream_t stream);
 /* tcgen05 path: TF32 inputs, fp32 accumulation in TMEM; feat (n_in, C_in) contiguous and 16-byte aligned (rows are
  * gathered with cp.async); weight contiguous [C_out,K,C_in]; C_in in {4,8,16,32,64}, C_out in {16,32,64,128}, K <= 27, else
- * CRB3D_ERR_UNSUPPORTED (use the f32 entry point). */
+ * CRB3D_ERR_UNSUPPORTED (use the f32 entry point). relu: bit 0 = ReLU, bit 1 = store TF32-rounded values (round to nearest:
+ * a following tensor-core layer then reads exactly what was stored instead of truncating). */
 int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int* nbr, const float* weight, int n_out, int K, int cin,
                               int cout, const int* kmap, const float* scale, const float* shift, int relu, float* out,
                               const int* n_dev, cudaStream_t stream);
