@@ -20,15 +20,7 @@ import numpy as np
 import torch
 
 from . import crb_host, ops
-
-
-def _get(cfg, path, default=None):
-    cur = cfg
-    for key in path.split("."):
-        if cur is None:
-            return default
-        cur = cur.get(key, None) if isinstance(cur, dict) else getattr(cur, key, None)
-    return default if cur is None else cur
+from .strategy import Strategy, _cfg_get as _get
 
 
 def sigmoid_focal_loss_grad(logits, labels, alpha=0.25, gamma=2.0):
@@ -52,14 +44,12 @@ def sigmoid_focal_loss_grad(logits, labels, alpha=0.25, gamma=2.0):
     return (dfocal * bce + focal * dbce) / norm
 
 
-class CRBSampling(object):
+class CRBSampling(Strategy):
+    """A `Strategy` (crb3d/strategy.py = pcdet/query_strategies/strategy.py:5-81): `build_strategy('crb', ...)` of the reference
+    returns this class when crb3d.dropin is installed (alias pcdet.query_strategies.crb_sampling)."""
+
     def __init__(self, model, labelled_loader, unlabelled_loader, rank, active_label_dir, cfg):
-        self.model = model
-        self.labelled_loader = labelled_loader
-        self.unlabelled_loader = unlabelled_loader
-        self.rank = rank
-        self.active_label_dir = active_label_dir
-        self.cfg = cfg
+        super(CRBSampling, self).__init__(model, labelled_loader, unlabelled_loader, rank, active_label_dir, cfg)
         self.k1 = _get(cfg, "ACTIVE_TRAIN.ACTIVE_CONFIG.K1", 5)
         self.k2 = _get(cfg, "ACTIVE_TRAIN.ACTIVE_CONFIG.K2", 3)
         self.bandwidth = _get(cfg, "ACTIVE_TRAIN.ACTIVE_CONFIG.BANDWDITH", 5)   # sic: the reference reads the typo
@@ -67,6 +57,7 @@ class CRBSampling(object):
         self.select_nums = int(_get(cfg, "ACTIVE_TRAIN.SELECT_NUMS", 100))
         self.alpha = 0.95
         self.last_stage = {}
+        self._gt_boxes = {}
 
     # ------------------------------------------------------------------------------------------------ stage 1
     def collect_pool(self):
@@ -79,7 +70,32 @@ class CRBSampling(object):
             pts = np.asarray(batch["points"])
             for b, fid in enumerate(batch["frame_id"]):
                 frames[fid] = pts[pts[:, 0] == b][:, 1:].astype(np.float32)
+                if "gt_boxes" in batch:      # dashboard statistics of strategy.save_points (detector3d_template.py:240-267)
+                    self._gt_boxes[fid] = np.asarray(batch["gt_boxes"][b], dtype=np.float32)
         return frames
+
+    def _point_stats(self, fid, points, class_names):
+        """num_bbox / mean / median / variance of the points inside the frame's ground-truth boxes per class
+        (detector3d_template.py:240-267; zeros when the loader carries no gt_boxes, e.g. a raw unlabelled pool)."""
+        stats = {k: {c: 0 for c in class_names} for k in ("num_bbox", "mean_points", "median_points", "variance_points")}
+        gt = self._gt_boxes.get(fid)
+        if gt is None or len(gt) == 0:
+            return stats
+        dev = next(self.model.parameters()).device
+        pts = torch.from_numpy(np.ascontiguousarray(points[:, :3], dtype=np.float32)).to(dev).view(1, -1, 3)
+        for ci, cname in enumerate(class_names):
+            sel = gt[gt[:, -1] == ci + 1]
+            stats["num_bbox"][cname] = int(len(sel))
+            if len(sel) == 0:
+                continue
+            idx = ops.points_in_boxes(torch.from_numpy(np.ascontiguousarray(sel[:, :7])).to(dev).view(1, -1, 7), pts).view(-1)
+            cnt = torch.bincount(idx[idx >= 0].long(), minlength=1).float()
+            cnt = cnt[cnt > 0]          # the reference counts the boxes that appear in torch.unique (boxes that own a point)
+            if cnt.numel():
+                stats["mean_points"][cname] = float(cnt.mean())
+                stats["median_points"][cname] = float(cnt.median())
+                stats["variance_points"][cname] = float(cnt.var(unbiased=False))
+        return stats
 
     def stage1(self, scorer, frames):
         ids = list(frames.keys())
@@ -138,9 +154,14 @@ class CRBSampling(object):
         if scorer is None:
             dev = next(self.model.parameters()).device
             scorer = PoolScorer(self.model, dev, batch_size=4)
-        num_class = len(self.model.cfg["class_names"]) if hasattr(self.model, "cfg") else len(self.labelled_loader.dataset.class_names)
+        class_names = list(self.model.cfg["class_names"]) if hasattr(self.model, "cfg") else list(self.labelled_loader.dataset.class_names)
+        num_class = len(class_names)
         self.model.eval()
+        if hasattr(self.model, "ensure_inference_current"):   # the model may have been trained since the plan / graphs were built
+            self.model.ensure_inference_current()
         frames = self.collect_pool()
+        for fid, pts in frames.items():
+            self.save_points(fid, self._point_stats(fid, pts, class_names))
         recs, shortlist = self.stage1(scorer, frames)
         prototypes = self.stage2(scorer, frames, shortlist, embedding_fn)
         selected = self.stage3(scorer, recs, prototypes, num_class)

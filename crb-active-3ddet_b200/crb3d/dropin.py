@@ -16,6 +16,8 @@ ALIASES = {
     "pcdet.ops.roiaware_pool3d.roiaware_pool3d_cuda": "pcdet_ops.roiaware_pool3d_cuda",
     "pcdet.ops.pointnet2.pointnet2_stack.pointnet2_stack_cuda": "pcdet_ops.pointnet2_stack_cuda",
     "pcdet.ops.voxel": "pcdet_ops.voxel",
+    # build_strategy('crb', ...) of pcdet/query_strategies/__init__.py:13-29 then returns the crb3d CRBSampling
+    "pcdet.query_strategies.crb_sampling": "crb3d.crb_strategy",
 }
 EXPECTED = {
     "pcdet.ops.iou3d_nms.iou3d_nms_cuda": ["boxes_overlap_bev_gpu", "boxes_iou_bev_gpu", "nms_gpu", "nms_normal_gpu",
@@ -27,6 +29,7 @@ EXPECTED = {
         "three_interpolate_wrapper", "three_interpolate_grad_wrapper", "query_stacked_local_neighbor_idxs_wrapper_stack",
         "query_three_nn_by_stacked_local_idxs_wrapper_stack", "vector_pool_wrapper", "vector_pool_grad_wrapper"],
     "pcdet.ops.voxel": ["hard_voxelize"],
+    "pcdet.query_strategies.crb_sampling": ["CRBSampling"],
 }
 
 

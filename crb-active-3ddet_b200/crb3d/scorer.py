@@ -66,6 +66,8 @@ class PoolScorer(object):
         buffers, one graph launch, D2H of the record into pinned memory - so the narrow tail of one batch runs under the
         wide kernels of the next. Returns the list of pinned host records (dict of tensors, plus "counts") after one final
         synchronisation; a batch whose counts exceed the static capacities must be re-scored with score_host."""
+        if hasattr(self.model, "ensure_inference_current"):
+            self.model.ensure_inference_current()
         graphs = getattr(self.model, "_full_graphs", None)
         if not graphs:
             return [dict((k, torch.from_numpy(v)) for k, v in self.score_host(b).items()) for b in staged_batches]
@@ -161,6 +163,8 @@ class PoolScorer(object):
         batches overlap on alternating graph copies); a partial last batch, a batch that does not fit the static buffers
         or one whose row counts exceeded a static capacity is scored on the eager path (score_host)."""
         world, rank = _world_rank()
+        if hasattr(self.model, "ensure_inference_current"):   # retrained since the plan / graphs were built?
+            self.model.ensure_inference_current()
         ids = list(range(len(frames))) if frame_ids is None else list(frame_ids)
         mine = shard_indices(len(frames), rank, world)
         sels = [mine[s:s + self.batch_size] for s in range(0, len(mine), self.batch_size)]

@@ -358,7 +358,48 @@ class SECONDNet(nn.Module):
             self.dense_head.build_inference_plan()
         if spconv_tf32 is not None:
             ops.SPCONV_TF32 = bool(spconv_tf32)
+        self._inference_args = (fold_bev_bn, spconv_tf32)
+        self._inference_key = self._state_key()
         return self
+
+    # -- cached inference state (folded BEV / head weights, captured graphs) vs training ------------------------------
+    def _state_key(self):
+        """Version counter + address of every parameter and buffer: changes on optimizer steps, load_state_dict, BatchNorm
+        running-statistic updates and device moves (the same key SparseSequential._bn_affine uses per layer)."""
+        return tuple((t._version, t.data_ptr()) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _drop_inference_state(self):
+        self.backbone_2d._plan = None
+        self.dense_head._plan = None
+        for name in ("_graph", "_full_graph", "_full_graphs"):
+            if hasattr(self, name):
+                delattr(self, name)
+
+    def train(self, mode=True):
+        """Training invalidates the inference plan and every captured graph (they hold folded copies of the weights and
+        raw pointers to the BatchNorm affine tensors): the next ensure_inference_current() rebuilds them."""
+        if mode:
+            self._drop_inference_state()
+        return super().train(mode)
+
+    def ensure_inference_current(self):
+        """Rebuilds the inference plan and re-captures the whole-step graphs when any parameter / buffer changed since they
+        were built (active learning alternates train -> query -> train: CRBSampling.query and PoolScorer call this before
+        scoring). Returns True when something was rebuilt."""
+        args = getattr(self, "_inference_args", None)
+        if args is None:
+            return False
+        stale = getattr(self, "_inference_key", None) != self._state_key()
+        missing = (args[0] and self.backbone_2d._plan is None) or \
+                  (getattr(self, "_graph_cfg", None) is not None and not hasattr(self, "_full_graph"))
+        if not stale and not missing:
+            return False
+        gcfg = getattr(self, "_graph_cfg", None)
+        self._drop_inference_state()
+        self.prepare_inference(*args)
+        if gcfg is not None:
+            self.enable_full_graph(*gcfg)
+        return True
 
     # ------------------------------------------------------------------------------------------- forward pieces
     def voxelize(self, points, frame_offsets, batch_size, training=False):
@@ -546,6 +587,7 @@ class SECONDNet(nn.Module):
         slots > 1 captures that many independent copies (own static buffers): replayed on different streams, consecutive
         batches overlap - the narrow tail of one step (greedy NMS pass, top-k sort, small rulebook kernels, ~10 % of the
         step on a handful of SMs) runs under the wide kernels of the next one."""
+        self._graph_cfg = (batch_size, max_points_per_frame, tuple(growth), slots)
         if slots > 1:
             copies = []
             for i in range(slots):
@@ -555,6 +597,7 @@ class SECONDNet(nn.Module):
             self._next_slot = 0
             self._full_graphs = copies
             self._full_graph = copies[0]
+            self._graph_cfg = (batch_size, max_points_per_frame, tuple(growth), slots)
             return self
         dev = next(self.parameters()).device
         d = self.cfg["data"]
@@ -662,6 +705,8 @@ def calibrate_batchnorm(model, points, frame_offsets, batch_size):
         model.backbone_2d.build_inference_plan()
     if planh is not None:
         model.dense_head.build_inference_plan()
+    if getattr(model, "_inference_args", None) is not None:
+        model._inference_key = model._state_key()      # the plans above were built from the calibrated statistics
     return model
 
 
@@ -688,4 +733,6 @@ def calibrate_head_bias(model, points, frame_offsets, batch_size, target_fractio
             model.backbone_2d.build_inference_plan()
         if getattr(model.dense_head, "_plan", None) is not None:
             model.dense_head.build_inference_plan()
+        if getattr(model, "_inference_args", None) is not None:
+            model._inference_key = model._state_key()
     return model

@@ -74,6 +74,32 @@ def build_ref(force=False, verbose=False):
     return out
 
 
+STAGE = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
+
+
+def stage_reference_python(force=False):
+    """Stages the reference's pure-Python package (pcdet/**/*.py) and its model configs (tools/cfgs/**/*.yaml) under
+    git-ignored baseline/_ref/ - verbatim copies, never part of the repo's history - so that the GPU box (which has no
+    /root/reference) can run the reference's UNMODIFIED wrappers, modules and detector classes over the drop-in
+    (tests/ref_env.py). Returns the staged root or None when neither the reference nor a previous staging exists."""
+    import shutil
+    marker = os.path.join(STAGE, "pcdet", "models", "detectors", "detector3d_template.py")
+    if not os.path.isdir(REFERENCE):
+        return STAGE if os.path.exists(marker) else None
+    if os.path.exists(marker) and not force:
+        return STAGE
+    for sub, pat in (("pcdet", ".py"), (os.path.join("tools", "cfgs"), ".yaml")):
+        for root, _, files in os.walk(os.path.join(REFERENCE, sub)):
+            for f in files:
+                if f.endswith(pat):
+                    src = os.path.join(root, f)
+                    dst = os.path.join(STAGE, os.path.relpath(src, REFERENCE))
+                    os.makedirs(os.path.dirname(dst), exist_ok=True)
+                    shutil.copyfile(src, dst)
+    return STAGE
+
+
 if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv))
     print(build_ref(force="--force" in sys.argv, verbose=True))
+    print(stage_reference_python(force="--force" in sys.argv))

@@ -172,33 +172,16 @@ def test_record_all_gather_world2_gloo():
     assert res[0][2][5] == (0.5, [1, 2], [50.0, 50.0])
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/pcdet"), reason="reference tree not present")
 def test_reference_wrappers_import_unmodified_on_dropin():
-    """The REFERENCE's own pcdet/ops/*_utils.py files, loaded as they are, resolve `from . import *_cuda` to the crb3d
-    stand-ins - exercised here through their CPU entry points (no GPU in this container)."""
-    import importlib.util
-    import types
-    from crb3d import dropin
+    """The REFERENCE's own pcdet/ops/*_utils.py files, loaded as they are (tests/ref_env.py: /root/reference here, the
+    verbatim staging baseline/_ref elsewhere), resolve `from . import *_cuda` to the crb3d stand-ins -
+    exercised here through their CPU entry points (no GPU in this container)."""
+    import ref_env
     from oracle import boxes as ob
-    dropin.install()
-    for name in ("pcdet", "pcdet.ops", "pcdet.ops.iou3d_nms", "pcdet.ops.roiaware_pool3d", "pcdet.utils"):
-        if name not in sys.modules:
-            m = types.ModuleType(name)
-            m.__path__ = ["/root/reference/" + name.replace(".", "/")]
-            sys.modules[name] = m
-    cu_mod = types.ModuleType("pcdet.utils.common_utils")       # the wrappers only use check_numpy_to_torch from it
-    cu_mod.check_numpy_to_torch = lambda x: (torch.from_numpy(x).float(), True) if isinstance(x, np.ndarray) else (x, False)
-    sys.modules["pcdet.utils.common_utils"] = cu_mod
-    sys.modules["pcdet.utils"].common_utils = cu_mod
-
-    def load(mod, path):
-        spec = importlib.util.spec_from_file_location(mod, path)
-        m = importlib.util.module_from_spec(spec)
-        sys.modules[mod] = m
-        spec.loader.exec_module(m)
-        return m
-    iou_utils = load("pcdet.ops.iou3d_nms.iou3d_nms_utils", "/root/reference/pcdet/ops/iou3d_nms/iou3d_nms_utils.py")
-    roi_utils = load("pcdet.ops.roiaware_pool3d.roiaware_pool3d_utils", "/root/reference/pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py")
+    if ref_env.reference_root() is None:
+        pytest.skip("no reference tree (neither /root/reference nor baseline/_ref)")
+    iou_utils = ref_env.ref("pcdet.ops.iou3d_nms.iou3d_nms_utils")
+    roi_utils = ref_env.ref("pcdet.ops.roiaware_pool3d.roiaware_pool3d_utils")
     assert iou_utils.iou3d_nms_cuda.__name__ == "pcdet_ops.iou3d_nms_cuda"
     from util import rand_boxes
     rng = np.random.default_rng(5)
@@ -209,6 +192,28 @@ def test_reference_wrappers_import_unmodified_on_dropin():
     for fn in ("boxes_iou3d_gpu", "nms_gpu", "nms_normal_gpu", "boxes_iou_bev"):
         assert callable(getattr(iou_utils, fn))
     assert callable(roi_utils.points_in_boxes_gpu) and callable(roi_utils.RoIAwarePool3d)
+
+
+def test_reference_strategy_registry_resolves_crb_to_dropin():
+    """pcdet/query_strategies/__init__.py of the reference (build_strategy, :13-29) imports `.crb_sampling`; with the drop-in
+    installed that name is crb3d.crb_strategy, whose CRBSampling is a Strategy with the attributes and methods
+    select_active_labels uses (active_training_utils.py:252-293)."""
+    import ref_env
+    if ref_env.reference_root() is None:
+        pytest.skip("no reference tree")
+    ref_env.install()
+    mod = ref_env.ref("pcdet.query_strategies.crb_sampling")
+    assert mod.__name__ == "crb3d.crb_strategy"
+    from crb3d import crb_strategy, strategy
+    assert issubclass(crb_strategy.CRBSampling, strategy.Strategy)
+    for name in ("query", "save_points", "save_active_labels", "update_dashboard"):
+        assert callable(getattr(crb_strategy.CRBSampling, name))
+    s = crb_strategy.CRBSampling(torch.nn.Linear(1, 1), {}, {"a": None, "b": None}, 0, None, {"ACTIVE_TRAIN": {"SELECT_NUMS": 1}})
+    assert [p[0] for p in s.pairs] == ["a", "b"] and s.labelled_set is None and s.bbox_records == {}
+    s.save_points("a", dict(num_bbox={"Car": 2}, mean_points={"Car": 5.0}, median_points={"Car": 4.0}, variance_points={"Car": 1.0}))
+    s.save_active_labels(selected_frames=["a"], cur_epoch=0)
+    s.update_dashboard(cur_epoch=0, accumulated_iter=3)
+    assert ({"active_selection/total_bbox_selected": 2} in [p for _, p in s.dashboard_log])
 
 
 def test_furthest_first_host_logic_cpu():
