@@ -73,8 +73,8 @@ def test_reference_op_wrappers_run_unmodified_on_dropin(cuda):
 @needs_ref
 def test_reference_second_modules_over_dropin_equal_crb3d(cuda):
     """The reference's VoxelBackBone8x + HeightCompression + BaseBEVBackbone + AnchorHeadSingle (built by ITS SECONDNet class
-    from ITS second.yaml) over the spconv shim vs crb3d.second.SECONDNet with the same state_dict: the sparse backbone is
-    bit-equal (same kernels underneath), the dense stack agrees to fp32 round-off (NCHW vs channels-last cuDNN algorithms),
+    from ITS second.yaml) over the spconv shim vs crb3d.second.SECONDNet with the same state_dict: the sparse backbone has
+    identical rows and activations within 1e-5 (same conv kernels; BatchNorm fused vs separate), the dense stack agrees to fp32 round-off (NCHW vs channels-last cuDNN algorithms),
     the decoded boxes agree with the fused head kernels, and the reference checkpoint keys load into crb3d.second unchanged."""
     from crb3d import head_ops, ops, second
     reg = ref_env.register_model_families()
@@ -99,10 +99,13 @@ def test_reference_second_modules_over_dropin_equal_crb3d(cuda):
     finally:
         torch.backends.cudnn.allow_tf32, ops.SPCONV_TF32 = old_tf32, old_sp
     enc_r, enc_m = rd["encoded_spconv_tensor"], md["encoded_spconv_tensor"]
-    assert torch.equal(enc_r.indices, enc_m.indices) and torch.equal(enc_r.features, enc_m.features)
+    def close(a, b, rel=1e-5):      # same conv kernels; the reference applies BatchNorm1d + ReLU as separate torch ops,
+        return float((a - b).abs().max()) <= rel * float(a.abs().max())   # crb3d fuses them into the conv epilogue (one fma)
+    assert torch.equal(enc_r.indices, enc_m.indices) and close(enc_r.features, enc_m.features)
     for k in ("x_conv1", "x_conv2", "x_conv3", "x_conv4"):
-        assert torch.equal(rd["multi_scale_3d_features"][k].features, md["multi_scale_3d_features"][k].features)
-    assert torch.equal(rd["spatial_features"], md["spatial_features"].contiguous())
+        assert torch.equal(rd["multi_scale_3d_features"][k].indices, md["multi_scale_3d_features"][k].indices)
+        assert close(rd["multi_scale_3d_features"][k].features, md["multi_scale_3d_features"][k].features)
+    assert close(rd["spatial_features"], md["spatial_features"].contiguous())
     s = float(rd["spatial_features_2d"].abs().max())
     assert float((rd["spatial_features_2d"] - md["spatial_features_2d"]).abs().max()) <= 1e-4 * s
     # reference decode (anchor_head_template.generate_predicted_boxes) vs the fused decode kernel on the same head outputs
@@ -121,6 +124,7 @@ def test_reference_pvrcnn_detector_forward_over_dropin(cuda):
     compiled op answered by this library; its records are what CRBSampling.query consumes (crb_sampling.py:72-103)."""
     reg = ref_env.register_model_families()
     cfg = ref_env.load_cfg("active-kitti_models/pv_rcnn_active_crb.yaml")
+    ref_env.set_global_cfg(cfg)
     ds = ref_env.dataset_stub(cfg.DATA_CONFIG, cfg.CLASS_NAMES)
     torch.manual_seed(0)
     model = reg["PVRCNN"](model_cfg=cfg.MODEL, num_class=len(cfg.CLASS_NAMES), dataset=ds).cuda().eval()
