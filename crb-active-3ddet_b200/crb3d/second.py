@@ -468,7 +468,7 @@ class SECONDNet(nn.Module):
         valid = torch.arange(P, device=dev).view(1, P) < num.view(B, 1)
         dens = torch.where(valid, dens.view(B, P), torch.zeros((), device=dev))   # padded slots: 0, not 0/0
         return dict(entropy=entropy, num_boxes=num, labels=final_labels, density=dens, point_counts=cnt.view(B, P),
-                    boxes=final_boxes, scores=final_scores)
+                    boxes=final_boxes, scores=final_scores, anchor_idx=anchor_of_kept)
 
     @torch.no_grad()
     def enable_cuda_graph(self, batch_size, max_points_per_frame=32768):

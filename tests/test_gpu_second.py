@@ -333,3 +333,115 @@ def test_pool_scoring_graph_overflow_fallback_and_partial_batch(setup, cuda):
             model.backbone_2d._plan = None
             model.dense_head._plan = None
             ops.SPCONV_TF32 = False
+
+
+def _oracle_post_on_gpu_scores(model, bd, frames, b):
+    """CPU restatement of post_processing for frame b of a batch (detector3d_template.py:186-409 via
+    model_nms_utils.class_agnostic_nms:6-25) fed with the GPU's per-anchor scores / labels and decoded boxes, so that every
+    INDEX it produces is comparable exactly: candidates = score >= SCORE_THRESH ordered by (score desc, anchor index asc)
+    - the tie rule the device top-k implements with its (score bits, ~index) keys - cut at NMS_PRE_MAXSIZE, greedy rotated
+    NMS (oracle/boxes.py = iou3d_cpu.cpp + iou3d_nms.cpp:121-132), cut at NMS_POST_MAXSIZE, first-box-wins point counts."""
+    from crb3d import head_ops
+    from oracle import boxes as ob, crb as oc
+    cfg = model.cfg
+    A = model.dense_head.num_anchors
+    score, label = head_ops.anchor_head_scores(bd["cls_preds"][b:b + 1], model.num_class)
+    score, label = score.view(A).cpu().numpy(), label.view(A).cpu().numpy()
+    cand = np.nonzero(score >= np.float32(cfg["score_thresh"]))[0]
+    idx = cand[np.lexsort((cand, -score[cand]))][: cfg["nms_pre_maxsize"]]
+    if len(idx) == 0:
+        return dict(anchor_idx=idx, labels=label[:0], point_counts=np.zeros(0, np.int32), density=np.zeros(0, np.float32), entropy=0.0)
+    sel = torch.from_numpy(idx.astype(np.int64)).to(bd["box_preds"].device).view(1, -1)
+    boxes = head_ops.anchor_decode_select(bd["box_preds"][b:b + 1], bd["dir_cls_preds"][b:b + 1], sel, model.dense_head.spec, A)[0].cpu().numpy()
+    keep, iou = ob.nms_sorted(boxes, cfg["nms_thresh"], return_iou=True)
+    near = np.abs(iou[np.triu_indices(len(boxes), 1)] - np.float32(cfg["nms_thresh"])).min() <= 1e-6 if len(boxes) > 1 else False
+    keep = keep[: cfg["nms_post_maxsize"]]
+    dens, cnt, _ = ob.box_density(boxes[keep], frames[b][:, :3])
+    labels = label[idx[keep]]
+    return dict(anchor_idx=idx[keep], labels=labels, point_counts=cnt, density=dens, entropy=oc.label_entropy(labels, model.num_class),
+                boxes=boxes[keep], iou_on_threshold=bool(near))
+
+
+def test_pool_stage1_indices_and_ranking_exact(setup, cuda, tmp_path):
+    """North-star parity of CRB stage 1 on a 64-frame pool: per frame the kept ANCHOR INDICES, labels and per-box point
+    counts equal the CPU restatement exactly, densities / entropies to 1e-6, and the stage-1 shortlist (crb_sampling.py
+    :119-121) is identical. The restatement consumes the device's per-anchor scores and decoded boxes (both separately
+    checked against fp32 torch), so float round-off cannot reorder candidates between the two sides.
+    Then the SAME pool in the benchmarked TF32 configuration: keep-set and ranking agreement with exact fp32 are REPORTED
+    (gpurun_out/r02_tf32_agreement.json, printed) - TF32 is in contract for the tensor-core layers, its effect is measured."""
+    import json
+    import os
+    from crb3d import crb_host, ops, second, synth
+    model, _, _, _, _ = setup
+    B, n_frames, K1 = 4, 64, 16
+    pool = [synth.make_frame(100 + i) for i in range(n_frames)]
+    old_cudnn, old_sp = torch.backends.cudnn.allow_tf32, ops.SPCONV_TF32
+    plans = (getattr(model.backbone_2d, "_plan", None), getattr(model.dense_head, "_plan", None))
+
+    def run(tf32):
+        torch.backends.cudnn.allow_tf32 = tf32
+        if tf32:
+            model.prepare_inference(fold_bev_bn=True, spconv_tf32=True)
+        else:
+            ops.SPCONV_TF32 = False
+            model.backbone_2d._plan = model.dense_head._plan = None
+        recs, heads = [], []
+        with torch.no_grad():
+            for s in range(0, n_frames, B):
+                fr = pool[s:s + B]
+                offs = torch.from_numpy(np.cumsum([0] + [len(f) for f in fr]).astype(np.int32)).to(cuda)
+                pts = torch.from_numpy(np.concatenate(fr)).to(cuda)
+                geom = model.geometry(pts, offs, B)
+                rec = model.score_batch(pts, offs, B, max(len(f) for f in fr), geom=geom)
+                recs.append({k: v.cpu().numpy() for k, v in rec.items()})
+                if not tf32:
+                    heads.append(model.forward_features(pts, offs, B, geom=geom))
+        return recs, heads
+
+    try:
+        exact, heads = run(False)
+        ents_gpu, ents_cpu, flagged = [], [], 0
+        for bi, (rec, bd) in enumerate(zip(exact, heads)):
+            for b in range(B):
+                o = _oracle_post_on_gpu_scores(model, bd, pool[bi * B:bi * B + B], b)
+                n = int(rec["num_boxes"][b])
+                ents_gpu.append(float(rec["entropy"][b]))
+                ents_cpu.append(float(o["entropy"]))
+                if o.get("iou_on_threshold"):      # an IoU within 1e-6 of NMS_THRESH: the greedy decision is not comparable
+                    flagged += 1
+                    continue
+                assert n == len(o["anchor_idx"]), (bi, b, n, len(o["anchor_idx"]))
+                assert np.array_equal(rec["anchor_idx"][b, :n], o["anchor_idx"]), (bi, b)
+                assert np.array_equal(rec["labels"][b, :n], o["labels"])
+                assert np.array_equal(rec["point_counts"][b, :n], o["point_counts"])
+                assert np.allclose(rec["density"][b, :n], o["density"], rtol=1e-6, atol=1e-9)
+                assert abs(ents_gpu[-1] - ents_cpu[-1]) <= 1e-6
+        assert flagged <= n_frames // 8
+        ids = list(range(n_frames))
+        if flagged == 0:
+            assert crb_host.shortlist_by_entropy(ids, ents_gpu, K1) == crb_host.shortlist_by_entropy(ids, ents_cpu, K1)
+        # ---- the benchmarked configuration (TF32 sparse convs + TF32 BEV / head plan) against exact fp32
+        tf, _ = run(True)
+        jac, dn, ents_tf = [], [], []
+        for re_, rt in zip(exact, tf):
+            for b in range(B):
+                a = set(re_["anchor_idx"][b, : int(re_["num_boxes"][b])].tolist())
+                c = set(rt["anchor_idx"][b, : int(rt["num_boxes"][b])].tolist())
+                jac.append(len(a & c) / max(1, len(a | c)))
+                dn.append(abs(len(a) - len(c)))
+                ents_tf.append(float(rt["entropy"][b]))
+        sl_e, sl_t = crb_host.shortlist_by_entropy(ids, ents_gpu, K1), crb_host.shortlist_by_entropy(ids, ents_tf, K1)
+        rk_e, rk_t = np.argsort(np.argsort(ents_gpu)), np.argsort(np.argsort(ents_tf))
+        report = dict(frames=n_frames, keep_set_jaccard_mean=float(np.mean(jac)), keep_set_jaccard_min=float(np.min(jac)),
+                      kept_count_abs_diff_mean=float(np.mean(dn)), entropy_abs_diff_max=float(np.max(np.abs(np.asarray(ents_gpu) - ents_tf))),
+                      shortlist_k=K1, shortlist_overlap=len(set(sl_e) & set(sl_t)) / K1,
+                      entropy_rank_spearman=float(np.corrcoef(rk_e, rk_t)[0, 1]),
+                      frames_with_iou_on_threshold=flagged)
+        print("TF32 vs exact-fp32 stage-1 agreement:", json.dumps(report))
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        json.dump(report, open(os.path.join(out, "r02_tf32_agreement.json"), "w"))
+        assert report["keep_set_jaccard_mean"] > 0.3 and report["entropy_rank_spearman"] > 0.3
+    finally:
+        torch.backends.cudnn.allow_tf32, ops.SPCONV_TF32 = old_cudnn, old_sp
+        model.backbone_2d._plan, model.dense_head._plan = plans
