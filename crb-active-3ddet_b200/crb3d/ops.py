@@ -79,6 +79,13 @@ def _ws(nbytes, device):
     return buf
 
 
+def drop_workspaces(tags):
+    """Frees the scratch buffers of graph copies that are being discarded (keys carry the copy's WS_TAG)."""
+    tags = set(tags)
+    for key in [k for k in _WS if k[2] in tags]:
+        del _WS[key]
+
+
 def _ws_bytes(fn, *args):
     n = c_size_t(0)
     _lib.call(fn, *args, byref(n))

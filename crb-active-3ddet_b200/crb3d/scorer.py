@@ -156,40 +156,103 @@ class PoolScorer(object):
         out[:, 3 + self.P:] = rec["density"]
         return out
 
+    def _slot_buffers(self, fg, n_slots):
+        """Reusable pinned staging per graph copy: input points / offsets and the record fields coming back (a real pool is
+        thousands of frames: nothing here grows with the pool size)."""
+        key = (fg["cap"], fg["B"], n_slots, len(fg["caps"]))
+        if getattr(self, "_pool_bufs", None) is not None and self._pool_bufs[0] == key:
+            return self._pool_bufs[1]
+        B, P = fg["B"], self.P
+        bufs = []
+        for _ in range(n_slots):
+            bufs.append(dict(
+                pts=torch.empty((fg["cap"], self.n_feat), dtype=torch.float32).pin_memory(),
+                offs=torch.zeros((B + 1,), dtype=torch.int32).pin_memory(),
+                entropy=torch.empty((B,), dtype=torch.float32).pin_memory(), num_boxes=torch.empty((B,), dtype=torch.int32).pin_memory(),
+                labels=torch.empty((B, P), dtype=torch.int32).pin_memory(), density=torch.empty((B, P), dtype=torch.float32).pin_memory(),
+                counts=torch.empty((len(fg["caps"]),), dtype=torch.int32).pin_memory(), event=torch.cuda.Event(), sel=None))
+        self._pool_bufs = (key, bufs)
+        return bufs
+
     def score_pool(self, frames, frame_ids=None):
         """Scores this rank's shard of `frames` (all ranks pass the same list) and all-gathers the records.
         Returns a dict frame_id -> dict(entropy, labels (n,), density (n,)) identical on every rank.
-        Full batches go through the captured whole-step graphs when they are enabled (score_host_stream: consecutive
-        batches overlap on alternating graph copies); a partial last batch, a batch that does not fit the static buffers
-        or one whose row counts exceeded a static capacity is scored on the eager path (score_host)."""
+        Full batches stream through the captured whole-step graphs (one copy per stream): frames are packed into a reusable
+        pinned buffer of the copy, copied to the device, the graph replayed and the record copied back into pinned memory,
+        while the host already packs the next batch; at most `slots` batches are in flight and every batch's row counts
+        are checked against the static capacities as it completes. A partial last batch, a batch that does not fit the
+        static buffers or one that exceeded a capacity is scored on the eager path (host-visible counts)."""
         world, rank = _world_rank()
         if hasattr(self.model, "ensure_inference_current"):   # retrained since the plan / graphs were built?
             self.model.ensure_inference_current()
         ids = list(range(len(frames))) if frame_ids is None else list(frame_ids)
         mine = shard_indices(len(frames), rank, world)
         sels = [mine[s:s + self.batch_size] for s in range(0, len(mine), self.batch_size)]
-        staged = [self.stage_host([frames[i] for i in sel]) for sel in sels]
+        P = self.P
+        rows = np.zeros((len(mine), 3 + 2 * P), dtype=np.float32)
+        row_of = {fi: r for r, fi in enumerate(mine)}
+        graphs = getattr(self.model, "_full_graphs", None)
         fg = getattr(self.model, "_full_graph", None)
-        fits = [fg is not None and fg["B"] == len(sel) and st[0].shape[0] <= fg["cap"] and st[2] <= fg["max_pts"]
-                for sel, st in zip(sels, staged)]
-        host = [None] * len(sels)
-        fast = [i for i, f in enumerate(fits) if f]
-        if fast:
-            caps = np.asarray(fg["caps"])
-            for i, o in zip(fast, self.score_host_stream([staged[i] for i in fast])):
-                if bool((o["counts"].numpy() <= caps).all()):
-                    host[i] = {k: o[k].numpy() for k in RECORD_FIELDS}
-        for i in range(len(sels)):
-            if host[i] is None:
-                host[i] = self._score_host_eager(staged[i])
-        rows = np.zeros((len(mine), 3 + 2 * self.P), dtype=np.float32)
-        r = 0
-        for sel, h in zip(sels, host):
+        eager = []
+
+        def put(sel, h):
             for j, fi in enumerate(sel):
+                r = row_of[fi]
                 rows[r, 0], rows[r, 1], rows[r, 2] = fi, h["num_boxes"][j], h["entropy"][j]
-                rows[r, 3:3 + self.P] = h["labels"][j]
-                rows[r, 3 + self.P:] = h["density"][j]
-                r += 1
+                rows[r, 3:3 + P] = h["labels"][j]
+                rows[r, 3 + P:] = h["density"][j]
+
+        if graphs and fg is not None:
+            caps = np.asarray(fg["caps"])
+            bufs = self._slot_buffers(fg, len(graphs))
+            main = torch.cuda.current_stream(self.device)
+            if getattr(self, "_slot_streams", None) is None or len(self._slot_streams) != len(graphs):
+                self._slot_streams = [torch.cuda.Stream(self.device) for _ in graphs]
+            for st in self._slot_streams:
+                st.wait_stream(main)
+
+            def drain(buf):
+                if buf["sel"] is None:
+                    return
+                buf["event"].synchronize()
+                if bool((buf["counts"].numpy() <= caps).all()):
+                    put(buf["sel"], {k: buf[k].numpy() for k in RECORD_FIELDS})
+                else:
+                    eager.append(buf["sel"])
+                buf["sel"] = None
+
+            i = 0
+            for sel in sels:
+                n = sum(len(frames[fi]) for fi in sel)
+                mx = max(len(frames[fi]) for fi in sel)
+                if len(sel) != fg["B"] or n > fg["cap"] or mx > fg["max_pts"]:
+                    eager.append(sel)
+                    continue
+                sl = i % len(graphs)
+                buf = bufs[sl]
+                drain(buf)                                   # the copy's previous batch: record consumed, pinned buffers free
+                pts_np, offs_np = buf["pts"].numpy(), buf["offs"].numpy()
+                o = 0
+                for j, fi in enumerate(sel):
+                    f = frames[fi]
+                    pts_np[o:o + len(f)] = f[:, -self.n_feat:]
+                    o += len(f)
+                    offs_np[j + 1] = o
+                with torch.cuda.stream(self._slot_streams[sl]):
+                    rec = self.model.full_graph_replay(buf["pts"][:n], buf["offs"], slot=sl)
+                    for k in RECORD_FIELDS + ("counts",):
+                        buf[k].copy_(rec[k], non_blocking=True)
+                    buf["event"].record()
+                buf["sel"] = sel
+                i += 1
+            for buf in bufs:
+                drain(buf)
+            for st in self._slot_streams:
+                main.wait_stream(st)
+        else:
+            eager = list(sels)
+        for sel in eager:
+            put(sel, self._score_host_eager(self.stage_host([frames[fi] for fi in sel])))
         local = torch.from_numpy(rows).to(self.device)
         out = gather_records(local, len(frames), self.P, self.device)
         return {ids[k]: v for k, v in out.items()}

@@ -371,6 +371,7 @@ class SECONDNet(nn.Module):
     def _drop_inference_state(self):
         self.backbone_2d._plan = None
         self.dense_head._plan = None
+        ops.drop_workspaces([id(g) for g in getattr(self, "_full_graphs", [])])
         for name in ("_graph", "_full_graph", "_full_graphs"):
             if hasattr(self, name):
                 delattr(self, name)
@@ -589,6 +590,7 @@ class SECONDNet(nn.Module):
         step on a handful of SMs) runs under the wide kernels of the next one."""
         self._graph_cfg = (batch_size, max_points_per_frame, tuple(growth), slots)
         if slots > 1:
+            ops.drop_workspaces([id(g) for g in getattr(self, "_full_graphs", [])])     # re-capture: the old copies go away
             copies = []
             for i in range(slots):
                 self._next_slot = i

@@ -112,8 +112,15 @@ def decode_boxes(box, dr, anchors, cfg):
     return out
 
 
-def score_frames(sd, cfg, frames, anchors, collect=None, threads=None):
-    """Full CPU path for a list of per-frame point arrays. Returns a list of per-frame records."""
+def score_frames(sd, cfg, frames, anchors, collect=None, threads=None, timers=None):
+    """Full CPU path for a list of per-frame point arrays. Returns a list of per-frame records.
+    timers (optional dict): accumulates wall seconds per stage (voxelize, sparse_backbone, dense, bev_head, post, density)."""
+    import time as _time
+
+    def tick(name, t0):
+        if timers is not None:
+            timers[name] = timers.get(name, 0.0) + (_time.perf_counter() - t0)
+        return _time.perf_counter()
     if threads:
         torch.set_num_threads(threads)
     d = cfg["data"]
@@ -121,13 +128,18 @@ def score_frames(sd, cfg, frames, anchors, collect=None, threads=None):
         sd = {k: v.detach().cpu() for k, v in sd.items()}
     B = len(frames)
     with torch.no_grad():
+        t0 = _time.perf_counter()
         feats, coords, _, _ = voxel.voxelize_batch(frames, d["pc_range"], d["voxel_size"], d["max_pts"], d["max_voxels_test"])
+        t0 = tick("voxelize", t0)
         x, c4, shape = backbone3d(sd, feats, coords, B, d["sparse_shape"], collect)
+        t0 = tick("sparse_backbone", t0)
         dense = spconv_ref.dense(x, c4, B, shape)
         spatial = dense.view(B, -1, shape[1], shape[2])
+        t0 = tick("dense", t0)
         if collect is not None:
             collect["spatial_features"] = spatial.clone()
         cls, box, dr = bev_head(sd, spatial, cfg)
+        t0 = tick("bev_head", t0)
         if collect is not None:
             collect["cls_preds"], collect["box_preds"], collect["dir_cls_preds"] = cls, box, dr
         boxes_all = decode_boxes(box, dr, anchors, cfg)
@@ -145,7 +157,9 @@ def score_frames(sd, cfg, frames, anchors, collect=None, threads=None):
                 fb, fs, fl = cand[keep], top[keep], lab_m[idx][keep]
             else:
                 fb, fs, fl = box_m[:0], conf_m[:0], lab_m[:0]
+            t0 = tick("post", t0)
             dens, cnt, _ = ob.box_density(fb.numpy(), frames[b][:, :3]) if len(fb) else (np.zeros(0, np.float32), np.zeros(0, np.int32), None)
             recs.append(dict(boxes=fb.numpy(), scores=fs.numpy(), labels=fl.numpy(), density=dens, point_counts=cnt,
                              entropy=oc.label_entropy(fl.numpy(), len(cfg["class_names"]))))
+            t0 = tick("density", t0)
     return recs
