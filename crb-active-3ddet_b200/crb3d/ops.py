@@ -356,6 +356,35 @@ def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None, round_out=False):
     return out
 
 
+def pack_conv_gemm_weight(weight):
+    """(C_out, C_in, k, k) conv weight -> [C_out][k*k][C_in] TF32-rounded, the layout of crb3d_bev_conv_gemm_tf32."""
+    cout, cin, kh, kw = weight.shape
+    return round_tf32(weight.detach().float().permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).contiguous())
+
+
+def bev_conv_gemm(x_nhwc, w2, bias, ksize, stride, pad, relu=True, round_out=False):
+    """k x k conv (+bias, ReLU) as an implicit GEMM over strided TMA boxes (csrc/bev_gemm_tc.cu, CONV mode).
+    x_nhwc: (B, H, W, C_in) contiguous fp32 CUDA; w2: pack_conv_gemm_weight(...). Returns (B, H_out, W_out, C_out)."""
+    _need_cuda(x_nhwc, w2)
+    assert x_nhwc.dtype == torch.float32 and x_nhwc.is_contiguous() and w2.is_contiguous()
+    B, H, W, cin = x_nhwc.shape
+    cout = w2.shape[0]
+    assert w2.shape[1] == ksize * ksize * cin
+    ho, wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    out = torch.empty((B, ho, wo, cout), dtype=torch.float32, device=x_nhwc.device)
+    prof = PROFILE
+    timed = prof is not None and prof.get("mode") == "time" and "conv2d" in prof
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(x_nhwc.device))
+    _lib.call("crb3d_bev_conv_gemm_tf32", _p(x_nhwc), B, H, W, cin, _p(w2), cout, ksize, stride, pad,
+              _p(_f32c(bias)) if bias is not None else None, int(bool(relu)) | (2 if round_out else 0), _p(out), _stream(x_nhwc.device))
+    if timed:
+        e1.record(torch.cuda.current_stream(x_nhwc.device))
+        prof["conv2d"].append((e0, e1, 2.0 * ksize * ksize * cin * cout * B * ho * wo))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- dense
 def sparse_to_dense(feat, coords, batch_size, spatial_shape, channels_last_bev=False, out=None, n_dev=None):
     """(B,C,D,H,W) dense tensor (reference .dense()); channels_last_bev=True returns (B,H,W,C*D) memory whose

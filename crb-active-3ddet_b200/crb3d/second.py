@@ -192,11 +192,14 @@ class BaseBEVBackbone(nn.Module):
                 convs = [(mods[1], mods[2], (1, 1))] + [(mods[j], mods[j + 1], mods[j].padding) for j in range(4, len(mods), 3)]
                 for conv, bn, pad in convs:                              # ZeroPad2d(1) + conv(pad 0) == conv(pad 1)
                     w, b = self._fold(conv.weight, bn)
-                    wpack = None
+                    wpack = w2 = None
                     if (conv.kernel_size == (3, 3) and conv.stride == (1, 1) and tuple(pad) == (1, 1) and w.shape[0] % 128 == 0
                             and w.shape[1] % 16 == 0 and w.is_cuda):
                         wpack = ops.pack_conv3x3_weight(w)
-                    layers.append((w, b, conv.stride, tuple(pad), wpack))
+                    if (conv.kernel_size in ((3, 3), (1, 1)) and conv.stride in ((1, 1), (2, 2)) and pad[0] == pad[1]
+                            and w.shape[0] in (128, 256) and w.shape[1] % 32 == 0 and w.is_cuda):
+                        w2 = ops.pack_conv_gemm_weight(w)         # implicit GEMM over strided TMA boxes: the stride-2 layer
+                    layers.append((w, b, conv.stride, tuple(pad), wpack, w2))
                 dw, db = self._fold(de[0].weight, de[1], transposed=True)
                 st = de[0].stride[0] if isinstance(de[0], nn.ConvTranspose2d) else 0
                 cin, cout = dw.shape[0], dw.shape[1]
@@ -211,16 +214,15 @@ class BaseBEVBackbone(nn.Module):
 
     @staticmethod
     def _tc_conv_pays(B, H, W, cout, cin=128):
-        """The halo-tile kernel is persistent: 74 CTA pairs take work items of 4 tiles (128 pixels x 128 channels each) in
-        turn. Use it when the items fill whole rounds of the 74 pairs, otherwise cuDNN's finer tiles win
-        (BEV_CONV_TC = True/False overrides)."""
+        """Halo-tile CTA-pair kernel (crb3d_bev_conv3x3_tf32) vs the implicit GEMM over strided TMA boxes
+        (crb3d_bev_conv_gemm_tf32) for a 3x3 stride-1 layer both can take: the pair kernel is persistent over 74 CTA pairs
+        per 128-channel slice and picks 1- or 2-tile work items itself, so it wins as soon as its (tile, slice) units give
+        every CTA something to do; tiny maps go to the finer-grained implicit GEMM (BEV_CONV_TC = True/False overrides)."""
         if BEV_CONV_TC != "auto":
             return bool(BEV_CONV_TC)
-        if cout > 128:     # measured on B200 (tools/bench_bev.py, 256->256 at 100x88): cuDNN 60 us / 690 TF/s, ours 83 us
-            return False
         u, v = (H, W) if H % 8 == 0 or W % 8 != 0 else (W, H)
-        items = -(-(B * -(-u // 8) * -(-v // 16)) // 4)
-        return items / (-(-items // 74) * 74.0) >= 0.8
+        tiles = B * -(-u // 8) * -(-v // 16)
+        return tiles * max(1, cout // 128) >= 148
 
     def forward_inference(self, x, mark=None):
         B = x.shape[0]
@@ -234,9 +236,11 @@ class BaseBEVBackbone(nn.Module):
         xh = xh if xh.is_contiguous() else xh.contiguous()
         ups, c0 = [], 0
         for layers, (dw, db, ds), gemm in self._plan:
-            for w, b, stride, pad, wpack in layers:
-                if wpack is not None and self._tc_conv_pays(B, xh.shape[1], xh.shape[2], w.shape[0], w.shape[1]):
+            for w, b, stride, pad, wpack, w2 in layers:
+                if wpack is not None and (w2 is None or self._tc_conv_pays(B, xh.shape[1], xh.shape[2], w.shape[0], w.shape[1])):
                     xh = ops.bev_conv3x3(xh, wpack, b, True, round_out=True)   # the next layer reads TF32 exactly
+                elif w2 is not None and BEV_CONV_TC is not False:
+                    xh = ops.bev_conv_gemm(xh, w2, b, w.shape[2], stride[0], pad[0], True, round_out=True)
                 else:
                     xh = torch.cudnn_convolution_relu(xh.permute(0, 3, 1, 2), w, b, stride, pad, (1, 1), 1).permute(0, 2, 3, 1)
                     xh = xh if xh.is_contiguous() else xh.contiguous()

@@ -286,8 +286,9 @@ __global__ void __launch_bounds__(THREADS, 1) bev_conv3x3_tc(const __grid_consta
 // MMAs and multicasts the commits to both CTAs, the epilogue warps of both CTAs arrive on the leader's acc_empty.
 namespace pair {
 
-constexpr int IT = 2;                           // tiles per CTA per work item
-constexpr int ITEM_A = IT * TILE_A;             // 24576 B per (item, chunk)
+// IT = tiles per CTA per work item (template parameter): 2 by default (a weight stage feeds 2 x 2 tiles); 1 when the layer
+// has so few tiles that whole rounds of 2-tile items would leave most of the 74 pairs idle in the last round (block 2 of the
+// KITTI BEV backbone: 312 tiles of 100 x 88 maps -> 5 rounds of 1-tile items instead of 3 rounds of 2-tile items)
 constexpr int NSA = 4;
 constexpr int HALF_B = STAGE_B / 2;             // 4096 B: 64 output channels x 16 input channels of one tap
 constexpr int ROW_B = 3 * HALF_B;               // a weight stage = the three taps of one kernel row: 12 MMAs per barrier round trip
@@ -295,7 +296,7 @@ constexpr int NSB = 4;
 constexpr int EPW = 8;                          // epilogue warps: (tile, TMEM lane quarter)
 constexpr int SPITCH = 64 + 4;                  // staging row pitch (floats): 64-column halves
 constexpr int STAGING = EPW * 32 * SPITCH * 4;  // 69632 B
-constexpr int SMEM = NSA * ITEM_A + NSB * ROW_B + STAGING;   // 217088
+constexpr int smem_bytes(int it) { return NSA * it * TILE_A + NSB * ROW_B + STAGING; }   // 217088 for IT = 2
 constexpr int NTHREADS = 32 * (3 + EPW);
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -334,9 +335,11 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {               // a
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+template <int IT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap, int n_chunks,
                     const float* __restrict__ bias, int relu, float* __restrict__ out, const __grid_constant__ ConvGeom g) {
+    constexpr int ITEM_A = IT * TILE_A;             // bytes per (item, chunk) and CTA
     extern __shared__ uint8_t smem_raw[];
     // the dynamic window starts at the same offset in both CTAs; descriptors address both CTAs with one offset
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -502,6 +505,12 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
             mbar_wait(&acc_full[set], (it >> 1) & 1, (CRB3D_K_BEV_CONV_PAIR << 8) | 5);
             if (tracing) w_full += clock64() - t0;
             tc_fence_after();
+            if (t >= IT) {                       // 1-tile items: the second tile's four warps only take part in the handshake
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) remote_arrive(acc_empty_leader[set]);
+                continue;
+            }
             const int ti = (item * 2 + (int)rank) * IT + t;
             const bool live = ti < g.n_tiles;        // uniform per warp
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * (IT * N) + t * N);
@@ -604,7 +613,8 @@ extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int 
     const int dev = crb3d_current_device();
     if (!attr_set[dev]) {
         CRB3D_CUDA(cudaFuncSetAttribute(bev_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + 1024));
-        CRB3D_CUDA(cudaFuncSetAttribute(pair::bev_conv3x3_pair_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM + 1024));
+        CRB3D_CUDA(cudaFuncSetAttribute(pair::bev_conv3x3_pair_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::smem_bytes(2) + 1024));
+        CRB3D_CUDA(cudaFuncSetAttribute(pair::bev_conv3x3_pair_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::smem_bytes(1) + 1024));
         attr_set[dev] = true;
     }
     if (!((relu >> 8) & 1)) {
@@ -617,12 +627,20 @@ extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int 
         int rc = make_map_f32(&wmap, wpack, 2, wdims, wstr, wbox, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
         const int ny = cout / N;
-        const int n_items = (int)crb3d_divup(g.n_tiles, 2 * pair::IT);
         int n_clusters = crb3d_num_sms() / 2 / ny;
         if (n_clusters < 1) n_clusters = 1;
+        // item size: rounds(IT) * IT = time in units of one tile per CTA; 1-tile items when they save a whole such unit
+        const long long items2 = crb3d_divup(g.n_tiles, 4), items1 = crb3d_divup(g.n_tiles, 2);
+        const long long cost2 = crb3d_divup(items2, n_clusters) * 2, cost1 = crb3d_divup(items1, n_clusters);
+        const int it_sel = (((relu >> 8) & 4) || cost1 < cost2) && !((relu >> 8) & 8) ? 1 : 2;
+        const int n_items = (int)(it_sel == 1 ? items1 : items2);
         if (n_clusters > n_items) n_clusters = n_items;
-        pair::bev_conv3x3_pair_tc<<<dim3((unsigned)(2 * n_clusters), (unsigned)ny), pair::NTHREADS, pair::SMEM + 1024, stream>>>(
-            amap, wmap, cin / KC, bias, relu, out, g);
+        if (it_sel == 1)
+            pair::bev_conv3x3_pair_tc<1><<<dim3((unsigned)(2 * n_clusters), (unsigned)ny), pair::NTHREADS, pair::smem_bytes(1) + 1024, stream>>>(
+                amap, wmap, cin / KC, bias, relu, out, g);
+        else
+            pair::bev_conv3x3_pair_tc<2><<<dim3((unsigned)(2 * n_clusters), (unsigned)ny), pair::NTHREADS, pair::smem_bytes(2) + 1024, stream>>>(
+                amap, wmap, cin / KC, bias, relu, out, g);
         CRB3D_CHECK_LAUNCH();
         return CRB3D_OK;
     }

@@ -40,6 +40,14 @@ struct GemmOut {
     int in_w, in_h;           // input spatial size when up == 2
 };
 
+// CONV mode: the GEMM rows are the output pixels of a k x k convolution (stride s, zero padding p) over a channels-last map,
+// a 128-row tile = 8 x 16 output pixels, and k-block kb = (tap, 32-channel block): its A operand is ONE 4-D TMA box
+// {32 channels, 16 x, 8 y, 1 image} whose traversal stride along x and y is the conv stride and whose out-of-bounds
+// pixels are zero-filled by the TMA unit (that is the padding). Weights: [N][tap][C_in] = K index tap * C_in + c.
+struct ConvArgs {
+    int tiles_x, tiles_y, h_out, w_out, stride, pad, cblocks, ksize;
+};
+
 template <int N>
 struct Cfg {
     static constexpr int TMEM_N = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));   // columns per accumulator
@@ -58,11 +66,11 @@ struct Cfg {
 //   BRES = false: weight k-blocks stream with the activations (L2 hits) - used when N*K*4 does not fit.
 // Two TMEM accumulators: the MMA warp fills one while the epilogue warps drain the other, so loads, MMAs and stores of
 // consecutive tiles overlap and the kernel runs at the HBM rate of its activation read + output write.
-template <int N, int STAGES, bool BRES, bool DENSE>
+template <int N, int STAGES, bool BRES, bool DENSE, bool CONV = false>
 __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CUtensorMap amap,
                                                       const __grid_constant__ CUtensorMap wmap, int M, int K,
                                                       int ctas_per_slice, int halves, const float* __restrict__ bias, int relu,
-                                                      const __grid_constant__ GemmOut out) {
+                                                      const __grid_constant__ GemmOut out, const __grid_constant__ ConvArgs cv) {
     using C = Cfg<N>;
     constexpr int STAGE_BYTES = C::A_BYTES + (BRES ? 0 : C::B_BYTES);
     extern __shared__ uint8_t smem_raw[];
@@ -76,7 +84,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
     const int slice = blockIdx.x / ctas_per_slice, rank = blockIdx.x - slice * ctas_per_slice;
     const int sub = slice / halves, half = slice - sub * halves;   // transposed-conv sub-position, column block
     const int nkb = K / BK;
-    const int n_tiles = (M + TILE_M - 1) / TILE_M;
+    const int n_tiles = CONV ? M : (M + TILE_M - 1) / TILE_M;    // CONV: M counts 8 x 16 pixel tiles
     const int my_tiles = rank < n_tiles ? (n_tiles - rank + ctas_per_slice - 1) / ctas_per_slice : 0;
 
     if (tid == 0) {
@@ -117,13 +125,26 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
             }
             int it = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                const int m0 = (rank + i * ctas_per_slice) * TILE_M;
+                const int t = rank + i * ctas_per_slice;
+                const int m0 = t * TILE_M;
+                int cb_img = 0, cx0 = 0, cy0 = 0;
+                if (CONV) {
+                    const int per_img = cv.tiles_x * cv.tiles_y;
+                    cb_img = t / per_img;
+                    const int rem = t - cb_img * per_img;
+                    cy0 = (rem / cv.tiles_x) * 8 * cv.stride - cv.pad;
+                    cx0 = (rem % cv.tiles_x) * 16 * cv.stride - cv.pad;
+                }
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int stage = it % STAGES;
                     if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1, (CRB3D_K_BEV_GEMM << 8) | 9);
                     const uint32_t a_dst = ring_base + stage * STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    tma_load_2d(a_dst, &amap, kb * BK, m0, &full_bar[stage]);
+                    if (CONV) {
+                        const int tap = kb / cv.cblocks, cb = kb - tap * cv.cblocks;
+                        tma_load_4d(a_dst, &amap, cb * BK, cx0 + tap % cv.ksize, cy0 + tap / cv.ksize, cb_img, &full_bar[stage]);
+                    } else
+                        tma_load_2d(a_dst, &amap, kb * BK, m0, &full_bar[stage]);
                     if (!BRES) tma_load_2d(a_dst + C::A_BYTES, &wmap, kb * BK, wrow, &full_bar[stage]);
                 }
             }
@@ -168,7 +189,12 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
                 const int acc = i & 1;
                 const long long m = (long long)(rank + i * ctas_per_slice) * TILE_M + r;
                 long long orow = -1;                      // output row of this lane's tile row; -1 = beyond M
-                if (m < M) {
+                if (CONV) {                               // tile row r = pixel (y0 + r / 16, x0 + r % 16) of image b
+                    const int t = rank + i * ctas_per_slice, per_img = cv.tiles_x * cv.tiles_y;
+                    const int b = t / per_img, rem = t - b * per_img;
+                    const int y = (rem / cv.tiles_x) * 8 + (r >> 4), x = (rem % cv.tiles_x) * 16 + (r & 15);
+                    if (y < cv.h_out && x < cv.w_out) orow = ((long long)b * cv.h_out + y) * cv.w_out + x;
+                } else if (m < M) {
                     if (out.up == 2) {
                         const int hw = out.in_w * out.in_h;
                         const int b = (int)(m / hw), rem = (int)(m - (long long)b * hw);
@@ -303,7 +329,55 @@ int launch_gemm(const float* A, long long M, int K, long long lda, const float* 
     int per_slice = crb3d_num_sms() / n_slices;
     if (per_slice < 1) per_slice = 1;
     if (per_slice > n_tiles) per_slice = n_tiles;
-    kern<<<(unsigned)(n_slices * per_slice), 320, smem, stream>>>(amap, wmap, (int)M, K, per_slice, halves, bias, relu, out);
+    kern<<<(unsigned)(n_slices * per_slice), 320, smem, stream>>>(amap, wmap, (int)M, K, per_slice, halves, bias, relu, out, ConvArgs{});
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+// k x k conv (stride, zero padding) as an implicit GEMM on the same persistent kernel (CONV mode): N = 128 output channels
+// per CTA (two slices for 256), weights streamed with the activations.
+template <int N, int STAGES>
+int launch_conv_gemm(const float* in, int B, int H, int W, int cin, const float* w2, int cout, int ksize, int stride, int pad,
+                     const float* bias, int relu, float* out_ptr, cudaStream_t stream) {
+    using C = Cfg<N>;
+    ConvArgs cv;
+    cv.h_out = (H + 2 * pad - ksize) / stride + 1;
+    cv.w_out = (W + 2 * pad - ksize) / stride + 1;
+    cv.tiles_x = (int)crb3d_divup(cv.w_out, 16);
+    cv.tiles_y = (int)crb3d_divup(cv.h_out, 8);
+    cv.stride = stride; cv.pad = pad; cv.cblocks = cin / BK; cv.ksize = ksize;
+    const int K = ksize * ksize * cin;
+    const int n_slices = cout / N;
+    CUtensorMap amap, wmap;
+    {
+        const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)cin * 4, (uint64_t)W * cin * 4, (uint64_t)H * W * cin * 4};
+        const uint32_t box[4] = {BK, 16, 8, 1};
+        const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        int rc = make_map_f32(&amap, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, es);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)cout}, strides[1] = {(uint64_t)K * 4};
+        const uint32_t box[2] = {BK, (uint32_t)N};
+        int rc = make_map_f32(&wmap, w2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    const size_t smem = 1024 + C::staging_bytes(false) + (size_t)STAGES * (C::A_BYTES + C::B_BYTES);
+    auto kern = bev_gemm_tc<N, STAGES, false, false, true>;
+    static size_t smem_set[CRB3D_MAX_DEVICES] = {};
+    const int dev = crb3d_current_device();
+    if (smem > smem_set[dev]) {
+        CRB3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[dev] = smem;
+    }
+    GemmOut o{};
+    o.n_seg = 1; o.up = 0; o.ptr[0] = out_ptr; o.col_begin[0] = 0; o.width[0] = cout; o.row_stride[0] = cout;
+    const int n_tiles = B * cv.tiles_x * cv.tiles_y;
+    int per_slice = crb3d_num_sms() / n_slices;
+    if (per_slice < 1) per_slice = 1;
+    if (per_slice > n_tiles) per_slice = n_tiles;
+    kern<<<(unsigned)(n_slices * per_slice), 320, smem, stream>>>(amap, wmap, n_tiles, K, per_slice, n_slices, bias, relu, o, cv);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -354,3 +428,18 @@ extern "C" int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long
 }
 
 CRB3D_DIAG_DEFINE_SETTER(bev_gemm)
+
+// k x k convolution (ksize in {1, 3}, stride in {1, 2}, zero padding pad) + bias + ReLU over a channels-last map as an
+// implicit GEMM whose A tiles are strided 4-D TMA boxes (CONV mode above). Replaces the cuDNN call behind the stride-2
+// first conv of a BEV block (pcdet/models/backbones_2d/base_bev_backbone.py:33-40: ZeroPad2d(1) + Conv2d(3, stride 2)); also
+// the fallback for 3x3 stride-1 layers the halo-tile kernel does not take.
+// in: (B, H, W, C_in) fp32; w2: [C_out][ksize*ksize][C_in] (= weight.permute(0,2,3,1)), TF32-rounded by the caller;
+// out: (B, H_out, W_out, C_out). Supported: C_in % 32 == 0, C_out in {128, 256}. relu bits as crb3d_bev_gemm_tf32.
+extern "C" int crb3d_bev_conv_gemm_tf32(const float* in, int B, int H, int W, int cin, const float* w2, int cout, int ksize,
+                                        int stride, int pad, const float* bias, int relu, float* out, cudaStream_t stream) {
+    if (!in || !w2 || !out || B <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) return CRB3D_ERR_ARG;
+    if (cin % BK != 0 || (cout != 128 && cout != 256) || (ksize != 1 && ksize != 3) || (stride != 1 && stride != 2) || pad < 0 ||
+        pad >= ksize || H + 2 * pad < ksize || W + 2 * pad < ksize)
+        return CRB3D_ERR_UNSUPPORTED;
+    return launch_conv_gemm<128, 5>(in, B, H, W, cin, w2, cout, ksize, stride, pad, bias, relu, out, stream);
+}

@@ -165,13 +165,15 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 // fp32 tensor map of rank `rank`: dims[] innermost first (elements), strides[] in BYTES for dims 1..rank-1, box[] elements
+// elem_strides (nullable): traversal stride per dimension (a box then takes every elem_strides[i]-th element of dimension
+// i - how a stride-2 convolution reads its input pixels)
 inline int make_map_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                        const uint32_t* box, CUtensorMapSwizzle swz) {
+                        const uint32_t* box, CUtensorMapSwizzle swz, const uint32_t* elem_strides = nullptr) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return CRB3D_ERR_CUDA;
     cuuint64_t d[5], s[4];
     cuuint32_t b[5], e[5];
-    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = elem_strides ? elem_strides[i] : 1; }
     for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

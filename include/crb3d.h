@@ -200,6 +200,13 @@ int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long lda, const
  *      [C_out/128][ky*3+kx][C_in/16][4][128][4]). Supported: C_in % 16 == 0, C_out % 128 == 0. */
 int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int cin, const float* wpack, int cout, const float* bias,
                            int relu, float* out, cudaStream_t stream);
+/* k x k convolution (ksize in {1,3}, stride in {1,2}, zero padding) + bias + ReLU over a channels-last map as an implicit
+ * GEMM whose A tiles are strided 4-D TMA boxes: the stride-2 first conv of a BEV block (base_bev_backbone.py:33-40) and
+ * the fallback for 3x3 stride-1 layers the halo-tile kernel does not take - no cuDNN on the inference path.
+ * in (B,H,W,C_in); w2 [C_out][ksize*ksize][C_in] (= weight.permute(0,2,3,1)); out (B,H_out,W_out,C_out).
+ * Supported: C_in % 32 == 0, C_out in {128, 256}. relu bits as crb3d_bev_gemm_tf32. */
+int crb3d_bev_conv_gemm_tf32(const float* in, int B, int H, int W, int cin, const float* w2, int cout, int ksize, int stride,
+                             int pad, const float* bias, int relu, float* out, cudaStream_t stream);
 /* debug: per-CTA phase stamps (16 int64 per CTA) of the last launch made with relu bit 9 set (tools/bench_bev.py trace). */
 int crb3d_bev_conv3x3_trace(long long* host_out, int n_ctas);
 

@@ -240,13 +240,12 @@ def test_furthest_first_host_logic_cpu():
 
 
 def test_bev_conv_kernel_selection_heuristic():
-    """BaseBEVBackbone._tc_conv_pays (host logic): the persistent CTA-pair conv kernel is chosen when its 4-tile work items
-    fill whole rounds of the 74 CTA pairs and the layer has 128 output channels; cuDNN keeps the rest."""
+    """BaseBEVBackbone._tc_conv_pays (host logic): the persistent CTA-pair conv kernel is chosen when its (tile, 128-channel
+    slice) units give all 148 CTAs work; smaller maps go to the implicit-GEMM conv kernel. No layer is left to cuDNN."""
     from crb3d import second
     pays = second.BaseBEVBackbone._tc_conv_pays
     assert second.BEV_CONV_TC == "auto"
-    assert pays(4, 200, 176, 128, 128) and pays(4, 200, 176, 128, 256)       # KITTI block 1: 275 items -> 4 rounds, 93 %
-    assert pays(8, 200, 176, 128, 128)
-    assert not pays(4, 100, 88, 256, 256)                                     # block 2: cuDNN is faster (measured)
-    assert not pays(1, 16, 16, 128, 16)                                       # a handful of items cannot fill 74 pairs
-    assert pays(1, 200, 176, 128, 128) == (69 / 74.0 >= 0.8)                  # 275 tiles -> 69 items -> one round at 93 %
+    assert pays(4, 200, 176, 128, 128) and pays(4, 200, 176, 128, 256)       # KITTI block 1: 1100 tiles
+    assert pays(4, 100, 88, 256, 256)                                         # block 2: 308 tiles x 2 slices (1-tile items)
+    assert pays(1, 200, 176, 128, 128)                                        # 275 tiles
+    assert not pays(1, 16, 16, 128, 32)                                       # a handful of tiles cannot fill 74 pairs

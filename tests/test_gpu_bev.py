@@ -191,3 +191,58 @@ def test_dropin_accelerate_bev_backbone(cuda):
     assert tuple(out.shape) == tuple(ref.shape) == (4, 512, 200, 176)
     err = (out.double() - ref.double()).pow(2).mean().sqrt()
     assert float(err) <= 2e-3 * float(ref.double().pow(2).mean().sqrt())
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,k,stride,pad", [(2, 200, 176, 128, 256, 3, 2, 1), (1, 37, 29, 64, 128, 3, 2, 1),
+                                                         (3, 24, 40, 32, 256, 3, 1, 1), (1, 9, 7, 32, 128, 3, 2, 1),
+                                                         (2, 16, 16, 96, 128, 1, 1, 0), (1, 100, 88, 256, 256, 3, 1, 1)])
+def test_bev_conv_gemm_strided_boxes(cuda, B, H, W, cin, cout, k, stride, pad):
+    """k x k conv (stride 1 / 2, zero padding) + bias + ReLU as an implicit GEMM over strided 4-D TMA boxes (the stride-2
+    first conv of BEV block 2, base_bev_backbone.py:33-40): odd sizes, both strides, C_out split over two CTA slices."""
+    from crb3d import ops
+    _fp32_reference_mode()
+    g = torch.Generator(device="cpu").manual_seed(H * W + cin + stride)
+    x = torch.randn(B, H, W, cin, generator=g).to(cuda)
+    w = (torch.randn(cout, cin, k, k, generator=g) / (k * np.sqrt(cin))).to(cuda)
+    b = torch.randn(cout, generator=g).to(cuda)
+    out = ops.bev_conv_gemm(x, ops.pack_conv_gemm_weight(w), b, k, stride, pad, True)
+    ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=stride, padding=pad)).permute(0, 2, 3, 1)
+    assert tuple(out.shape) == tuple(ref.shape)
+    _check(out, ref, "conv gemm")
+
+
+@pytest.mark.parametrize("variant", [4, 8])
+def test_bev_conv3x3_pair_item_sizes(cuda, variant, monkeypatch):
+    """Both work-item sizes of the CTA-pair kernel (flag bits 10 / 11 force 1-tile / 2-tile items) on the block-2 shape."""
+    from crb3d import ops
+    _fp32_reference_mode()
+    monkeypatch.setattr(ops, "CONV_VARIANT", variant)
+    g = torch.Generator(device="cpu").manual_seed(variant)
+    x = torch.randn(4, 100, 88, 256, generator=g).to(cuda)
+    w = (torch.randn(256, 256, 3, 3, generator=g) / 48).to(cuda)
+    b = torch.randn(256, generator=g).to(cuda)
+    out = ops.bev_conv3x3(x, ops.pack_conv3x3_weight(w, split=True), b, True)
+    ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=1)).permute(0, 2, 3, 1)
+    _check(out, ref, "conv3x3 pair variant %d" % variant)
+
+
+def test_bev_inference_plan_has_no_cudnn_layer(cuda):
+    """Every conv of the KITTI BEV backbone runs on a kernel of this library in the inference plan (round 1 left block 2 and the
+    stride-2 conv to cuDNN): the plan must name a packed weight for each layer and the profiler must see no cudnn/cutlass kernel."""
+    from crb3d import second
+    torch.manual_seed(0)
+    model = second.SECONDNet().eval().to_device(cuda)
+    model.prepare_inference(fold_bev_bn=True)
+    for layers, _, gemm in model.backbone_2d._plan:
+        assert gemm is not None
+        for w, b, stride, pad, wpack, w2 in layers:
+            assert wpack is not None or w2 is not None, (tuple(w.shape), stride)
+    x = torch.randn(4, 256, 200, 176, device=cuda).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        model.dense_head(model.backbone_2d(dict(spatial_features=x)))
+        torch.cuda.synchronize()
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            model.dense_head(model.backbone_2d(dict(spatial_features=x)))
+            torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages()]
+    assert names and not [n for n in names if "cudnn" in n.lower() or "cutlass" in n.lower() or "implicit_gemm" in n.lower()], names
