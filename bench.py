@@ -51,12 +51,12 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16, help="one step = 256 frames of the pool (default 16 steps = the 4096-frame pool of configs[3])")
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=16, help="frames per graph replay (the reference's eval batch, scripts/kitti/train_kitti_crb.sh:18)")
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary lines (exact fp32, train step, Waymo)")
-    ap.add_argument("--slots", type=int, default=4, help="independent copies of the whole-step graph replayed on alternating streams")
+    ap.add_argument("--slots", type=int, default=2, help="independent copies of the whole-step graph replayed on alternating streams")
     ap.add_argument("--exact-fp32", action="store_true", help="sparse convs on the exact-fp32 SIMT kernel instead of tcgen05 TF32")
     return ap.parse_args()
 
@@ -125,7 +125,7 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ model / data
-FRAMES_PER_STEP = 256          # one step = 256 frames of the pool (64 batches of 4), shared out over the ranks
+FRAMES_PER_STEP = 256          # one step = 256 frames of the pool (16 replays of 16 frames), shared out over the ranks
 
 
 def build_model(device, cfg=None):
@@ -143,7 +143,7 @@ def distinct_frames(n=N_DISTINCT_FRAMES, cfg=None):
 def workload_config(batch, n_gpus, steps):
     pool = steps * FRAMES_PER_STEP
     return {"workload": "CRB stage-1 scoring of a synthetic unlabelled pool, SECOND backbone (configs[3] workload on configs[1] shapes: "
-                        "~20k pts/frame, 1408x1600x40 voxel grid, batch=%d per replay): forward + per-frame score record "
+                        "~20k pts/frame, 1408x1600x40 voxel grid, %d frames per graph replay = the reference's eval batch): forward + per-frame score record "
                         "(label entropy + per-box labels and point densities), frame i -> rank i mod W, ONE all-gather of "
                         "every record at the end (inside the timed region)" % batch,
             "pool_frames": pool, "frames_per_step": FRAMES_PER_STEP, "batch_per_replay": batch, "frames_distinct": N_DISTINCT_FRAMES,
@@ -479,6 +479,7 @@ def extra_measurements(args, model, ps, frames, device, l2_flush, progress):
     B = args.batch
     slots = max(1, args.slots)
     batches = [ps.to_device(ps.stage_host(frames[s:s + B])) for s in range(0, len(frames) - B + 1, B)]
+    b4 = ps.to_device(ps.stage_host(frames[:4]))
 
     def replay_rate(n, streams):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -498,7 +499,7 @@ def extra_measurements(args, model, ps, frames, device, l2_flush, progress):
         return n * B / (ev0.elapsed_time(ev1) / 1e3)
 
     streams = [torch.cuda.Stream(device) for _ in range(slots)]
-    out["round1_line_20_replays_frames_per_s"] = replay_rate(20, streams)
+    out["replays_20_frames_per_s"] = replay_rate(20, streams)
     # exact fp32 sparse convs (the parity configuration: tests/test_gpu_second.py::test_pool_stage1_indices_and_ranking_exact)
     try:
         old = ops.SPCONV_TF32
@@ -517,11 +518,11 @@ def extra_measurements(args, model, ps, frames, device, l2_flush, progress):
         tm.train()
         opt = torch.optim.SGD(tm.parameters(), lr=1e-4)
         gen = torch.Generator(device=device).manual_seed(0)
-        pts, offs, _ = batches[0]
+        pts, offs, _ = b4
 
         def train_step():
             opt.zero_grad(set_to_none=True)
-            bd = tm.forward_features(pts, offs, B)
+            bd = tm.forward_features(pts, offs, 4)
             loss = sum((bd[k] * torch.randn(bd[k].shape[-1], device=device, generator=gen)).mean() for k in ("cls_preds", "box_preds", "dir_cls_preds"))
             loss.backward()
             opt.step()
@@ -538,7 +539,7 @@ def extra_measurements(args, model, ps, frames, device, l2_flush, progress):
         torch.cuda.synchronize(device)
         ops.SPCONV_TF32 = old
         ms = ev0.elapsed_time(ev1) / 10
-        out["train_step_fwd_bwd_batch4"] = {"ms_per_step": ms, "frames_per_s": B / (ms / 1e3),
+        out["train_step_fwd_bwd_batch4"] = {"ms_per_step": ms, "frames_per_s": 4 / (ms / 1e3),
                                             "note": "voxelize + 8 rulebooks + 12 sparse convs fwd/dX/dW + BEV stack fwd/bwd (cuDNN autograd) + SGD; "
                                                     "surrogate loss (anchor-head losses / target assignment = SURVEY 8f2, not built)"}
         del tm, opt

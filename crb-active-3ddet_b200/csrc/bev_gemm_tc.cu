@@ -352,7 +352,8 @@ int launch_conv_gemm(const float* in, int B, int H, int W, int cin, const float*
     {
         const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
         const uint64_t strides[3] = {(uint64_t)cin * 4, (uint64_t)W * cin * 4, (uint64_t)H * W * cin * 4};
-        const uint32_t box[4] = {BK, 16, 8, 1};
+        // with a traversal stride the box is the EXTENT walked in the tensor: ceil(box / stride) elements are copied
+        const uint32_t box[4] = {BK, (uint32_t)(16 * stride), (uint32_t)(8 * stride), 1};
         const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         int rc = make_map_f32(&amap, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, es);
         if (rc) return rc;
