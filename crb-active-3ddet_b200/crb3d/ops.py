@@ -385,6 +385,38 @@ def bev_conv_gemm(x_nhwc, w2, bias, ksize, stride, pad, relu=True, round_out=Fal
     return out
 
 
+# ----------------------------------------------------------------------------------------------- PV-RCNN fused layers
+def sa_group_mlp_maxpool(xyz, xyz_cnt, feat, new_xyz, new_cnt, idx, widths, packed, out):
+    """One scale of StackSAModuleMSG fused (csrc/sa_mlp.cu): group + MLP + max-pool. `out` is a (M, stride) VIEW whose first
+    widths[-1] columns receive the pooled features (column slice of the concatenated multi-scale output)."""
+    _need_cuda(xyz, new_xyz, idx, packed, out)
+    xyz, new_xyz = _f32c(xyz), _f32c(new_xyz)
+    xyz_cnt, new_cnt, idx = _i32c(xyz_cnt), _i32c(new_cnt), _i32c(idx)
+    C = 0 if feat is None else feat.shape[1]
+    if feat is not None:
+        feat = _f32c(feat)
+    M, ns = idx.shape
+    assert out.dtype == torch.float32 and out.stride(1) == 1 and out.shape[0] == M and out.shape[1] >= widths[-1]
+    w = (ctypes.c_int * len(widths))(*[int(x) for x in widths])
+    _lib.call("crb3d_sa_group_mlp_maxpool", int(xyz_cnt.numel()), _p(xyz), _p(xyz_cnt), _p(feat), C, _p(new_xyz), _p(new_cnt), M,
+              _p(idx), ns, len(widths) - 1, w, _p(_f32c(packed)), _p(out), out.stride(0), _stream(xyz.device))
+    return out
+
+
+def fc_gemm(a, weight, scale=None, shift=None, relu=False):
+    """relu?((a (M,K) @ weight (N,K)^T) * scale + shift): split-K tcgen05 GEMM for few rows and a long K (csrc/fc_gemm_tc.cu)."""
+    _need_cuda(a, weight)
+    assert a.dtype == torch.float32 and a.dim() == 2 and a.stride(1) == 1
+    weight = _f32c(weight)
+    M, K = a.shape
+    N = weight.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    ws = _ws(_ws_bytes("crb3d_fc_gemm_workspace_bytes", M, N, K), a.device)
+    _lib.call("crb3d_fc_gemm_tf32", _p(a), M, K, a.stride(0), _p(weight), N, _p(_f32c(scale)) if scale is not None else None,
+              _p(_f32c(shift)) if shift is not None else None, int(bool(relu)), _p(out), _p(ws), ws.numel(), _stream(a.device))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- dense
 def sparse_to_dense(feat, coords, batch_size, spatial_shape, channels_last_bev=False, out=None, n_dev=None):
     """(B,C,D,H,W) dense tensor (reference .dense()); channels_last_bev=True returns (B,H,W,C*D) memory whose

@@ -11,6 +11,7 @@ extern "C" int crb3d_diag_set_bev_conv(void*, unsigned int);
 extern "C" int crb3d_diag_set_bev_gemm(void*, unsigned int);
 extern "C" int crb3d_diag_set_rulebook(void*, unsigned int);
 extern "C" int crb3d_diag_set_voxelize(void*, unsigned int);
+extern "C" int crb3d_diag_set_fc_gemm(void*, unsigned int);
 
 namespace {
 // debug markers (tools/stress_hang.py): 64 ints of zero-copy host memory behind the record; a one-thread kernel stores a
@@ -57,6 +58,7 @@ extern "C" int crb3d_diag_init(void) {
     if ((rc = crb3d_diag_set_bev_gemm(dptr, (unsigned)d))) return rc;
     if ((rc = crb3d_diag_set_rulebook(dptr, (unsigned)d))) return rc;
     if ((rc = crb3d_diag_set_voxelize(dptr, (unsigned)d))) return rc;
+    if ((rc = crb3d_diag_set_fc_gemm(dptr, (unsigned)d))) return rc;
     g_dev_init[d] = true;
     return CRB3D_OK;
 }

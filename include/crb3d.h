@@ -207,6 +207,24 @@ int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int cin, const 
  * Supported: C_in % 32 == 0, C_out in {128, 256}. relu bits as crb3d_bev_gemm_tf32. */
 int crb3d_bev_conv_gemm_tf32(const float* in, int B, int H, int W, int cin, const float* w2, int cout, int ksize, int stride,
                              int pad, const float* bias, int relu, float* out, cudaStream_t stream);
+
+/* ---- PV-RCNN: fused set-abstraction layer and the RoI-head FC GEMM -------------------------------------------------------
+ * crb3d_sa_group_mlp_maxpool: one scale of StackSAModuleMSG.forward (pcdet/ops/pointnet2/pointnet2_stack/
+ * pointnet2_modules.py:78-112: QueryAndGroup + shared 1x1-conv MLP + BatchNorm + ReLU + max-pool over the samples) in one
+ * pass, nothing materialised; used by VoxelSetAbstraction (voxel_set_abstraction.py:334-411) and PVRCNNHead.roi_grid_pool
+ * (pvrcnn_head.py:68-114). idx (M,nsample) int32 comes from crb3d_ball_query_stack (idx[m][0] = -1: empty ball).
+ * widths (HOST int[n_layers+1]): widths[0] = 3 + C, then the layer widths (<= 128, n_layers <= 3); packed (DEVICE): per
+ * layer the TRANSPOSED weight [widths[l]][widths[l+1]] with the BatchNorm scale folded in, then the bias [widths[l+1]].
+ * out: row m -> out + m*out_stride, columns [0, widths[n_layers]). Exact fp32. */
+int crb3d_sa_group_mlp_maxpool(int B, const float* xyz, const int* xyz_cnt, const float* feat, int C, const float* new_xyz,
+                               const int* new_cnt, int M, const int* idx, int nsample, int n_layers, const int* widths,
+                               const float* packed, float* out, int out_stride, cudaStream_t stream);
+/* crb3d_fc_gemm_tf32: out (M,N) = relu?((A (M,K) @ W (N,K)^T) * scale + shift), split-K tcgen05 GEMM for few rows and a long
+ * K: the first shared FC of PVRCNNHead (pvrcnn_head.py:21-33: Conv1d(27648 -> 256, k = 1) + BatchNorm1d + ReLU on 128 RoIs
+ * per frame). N % 128 == 0, K % 32 == 0, lda % 4 == 0; scale / shift nullable; deterministic (fixed split order). */
+int crb3d_fc_gemm_workspace_bytes(long long M, int N, int K, size_t* bytes);
+int crb3d_fc_gemm_tf32(const float* A, long long M, int K, long long lda, const float* W, int N, const float* scale,
+                       const float* shift, int relu, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 /* debug: per-CTA phase stamps (16 int64 per CTA) of the last launch made with relu bit 9 set (tools/bench_bev.py trace). */
 int crb3d_bev_conv3x3_trace(long long* host_out, int n_ctas);
 

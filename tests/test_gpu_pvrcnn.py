@@ -1,0 +1,157 @@
+"""-m gpu: PV-RCNN rows: the fused set-abstraction kernel and the split-K RoI-head GEMM against plain fp32
+torch restatements of the reference modules, then `crb3d.pvrcnn.accelerate` on the REFERENCE's own PVRCNN detector (built
+from its pv_rcnn_active_crb.yaml over the drop-in): same records as the reference's module code, Monte-Carlo rounds included,
+and CRB stage 2 (the RoI-head gradient embedding) equal to what `loss.backward()` leaves in shared_fc_layer[4].weight.grad."""
+import numpy as np
+import pytest
+import torch
+
+import ref_env
+from util import cu
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(ref_env.reference_root() is None, reason="no reference tree (/root/reference or baseline/_ref)")
+
+
+def _fp32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+@pytest.mark.parametrize("C,mlps,radii,ns", [(16, [[16, 16], [16, 16]], [0.4, 0.8], [16, 16]),
+                                             (64, [[64, 64], [64, 64]], [1.2, 2.4], [16, 32]),
+                                             (128, [[64, 64], [64, 64]], [0.8, 1.6], [16, 16]),
+                                             (1, [[16, 16], [16, 16]], [0.4, 0.8], [16, 16]),
+                                             (32, [[32, 48, 96]], [1.0], [8])])
+def test_fused_sa_module_matches_torch_modules(cuda, C, mlps, radii, ns):
+    """StackSAModuleMSG (crb3d.pointnet2_modules mirrors pointnet2_modules.py:30-112 on the same ops) in eval mode: module
+    forward (group -> Conv2d/BN/ReLU -> max_pool2d, everything materialised) vs the fused kernel: <= 1e-5 relative."""
+    from crb3d import pointnet2_modules as pm, pvrcnn
+    _fp32()
+    rng = np.random.default_rng(C + len(mlps))
+    cnt, ncnt = np.array([2500, 1800], np.int32), np.array([300, 260], np.int32)
+    xyz = rng.uniform(-6, 6, (int(cnt.sum()), 3)).astype(np.float32)
+    new_xyz = np.concatenate([xyz[:300] + np.float32(0.05), xyz[2500:2760] + np.float32(0.05)])
+    new_xyz[11] = 100.0                                          # an empty ball
+    feat = rng.normal(size=(int(cnt.sum()), C)).astype(np.float32)
+    torch.manual_seed(0)
+    sa = pm.StackSAModuleMSG(radii, ns, [[C] + m for m in mlps]).to(cuda).eval()
+    g = torch.Generator().manual_seed(1)
+    for m in sa.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.2)
+    args = (cu(xyz, cuda), cu(cnt, cuda), cu(new_xyz, cuda), cu(ncnt, cuda), cu(feat, cuda))
+    with torch.no_grad():
+        _, ref = sa(*args)
+        pvrcnn.accelerate_sa_module(sa)
+        _, got = sa(*args)
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("M,K,N,relu", [(512, 27648, 256, True), (130, 512, 128, False), (1, 64, 128, True), (1280, 4096, 256, True)])
+def test_fc_gemm_split_k(cuda, M, K, N, relu):
+    """relu((A @ W^T) * scale + shift): TF32 inputs, fp32 accumulation, deterministic split-K; vs fp64 torch."""
+    from crb3d import ops
+    g = torch.Generator().manual_seed(M + K)
+    a = torch.randn(M, K, generator=g).to(cuda)
+    w = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(cuda)
+    scale, shift = (torch.rand(N, generator=g) + 0.5).to(cuda), torch.randn(N, generator=g).to(cuda)
+    out = ops.fc_gemm(a, ops.round_tf32(w), scale, shift, relu)
+    ref = (a.double() @ w.double().t()) * scale.double() + shift.double()
+    if relu:
+        ref = torch.relu(ref)
+    rms = float(ref.pow(2).mean().sqrt())
+    err = (out.double() - ref).abs()
+    assert float(err.pow(2).mean().sqrt()) <= 1e-3 * rms and float(err.max()) <= 8e-3 * rms
+    assert torch.equal(out, ops.fc_gemm(a, ops.round_tf32(w), scale, shift, relu))        # deterministic
+
+
+def _reference_pvrcnn(cuda):
+    from test_gpu_reference_dropin import _batch
+    reg = ref_env.register_model_families()
+    cfg = ref_env.load_cfg("active-kitti_models/pv_rcnn_active_crb.yaml")
+    ref_env.set_global_cfg(cfg)
+    ds = ref_env.dataset_stub(cfg.DATA_CONFIG, cfg.CLASS_NAMES)
+    torch.manual_seed(0)
+    model = reg["PVRCNN"](model_cfg=cfg.MODEL, num_class=len(cfg.CLASS_NAMES), dataset=ds).cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    for m in model.modules():      # non-trivial eval-mode BatchNorm statistics
+        if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.05)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.5 + 0.75)
+    return model, cfg, _batch
+
+
+@needs_ref
+def test_accelerated_pvrcnn_matches_reference_modules(cuda):
+    """Reference PVRCNN eval forward with the reference's module code vs the same instance after crb3d.pvrcnn.accelerate:
+    VSA keypoint features (fp32 fused kernel) within 1e-4, the RoI head's Monte-Carlo logits (TF32 tensor-core FC) within 2e-3
+    of their RMS with IDENTICAL dropout masks (same seed, same draw order), same proposals."""
+    from crb3d import pvrcnn
+    _fp32()
+    model, cfg, _batch = _reference_pvrcnn(cuda)
+    for m in model.modules():                       # crb_sampling.py:38-45 enable_dropout: MC dropout at test time
+        if m.__class__.__name__.startswith("Dropout"):
+            m.train()
+    bd, frames, pts, offs_t = _batch(cuda, 2, cfg.DATA_CONFIG)
+
+    def run():
+        torch.manual_seed(123)
+        d = dict(bd)
+        with torch.no_grad():
+            for mod in model.module_list:
+                d = mod(d)
+        return d
+    ref = run()
+    pvrcnn.accelerate(model)
+    assert isinstance(model.roi_head.shared_fc_layer, pvrcnn.FusedSharedFC) and model.pfe.SA_layers[0]._crb3d_fused
+    got = run()
+    s = float(ref["point_features_before_fusion"].abs().max())
+    assert float((ref["point_features_before_fusion"] - got["point_features_before_fusion"]).abs().max()) <= 1e-4 * s
+    assert torch.allclose(ref["rois"], got["rois"], atol=1e-3)
+    for k in ("rcnn_cls", "rcnn_reg"):
+        assert ref[k].shape == got[k].shape and ref[k].shape[0] == cfg.MODEL.ROI_HEAD.SAMPLING_ROUND
+        rms = float(ref[k].pow(2).mean().sqrt())
+        assert float((ref[k] - got[k]).pow(2).mean().sqrt()) <= 2e-3 * rms, k
+    assert float((ref["rcnn_cls"][0] - ref["rcnn_cls"][1]).abs().max()) > 0      # the rounds really differ (dropout active)
+    with torch.no_grad():
+        torch.manual_seed(123)
+        pred, _ = model(dict(bd))
+    assert len(pred) == 2 and all(torch.isfinite(p["pred_box_unique_density"]).all() for p in pred)
+
+
+@needs_ref
+def test_crb_stage2_roi_head_embedding_equals_backward(cuda):
+    """crb_sampling.py:187-207 on the reference PVRCNN: the embedding from crb3d.pvrcnn.roi_head_gradient_embedding
+    (autograd.grad w.r.t. shared_fc_layer[4].weight only) equals the reference's `loss.backward()` + `.weight.grad`."""
+    from crb3d import pvrcnn
+    _fp32()
+    model, cfg, _batch = _reference_pvrcnn(cuda)
+    bd, frames, pts, offs_t = _batch(cuda, 1, cfg.DATA_CONFIG)
+    with torch.no_grad():
+        torch.manual_seed(7)
+        pred, _ = model(dict(bd))
+    cls_h, reg_h = pred[0]["batch_rcnn_cls"], pred[0]["batch_rcnn_reg"]       # stage-1 hypothetical labels (MC means)
+    model.train()
+
+    def reference_way():
+        torch.manual_seed(11)
+        np.random.seed(11)
+        out, _, _ = model(dict(bd))
+        cls_loss, _ = model.roi_head.get_box_cls_layer_loss({"rcnn_cls": out["rcnn_cls"], "rcnn_cls_labels": cls_h})
+        reg_loss = model.roi_head.get_box_reg_layer_loss({"rcnn_reg": out["rcnn_reg"], "reg_sample_targets": reg_h})
+        loss = cls_loss + reg_loss.mean()
+        model.zero_grad()
+        loss.backward()
+        return model.roi_head.shared_fc_layer[4].weight.grad.clone().detach().reshape(-1)
+    g_ref = reference_way()
+    torch.manual_seed(11)
+    np.random.seed(11)
+    g_mine = pvrcnn.roi_head_gradient_embedding(model, dict(bd), cls_h, reg_h)
+    assert g_mine.shape == g_ref.shape == (256 * 256,)
+    assert float(g_ref.abs().max()) > 0
+    assert float((g_mine - g_ref).abs().max()) <= 1e-5 * float(g_ref.abs().max())
