@@ -237,6 +237,114 @@ __global__ void __launch_bounds__(1024) fps_kernel(int n_fixed, int m_fixed, con
     }
 }
 
+// ---- the same selection on a thread-block CLUSTER: FPS_CS CTAs x 1024 threads share one frame, so that clouds of up to
+// FPS_CS * 1024 * 8 points keep every coordinate and running distance in registers (a 20 k-point KITTI cloud is 3 points per
+// thread; the single-CTA kernel above falls back to distances in global memory beyond 8 k points: 5.9 us per round, 12 ms per
+// frame, 64 % of a PV-RCNN forward in profiles/r02_pvrcnn.txt). Per round: per-thread best -> warp shuffles -> CTA best ->
+// every CTA writes its packed (distance, tie) key into every peer's shared memory (DSMEM) -> ONE cluster barrier -> all take
+// the maximum. The key is a total order that does not depend on how the points are split over threads, so the indices are
+// the reference's, bit for bit. Slots are double-buffered by round parity (a fast CTA may already publish round j+1 while a
+// slow one still reads round j).
+constexpr int FPS_CS = 8;
+
+template <int PPT>
+__global__ void __cluster_dims__(FPS_CS, 1, 1) __launch_bounds__(1024) fps_cluster_kernel(
+    int n_fixed, int m_fixed, const float* __restrict__ dataset, float* __restrict__ temp, const int* __restrict__ xyz_cnt,
+    const int* __restrict__ m_cnt, int* __restrict__ idxs, int ref_block_log2_fixed) {
+    __shared__ unsigned long long wbest[32];
+    __shared__ unsigned long long slots[2][FPS_CS];
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int b = blockIdx.x / FPS_CS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int n, m, start = 0, ostart = 0, rbl;
+    if (xyz_cnt) {
+        for (int k = 0; k < b; ++k) { start += xyz_cnt[k]; ostart += m_cnt[k]; }
+        n = xyz_cnt[b]; m = m_cnt[b]; rbl = 10;
+    } else {
+        n = n_fixed; m = m_fixed; start = b * n; ostart = b * m; rbl = ref_block_log2_fixed;
+    }
+    if (m <= 0) return;                               // uniform over the cluster
+    const float* pts = dataset + (size_t)start * 3;
+    float* tmp = temp + start;
+    int* out = idxs + ostart;
+    const int out_base = xyz_cnt ? start : 0;
+    const int g = (int)rank * 1024 + tid;
+    float px[PPT], py[PPT], pz[PPT], pd[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int k = g + i * (FPS_CS * 1024);
+        if (k < n) { px[i] = pts[(size_t)k * 3]; py[i] = pts[(size_t)k * 3 + 1]; pz[i] = pts[(size_t)k * 3 + 2]; pd[i] = tmp[k]; }
+        else { px[i] = py[i] = pz[i] = 0.f; pd[i] = 0.f; }
+    }
+    // this CTA's slot [parity][rank] in every CTA of the cluster (lane r of warp 0 addresses CTA r)
+    uint32_t remote[2] = {0u, 0u};
+    if (warp == 0 && lane < FPS_CS) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const uint32_t local = (uint32_t)__cvta_generic_to_shared(&slots[p][rank]);
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote[p]) : "r"(local), "r"(lane));
+        }
+    }
+    int old = 0;
+    if (rank == 0 && tid == 0) out[0] = out_base;
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers are running
+    for (int j = 1; j < m; ++j) {
+        const float x1 = __ldg(&pts[(size_t)old * 3]), y1 = __ldg(&pts[(size_t)old * 3 + 1]), z1 = __ldg(&pts[(size_t)old * 3 + 2]);
+        unsigned long long key = 0ull;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int k = g + i * (FPS_CS * 1024);
+            if (k < n) {
+                const float d2 = fminf(sqdist3(px[i], py[i], pz[i], x1, y1, z1), pd[i]);
+                pd[i] = d2;
+                if (d2 > -1.0f) {                     // the reference's running best starts at -1 with a strict '>'
+                    const unsigned long long kk = fps_key(d2, k, rbl);
+                    key = kk > key ? kk : key;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        if (lane == 0) wbest[warp] = key;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long k2 = wbest[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, k2, o);
+                k2 = other > k2 ? other : k2;
+            }
+            if (lane < FPS_CS) asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(remote[j & 1]), "l"(k2) : "memory");
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int r = 0; r < FPS_CS; ++r) {
+            const unsigned long long v = slots[j & 1][r];
+            best = v > best ? v : best;
+        }
+        int win = 0;
+        if (best != 0ull) {
+            const unsigned int tie = ~(unsigned int)(best & 0xFFFFFFFFull);
+            const unsigned int rev = tie >> 21;
+            const unsigned int t = rbl ? (__brev(rev) >> (32 - rbl)) : 0u;
+            win = (int)((tie & ((1u << 21) - 1u)) << rbl) | (int)t;
+        }
+        if (rank == 0 && tid == 0) out[j] = win + out_base;
+        old = win;
+    }
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int k = g + i * (FPS_CS * 1024);
+        if (k < n) tmp[k] = pd[i];
+    }
+    // no CTA may leave while a peer can still write into its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ 3-NN + interpolation
 __global__ void __launch_bounds__(256) three_nn_kernel(int B, int N, const float* __restrict__ unknown,
                                                        const int* __restrict__ unknown_cnt, const float* __restrict__ known,
@@ -314,7 +422,11 @@ int fps_dispatch(int grid, int n_max, int n, int m, const float* d, float* t, co
     if (n_max <= 1024) launch_fps<1>(grid, n, m, d, t, xc, mc, idx, rbl, s);
     else if (n_max <= 2048) launch_fps<2>(grid, n, m, d, t, xc, mc, idx, rbl, s);
     else if (n_max <= 4096) launch_fps<4>(grid, n, m, d, t, xc, mc, idx, rbl, s);
-    else if (n_max <= 8192) launch_fps<8>(grid, n, m, d, t, xc, mc, idx, rbl, s);
+    else if (n_max <= FPS_CS * 1024 * 1) fps_cluster_kernel<1><<<grid * FPS_CS, 1024, 0, s>>>(n, m, d, t, xc, mc, idx, rbl);
+    else if (n_max <= FPS_CS * 1024 * 2) fps_cluster_kernel<2><<<grid * FPS_CS, 1024, 0, s>>>(n, m, d, t, xc, mc, idx, rbl);
+    else if (n_max <= FPS_CS * 1024 * 3) fps_cluster_kernel<3><<<grid * FPS_CS, 1024, 0, s>>>(n, m, d, t, xc, mc, idx, rbl);
+    else if (n_max <= FPS_CS * 1024 * 4) fps_cluster_kernel<4><<<grid * FPS_CS, 1024, 0, s>>>(n, m, d, t, xc, mc, idx, rbl);
+    else if (n_max <= FPS_CS * 1024 * 8) fps_cluster_kernel<8><<<grid * FPS_CS, 1024, 0, s>>>(n, m, d, t, xc, mc, idx, rbl);
     else launch_fps<0>(grid, n, m, d, t, xc, mc, idx, rbl, s);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;

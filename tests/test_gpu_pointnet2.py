@@ -63,7 +63,7 @@ def test_group_points_and_grad(cuda, C, ns):
     assert np.allclose(gf.cpu().numpy(), op.group_points_grad(g, idx, idx_cnt, feat_cnt, 5000), rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("n,m", [(20000, 2048), (16384, 1024), (5000, 512), (1024, 256), (1000, 128), (700, 700), (33, 8), (1, 1)])
+@pytest.mark.parametrize("n,m", [(20000, 2048), (40000, 2048), (65000, 300), (70000, 64), (16384, 1024), (5000, 512), (1024, 256), (1000, 128), (700, 700), (33, 8), (1, 1)])
 def test_farthest_point_sampling(cuda, n, m):
     from crb3d import ops
     from oracle import pointnet2 as op
