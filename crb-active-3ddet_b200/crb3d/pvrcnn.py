@@ -135,11 +135,50 @@ class FusedSharedFC(nn.Sequential):
         return h
 
 
+def accelerate_keypoint_sampling(pfe):
+    """VoxelSetAbstraction.get_sampled_points (voxel_set_abstraction.py:227-283) samples the frames one after the other - 2048
+    dependent FPS rounds each. With POINT_SOURCE = raw_points and SAMPLE_METHOD = FPS the frames are independent: ONE launch of
+    the stacked FPS kernel (one thread-block cluster per frame) samples them side by side. Same indices: for clouds of at
+    least 1024 points the stacked and the per-frame kernels of the reference share the 1024-thread tie rule (sampling_gpu.cu)."""
+    cfg = getattr(pfe, "model_cfg", None)
+    if cfg is None or getattr(pfe, "_crb3d_fps", False):
+        return pfe
+    get = (lambda k, d=None: cfg.get(k, d)) if hasattr(cfg, "get") else (lambda k, d=None: getattr(cfg, k, d))
+    if get("POINT_SOURCE") != "raw_points" or get("SAMPLE_METHOD") != "FPS":
+        return pfe
+    original = pfe.get_sampled_points
+    K = int(get("NUM_KEYPOINTS"))
+
+    def get_sampled_points(self, batch_dict):
+        pts = batch_dict["points"]
+        B = int(batch_dict["batch_size"])
+        if not pts.is_cuda or torch.is_grad_enabled():
+            return original(batch_dict)
+        bidx = pts[:, 0].long()
+        cnt = torch.bincount(bidx, minlength=B).int()
+        n_min, n_max = int(cnt.min()), int(cnt.max())          # one host read (the reference does several per frame)
+        sorted_ok = bool((bidx[1:] >= bidx[:-1]).all()) if pts.shape[0] > 1 else True
+        if n_min < max(K, 1024) or not sorted_ok:
+            return original(batch_dict)
+        xyz = pts[:, 1:4].contiguous()
+        temp = torch.full((xyz.shape[0],), 1e10, dtype=torch.float32, device=pts.device)
+        idx = torch.empty((B * K,), dtype=torch.int32, device=pts.device)
+        ops.stack_farthest_point_sampling(xyz, temp, cnt, idx, torch.full((B,), K, dtype=torch.int32, device=pts.device), n_max=n_max)
+        kp = xyz[idx.long()]
+        b = torch.arange(B, device=pts.device, dtype=torch.float32).view(-1, 1).repeat(1, K).view(-1, 1)
+        return torch.cat((b, kp), dim=1)
+
+    pfe.get_sampled_points = types.MethodType(get_sampled_points, pfe)
+    pfe._crb3d_fps = True
+    return pfe
+
+
 def accelerate(model, bev=True):
     """Patches a PV-RCNN detector instance in place (see the module docstring) and returns it. bev=True also applies
     crb3d.dropin.accelerate_bev_backbone (TF32 tensor-core plan) to its BEV backbone when that has the reference structure."""
     pfe = getattr(model, "pfe", None)
     if pfe is not None:
+        accelerate_keypoint_sampling(pfe)
         if hasattr(pfe, "SA_rawpoints"):
             accelerate_sa_module(pfe.SA_rawpoints)
         for sa in getattr(pfe, "SA_layers", []):
