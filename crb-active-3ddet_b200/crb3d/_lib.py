@@ -62,6 +62,10 @@ SIGNATURES = {
     "crb3d_bev_gemm_tf32": [P, c_int64, c_int, c_int64, P, c_int, c_int, P, c_int, c_int, P, P, P, P, c_int, c_int, c_int, P],
     "crb3d_bev_conv3x3_tf32": [P, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, P],
     "crb3d_bev_conv_gemm_tf32": [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, P, c_int, P, P],
+    "crb3d_mask_collate_points_workspace_bytes": [c_int64, POINTER(c_size_t)],
+    "crb3d_mask_collate_points": [P, c_int64, c_int, c_int, P, c_int, P, P, P, P, c_size_t, P],
+    "crb3d_furthest_first_workspace_bytes": [c_int, POINTER(c_size_t)],
+    "crb3d_furthest_first": [P, c_int, c_int, P, c_int, P, P, c_size_t, P],
     "crb3d_sa_group_mlp_maxpool": [c_int, P, P, P, c_int, P, P, c_int, P, c_int, c_int, P, P, P, c_int, P],
     "crb3d_fc_gemm_workspace_bytes": [c_int64, c_int, c_int, POINTER(c_size_t)],
     "crb3d_fc_gemm_tf32": [P, c_int64, c_int, c_int64, P, c_int, P, P, c_int, P, P, c_size_t, P],
@@ -119,7 +123,7 @@ KERNELS_PER_CALL = {
     "crb3d_three_nn_stack": 1, "crb3d_three_interpolate_stack": 1, "crb3d_three_interpolate_grad_stack": 1,
     "crb3d_label_entropy": 1, "crb3d_label_entropy_ranges": 1, "crb3d_pairwise_sqdist_f64": 1,
     "crb3d_anchor_head_scores": 1, "crb3d_anchor_head_scores_topk": 2, "crb3d_anchor_decode_select": 1, "crb3d_gather_rows_f32": 1, "crb3d_gather_rows_i32": 1,
-    "crb3d_spconv_forward_tf32": 1, "crb3d_bev_gemm_tf32": 1, "crb3d_bev_conv3x3_tf32": 1, "crb3d_bev_conv_gemm_tf32": 1, "crb3d_sa_group_mlp_maxpool": 1, "crb3d_fc_gemm_tf32": 2,
+    "crb3d_spconv_forward_tf32": 1, "crb3d_bev_gemm_tf32": 1, "crb3d_bev_conv3x3_tf32": 1, "crb3d_bev_conv_gemm_tf32": 1, "crb3d_sa_group_mlp_maxpool": 1, "crb3d_fc_gemm_tf32": 2, "crb3d_mask_collate_points": 6,
 }
 LAUNCHES = {"kernels": 0, "calls": 0}
 

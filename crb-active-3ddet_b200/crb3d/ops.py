@@ -41,6 +41,21 @@ def _need_cuda(*ts):
             raise RuntimeError("crb3d ops run on CUDA tensors only (no CPU fallback)")
 
 
+def _check(**named):
+    """CHECK_INPUT of the reference's pybind wrappers (e.g. pointnet2_stack/src/ball_query.cpp:14-17: CUDA + contiguous) plus
+    the dtype the kernel reads: the C ABI takes raw addresses, so a strided view, an int64 count vector or a half tensor would
+    silently produce garbage. name=(tensor, dtype); None tensors are skipped."""
+    for name, (t, dtype) in named.items():
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("crb3d: %s must be a CUDA tensor (no CPU fallback)" % name)
+        if t.dtype != dtype:
+            raise TypeError("crb3d: %s must be %s, got %s" % (name, dtype, t.dtype))
+        if not t.is_contiguous():
+            raise ValueError("crb3d: %s must be contiguous" % name)
+
+
 def _f32c(t):
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
@@ -385,6 +400,39 @@ def bev_conv_gemm(x_nhwc, w2, bias, ksize, stride, pad, relu=True, round_out=Fal
     return out
 
 
+# ----------------------------------------------------------------------------------------------- data path / selection
+def mask_collate_points(points, frame_offsets, pc_range, xcol=0, sync=True):
+    """mask_points_by_range + collate_batch's batch-index column for a whole batch on the device (csrc/data_prims.cu).
+    points (N, C) raw clouds back to back, frame_offsets (B+1) int32. Returns (out (M, 1+C) [b, cols...], out_offsets (B+1));
+    sync=False keeps out capacity-sized (N rows) and the counts on the device."""
+    _need_cuda(points, frame_offsets)
+    points, frame_offsets = _f32c(points), _i32c(frame_offsets)
+    n, stride = points.shape
+    B = frame_offsets.numel() - 1
+    out = torch.empty((max(n, 1), stride + 1), dtype=torch.float32, device=points.device)
+    out_off = torch.empty((B + 1,), dtype=torch.int32, device=points.device)
+    ws = _ws(_ws_bytes("crb3d_mask_collate_points_workspace_bytes", n), points.device)
+    r = (ctypes.c_float * 4)(float(pc_range[0]), float(pc_range[1]), float(pc_range[3]), float(pc_range[4]))
+    _lib.call("crb3d_mask_collate_points", _p(points), n, stride, int(xcol), _p(frame_offsets), B, r, _p(out), _p(out_off), _p(ws),
+              ws.numel(), _stream(points.device))
+    if not sync:
+        return out, out_off
+    return out[: int(out_off[-1].item())], out_off
+
+
+def furthest_first(X, min_dist, n_pick):
+    """Greedy k-centre picks (coreset_sampling.py:31-52) on the device: X (m, d) f32, min_dist (m) f32 start distances (updated
+    in place). Returns a LongTensor (n_pick,) on X's device; no host synchronisation."""
+    _need_cuda(X, min_dist)
+    X = _f32c(X)
+    _check(min_dist=(min_dist, torch.float32))
+    m, d = X.shape
+    out = torch.empty((n_pick,), dtype=torch.int64, device=X.device)
+    ws = _ws(_ws_bytes("crb3d_furthest_first_workspace_bytes", m), X.device)
+    _lib.call("crb3d_furthest_first", _p(X), m, d, _p(min_dist), int(n_pick), _p(out), _p(ws), ws.numel(), _stream(X.device))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- PV-RCNN fused layers
 def sa_group_mlp_maxpool(xyz, xyz_cnt, feat, new_xyz, new_cnt, idx, widths, packed, out):
     """One scale of StackSAModuleMSG fused (csrc/sa_mlp.cu): group + MLP + max-pool. `out` is a (M, stride) VIEW whose first
@@ -540,6 +588,7 @@ def points_in_boxes_cpu(boxes, pts, out):
 def roiaware_pool3d_forward(rois, pts, pts_feature, argmax, pts_idx_of_voxels, pooled, pool_method):
     _need_cuda(rois, pts, pts_feature, argmax, pts_idx_of_voxels, pooled)
     rois, pts, pts_feature = _f32c(rois), _f32c(pts), _f32c(pts_feature)
+    _check(argmax=(argmax, torch.int32), pts_idx_of_voxels=(pts_idx_of_voxels, torch.int32), pooled=(pooled, torch.float32))
     n_boxes, ox, oy, oz, C = pooled.shape
     _lib.call("crb3d_roiaware_pool3d_forward", _p(rois), _p(pts), _p(pts_feature), n_boxes, pts.shape[0], C,
               pts_idx_of_voxels.shape[4], ox, oy, oz, _p(argmax), _p(pts_idx_of_voxels), _p(pooled), int(pool_method),
@@ -548,6 +597,7 @@ def roiaware_pool3d_forward(rois, pts, pts_feature, argmax, pts_idx_of_voxels, p
 
 def roiaware_pool3d_backward(pts_idx_of_voxels, argmax, grad_out, grad_in, pool_method):
     _need_cuda(pts_idx_of_voxels, argmax, grad_out, grad_in)
+    _check(pts_idx_of_voxels=(pts_idx_of_voxels, torch.int32), argmax=(argmax, torch.int32), grad_in=(grad_in, torch.float32))
     n_boxes, ox, oy, oz, C = grad_out.shape
     _lib.call("crb3d_roiaware_pool3d_backward", _p(pts_idx_of_voxels), _p(argmax), _p(_f32c(grad_out)), _p(grad_in),
               n_boxes, ox, oy, oz, C, pts_idx_of_voxels.shape[4], int(pool_method), _stream(grad_in.device))
@@ -556,29 +606,34 @@ def roiaware_pool3d_backward(pts_idx_of_voxels, argmax, grad_out, grad_in, pool_
 # ----------------------------------------------------------------------------------------------- pointnet2 (stack)
 def ball_query(B, M, radius, nsample, new_xyz, new_xyz_batch_cnt, xyz, xyz_batch_cnt, idx, max_queries_per_frame=0):
     _need_cuda(new_xyz, new_xyz_batch_cnt, xyz, xyz_batch_cnt, idx)
+    _check(new_xyz=(new_xyz, torch.float32), new_xyz_batch_cnt=(new_xyz_batch_cnt, torch.int32), xyz=(xyz, torch.float32), xyz_batch_cnt=(xyz_batch_cnt, torch.int32), idx=(idx, torch.int32))
     _lib.call("crb3d_ball_query_stack", B, M, float(radius), int(nsample), _p(new_xyz), _p(new_xyz_batch_cnt), _p(xyz),
               _p(xyz_batch_cnt), _p(idx), int(max_queries_per_frame), _stream(idx.device))
 
 
 def group_points(B, M, C, nsample, features, features_batch_cnt, idx, idx_batch_cnt, out):
     _need_cuda(features, features_batch_cnt, idx, idx_batch_cnt, out)
+    _check(features=(features, torch.float32), features_batch_cnt=(features_batch_cnt, torch.int32), idx=(idx, torch.int32), idx_batch_cnt=(idx_batch_cnt, torch.int32), out=(out, torch.float32))
     _lib.call("crb3d_group_points_stack", B, M, C, nsample, _p(features), _p(features_batch_cnt), _p(idx),
               _p(idx_batch_cnt), _p(out), _stream(out.device))
 
 
 def group_points_grad(B, M, C, N, nsample, grad_out, idx, idx_batch_cnt, features_batch_cnt, grad_features):
     _need_cuda(grad_out, idx, idx_batch_cnt, features_batch_cnt, grad_features)
+    _check(grad_out=(grad_out, torch.float32), idx=(idx, torch.int32), idx_batch_cnt=(idx_batch_cnt, torch.int32), features_batch_cnt=(features_batch_cnt, torch.int32), grad_features=(grad_features, torch.float32))
     _lib.call("crb3d_group_points_grad_stack", B, M, C, N, nsample, _p(grad_out), _p(idx), _p(idx_batch_cnt),
               _p(features_batch_cnt), _p(grad_features), _stream(grad_out.device))
 
 
 def farthest_point_sampling(b, n, m, points, temp, idx):
     _need_cuda(points, temp, idx)
+    _check(points=(points, torch.float32), temp=(temp, torch.float32), idx=(idx, torch.int32))
     _lib.call("crb3d_farthest_point_sampling", b, n, m, _p(points), _p(temp), _p(idx), _stream(idx.device))
 
 
 def stack_farthest_point_sampling(points, temp, xyz_batch_cnt, idx, num_sampled_points, n_max=None):
     _need_cuda(points, temp, xyz_batch_cnt, idx, num_sampled_points)
+    _check(points=(points, torch.float32), temp=(temp, torch.float32), xyz_batch_cnt=(xyz_batch_cnt, torch.int32), idx=(idx, torch.int32), num_sampled_points=(num_sampled_points, torch.int32))
     B = xyz_batch_cnt.numel()
     if n_max is None:
         n_max = int(xyz_batch_cnt.max().item())
@@ -588,17 +643,20 @@ def stack_farthest_point_sampling(points, temp, xyz_batch_cnt, idx, num_sampled_
 
 def three_nn(B, N, M, unknown, unknown_batch_cnt, known, known_batch_cnt, dist2, idx):
     _need_cuda(unknown, unknown_batch_cnt, known, known_batch_cnt, dist2, idx)
+    _check(unknown=(unknown, torch.float32), unknown_batch_cnt=(unknown_batch_cnt, torch.int32), known=(known, torch.float32), known_batch_cnt=(known_batch_cnt, torch.int32), dist2=(dist2, torch.float32), idx=(idx, torch.int32))
     _lib.call("crb3d_three_nn_stack", B, N, M, _p(unknown), _p(unknown_batch_cnt), _p(known), _p(known_batch_cnt),
               _p(dist2), _p(idx), _stream(idx.device))
 
 
 def three_interpolate(N, C, features, idx, weight, out):
     _need_cuda(features, idx, weight, out)
+    _check(features=(features, torch.float32), idx=(idx, torch.int32), weight=(weight, torch.float32), out=(out, torch.float32))
     _lib.call("crb3d_three_interpolate_stack", N, C, _p(features), _p(idx), _p(weight), _p(out), _stream(out.device))
 
 
 def three_interpolate_grad(N, C, grad_out, idx, weight, grad_features):
     _need_cuda(grad_out, idx, weight, grad_features)
+    _check(grad_out=(grad_out, torch.float32), idx=(idx, torch.int32), weight=(weight, torch.float32), grad_features=(grad_features, torch.float32))
     _lib.call("crb3d_three_interpolate_grad_stack", N, C, _p(grad_out), _p(idx), _p(weight), _p(grad_features),
               _stream(grad_out.device))
 

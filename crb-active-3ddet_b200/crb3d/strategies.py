@@ -23,19 +23,14 @@ def pairwise_squared_distances(x, y):
 def furthest_first(X, X_set, n):
     """coreset_sampling.py:31-52. Starts from the MEAN distance to the labelled set (the reference's `min_dist =
     dist_ctr.mean(1)`), then n greedy picks: arg-max, then element-wise min with the distance to the new centre. The
-    reference updates `min_dist` with a Python loop over all m elements per pick; here every pick is three device ops and
-    the index never visits the host. Returns a LongTensor (n,) on X's device."""
+    reference updates `min_dist` with a Python loop over all m elements per pick; on CUDA tensors the whole loop runs in
+    crb3d_furthest_first (distance to the new centre + running minimum + next arg-max in one pass per pick); the index never
+    visits the host. CUDA tensors only (no CPU path). Returns a LongTensor (n,) on X's device."""
     m = X.shape[0]
     X = X.reshape(m, -1).float()
     min_dist = pairwise_squared_distances(X, X_set).mean(1)
-    idxs = torch.empty((n,), dtype=torch.long, device=X.device)
-    for i in range(n):
-        idx = torch.argmax(min_dist)
-        idxs[i] = idx
-        if i < n - 1:
-            d_new = pairwise_squared_distances(X, X.index_select(0, idx.view(1)))[:, 0]
-            min_dist = torch.minimum(min_dist, d_new)
-    return idxs
+    # the greedy loop as two kernel launches per pick (csrc/data_prims.cu), no per-pick host traffic; CUDA tensors only
+    return ops.furthest_first(X.contiguous(), min_dist.contiguous(), n)
 
 
 def kmeans_pp_select(embeddings, n, seed=0):

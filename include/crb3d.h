@@ -208,6 +208,19 @@ int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int cin, const 
 int crb3d_bev_conv_gemm_tf32(const float* in, int B, int H, int W, int cin, const float* w2, int cout, int ksize, int stride,
                              int pad, const float* bias, int relu, float* out, cudaStream_t stream);
 
+/* ---- device-side data path upstream of the voxelizer + selection primitives of the other strategies ----
+ * crb3d_mask_collate_points: mask_points_by_range (pcdet/utils/common_utils.py:60-63 via data_processor.py:78-90: keep
+ * x0 <= x <= x1 and y0 <= y <= y1, z untested) + collate_batch's batch-index column (pcdet/datasets/dataset.py:173-178) for a
+ * whole batch: stable compaction, out (n, 1+stride) [b, cols...], out_offsets (B+1) device-side row offsets. range4 is HOST.
+ * crb3d_furthest_first: the greedy k-centre loop of pcdet/query_strategies/coreset_sampling.py:31-52 without host round trips:
+ * min_dist (m) holds the start distances and is updated in place, out_idx (n_pick) int64 on the device (ties: lowest row). */
+int crb3d_mask_collate_points_workspace_bytes(int64_t n, size_t* bytes);
+int crb3d_mask_collate_points(const float* points, int64_t n, int stride, int xcol, const int* frame_offsets, int B,
+                              const float* range4, float* out, int* out_offsets, void* ws, size_t ws_bytes, cudaStream_t stream);
+int crb3d_furthest_first_workspace_bytes(int m, size_t* bytes);
+int crb3d_furthest_first(const float* X, int m, int d, float* min_dist, int n_pick, long long* out_idx, void* ws, size_t ws_bytes,
+                         cudaStream_t stream);
+
 /* ---- PV-RCNN: fused set-abstraction layer and the RoI-head FC GEMM -------------------------------------------------------
  * crb3d_sa_group_mlp_maxpool: one scale of StackSAModuleMSG.forward (pcdet/ops/pointnet2/pointnet2_stack/
  * pointnet2_modules.py:78-112: QueryAndGroup + shared 1x1-conv MLP + BatchNorm + ReLU + max-pool over the samples) in one

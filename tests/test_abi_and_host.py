@@ -216,29 +216,6 @@ def test_reference_strategy_registry_resolves_crb_to_dropin():
     assert ({"active_selection/total_bbox_selected": 2} in [p for _, p in s.dashboard_log])
 
 
-def test_furthest_first_host_logic_cpu():
-    """crb3d.strategies.furthest_first is plain tensor code: on CPU tensors it must reproduce the reference loop
-    (coreset_sampling.py:31-52: mean-initialised distances, arg-max, element-wise min) restated in numpy."""
-    import numpy as np
-    import torch
-    from crb3d import strategies
-    rng = np.random.default_rng(11)
-    X = (rng.normal(size=(120, 16)) * rng.uniform(0.5, 3.0, size=(120, 1))).astype(np.float32)
-    Xs = rng.normal(size=(20, 16)).astype(np.float32)
-
-    def sq(a, b):
-        a, b = a.astype(np.float64), b.astype(np.float64)
-        return np.clip((a ** 2).sum(1)[:, None] + (b ** 2).sum(1)[None, :] - 2.0 * a @ b.T, 0, None)
-    md = sq(X, Xs).mean(1)
-    ref = []
-    for _ in range(12):
-        j = int(np.argmax(md))
-        ref.append(j)
-        md = np.minimum(md, sq(X, X[j:j + 1])[:, 0])
-    got = strategies.furthest_first(torch.from_numpy(X), torch.from_numpy(Xs), 12).numpy()
-    assert np.array_equal(got, np.asarray(ref))
-
-
 def test_bev_conv_kernel_selection_heuristic():
     """BaseBEVBackbone._tc_conv_pays (host logic): the persistent CTA-pair conv kernel is chosen when its (tile, 128-channel
     slice) units give all 148 CTAs work; smaller maps go to the implicit-GEMM conv kernel. No layer is left to cuDNN."""

@@ -205,3 +205,47 @@ def test_spconv_tcgen05_tf32(cuda, cin, cout):
             dx_ref, _ = spconv_ref.conv_backward(feat, nbr_ref, ww, dout, dtype=torch.float64)
             dx = ops.spconv_forward(cu(dout, cuda), nbr_t, cu(ww, cuda), transpose=True, tf32=True)
             assert float((dx.cpu().double() - dx_ref).abs().max()) <= 2e-3 * float(dx_ref.abs().max())
+
+
+def test_mask_collate_points_matches_numpy(cuda):
+    """mask_points_by_range (common_utils.py:60-63: x and y only, closed interval) + collate_batch's batch column
+    (dataset.py:173-178) for a whole batch on the device: same rows, same order as the numpy code of the reference."""
+    from crb3d import ops
+    rng = np.random.default_rng(4)
+    pc_range = [0.0, -40.0, -3.0, 70.4, 40.0, 1.0]
+    frames = []
+    for n in (5000, 1, 0, 7321):
+        f = rng.uniform([-10, -50, -5, 0], [80, 50, 3, 1], (n, 4)).astype(np.float32)
+        if n > 10:
+            f[0, 0], f[1, 0], f[2, 1], f[3, 1] = 0.0, 70.4, -40.0, 40.0      # on the boundary: kept (closed interval)
+            f[4, 0] = np.nan
+            f[5, 2] = 100.0                                                    # z is not tested
+        frames.append(f)
+    offs = np.cumsum([0] + [len(f) for f in frames]).astype(np.int32)
+    pts = np.concatenate(frames)
+    out, out_off = ops.mask_collate_points(torch.from_numpy(pts).to(cuda), torch.from_numpy(offs).to(cuda), pc_range)
+    ref, ref_off = [], [0]
+    for i, f in enumerate(frames):
+        m = (f[:, 0] >= pc_range[0]) & (f[:, 0] <= pc_range[3]) & (f[:, 1] >= pc_range[1]) & (f[:, 1] <= pc_range[4])
+        ref.append(np.pad(f[m], ((0, 0), (1, 0)), mode="constant", constant_values=i))
+        ref_off.append(ref_off[-1] + int(m.sum()))
+    ref = np.concatenate(ref)
+    assert np.array_equal(out_off.cpu().numpy(), np.asarray(ref_off, np.int32))
+    assert np.array_equal(out.cpu().numpy(), ref, equal_nan=True)
+
+
+def test_raw_pointer_wrappers_reject_wrong_dtype_and_layout(cuda):
+    """CHECK_INPUT of the reference's pybind layer (CUDA + contiguous) plus the dtype: an int64 count vector or a strided view
+    must raise instead of producing garbage indices."""
+    from crb3d import ops
+    xyz = torch.rand(100, 3, device=cuda)
+    idx = torch.zeros((10, 4), dtype=torch.int32, device=cuda)
+    cnt64 = torch.tensor([100], dtype=torch.int64, device=cuda)
+    cnt = torch.tensor([100], dtype=torch.int32, device=cuda)
+    ncnt = torch.tensor([10], dtype=torch.int32, device=cuda)
+    with pytest.raises(TypeError):
+        ops.ball_query(1, 10, 0.5, 4, xyz[:10].contiguous(), ncnt, xyz, cnt64, idx)
+    with pytest.raises(ValueError):
+        ops.ball_query(1, 10, 0.5, 4, xyz[::10], ncnt, xyz, cnt, idx)
+    with pytest.raises(RuntimeError):
+        ops.ball_query(1, 10, 0.5, 4, xyz[:10].cpu(), ncnt, xyz, cnt, idx)
