@@ -66,6 +66,15 @@ SIGNATURES = {
     "crb3d_mask_collate_points": [P, c_int64, c_int, c_int, P, c_int, P, P, P, P, c_size_t, P],
     "crb3d_furthest_first_workspace_bytes": [c_int, POINTER(c_size_t)],
     "crb3d_furthest_first": [P, c_int, c_int, P, c_int, P, P, c_size_t, P],
+    "crb3d_voxel_query_stack": [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P, P, P, P, P],
+    "crb3d_ball_query_batch": [c_int, c_int, c_int, c_float, c_int, P, P, P, P],
+    "crb3d_group_points_batch": [c_int, c_int, c_int, c_int, c_int, P, P, P, P],
+    "crb3d_group_points_grad_batch": [c_int, c_int, c_int, c_int, c_int, P, P, P, P],
+    "crb3d_three_nn_batch": [c_int, c_int, c_int, P, P, P, P, P],
+    "crb3d_three_interpolate_batch": [c_int, c_int, c_int, c_int, P, P, P, P, P],
+    "crb3d_three_interpolate_grad_batch": [c_int, c_int, c_int, c_int, P, P, P, P, P],
+    "crb3d_roipoint_pool3d_workspace_bytes": [c_int, c_int, c_int, POINTER(c_size_t)],
+    "crb3d_roipoint_pool3d_forward": [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P],
     "crb3d_sa_group_mlp_maxpool": [c_int, P, P, P, c_int, P, P, c_int, P, c_int, c_int, P, P, P, c_int, P],
     "crb3d_fc_gemm_workspace_bytes": [c_int64, c_int, c_int, POINTER(c_size_t)],
     "crb3d_fc_gemm_tf32": [P, c_int64, c_int, c_int64, P, c_int, P, P, c_int, P, P, c_size_t, P],
@@ -124,6 +133,9 @@ KERNELS_PER_CALL = {
     "crb3d_label_entropy": 1, "crb3d_label_entropy_ranges": 1, "crb3d_pairwise_sqdist_f64": 1,
     "crb3d_anchor_head_scores": 1, "crb3d_anchor_head_scores_topk": 2, "crb3d_anchor_decode_select": 1, "crb3d_gather_rows_f32": 1, "crb3d_gather_rows_i32": 1,
     "crb3d_spconv_forward_tf32": 1, "crb3d_bev_gemm_tf32": 1, "crb3d_bev_conv3x3_tf32": 1, "crb3d_bev_conv_gemm_tf32": 1, "crb3d_sa_group_mlp_maxpool": 1, "crb3d_fc_gemm_tf32": 2, "crb3d_mask_collate_points": 6,
+    "crb3d_voxel_query_stack": 1, "crb3d_ball_query_batch": 1, "crb3d_group_points_batch": 1, "crb3d_group_points_grad_batch": 1,
+    "crb3d_three_nn_batch": 1, "crb3d_three_interpolate_batch": 1, "crb3d_three_interpolate_grad_batch": 1,
+    "crb3d_roipoint_pool3d_forward": 1,
 }
 LAUNCHES = {"kernels": 0, "calls": 0}
 

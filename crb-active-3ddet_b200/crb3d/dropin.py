@@ -1,6 +1,7 @@
 """Registers the crb3d stand-ins under the import names of the reference's compiled extension modules, so the unmodified
 reference wrappers (`from . import iou3d_nms_cuda` in pcdet/ops/iou3d_nms/iou3d_nms_utils.py:8, `roiaware_pool3d_cuda`
-in roiaware_pool3d_utils.py:6, `pointnet2_stack_cuda` in pointnet2_stack/pointnet2_utils.py:5) and `import spconv` /
+in roiaware_pool3d_utils.py:6, `pointnet2_stack_cuda` in pointnet2_stack/pointnet2_utils.py:5, `pointnet2_batch_cuda` in
+pointnet2_batch/pointnet2_utils.py:7, `roipoint_pool3d_cuda` in roipoint_pool3d_utils.py:6) and `import spconv` /
 `cumm` resolve to this library. Call before importing pcdet:
 
     import sys; sys.path.insert(0, "<repo>/crb-active-3ddet_b200")
@@ -15,6 +16,8 @@ ALIASES = {
     "pcdet.ops.iou3d_nms.iou3d_nms_cuda": "pcdet_ops.iou3d_nms_cuda",
     "pcdet.ops.roiaware_pool3d.roiaware_pool3d_cuda": "pcdet_ops.roiaware_pool3d_cuda",
     "pcdet.ops.pointnet2.pointnet2_stack.pointnet2_stack_cuda": "pcdet_ops.pointnet2_stack_cuda",
+    "pcdet.ops.pointnet2.pointnet2_batch.pointnet2_batch_cuda": "pcdet_ops.pointnet2_batch_cuda",
+    "pcdet.ops.roipoint_pool3d.roipoint_pool3d_cuda": "pcdet_ops.roipoint_pool3d_cuda",
     "pcdet.ops.voxel": "pcdet_ops.voxel",
     # build_strategy('crb', ...) of pcdet/query_strategies/__init__.py:13-29 then returns the crb3d CRBSampling
     "pcdet.query_strategies.crb_sampling": "crb3d.crb_strategy",
@@ -28,6 +31,11 @@ EXPECTED = {
         "stack_farthest_point_sampling_wrapper", "group_points_wrapper", "group_points_grad_wrapper", "three_nn_wrapper",
         "three_interpolate_wrapper", "three_interpolate_grad_wrapper", "query_stacked_local_neighbor_idxs_wrapper_stack",
         "query_three_nn_by_stacked_local_idxs_wrapper_stack", "vector_pool_wrapper", "vector_pool_grad_wrapper"],
+    "pcdet.ops.pointnet2.pointnet2_batch.pointnet2_batch_cuda": [
+        "ball_query_wrapper", "group_points_wrapper", "group_points_grad_wrapper", "gather_points_wrapper",
+        "gather_points_grad_wrapper", "farthest_point_sampling_wrapper", "three_nn_wrapper", "three_interpolate_wrapper",
+        "three_interpolate_grad_wrapper"],
+    "pcdet.ops.roipoint_pool3d.roipoint_pool3d_cuda": ["forward"],
     "pcdet.ops.voxel": ["hard_voxelize"],
     "pcdet.query_strategies.crb_sampling": ["CRBSampling"],
 }

@@ -310,6 +310,19 @@ def round_tf32(t):
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+def tf32_weight(conv):
+    """A conv module's weight rounded to TF32 (round to nearest) once per parameter version: the tensor core truncates fp32
+    operands, a systematic shrink of ~3e-4 per operand per layer (the BEV stack does the same in its inference plan). Used by
+    both inference routes of the sparse convs (module forward and the captured static step) so that they stay bit-identical."""
+    w = conv.weight
+    key = (w._version, w.data_ptr())
+    c = getattr(conv, "_crb3d_w_tf32", None)
+    if c is None or c[0] != key:
+        c = (key, round_tf32(w))
+        conv._crb3d_w_tf32 = c
+    return c[1]
+
+
 def bev_gemm(a, weight, bias, relu, segs, n_sub=1, up=0, in_hw=(0, 0), round_out=False):
     """D = A @ W^T (+bias) (ReLU) on the tensor cores with fused output placement (csrc/bev_gemm_tc.cu).
     a: (M, K) fp32 CUDA, unit column stride (row stride = a.stride(0)); weight: contiguous (n_sub*N, K);
@@ -431,6 +444,71 @@ def furthest_first(X, min_dist, n_pick):
     ws = _ws(_ws_bytes("crb3d_furthest_first_workspace_bytes", m), X.device)
     _lib.call("crb3d_furthest_first", _p(X), m, d, _p(min_dist), int(n_pick), _p(out), _p(ws), ws.numel(), _stream(X.device))
     return out
+
+
+# ----------------------------------------------------------------------------------------------- remaining op families
+def voxel_query(M, R1, R2, R3, nsample, radius, z_range, y_range, x_range, new_xyz, xyz, new_coords, point_indices, idx):
+    """voxel_query_wrapper_stack (pointnet2_stack/src/voxel_query.cpp:28-45): same argument order."""
+    _need_cuda(new_xyz, xyz, new_coords, point_indices, idx)
+    _check(new_xyz=(new_xyz, torch.float32), xyz=(xyz, torch.float32), new_coords=(new_coords, torch.int32),
+           point_indices=(point_indices, torch.int32), idx=(idx, torch.int32))
+    _lib.call("crb3d_voxel_query_stack", int(M), int(R1), int(R2), int(R3), int(nsample), float(radius), int(z_range), int(y_range),
+              int(x_range), _p(new_xyz), _p(xyz), _p(new_coords), _p(point_indices), _p(idx), _stream(idx.device))
+
+
+def ball_query_batch(b, n, m, radius, nsample, new_xyz, xyz, idx):
+    """ball_query_wrapper_fast (pointnet2_batch/src/ball_query.cpp). idx must come in zero-filled, as the reference's does."""
+    _need_cuda(new_xyz, xyz, idx)
+    _check(new_xyz=(new_xyz, torch.float32), xyz=(xyz, torch.float32), idx=(idx, torch.int32))
+    _lib.call("crb3d_ball_query_batch", int(b), int(n), int(m), float(radius), int(nsample), _p(new_xyz), _p(xyz), _p(idx),
+              _stream(idx.device))
+
+
+def group_points_batch(b, c, n, npoints, nsample, points, idx, out):
+    _need_cuda(points, idx, out)
+    _check(points=(points, torch.float32), idx=(idx, torch.int32), out=(out, torch.float32))
+    _lib.call("crb3d_group_points_batch", int(b), int(c), int(n), int(npoints), int(nsample), _p(points), _p(idx), _p(out),
+              _stream(out.device))
+
+
+def group_points_grad_batch(b, c, n, npoints, nsample, grad_out, idx, grad_points):
+    _need_cuda(grad_out, idx, grad_points)
+    _check(grad_out=(grad_out, torch.float32), idx=(idx, torch.int32), grad_points=(grad_points, torch.float32))
+    _lib.call("crb3d_group_points_grad_batch", int(b), int(c), int(n), int(npoints), int(nsample), _p(grad_out), _p(idx),
+              _p(grad_points), _stream(grad_out.device))
+
+
+def three_nn_batch(b, n, m, unknown, known, dist2, idx):
+    _need_cuda(unknown, known, dist2, idx)
+    _check(unknown=(unknown, torch.float32), known=(known, torch.float32), dist2=(dist2, torch.float32), idx=(idx, torch.int32))
+    _lib.call("crb3d_three_nn_batch", int(b), int(n), int(m), _p(unknown), _p(known), _p(dist2), _p(idx), _stream(idx.device))
+
+
+def three_interpolate_batch(b, c, m, n, points, idx, weight, out):
+    _need_cuda(points, idx, weight, out)
+    _check(points=(points, torch.float32), idx=(idx, torch.int32), weight=(weight, torch.float32), out=(out, torch.float32))
+    _lib.call("crb3d_three_interpolate_batch", int(b), int(c), int(m), int(n), _p(points), _p(idx), _p(weight), _p(out),
+              _stream(out.device))
+
+
+def three_interpolate_grad_batch(b, c, n, m, grad_out, idx, weight, grad_points):
+    _need_cuda(grad_out, idx, weight, grad_points)
+    _check(grad_out=(grad_out, torch.float32), idx=(idx, torch.int32), weight=(weight, torch.float32),
+           grad_points=(grad_points, torch.float32))
+    _lib.call("crb3d_three_interpolate_grad_batch", int(b), int(c), int(n), int(m), _p(grad_out), _p(idx), _p(weight),
+              _p(grad_points), _stream(grad_out.device))
+
+
+def roipoint_pool3d_forward(xyz, boxes3d, pts_feature, pooled, empty_flag):
+    """roipool3d_gpu (roipoint_pool3d/src/roipoint_pool3d.cpp:23-46): sizes come from the tensors, as there."""
+    _need_cuda(xyz, boxes3d, pts_feature, pooled, empty_flag)
+    _check(xyz=(xyz, torch.float32), boxes3d=(boxes3d, torch.float32), pts_feature=(pts_feature, torch.float32),
+           pooled=(pooled, torch.float32), empty_flag=(empty_flag, torch.int32))
+    B, N = xyz.shape[0], xyz.shape[1]
+    M, C, S = boxes3d.shape[1], pts_feature.shape[2], pooled.shape[2]
+    ws = _ws(_ws_bytes("crb3d_roipoint_pool3d_workspace_bytes", B, M, S), xyz.device)
+    _lib.call("crb3d_roipoint_pool3d_forward", B, N, M, C, S, _p(xyz), _p(boxes3d), _p(pts_feature), _p(pooled), _p(empty_flag),
+              _p(ws), ws.numel(), _stream(xyz.device))
 
 
 # ----------------------------------------------------------------------------------------------- PV-RCNN fused layers

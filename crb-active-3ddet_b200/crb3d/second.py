@@ -56,16 +56,7 @@ MARKERS = bool(int(os.environ.get("CRB3D_MARKERS", "0")))
 BEV_CONV_TC = {"0": False, "1": True}.get(os.environ.get("CRB3D_BEV_CONV_TC", ""), "auto")
 
 
-def _tf32_weight(conv):
-    """The conv's weight rounded to TF32 (round to nearest) once per parameter version: the tensor core truncates fp32
-    operands, a systematic shrink of ~3e-4 per operand per layer (the BEV stack does the same in its inference plan)."""
-    w = conv.weight
-    key = (w._version, w.data_ptr())
-    c = getattr(conv, "_crb3d_w_tf32", None)
-    if c is None or c[0] != key:
-        c = (key, ops.round_tf32(w))
-        conv._crb3d_w_tf32 = c
-    return c[1]
+_tf32_weight = ops.tf32_weight
 
 
 def post_act_block(in_channels, out_channels, kernel_size, indice_key=None, stride=1, padding=0, conv_type="subm", norm_fn=None):

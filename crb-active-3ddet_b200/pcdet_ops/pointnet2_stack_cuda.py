@@ -1,6 +1,6 @@
 """Stand-in for `pcdet.ops.pointnet2.pointnet2_stack.pointnet2_stack_cuda`
-(pcdet/ops/pointnet2/pointnet2_stack/src/pointnet2_api.cpp:13-30). The Voxel-RCNN / PV-RCNN++ entry points
-(voxel_query, vector_pool*) are outside the CRB hot path and raise NotImplementedError."""
+(pcdet/ops/pointnet2/pointnet2_stack/src/pointnet2_api.cpp:13-30). The PV-RCNN++ entry points (vector_pool*, the stacked
+local-neighbour queries behind them) are outside the CRB hot path and raise NotImplementedError."""
 from crb3d import ops
 
 
@@ -42,14 +42,18 @@ def three_interpolate_grad_wrapper(grad_out, idx, weight, grad_features):
     ops.three_interpolate_grad(grad_out.shape[0], grad_out.shape[1], grad_out, idx, weight, grad_features)
 
 
+def voxel_query_wrapper(M, R1, R2, R3, nsample, radius, z_range, y_range, x_range, new_xyz, xyz, new_coords, point_indices, idx):
+    ops.voxel_query(M, R1, R2, R3, nsample, radius, z_range, y_range, x_range, new_xyz, xyz, new_coords, point_indices, idx)
+    return 1
+
+
 def _not_on_path(name):
     def fn(*args, **kwargs):
-        raise NotImplementedError("%s belongs to Voxel-RCNN / PV-RCNN++ and is outside the CRB hot path" % name)
+        raise NotImplementedError("%s belongs to PV-RCNN++ and is outside the CRB hot path" % name)
     fn.__name__ = name
     return fn
 
 
-voxel_query_wrapper = _not_on_path("voxel_query_wrapper")
 query_stacked_local_neighbor_idxs_wrapper_stack = _not_on_path("query_stacked_local_neighbor_idxs_wrapper_stack")
 query_three_nn_by_stacked_local_idxs_wrapper_stack = _not_on_path("query_three_nn_by_stacked_local_idxs_wrapper_stack")
 vector_pool_wrapper = _not_on_path("vector_pool_wrapper")

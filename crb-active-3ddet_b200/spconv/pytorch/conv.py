@@ -138,7 +138,11 @@ class SparseConvolution(SparseModule):
             nbr, nbr_t, out_idx, out_shape = datas.nbr, datas.nbr_t, datas.out_indices, datas.out_spatial_shape
         if fused_scale is not None and not torch.is_grad_enabled():
             shift = fused_shift if self.bias is None else fused_shift + fused_scale * self.bias
-            out = ops.spconv_forward(feat, nbr, self.weight, scale=fused_scale, shift=shift, relu=fused_relu)
+            # inference with the TF32 tensor-core kernel: weights rounded (not truncated) to TF32 once, outputs rounded in the
+            # epilogue - the same arithmetic as the captured static step (crb3d/second.py: _static_step)
+            tc = ops.SPCONV_TF32
+            out = ops.spconv_forward(feat, nbr, ops.tf32_weight(self) if tc else self.weight, scale=fused_scale, shift=shift,
+                                     relu=fused_relu, round_out=tc)
         else:
             out = _SparseConvFunction.apply(feat, self.weight, self.bias, nbr, nbr_t, self.subm and not self.inverse)
         res = SparseConvTensor(out, out_idx, out_shape, x.batch_size, x.grid, x.voxel_num, x.indice_dict, x.benchmark)

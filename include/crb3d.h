@@ -221,6 +221,42 @@ int crb3d_furthest_first_workspace_bytes(int m, size_t* bytes);
 int crb3d_furthest_first(const float* X, int m, int d, float* min_dist, int n_pick, long long* out_idx, void* ws, size_t ws_bytes,
                          cudaStream_t stream);
 
+/* ---- remaining op families of pcdet/ops (csrc/extra_ops.cu) ----------------------------------------
+ * crb3d_voxel_query_stack: pointnet2_stack/src/voxel_query_gpu.cu:13-98 + voxel_query.cpp:28-45 (Voxel-RCNN neighbour
+ *   search). new_coords (M,4) int32 (b,z,y,x); point_indices (B,R1,R2,R3) int32 (-1: empty voxel); idx (M,nsample) int32:
+ *   neighbours within `radius` (dist2 <= r2) in (dz,dy,dx) scan order, padded with the first, idx[m][0] = -1 when none.
+ * pointnet2_batch layout (pointnet2_batch/src/{ball_query,group_points,sampling,interpolate}_gpu.cu; pointnet2_api.cpp:10-24),
+ *   xyz (b,n,3), features (b,c,n):
+ *   crb3d_ball_query_batch: idx (b,m,nsample) int32, ZERO-FILLED by the caller (an empty ball keeps its zeros; this layout has
+ *     no -1 marker), hits with dist2 < r2 in ascending index order, padded with the first hit.
+ *   crb3d_group_points_batch / _grad_batch: out (b,c,npoints,nsample) = points[b,c,idx]; the gradient is accumulated into
+ *     grad_points (b,c,n) (caller zero-fills). gather_points[_grad] of sampling_gpu.cu:15-70 is the nsample = 1 case.
+ *   crb3d_three_nn_batch / crb3d_three_interpolate_batch / _grad_batch: dist2/idx (b,n,3) of the three nearest of known
+ *     (b,m,3) (strict <, ascending scan: the lowest index wins a tie); out (b,c,n) = sum_k weight[b,n,k] * points[b,c,idx].
+ *   farthest point sampling of this layout is crb3d_farthest_point_sampling (same launcher in the reference).
+ * crb3d_roipoint_pool3d_forward: roipoint_pool3d/src/roipoint_pool3d_kernel.cu:38-165 + roipoint_pool3d.cpp:23-46: for every
+ *   box (already enlarged by the caller) the first S inside points in index order, repeated cyclically when fewer, xyz +
+ *   features copied to pooled (B,M,S,3+C); empty_flag (B,M) int32 = 1 for a box without points (its pooled rows are not
+ *   written). Workspace instead of the reference's cudaMalloc of a (B,N,M) assignment matrix inside the call. */
+int crb3d_voxel_query_stack(int M, int R1, int R2, int R3, int nsample, float radius, int z_range, int y_range, int x_range,
+                            const float* new_xyz, const float* xyz, const int* new_coords, const int* point_indices, int* idx,
+                            cudaStream_t stream);
+int crb3d_ball_query_batch(int b, int n, int m, float radius, int nsample, const float* new_xyz, const float* xyz, int* idx,
+                           cudaStream_t stream);
+int crb3d_group_points_batch(int b, int c, int n, int npoints, int nsample, const float* points, const int* idx, float* out,
+                             cudaStream_t stream);
+int crb3d_group_points_grad_batch(int b, int c, int n, int npoints, int nsample, const float* grad_out, const int* idx,
+                                  float* grad_points, cudaStream_t stream);
+int crb3d_three_nn_batch(int b, int n, int m, const float* unknown, const float* known, float* dist2, int* idx, cudaStream_t stream);
+int crb3d_three_interpolate_batch(int b, int c, int m, int n, const float* points, const int* idx, const float* weight, float* out,
+                                  cudaStream_t stream);
+int crb3d_three_interpolate_grad_batch(int b, int c, int n, int m, const float* grad_out, const int* idx, const float* weight,
+                                       float* grad_points, cudaStream_t stream);
+int crb3d_roipoint_pool3d_workspace_bytes(int B, int M, int S, size_t* bytes);
+int crb3d_roipoint_pool3d_forward(int B, int N, int M, int C, int S, const float* xyz, const float* boxes3d,
+                                  const float* pts_feature, float* pooled, int* empty_flag, void* ws, size_t ws_bytes,
+                                  cudaStream_t stream);
+
 /* ---- PV-RCNN: fused set-abstraction layer and the RoI-head FC GEMM -------------------------------------------------------
  * crb3d_sa_group_mlp_maxpool: one scale of StackSAModuleMSG.forward (pcdet/ops/pointnet2/pointnet2_stack/
  * pointnet2_modules.py:78-112: QueryAndGroup + shared 1x1-conv MLP + BatchNorm + ReLU + max-pool over the samples) in one

@@ -30,36 +30,24 @@ def build_oracle(force=False):
     return LIB
 
 
-def build_ref(force=False, verbose=False):
-    """Compiles the reference's CUDA kernels (from where they lie under /root/reference) behind extern "C" wrappers
-    (oracle/ref_wrap/*.cu) into oracle/_ref/libpcdet_ref_kernels.so. Returns the path or None when the reference tree is
-    absent (GPU box: the prebuilt file travels with the snapshot)."""
-    out = os.path.join(REFDIR, "libpcdet_ref_kernels.so")
-    if not os.path.isdir(REFERENCE):
-        return out if os.path.exists(out) else None
-    os.makedirs(REFDIR, exist_ok=True)
-    wrap = os.path.join(HERE, "ref_wrap", "ref_kernels_wrap.cu")
-    ops = os.path.join(REFERENCE, "pcdet", "ops")
-    srcs = [
-        wrap,
-        os.path.join(ops, "iou3d_nms", "src", "iou3d_nms_kernel.cu"),
-        os.path.join(ops, "roiaware_pool3d", "src", "roiaware_pool3d_kernel.cu"),
-    ]
-    pn = os.path.join(ops, "pointnet2", "pointnet2_stack", "src")
-    pn_srcs = [os.path.join(pn, f) for f in ("ball_query_gpu.cu", "group_points_gpu.cu", "sampling_gpu.cu", "interpolate_gpu.cu")]
-    if not force and _newer(out, srcs + pn_srcs):
+def _build_ref_lib(out, wrap, ref_srcs, inc_dirs, force, verbose):
+    srcs = [wrap] + ref_srcs
+    if not force and _newer(out, srcs):
         return out
-    # the pointnet2 .cu files include headers that pull in <torch/serialize/tensor.h>; give nvcc torch's include dirs
+    # some of the reference .cu files include headers that pull in <torch/serialize/tensor.h>: give nvcc torch's include dirs
     import sysconfig
     import torch.utils.cpp_extension as ext
     inc = []
     for p in ext.include_paths():
         inc += ["-I", p]
-    inc += ["-I", sysconfig.get_paths()["include"], "-I", pn]
+    inc += ["-I", sysconfig.get_paths()["include"]]
+    for d in inc_dirs:
+        inc += ["-I", d]
     objs = []
+    tag = os.path.basename(out)[3:-3]
     os.makedirs(os.path.join(REFDIR, "obj"), exist_ok=True)
-    for i, s in enumerate(srcs + pn_srcs):
-        o = os.path.join(REFDIR, "obj", "%d_%s.o" % (i, os.path.basename(s)[:-3]))
+    for i, s in enumerate(srcs):
+        o = os.path.join(REFDIR, "obj", "%s_%d_%s.o" % (tag, i, os.path.basename(s)[:-3]))
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-w",
                *inc, "-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -72,6 +60,41 @@ def build_ref(force=False, verbose=False):
     if verbose:
         print("built", out)
     return out
+
+
+def build_ref(force=False, verbose=False):
+    """Compiles the reference's CUDA kernels (from where they lie under /root/reference) behind extern "C" wrappers
+    (oracle/ref_wrap/*.cu) into oracle/_ref/libpcdet_ref_kernels.so (iou3d_nms, roiaware_pool3d, pointnet2_stack) and
+    oracle/_ref/libpcdet_ref_kernels_batch.so (pointnet2_batch, voxel_query, roipoint_pool3d; see build_ref_batch). Returns the
+    path of the first or None when the reference tree is absent (GPU box: the prebuilt files travel with the snapshot)."""
+    out = os.path.join(REFDIR, "libpcdet_ref_kernels.so")
+    if not os.path.isdir(REFERENCE):
+        return out if os.path.exists(out) else None
+    os.makedirs(REFDIR, exist_ok=True)
+    ops = os.path.join(REFERENCE, "pcdet", "ops")
+    pn = os.path.join(ops, "pointnet2", "pointnet2_stack", "src")
+    srcs = [
+        os.path.join(ops, "iou3d_nms", "src", "iou3d_nms_kernel.cu"),
+        os.path.join(ops, "roiaware_pool3d", "src", "roiaware_pool3d_kernel.cu"),
+    ] + [os.path.join(pn, f) for f in ("ball_query_gpu.cu", "group_points_gpu.cu", "sampling_gpu.cu", "interpolate_gpu.cu")]
+    _build_ref_lib(out, os.path.join(HERE, "ref_wrap", "ref_kernels_wrap.cu"), srcs, [pn], force, verbose)
+    build_ref_batch(force, verbose)
+    return out
+
+
+def build_ref_batch(force=False, verbose=False):
+    """The second reference library: pointnet2_batch (its sampling_gpu.cu defines the same launcher name as the stack one,
+    hence a library of its own), voxel_query_gpu.cu of pointnet2_stack and roipoint_pool3d_kernel.cu."""
+    out = os.path.join(REFDIR, "libpcdet_ref_kernels_batch.so")
+    if not os.path.isdir(REFERENCE):
+        return out if os.path.exists(out) else None
+    os.makedirs(REFDIR, exist_ok=True)
+    ops = os.path.join(REFERENCE, "pcdet", "ops")
+    pb = os.path.join(ops, "pointnet2", "pointnet2_batch", "src")
+    srcs = [os.path.join(pb, f) for f in ("ball_query_gpu.cu", "group_points_gpu.cu", "sampling_gpu.cu", "interpolate_gpu.cu")]
+    srcs += [os.path.join(ops, "pointnet2", "pointnet2_stack", "src", "voxel_query_gpu.cu"),
+             os.path.join(ops, "roipoint_pool3d", "src", "roipoint_pool3d_kernel.cu")]
+    return _build_ref_lib(out, os.path.join(HERE, "ref_wrap", "ref_kernels_batch_wrap.cu"), srcs, [pb], force, verbose)
 
 
 STAGE = os.path.join(os.path.dirname(HERE), "baseline", "_ref")

@@ -310,6 +310,61 @@ void oracle_ball_query(int B, float radius, int nsample, const float* new_xyz, c
     }
 }
 
+/* pointnet2_stack/src/voxel_query_gpu.cu:13-98: neighbours through the voxel -> point table, (dz,dy,dx) scan order, kept when
+ * dist2 <= radius^2 (not <), first hit pads the row, idx[0] = -1 for an empty neighbourhood. idx zero-initialised by the caller. */
+void oracle_voxel_query(int M, int R1, int R2, int R3, int nsample, float radius, int zr, int yr, int xr, const float* new_xyz,
+                        const float* xyz, const int* new_coords, const int* point_indices, int* idx) {
+    float r2 = radius * radius;
+    for (int q = 0; q < M; ++q) {
+        const int* c = new_coords + (size_t)q * 4;
+        int* out = idx + (size_t)q * nsample;
+        int cnt = 0;
+        for (int dz = -zr; dz <= zr; ++dz) {
+            int z = c[1] + dz;
+            if (z < 0 || z >= R1) continue;
+            for (int dy = -yr; dy <= yr; ++dy) {
+                int y = c[2] + dy;
+                if (y < 0 || y >= R2) continue;
+                for (int dx = -xr; dx <= xr; ++dx) {
+                    int x = c[3] + dx;
+                    if (x < 0 || x >= R3) continue;
+                    int nb = point_indices[(((size_t)c[0] * R1 + z) * R2 + y) * R3 + x];
+                    if (nb < 0) continue;
+                    float d2 = sqdist(xyz[(size_t)nb * 3], xyz[(size_t)nb * 3 + 1], xyz[(size_t)nb * 3 + 2], new_xyz[(size_t)q * 3],
+                                      new_xyz[(size_t)q * 3 + 1], new_xyz[(size_t)q * 3 + 2]);
+                    if (d2 > r2) continue;
+                    if (cnt < nsample) {
+                        if (cnt == 0) for (int l = 0; l < nsample; ++l) out[l] = nb;
+                        out[cnt++] = nb;
+                    }
+                }
+            }
+        }
+        if (cnt == 0) out[0] = -1;
+    }
+}
+
+/* roipoint_pool3d/src/roipoint_pool3d_kernel.cu:38-140 (assign_pts_to_box3d + get_pooled_idx + roipool3d_forward) for one frame:
+ * first S inside points in index order, k % cnt duplication, empty flag; pooled (M,S,3+C) and empty (M) zero-initialised. */
+void oracle_roipoint_pool3d(int N, int M, int C, int S, const float* xyz, const float* boxes, const float* feat, float* pooled,
+                            int* empty) {
+    for (int m = 0; m < M; ++m) {
+        int cnt = 0;
+        float* dst = pooled + (size_t)m * S * (3 + C);
+        for (int k = 0; k < N && cnt < S; ++k) {
+            float lx, ly;
+            if (!pt_in_box(xyz + (size_t)k * 3, boxes + (size_t)m * 7, 1e-5f, &lx, &ly)) continue;
+            float* d = dst + (size_t)cnt * (3 + C);
+            for (int j = 0; j < 3; ++j) d[j] = xyz[(size_t)k * 3 + j];
+            for (int j = 0; j < C; ++j) d[3 + j] = feat[(size_t)k * C + j];
+            ++cnt;
+        }
+        if (cnt == 0) { empty[m] = 1; continue; }
+        for (int s = cnt; s < S; ++s)
+            for (int j = 0; j < 3 + C; ++j) dst[(size_t)s * (3 + C) + j] = dst[(size_t)(s % cnt) * (3 + C) + j];
+    }
+}
+
 /* pointnet2_stack/src/group_points_gpu.cu:71-102 */
 void oracle_group_points(int B, int C, int nsample, const float* feat, const int* feat_cnt, const int* idx,
                          const int* idx_cnt, float* out) {

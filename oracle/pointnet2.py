@@ -69,3 +69,28 @@ def three_nn(unknown, unknown_batch_cnt, known, known_batch_cnt):
 def three_interpolate(features, idx, weight):
     features, weight = f32(features), f32(weight)
     return (weight[:, 0:1] * features[idx[:, 0]] + weight[:, 1:2] * features[idx[:, 1]] + weight[:, 2:3] * features[idx[:, 2]]).astype(np.float32)
+
+
+def voxel_query(max_range, radius, nsample, xyz, new_xyz, new_coords, point_indices):
+    """pointnet2_stack/voxel_query_utils.py:12-42 + src/voxel_query_gpu.cu:13-98 -> raw idx (M, nsample) (idx[m, 0] = -1: empty)."""
+    import ctypes
+    xyz, new_xyz = f32(xyz), f32(new_xyz)
+    new_coords, point_indices = i32(new_coords), i32(point_indices)
+    B, Z, Y, X = point_indices.shape
+    M = len(new_xyz)
+    idx = np.zeros((M, nsample), np.int32)
+    zr, yr, xr = max_range
+    lib().oracle_voxel_query(M, Z, Y, X, int(nsample), ctypes.c_float(radius), int(zr), int(yr), int(xr), ptr(new_xyz), ptr(xyz),
+                             ptr(new_coords), ptr(point_indices), ptr(idx))
+    return idx
+
+
+def roipoint_pool3d(xyz, boxes, feat, S):
+    """roipoint_pool3d_kernel.cu:38-165 for one frame: xyz (N,3), boxes (M,7) (already enlarged), feat (N,C) ->
+    pooled (M,S,3+C), empty (M,) int32."""
+    xyz, boxes, feat = f32(xyz), f32(boxes), f32(feat)
+    N, M, C = len(xyz), len(boxes), feat.shape[1]
+    pooled = np.zeros((M, S, 3 + C), np.float32)
+    empty = np.zeros((M,), np.int32)
+    lib().oracle_roipoint_pool3d(N, M, C, int(S), ptr(xyz), ptr(boxes), ptr(feat), ptr(pooled), ptr(empty))
+    return pooled, empty

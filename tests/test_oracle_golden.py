@@ -59,6 +59,27 @@ def test_pointnet2_golden():
     assert np.array_equal(nidx, g["nn_idx"]) and np.array_equal(d2, g["nn_d2"])
 
 
+def test_extra_ops_golden():
+    """voxel query / roipoint pooling / batch-layout ball query + 3-NN of the oracle vs the reference kernels' outputs."""
+    from oracle import pointnet2 as op
+    g = _load("ref_kernels_extra.npz")
+    idx = op.voxel_query(tuple(int(v) for v in g["vq_range"]), float(g["vq_radius"]), 16, g["vq_xyz"], g["vq_new_xyz"], g["vq_coords"],
+                         g["vq_table"])
+    assert np.array_equal(idx, g["vq_idx"])
+    assert (idx[:, 0] == -1).any() and (idx[:, 0] >= 0).any()
+    pooled, empty = op.roipoint_pool3d(g["rp_pts"], g["rp_boxes"], g["rp_feat"], g["rp_pooled"].shape[1])
+    assert np.array_equal(empty, g["rp_empty"]) and empty[0] == 1 and empty[1] == 0
+    # host libm sinf/cosf vs CUDA: a point exactly on a face may flip -> at most one box may differ
+    assert (np.abs(pooled - g["rp_pooled"]).reshape(len(empty), -1).max(1) > 0).sum() <= 1
+    n, m = g["bq_xyz"].shape[1], g["bq_new"].shape[1]
+    for b in range(2):
+        o = op.ball_query(float(g["bq_radius"]), 16, g["bq_xyz"][b], np.array([n], np.int32), g["bq_new"][b], np.array([m], np.int32))
+        o[o[:, 0] == -1] = 0                       # the batch layout keeps the caller's zeros for an empty ball
+        assert np.array_equal(o, g["bq_idx"][b])
+        d2, nidx = op.three_nn(g["bq_new"][b], np.array([m], np.int32), g["bq_xyz"][b], np.array([n], np.int32))
+        assert np.array_equal(nidx, g["nn_idx"][b]) and np.array_equal(d2, g["nn_d2"][b])
+
+
 def test_fps_tie_rule_matches_reference_tree():
     """Exact duplicates: the reference's tree reduction ranks tied threads by bit-reversed thread id."""
     from oracle import pointnet2 as op

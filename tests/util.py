@@ -22,6 +22,21 @@ def ref_kernels():
     return _ref
 
 
+_ref_batch = None
+
+
+def ref_batch_kernels():
+    """The reference's pointnet2_batch / voxel_query / roipoint_pool3d kernels (oracle/_ref, second library). None if absent."""
+    global _ref_batch
+    if _ref_batch is None:
+        from oracle import build
+        path = build.build_ref_batch()
+        if path is None or not os.path.exists(path):
+            return None
+        _ref_batch = ctypes.CDLL(path)
+    return _ref_batch
+
+
 def P(t):
     return ctypes.c_void_p(t.data_ptr())
 
