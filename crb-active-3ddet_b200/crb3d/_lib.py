@@ -66,6 +66,8 @@ SIGNATURES = {
     "crb3d_mask_collate_points": [P, c_int64, c_int, c_int, P, c_int, P, P, P, P, c_size_t, P],
     "crb3d_furthest_first_workspace_bytes": [c_int, POINTER(c_size_t)],
     "crb3d_furthest_first": [P, c_int, c_int, P, c_int, P, P, c_size_t, P],
+    "crb3d_subm_rulebook_cellmap": [P, c_int, P, P, P, P, P, P, P, P],
+    "crb3d_sparse_rulebook_cellmap": [c_int, P, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_int64)],
     "crb3d_voxel_query_stack": [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P, P, P, P, P],
     "crb3d_ball_query_batch": [c_int, c_int, c_int, c_float, c_int, P, P, P, P],
     "crb3d_group_points_batch": [c_int, c_int, c_int, c_int, c_int, P, P, P, P],
@@ -122,7 +124,7 @@ def check(code, what):
 # CUDA kernels launched by one call of each entry point (read off csrc/*.cu; memsets are not counted). Used by
 # bench.py to report `gpu_launches` = kernels of THIS library launched inside the timed region.
 KERNELS_PER_CALL = {
-    "crb3d_voxelize": 12, "crb3d_subm_rulebook": 2, "crb3d_sparse_rulebook_coords": 6, "crb3d_sparse_rulebook_pairs": 1,
+    "crb3d_voxelize": 12, "crb3d_subm_rulebook": 2, "crb3d_sparse_rulebook_coords": 5, "crb3d_subm_rulebook_cellmap": 1, "crb3d_sparse_rulebook_pairs": 1,
     "crb3d_rulebook_compact_pairs": 6, "crb3d_spconv_forward_f32": 1, "crb3d_spconv_wgrad_f32": 2,
     "crb3d_sparse_to_dense": 1, "crb3d_dense_to_sparse": 1, "crb3d_boxes_overlap_bev": 1, "crb3d_boxes_iou_bev": 1,
     "crb3d_nms": 7, "crb3d_nms_batched": 7, "crb3d_nms_mask": 3, "crb3d_points_in_boxes": 1,

@@ -149,24 +149,45 @@ def conv_out_shape(in_shape, ksize, stride, padding, dilation=(1, 1, 1)):
     return [out[0], out[1], out[2]]
 
 
-def subm_rulebook(coords, spatial_shape, ksize, dilation=(1, 1, 1), n_dev=None):
+class CellMap(object):
+    """cell -> row map of a level produced by a strided rulebook: the output-cell bitmap and its word ranks, two views into
+    that call's private workspace (kept alive here). Valid for `coords` (the rows in rank order) and `shape` only."""
+
+    def __init__(self, ws, batch_size, shape, coords):
+        b_off, r_off, nw = c_size_t(0), c_size_t(0), ctypes.c_int64(0)
+        _lib.call("crb3d_sparse_rulebook_cellmap", int(batch_size), _i3(shape), byref(b_off), byref(r_off), byref(nw))
+        self.ws, self.shape, self.coords = ws, [int(v) for v in shape], coords
+        self.bitmap = ws.data_ptr() + int(b_off.value)
+        self.rank = ws.data_ptr() + int(r_off.value)
+
+    def matches(self, coords, shape):
+        return coords.data_ptr() == self.coords.data_ptr() and coords.shape[0] == self.coords.shape[0] and \
+            [int(v) for v in shape] == self.shape
+
+
+def subm_rulebook(coords, spatial_shape, ksize, dilation=(1, 1, 1), n_dev=None, cellmap=None):
     """Neighbour table (K, n) int32 for a submanifold conv (output rows == input rows). n_dev: device int32 row count when
-    `coords` is a capacity-sized static buffer (rows beyond it are not written)."""
+    `coords` is a capacity-sized static buffer (rows beyond it are not written). cellmap: the CellMap of the strided rulebook
+    that produced `coords` - the table is then read off its bitmap ranks instead of building and probing a hash table."""
     _need_cuda(coords)
     coords = _i32c(coords)
     n = coords.shape[0]
     k = _i3(ksize)
     K = k[0] * k[1] * k[2]
     nbr = torch.empty((K, n), dtype=torch.int32, device=coords.device)
+    if cellmap is not None and cellmap.matches(coords, spatial_shape):
+        _lib.call("crb3d_subm_rulebook_cellmap", _p(coords), n, _p(n_dev), _i3(spatial_shape), k, _i3(dilation),
+                  ctypes.c_void_p(cellmap.bitmap), ctypes.c_void_p(cellmap.rank), _p(nbr), _stream(coords.device))
+        return nbr
     ws = _ws(_ws_bytes("crb3d_subm_rulebook_workspace_bytes", n), coords.device)
     _lib.call("crb3d_subm_rulebook", _p(coords), n, _p(n_dev), _i3(spatial_shape), k, _i3(dilation), _p(nbr), _p(ws), ws.numel(),
               _stream(coords.device))
     return nbr
 
 
-def sparse_rulebook(coords, batch_size, in_shape, ksize, stride, padding, dilation=(1, 1, 1), want_transpose=True):
+def sparse_rulebook(coords, batch_size, in_shape, ksize, stride, padding, dilation=(1, 1, 1), want_transpose=True, want_cellmap=False):
     """Strided sparse conv rulebook. Returns (out_coords (n_out,4) ascending key order, out_shape, nbr (K,n_out),
-    nbr_t (K,n_in) | None). One host sync (reads n_out)."""
+    nbr_t (K,n_in) | None[, CellMap of the output level]). One host sync (reads n_out)."""
     _need_cuda(coords)
     coords = _i32c(coords)
     dev = coords.device
@@ -192,10 +213,13 @@ def sparse_rulebook(coords, batch_size, in_shape, ksize, stride, padding, dilati
     nbr = torch.empty((K, n_out), dtype=torch.int32, device=dev)
     nbr_t = torch.empty((K, n_in), dtype=torch.int32, device=dev) if want_transpose else None
     _lib.call("crb3d_sparse_rulebook_pairs", *args, n_out, _p(nbr), _p(nbr_t), _p(ws), wsb, _stream(dev))
+    if want_cellmap:
+        return out_coords, out_shape, nbr, nbr_t, CellMap(ws, batch_size, out_shape, out_coords)
     return out_coords, out_shape, nbr, nbr_t
 
 
-def sparse_rulebook_static(coords, n_in_dev, batch_size, in_shape, ksize, stride, padding, cap_out, dilation=(1, 1, 1)):
+def sparse_rulebook_static(coords, n_in_dev, batch_size, in_shape, ksize, stride, padding, cap_out, dilation=(1, 1, 1),
+                           want_cellmap=False):
     """Strided sparse conv rulebook without any host synchronisation (CUDA-graph capturable): `coords` (cap_in, 4) holds
     n_in_dev[0] valid rows; returns (out_coords (cap_out, 4), out_shape, nbr (K, cap_out), n_out_dev (1,) int32 device).
     n_out_dev is the TRUE count - if it exceeds cap_out the extra outputs were dropped (callers check it afterwards)."""
@@ -214,6 +238,8 @@ def sparse_rulebook_static(coords, n_in_dev, batch_size, in_shape, ksize, stride
     args = (_p(coords), cap_in, _p(n_in_dev), batch_size, _i3(in_shape), _i3(out_shape), k, _i3(stride), _i3(padding), _i3(dilation))
     _lib.call("crb3d_sparse_rulebook_coords", *args, _p(out_coords), cap_out, _p(n_out_dev), _p(ws), wsb, _stream(dev))
     _lib.call("crb3d_sparse_rulebook_pairs", *args, cap_out, _p(nbr), None, _p(ws), wsb, _stream(dev))
+    if want_cellmap:
+        return out_coords, out_shape, nbr, n_out_dev, CellMap(ws, batch_size, out_shape, out_coords)
     return out_coords, out_shape, nbr, n_out_dev
 
 

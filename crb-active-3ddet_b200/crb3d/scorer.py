@@ -100,7 +100,11 @@ class PoolScorer(object):
         yield dev_batch[1]
         yield geom["voxel_features"]
         yield geom["voxel_coords"]
-        for d in geom["rulebooks"].values():
+        for key, d in geom["rulebooks"].items():
+            if key == "_crb3d_cellmaps":          # cell -> row maps of the strided levels (spconv/pytorch/conv.py: _rulebook)
+                for cm in d.values():
+                    yield cm.ws
+                continue
             for t in (d.nbr, d.nbr_t, d.out_indices, d.indices):
                 if t is not None:
                     yield t

@@ -535,22 +535,28 @@ class SECONDNet(nn.Module):
         fork.record(main)
         side.wait_event(fork)
         books, counts, caps, plan = {}, [n_dev], [coords.shape[0]], []
+        cellmap = None          # cell -> row map of the current level (left behind by the strided rulebook that produced it)
+        g["_cellmaps"] = []     # keeps those workspaces alive for as long as the captured graph
         with torch.cuda.stream(side):
             for conv, bn, relu in self._sparse_layers():
                 mark_side(100 + len(plan))    # before this layer's rulebook (its event is recorded after, so the branch stays joined)
                 if conv.subm:
                     key = (conv.indice_key, tuple(conv.kernel_size))
                     if key not in books:
-                        nbr = ops.subm_rulebook(coords, shape, conv.kernel_size, conv.dilation, n_dev=n_dev)
+                        nbr = ops.subm_rulebook(coords, shape, conv.kernel_size, conv.dilation, n_dev=n_dev, cellmap=cellmap)
                         ev = torch.cuda.Event()
                         ev.record(side)
                         books[key] = (nbr, ev)
                     nbr, ev = books[key]
                 else:
-                    cap_out = int(min(B * np.prod(ops.conv_out_shape(shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)),
-                                      g["growth"][len(caps) - 1] * coords.shape[0]))
-                    coords, shape, nbr, n_dev = ops.sparse_rulebook_static(coords, n_dev, B, shape, conv.kernel_size, conv.stride,
-                                                                           conv.padding, cap_out, conv.dilation)
+                    cells = B * np.prod(ops.conv_out_shape(shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation))
+                    if g.get("row_caps") is not None:        # measured capacities (calibrate_row_caps): grids sized for the data
+                        cap_out = int(min(cells, g["row_caps"][len(caps) - 1]))
+                    else:
+                        cap_out = int(min(cells, g["growth"][len(caps) - 1] * coords.shape[0]))
+                    coords, shape, nbr, n_dev, cellmap = ops.sparse_rulebook_static(coords, n_dev, B, shape, conv.kernel_size, conv.stride,
+                                                                                    conv.padding, cap_out, conv.dilation, want_cellmap=True)
+                    g["_cellmaps"].append(cellmap)
                     ev = torch.cuda.Event()
                     ev.record(side)
                     counts.append(n_dev)
@@ -576,31 +582,57 @@ class SECONDNet(nn.Module):
         return out
 
     @torch.no_grad()
-    def enable_full_graph(self, batch_size, max_points_per_frame=32768, growth=(2.0, 1.0, 1.0, 1.0), slots=1):
+    @torch.no_grad()
+    def level_row_counts(self, points, frame_offsets, batch_size):
+        """Row counts of one batch at every level of the sparse backbone: [voxels, rows after each strided conv] (host ints)."""
+        geom = self.geometry(points, frame_offsets, batch_size)
+        counts = [int(geom["voxel_coords"].shape[0])]
+        seen = set()
+        for conv, _, _ in self._sparse_layers():
+            if not conv.subm and conv.indice_key not in seen:
+                seen.add(conv.indice_key)
+                counts.append(int(geom["rulebooks"][conv.indice_key].out_indices.shape[0]))
+        return counts
+
+    def calibrate_row_caps(self, batches, margin=1.3, slack=2048):
+        """Static row capacities of the strided-conv outputs for enable_full_graph(row_caps=...), measured on sample batches
+        [(points, frame_offsets, batch_size)]: max count per level x margin (+slack), rounded up to 128-row tiles. Every kernel
+        of the captured step launches a capacity-sized grid (rows beyond the device-side count exit at once), so capacities
+        sized for the data instead of the worst case (growth=2,1,1,1: every level as large as the first strided output) remove
+        most CTAs of the deep layers. A batch that exceeds a capacity is detected from `counts` and re-scored eagerly."""
+        mx = None
+        for p, o, b in batches:
+            c = self.level_row_counts(p, o, b)
+            mx = c if mx is None else [max(a, x) for a, x in zip(mx, c)]
+        return [int(-(-(int(c * margin) + slack) // 128) * 128) for c in mx[1:]]
+
+    def enable_full_graph(self, batch_size, max_points_per_frame=32768, growth=(2.0, 1.0, 1.0, 1.0), slots=1, row_caps=None):
         """Captures the WHOLE scoring step (_static_step) for a fixed batch size into one CUDA graph: every count stays on
         the device, so one replay replaces ~250 kernel launches and 5 host synchronisations (the eager step is host-bound).
-        growth[i]: capacity of the i-th strided conv's output rows relative to its input capacity.
+        growth[i]: capacity of the i-th strided conv's output rows relative to its input capacity; row_caps (optional, wins):
+        absolute capacities of the strided-conv outputs, e.g. from calibrate_row_caps().
         slots > 1 captures that many independent copies (own static buffers): replayed on different streams, consecutive
         batches overlap - the narrow tail of one step (greedy NMS pass, top-k sort, small rulebook kernels, ~10 % of the
         step on a handful of SMs) runs under the wide kernels of the next one."""
-        self._graph_cfg = (batch_size, max_points_per_frame, tuple(growth), slots)
+        row_caps = None if row_caps is None else tuple(int(c) for c in row_caps)
+        self._graph_cfg = (batch_size, max_points_per_frame, tuple(growth), slots, row_caps)
         if slots > 1:
             ops.drop_workspaces([id(g) for g in getattr(self, "_full_graphs", [])])     # re-capture: the old copies go away
             copies = []
             for i in range(slots):
                 self._next_slot = i
-                self.enable_full_graph(batch_size, max_points_per_frame, growth, slots=1)
+                self.enable_full_graph(batch_size, max_points_per_frame, growth, slots=1, row_caps=row_caps)
                 copies.append(self._full_graph)
             self._next_slot = 0
             self._full_graphs = copies
             self._full_graph = copies[0]
-            self._graph_cfg = (batch_size, max_points_per_frame, tuple(growth), slots)
+            self._graph_cfg = (batch_size, max_points_per_frame, tuple(growth), slots, row_caps)
             return self
         dev = next(self.parameters()).device
         d = self.cfg["data"]
         C, (D, H, W) = self.backbone_3d.num_point_features, self.bev_shape()
         g = dict(B=batch_size, cap=batch_size * max_points_per_frame, max_pts=max_points_per_frame, growth=list(growth),
-                 slot=getattr(self, "_next_slot", 0))
+                 row_caps=row_caps, slot=getattr(self, "_next_slot", 0))
         g["spatial"] = torch.zeros((batch_size, H, W, C * D), device=dev)
         g["points"] = torch.zeros((g["cap"], d["n_feat"]), device=dev)
         g["offsets"] = torch.zeros((batch_size + 1,), dtype=torch.int32, device=dev)

@@ -207,5 +207,6 @@ __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx,
 #define CRB3D_SCAN_TILE 2048
 int crb3d_scan_exclusive_i32(const int* in, int* out, int64_t n, int* block_sums, int* total, cudaStream_t stream);
 size_t crb3d_scan_ws_ints(int64_t n);
+int crb3d_scan_block_sums(int* sums, int64_t nb, int* total, cudaStream_t stream);
 int crb3d_fill_i32(int* p, size_t n, int v, cudaStream_t stream);
 int crb3d_fill_f32(float* p, size_t n, float v, cudaStream_t stream);

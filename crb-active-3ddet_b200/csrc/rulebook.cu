@@ -76,42 +76,129 @@ __device__ __forceinline__ bool out_coord(const ConvGeom& g, int4 c, int k, int&
     return oz < g.out_shape[0] && oy < g.out_shape[1] && ox < g.out_shape[2];
 }
 
+// The valid (offset, output cell) pairs of ONE input row, enumerated with per-axis pruning: a k=3, s=2 conv reaches 1..8 of
+// its 27 offsets per input (odd coordinates pair with two taps per axis, even ones with one), so one thread per row does the
+// work the first version spread over 27 mostly idle threads.
+template <typename F>
+__device__ __forceinline__ void for_each_output(const ConvGeom& g, int4 c, F f) {
+    for (int kz = 0; kz < g.k[0]; ++kz) {
+        const int z = c.y + g.p[0] - kz * g.d[0];
+        if (z < 0 || z % g.s[0]) continue;
+        const int oz = z / g.s[0];
+        if (oz >= g.out_shape[0]) continue;
+        for (int ky = 0; ky < g.k[1]; ++ky) {
+            const int y = c.z + g.p[1] - ky * g.d[1];
+            if (y < 0 || y % g.s[1]) continue;
+            const int oy = y / g.s[1];
+            if (oy >= g.out_shape[1]) continue;
+            for (int kx = 0; kx < g.k[2]; ++kx) {
+                const int x = c.w + g.p[2] - kx * g.d[2];
+                if (x < 0 || x % g.s[2]) continue;
+                const int ox = x / g.s[2];
+                if (ox >= g.out_shape[2]) continue;
+                f((kz * g.k[1] + ky) * g.k[2] + kx, lin_key(c.x, oz, oy, ox, g.out_shape));
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) sparse_mark(const int* __restrict__ coords, int n, ConvGeom g,
                                                    unsigned int* __restrict__ bitmap, const int* __restrict__ n_dev) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || (n_dev && i >= *n_dev)) return;
-    int4 c = __ldg(reinterpret_cast<const int4*>(coords) + i);
-    int oz, oy, ox;
-    if (!out_coord(g, c, k, oz, oy, ox)) return;
-    unsigned long long key = lin_key(c.x, oz, oy, ox, g.out_shape);
-    atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+    const int4 c = __ldg(reinterpret_cast<const int4*>(coords) + i);
+    for_each_output(g, c, [&](int, unsigned long long key) {
+        unsigned int* w = bitmap + (key >> 5);
+        const unsigned int bit = 1u << (key & 31);
+        // neighbouring inputs hit the same cells: test first (plain load, the bit only ever goes 0 -> 1), atomics for the rest
+        if (!(*reinterpret_cast<volatile unsigned int*>(w) & bit)) atomicOr(w, bit);
+    });
 }
 
-__global__ void __launch_bounds__(256) bitmap_popc(const unsigned int* __restrict__ bitmap, int64_t nwords,
-                                                   int* __restrict__ cnt) {
-    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < nwords) cnt[w] = __popc(bitmap[w]);
+// popcount + exclusive scan of the bitmap words + emission of the active output coordinates, in two passes over the bitmap
+// (tile sums, then ranks + coordinates) around the one-block scan of the tile sums; a tile = CRB3D_SCAN_TILE words
+constexpr int BM_ITEMS = CRB3D_SCAN_TILE / 256;   // 8 words per thread = two 16-byte loads
+static_assert(BM_ITEMS == 8, "bitmap kernels read two uint4 per thread");
+
+__device__ __forceinline__ void load_words8(const unsigned int* __restrict__ bitmap, int64_t base, int64_t nwords, unsigned int (&w)[8]) {
+    if (base + 8 <= nwords) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(bitmap + base)), b = __ldg(reinterpret_cast<const uint4*>(bitmap + base) + 1);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = (base + i < nwords) ? __ldg(bitmap + base + i) : 0u;
+    }
 }
 
-__global__ void __launch_bounds__(256) sparse_emit_coords(const unsigned int* __restrict__ bitmap, int64_t nwords,
-                                                          const int* __restrict__ rank, ConvGeom g,
-                                                          int* __restrict__ coords_out, int cap_out) {
-    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nwords) return;
-    unsigned int bits = bitmap[w];
-    int r = rank[w];
-    while (bits) {
-        int bit = __ffs(bits) - 1;
-        bits &= bits - 1;
-        if (r < cap_out) {
-            unsigned long long key = ((unsigned long long)w << 5) + bit;
-            int x = (int)(key % g.out_shape[2]); key /= g.out_shape[2];
-            int y = (int)(key % g.out_shape[1]); key /= g.out_shape[1];
-            int z = (int)(key % g.out_shape[0]); key /= g.out_shape[0];
-            reinterpret_cast<int4*>(coords_out)[r] = make_int4((int)key, z, y, x);
+__global__ void __launch_bounds__(256) bitmap_tile_sums(const unsigned int* __restrict__ bitmap, int64_t nwords, int* __restrict__ sums) {
+    __shared__ int sm[33];
+    unsigned int w[8];
+    load_words8(bitmap, (int64_t)blockIdx.x * CRB3D_SCAN_TILE + (int64_t)threadIdx.x * 8, nwords, w);
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += __popc(w[i]);
+    int tot;
+    block_excl_scan(s, sm, &tot);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256) bitmap_rank(const unsigned int* __restrict__ bitmap, int64_t nwords, const int* __restrict__ sums,
+                                                   int* __restrict__ rank) {
+    __shared__ int sm[33];
+    const int64_t base = (int64_t)blockIdx.x * CRB3D_SCAN_TILE + (int64_t)threadIdx.x * 8;
+    unsigned int w[8];
+    load_words8(bitmap, base, nwords, w);
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += __popc(w[i]);
+    int tot;
+    int ex = block_excl_scan(s, sm, &tot) + sums[blockIdx.x];
+    int r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r[i] = ex; ex += __popc(w[i]); }
+    if (base + 8 <= nwords) {
+        reinterpret_cast<int4*>(rank + base)[0] = make_int4(r[0], r[1], r[2], r[3]);
+        reinterpret_cast<int4*>(rank + base)[1] = make_int4(r[4], r[5], r[6], r[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (base + i < nwords) rank[base + i] = r[i];
+    }
+}
+
+// Active output coordinates in rank (= ascending key) order. A warp owns 32 consecutive bitmap words: every lane decodes the
+// coordinates of ITS word's first cell once (the only divisions), then the warp walks the non-empty words with lane = bit, so
+// a dense word emits its 32 rows in one step and an empty region costs one ballot.
+__global__ void __launch_bounds__(256) bitmap_emit_coords(const unsigned int* __restrict__ bitmap, int64_t nwords, const int* __restrict__ rank,
+                                                          ConvGeom g, int* __restrict__ coords_out, int cap_out) {
+    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned int word = wi < nwords ? __ldg(&bitmap[wi]) : 0u;
+    unsigned int nz = __ballot_sync(0xffffffffu, word != 0u);
+    if (!nz) return;
+    const int r0 = word ? __ldg(&rank[wi]) : 0;
+    unsigned long long key = (unsigned long long)wi << 5;
+    const int W = g.out_shape[2], H = g.out_shape[1], D = g.out_shape[0];
+    const int x0 = (int)(key % W); key /= W;
+    const int y0 = (int)(key % H); key /= H;
+    const int z0 = (int)(key % D);
+    const int b0 = (int)(key / D);
+    while (nz) {
+        const int src = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const unsigned int w = __shfl_sync(0xffffffffu, word, src);
+        const int r = __shfl_sync(0xffffffffu, r0, src);
+        int x = __shfl_sync(0xffffffffu, x0, src) + lane, y = __shfl_sync(0xffffffffu, y0, src);
+        int z = __shfl_sync(0xffffffffu, z0, src), bb = __shfl_sync(0xffffffffu, b0, src);
+        if ((w >> lane) & 1u) {
+            const int o = r + __popc(w & ((1u << lane) - 1u));
+            if (o < cap_out) {
+                while (x >= W) {           // the word straddles a row end (rows shorter than 32 cells wrap more than once)
+                    x -= W;
+                    if (++y == H) { y = 0; if (++z == D) { z = 0; ++bb; } }
+                }
+                reinterpret_cast<int4*>(coords_out)[o] = make_int4(bb, z, y, x);
+            }
         }
-        ++r;
     }
 }
 
@@ -120,19 +207,60 @@ __global__ void __launch_bounds__(256) sparse_fill_pairs(const int* __restrict__
                                                          const int* __restrict__ rank, int n_out,
                                                          int* __restrict__ nbr, int* __restrict__ nbr_t,
                                                          const int* __restrict__ n_dev) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || (n_dev && i >= *n_dev)) return;
-    int4 c = __ldg(reinterpret_cast<const int4*>(coords) + i);
-    int oz, oy, ox;
-    int o = -1;
-    if (out_coord(g, c, k, oz, oy, ox)) {
-        unsigned long long key = lin_key(c.x, oz, oy, ox, g.out_shape);
-        unsigned int word = __ldg(&bitmap[key >> 5]);
-        o = __ldg(&rank[key >> 5]) + __popc(word & ((1u << (key & 31)) - 1u));
-        if (o < n_out) nbr[(size_t)k * n_out + o] = i; else o = -1;
+    const int4 c = __ldg(reinterpret_cast<const int4*>(coords) + i);
+    if (nbr_t)
+        for (int k = 0; k < g.K; ++k) nbr_t[(size_t)k * n + i] = -1;      // coalesced per offset plane; the hits below overwrite
+    for_each_output(g, c, [&](int k, unsigned long long key) {
+        const unsigned int word = __ldg(&bitmap[key >> 5]);
+        const int o = __ldg(&rank[key >> 5]) + __popc(word & ((1u << (key & 31)) - 1u));
+        if (o < n_out) {
+            nbr[(size_t)k * n_out + o] = i;
+            if (nbr_t) nbr_t[(size_t)k * n + i] = o;
+        }
+    });
+}
+
+// SubM neighbour table of a level whose rows were ranked by a strided rulebook (its output-cell bitmap + word ranks =
+// cell -> row map): two loads per (z, y) line instead of a hash probe chain per neighbour, no table to build. One thread per
+// row walks its k^3 neighbourhood; consecutive kx share a bitmap word. A rank at or beyond the valid row count (truncated
+// level: the capacity was exceeded) reads as "no neighbour".
+__global__ void __launch_bounds__(256) subm_lookup_cellmap(const int* __restrict__ coords, int n, ConvGeom g,
+                                                           const unsigned int* __restrict__ bitmap, const int* __restrict__ rank,
+                                                           int* __restrict__ nbr, const int* __restrict__ n_dev) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nv = n_dev ? min(n, *n_dev) : n;
+    if (o >= nv) return;
+    const int4 c = __ldg(reinterpret_cast<const int4*>(coords) + o);
+    unsigned long long last_w = ~0ull;
+    unsigned int word = 0;
+    int base = 0, k = 0;
+    for (int kz = 0; kz < g.k[0]; ++kz) {
+        const int z = c.y - g.p[0] + kz * g.d[0];
+        for (int ky = 0; ky < g.k[1]; ++ky) {
+            const int y = c.z - g.p[1] + ky * g.d[1];
+            const bool line_ok = z >= 0 && z < g.in_shape[0] && y >= 0 && y < g.in_shape[1];
+            for (int kx = 0; kx < g.k[2]; ++kx, ++k) {
+                const int x = c.w - g.p[2] + kx * g.d[2];
+                int r = -1;
+                if (line_ok && x >= 0 && x < g.in_shape[2]) {
+                    const unsigned long long key = lin_key(c.x, z, y, x, g.in_shape);
+                    if ((key >> 5) != last_w) {
+                        last_w = key >> 5;
+                        word = __ldg(&bitmap[last_w]);
+                        base = word ? __ldg(&rank[last_w]) : 0;
+                    }
+                    const unsigned int bit = (unsigned int)(key & 31);
+                    if ((word >> bit) & 1u) {
+                        r = base + __popc(word & ((1u << bit) - 1u));
+                        if (r >= nv) r = -1;
+                    }
+                }
+                nbr[(size_t)k * n + o] = r;
+            }
+        }
     }
-    if (nbr_t) nbr_t[(size_t)k * n + i] = o;
 }
 
 // ---------------------------------------------------------------- compaction to spconv pair lists
@@ -216,6 +344,37 @@ extern "C" int crb3d_subm_rulebook(const int* coords, int n, const int* n_dev, c
     return CRB3D_OK;
 }
 
+// SubM table of a level produced by a strided rulebook, looked up through that rulebook's cell -> row map (the bitmap + word
+// ranks that crb3d_sparse_rulebook_coords leaves in its workspace; crb3d_sparse_rulebook_cellmap locates them). `coords` must be
+// the out_coords of that call (rows in rank order) and spatial_shape3 its out_shape3. Same table as crb3d_subm_rulebook.
+extern "C" int crb3d_subm_rulebook_cellmap(const int* coords, int n, const int* n_dev, const int* spatial_shape3, const int* ksize3,
+                                           const int* dilation3, const unsigned int* cell_bitmap, const int* cell_rank, int* nbr,
+                                           cudaStream_t stream) {
+    if (n < 0 || !spatial_shape3 || !ksize3 || (!nbr && n > 0) || !cell_bitmap || !cell_rank) return CRB3D_ERR_ARG;
+    int pad[3];
+    for (int j = 0; j < 3; ++j) {
+        if (ksize3[j] % 2 == 0) return CRB3D_ERR_UNSUPPORTED;
+        pad[j] = (ksize3[j] / 2) * (dilation3 ? dilation3[j] : 1);
+    }
+    ConvGeom g;
+    if (!make_geom(spatial_shape3, spatial_shape3, ksize3, nullptr, pad, dilation3, g)) return CRB3D_ERR_ARG;
+    if (n == 0) return CRB3D_OK;
+    subm_lookup_cellmap<<<(unsigned)crb3d_divup(n, 256), 256, 0, stream>>>(coords, n, g, cell_bitmap, cell_rank, nbr, n_dev);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+// byte offsets of the cell bitmap and its word ranks inside the workspace of crb3d_sparse_rulebook_coords, and the word count
+extern "C" int crb3d_sparse_rulebook_cellmap(int batch_size, const int* out_shape3, size_t* bitmap_offset, size_t* rank_offset,
+                                             long long* n_words) {
+    if (!out_shape3 || batch_size <= 0 || !bitmap_offset || !rank_offset || !n_words) return CRB3D_ERR_ARG;
+    const int64_t nw = bitmap_words(batch_size, out_shape3);
+    *bitmap_offset = 0;
+    *rank_offset = crb3d_align(sizeof(unsigned int) * nw);
+    *n_words = nw;
+    return CRB3D_OK;
+}
+
 extern "C" int crb3d_conv_out_shape(const int* in_shape3, const int* ksize3, const int* stride3, const int* pad3,
                                     const int* dilation3, int* out_shape3) {
     if (!in_shape3 || !ksize3 || !stride3 || !pad3 || !out_shape3) return CRB3D_ERR_ARG;
@@ -253,12 +412,14 @@ extern "C" int crb3d_sparse_rulebook_coords(const int* coords_in, int n_in, cons
     int* scan_ws = c.take<int>(crb3d_scan_ws_ints(nw));
     if (!c.ok) return CRB3D_ERR_WORKSPACE;
     CRB3D_CUDA(cudaMemsetAsync(bitmap, 0, sizeof(unsigned int) * nw, stream));
-    if (n_in > 0) sparse_mark<<<dim3((unsigned)crb3d_divup(n_in, 256), g.K), 256, 0, stream>>>(coords_in, n_in, g, bitmap, n_in_dev);
-    const unsigned nbw = (unsigned)crb3d_divup(nw, 256);
-    bitmap_popc<<<nbw, 256, 0, stream>>>(bitmap, nw, rank);
-    int rc = crb3d_scan_exclusive_i32(rank, rank, nw, scan_ws, n_out_dev, stream);
+    if (n_in > 0) sparse_mark<<<(unsigned)crb3d_divup(n_in, 256), 256, 0, stream>>>(coords_in, n_in, g, bitmap, n_in_dev);
+    const int64_t nt = crb3d_divup(nw, CRB3D_SCAN_TILE);
+    bitmap_tile_sums<<<(unsigned)nt, 256, 0, stream>>>(bitmap, nw, scan_ws);
+    int rc = crb3d_scan_block_sums(scan_ws, nt, n_out_dev, stream);
     if (rc) return rc;
-    if (coords_out && cap_out > 0) sparse_emit_coords<<<nbw, 256, 0, stream>>>(bitmap, nw, rank, g, coords_out, cap_out);
+    bitmap_rank<<<(unsigned)nt, 256, 0, stream>>>(bitmap, nw, scan_ws, rank);
+    if (coords_out && cap_out > 0)
+        bitmap_emit_coords<<<(unsigned)crb3d_divup(nw, 256), 256, 0, stream>>>(bitmap, nw, rank, g, coords_out, cap_out);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
@@ -283,8 +444,8 @@ extern "C" int crb3d_sparse_rulebook_pairs(const int* coords_in, int n_in, const
     if (!c.ok) return CRB3D_ERR_WORKSPACE;
     CRB3D_CUDA(cudaMemsetAsync(nbr, 0xFF, sizeof(int) * (size_t)g.K * n_out, stream));
     if (n_in > 0)
-        sparse_fill_pairs<<<dim3((unsigned)crb3d_divup(n_in, 256), g.K), 256, 0, stream>>>(coords_in, n_in, g, bitmap,
-                                                                                          rank, n_out, nbr, nbr_t, n_in_dev);
+        sparse_fill_pairs<<<(unsigned)crb3d_divup(n_in, 256), 256, 0, stream>>>(coords_in, n_in, g, bitmap, rank, n_out, nbr, nbr_t,
+                                                                              n_in_dev);
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }

@@ -82,6 +82,18 @@ int crb3d_scan_exclusive_i32(const int* in, int* out, int64_t n, int* block_sums
     return CRB3D_OK;
 }
 
+// exclusive scan of per-tile sums in place (sums[nb] and *total receive the grand total): the middle pass of a tiled scan whose
+// outer passes live elsewhere (csrc/rulebook.cu: popcount scan of the output-cell bitmap)
+int crb3d_scan_block_sums(int* sums, int64_t nb, int* total, cudaStream_t stream) {
+    if (nb <= 0) {
+        if (total) CRB3D_CUDA(cudaMemsetAsync(total, 0, sizeof(int), stream));
+        return CRB3D_OK;
+    }
+    scan_sums_one_block<<<1, 1024, 0, stream>>>(sums, nb, total);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
 namespace {
 template <typename T>
 __global__ void __launch_bounds__(256) fill_kernel(T* __restrict__ p, size_t n, T v) {

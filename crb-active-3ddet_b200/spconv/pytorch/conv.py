@@ -111,13 +111,16 @@ class SparseConvolution(SparseModule):
             if not self.subm and not datas.is_subm:
                 return datas
         if self.subm:
-            nbr = ops.subm_rulebook(x.indices, x.spatial_shape, self.kernel_size, self.dilation)
+            # rows ranked by a strided rulebook of this forward pass: read the table off its cell -> row map (no hash table)
+            cm = x.indice_dict.get("_crb3d_cellmaps", {}).get(x.indices.data_ptr())
+            nbr = ops.subm_rulebook(x.indices, x.spatial_shape, self.kernel_size, self.dilation, cellmap=cm)
             datas = IndiceData(x.indices, x.indices, nbr, None, x.spatial_shape, x.spatial_shape, self.kernel_size,
                                [1, 1, 1], [(k // 2) * d for k, d in zip(self.kernel_size, self.dilation)],
                                self.dilation, True)
         else:
-            oc, oshape, nbr, nbr_t = ops.sparse_rulebook(x.indices, x.batch_size, x.spatial_shape, self.kernel_size,
-                                                         self.stride, self.padding, self.dilation)
+            oc, oshape, nbr, nbr_t, cm = ops.sparse_rulebook(x.indices, x.batch_size, x.spatial_shape, self.kernel_size,
+                                                             self.stride, self.padding, self.dilation, want_cellmap=True)
+            x.indice_dict.setdefault("_crb3d_cellmaps", {})[oc.data_ptr()] = cm
             datas = IndiceData(oc, x.indices, nbr, nbr_t, oshape, x.spatial_shape, self.kernel_size, self.stride,
                                self.padding, self.dilation, False)
         if self.indice_key is not None:

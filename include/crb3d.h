@@ -77,6 +77,15 @@ int crb3d_subm_rulebook_workspace_bytes(int n, size_t* bytes);
  * can be recorded into one CUDA graph without reading any count back to the host. */
 int crb3d_subm_rulebook(const int* coords, int n, const int* n_dev, const int* spatial_shape3, const int* ksize3,
                         const int* dilation3, int* nbr, void* ws, size_t ws_bytes, cudaStream_t stream);
+/* SubM table of a level that a strided rulebook produced, through that rulebook's cell -> row map (output-cell bitmap + word
+ * ranks left in the workspace of crb3d_sparse_rulebook_coords; crb3d_sparse_rulebook_cellmap gives their byte offsets): two
+ * loads per (z,y) line instead of a hash probe chain per neighbour. coords = the out_coords of that call, spatial_shape3 = its
+ * out_shape3. Writes the same table as crb3d_subm_rulebook (spconv get_indice_pairs, subm=True). */
+int crb3d_subm_rulebook_cellmap(const int* coords, int n, const int* n_dev, const int* spatial_shape3, const int* ksize3,
+                                const int* dilation3, const unsigned int* cell_bitmap, const int* cell_rank, int* nbr,
+                                cudaStream_t stream);
+int crb3d_sparse_rulebook_cellmap(int batch_size, const int* out_shape3, size_t* bitmap_offset, size_t* rank_offset,
+                                  long long* n_words);
 int crb3d_conv_out_shape(const int* in_shape3, const int* ksize3, const int* stride3, const int* pad3,
                          const int* dilation3, int* out_shape3);
 int crb3d_sparse_rulebook_workspace_bytes(int batch_size, const int* out_shape3, size_t* bytes);

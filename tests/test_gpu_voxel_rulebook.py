@@ -90,6 +90,43 @@ def test_sparse_rulebook(cuda, k, s, p):
     assert np.array_equal(nbr_t.cpu().numpy(), rnbr_t)
 
 
+@pytest.mark.parametrize("k,s,p,ks", [((3, 3, 3), (2, 2, 2), (1, 1, 1), (3, 3, 3)), ((3, 3, 3), (2, 2, 2), (0, 1, 1), (3, 3, 3)),
+                                      ((3, 1, 1), (2, 1, 1), (0, 0, 0), (3, 3, 3)), ((3, 3, 3), (2, 2, 2), (1, 1, 1), (1, 3, 5))])
+def test_subm_rulebook_through_cellmap(cuda, k, s, p, ks):
+    """SubM table of a strided level read off the producing rulebook's bitmap ranks == the hash-table route == the oracle;
+    also with device-side counts on capacity-sized buffers, and with a capacity that truncates the level."""
+    from crb3d import ops
+    from oracle import spconv_ref
+    rng = np.random.default_rng(sum(k) + sum(p) + sum(ks))
+    shape = [21, 80, 72]
+    coords = _rand_coords(rng, 3, shape, 25000)
+    ct = cu(coords, cuda)
+    oc, oshape, nbr, nbr_t, cm = ops.sparse_rulebook(ct, 3, shape, k, s, p, want_cellmap=True)
+    via_map = ops.subm_rulebook(oc, oshape, ks, cellmap=cm)
+    via_hash = ops.subm_rulebook(oc, oshape, ks)
+    assert torch.equal(via_map, via_hash)
+    assert np.array_equal(via_map.cpu().numpy(), spconv_ref.subm_rulebook(oc.cpu().numpy(), oshape, ks))
+    assert not cm.matches(ct, shape)                       # a map only answers for the rows it ranked
+    # static route: padded input, device-side counts, capacity above / below the true output count
+    n_out = oc.shape[0]
+    pad = torch.cat([ct, torch.full((777, 4), 3, dtype=torch.int32, device=cuda)])
+    n_in_dev = torch.tensor([ct.shape[0]], dtype=torch.int32, device=cuda)
+    for cap in (n_out + 500, n_out - 1000):
+        soc, soshape, snbr, n_dev, scm = ops.sparse_rulebook_static(pad, n_in_dev, 3, shape, k, s, p, cap, want_cellmap=True)
+        assert int(n_dev.item()) == n_out and soshape == oshape
+        m = min(cap, n_out)
+        assert torch.equal(soc[:m], oc[:m]) and torch.equal(snbr[:, :m], nbr[:, :m])
+        t = ops.subm_rulebook(soc, soshape, ks, n_dev=n_dev, cellmap=scm)
+        h = ops.subm_rulebook(soc, soshape, ks, n_dev=n_dev)
+        if cap >= n_out:
+            assert torch.equal(t[:, :m], via_map)
+        else:                                               # truncated level: neighbours beyond the capacity read as absent
+            expect = via_map[:, :m].clone()
+            expect[expect >= m] = -1
+            assert torch.equal(t[:, :m], expect)
+        assert torch.equal(t[:, :m], h[:, :m]) or cap < n_out
+
+
 def test_sparse_rulebook_empty(cuda):
     from crb3d import ops
     oc, oshape, nbr, nbr_t = ops.sparse_rulebook(torch.zeros((0, 4), dtype=torch.int32, device=cuda), 1, [9, 8, 8],
