@@ -524,19 +524,24 @@ def extra_measurements(args, model, ps, frames, device, l2_flush, progress):
         model.prepare_inference(fold_bev_bn=True, spconv_tf32=old)
         model.enable_full_graph(B, max_points_per_frame=max(len(f) for f in frames) + 1024, slots=slots, row_caps=row_caps)
     progress("extra: exact fp32 done")
-    # forward + backward (configs[1] "fwd+bwd batch 4"): every layer's forward and backward + an SGD step. pcdet's anchor-head
-    # losses / target assignment are rows (f2) = not built: the loss here is a fixed random projection of the head outputs.
+    # forward + backward (configs[1] "fwd+bwd batch 4"): voxelize, rulebooks, every layer's forward and backward, target assignment,
+    # the three anchor-head losses (anchor_head_template.py:101-229 on csrc/train_ops.cu) and an SGD step
     try:
+        from crb3d import synth
         tm = build_model(device)
         tm.train()
         opt = torch.optim.SGD(tm.parameters(), lr=1e-4)
-        gen = torch.Generator(device=device).manual_seed(0)
         pts, offs, _ = b4
+        gts = [synth.make_frame(i, return_boxes=True)[1] for i in range(4)]
+        gt = np.zeros((4, max(len(g) for g in gts), 8), np.float32)
+        for i, g in enumerate(gts):
+            gt[i, :len(g)] = g
+        gt = torch.from_numpy(gt).to(device)
 
         def train_step():
             opt.zero_grad(set_to_none=True)
-            bd = tm.forward_features(pts, offs, 4)
-            loss = sum((bd[k] * torch.randn(bd[k].shape[-1], device=device, generator=gen)).mean() for k in ("cls_preds", "box_preds", "dir_cls_preds"))
+            tm.forward_features(pts, offs, 4, gt_boxes=gt)
+            loss, _ = tm.dense_head.get_loss()
             loss.backward()
             opt.step()
         old = ops.SPCONV_TF32
@@ -553,8 +558,8 @@ def extra_measurements(args, model, ps, frames, device, l2_flush, progress):
         ops.SPCONV_TF32 = old
         ms = ev0.elapsed_time(ev1) / 10
         out["train_step_fwd_bwd_batch4"] = {"ms_per_step": ms, "frames_per_s": 4 / (ms / 1e3),
-                                            "note": "voxelize + 8 rulebooks + 12 sparse convs fwd/dX/dW + BEV stack fwd/bwd (cuDNN autograd) + SGD; "
-                                                    "surrogate loss (anchor-head losses / target assignment = SURVEY 8f2, not built)"}
+                                            "note": "voxelize + 8 rulebooks + 12 sparse convs fwd/dX/dW + BEV stack fwd/bwd (cuDNN autograd) + "
+                                                    "axis-aligned target assignment + focal / smooth-L1 / direction losses (csrc/train_ops.cu) + SGD"}
         del tm, opt
     except Exception as e:  # pragma: no cover
         out["train_step_fwd_bwd_batch4"] = {"error": str(e).splitlines()[0][:200]}

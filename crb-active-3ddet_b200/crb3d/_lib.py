@@ -68,6 +68,11 @@ SIGNATURES = {
     "crb3d_furthest_first": [P, c_int, c_int, P, c_int, P, P, c_size_t, P],
     "crb3d_subm_rulebook_cellmap": [P, c_int, P, P, P, P, P, P, P, P],
     "crb3d_sparse_rulebook_cellmap": [c_int, P, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_int64)],
+    "crb3d_assign_targets_workspace_bytes": [c_int, c_int64, c_int, POINTER(c_size_t)],
+    "crb3d_assign_targets_axis_aligned": [P, c_int64, c_int, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P],
+    "crb3d_anchor_head_loss_workspace_bytes": [c_int, c_int64, POINTER(c_size_t)],
+    "crb3d_anchor_head_loss": [P, P, P, P, P, P, c_int, c_int64, c_int, c_int, P, c_float, c_float, c_float, c_float, P, P, P, P, P, P,
+                               c_size_t, P],
     "crb3d_voxel_query_stack": [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P, P, P, P, P],
     "crb3d_ball_query_batch": [c_int, c_int, c_int, c_float, c_int, P, P, P, P],
     "crb3d_group_points_batch": [c_int, c_int, c_int, c_int, c_int, P, P, P, P],
@@ -137,7 +142,7 @@ KERNELS_PER_CALL = {
     "crb3d_spconv_forward_tf32": 1, "crb3d_bev_gemm_tf32": 1, "crb3d_bev_conv3x3_tf32": 1, "crb3d_bev_conv_gemm_tf32": 1, "crb3d_sa_group_mlp_maxpool": 1, "crb3d_fc_gemm_tf32": 2, "crb3d_mask_collate_points": 6,
     "crb3d_voxel_query_stack": 1, "crb3d_ball_query_batch": 1, "crb3d_group_points_batch": 1, "crb3d_group_points_grad_batch": 1,
     "crb3d_three_nn_batch": 1, "crb3d_three_interpolate_batch": 1, "crb3d_three_interpolate_grad_batch": 1,
-    "crb3d_roipoint_pool3d_forward": 1,
+    "crb3d_roipoint_pool3d_forward": 1, "crb3d_assign_targets_axis_aligned": 2, "crb3d_anchor_head_loss": 3,
 }
 LAUNCHES = {"kernels": 0, "calls": 0}
 

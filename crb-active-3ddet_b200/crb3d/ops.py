@@ -291,7 +291,7 @@ def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transp
             w_tc = w_tc.permute(2, 1, 0).contiguous()
         _lib.call("crb3d_spconv_forward_tf32", _p(feat), feat.shape[0], _p(nbr), _p(w_tc), n_out, K, cin, cout, _p(kmap),
                   _p(_f32c(scale)) if scale is not None else None, _p(_f32c(shift)) if shift is not None else None,
-                  int(bool(relu)) | (2 if round_out else 0), _p(out), _p(n_dev), _stream(feat.device))
+                  int(bool(relu)) | (2 if round_out else 0) | (0 if SPCONV_GROUPED else 4), _p(out), _p(n_dev), _stream(feat.device))
     else:
         _lib.call("crb3d_spconv_forward_f32", _p(feat), _p(nbr), _p(weight), n_out, K, cin, cout, strides[0], strides[1],
                   strides[2], _p(kmap), _p(_f32c(scale)) if scale is not None else None,
@@ -307,6 +307,7 @@ def spconv_forward(feat, nbr, weight, scale=None, shift=None, relu=False, transp
 
 # tensor-core (tcgen05, TF32 inputs / fp32 accumulate) sparse conv for the layers it covers; False = exact-fp32 SIMT path
 SPCONV_TF32 = False
+SPCONV_GROUPED = True     # C_in <= 8 (the input layer) on the grouped-stage kernel (csrc/spconv_tc_grp.cu); False: one offset per stage
 
 # bench.py hook: None, or {"mode": "time" | "pairs", "records": []} (see bench.py roofline section)
 PROFILE = None

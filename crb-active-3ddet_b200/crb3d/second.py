@@ -26,10 +26,14 @@ KITTI_SECOND_CFG = dict(
     num_bev_features=256,
     layer_nums=[5, 5], layer_strides=[1, 2], num_filters=[128, 256], upsample_strides=[1, 2], num_upsample_filters=[256, 256],
     anchors=[
-        dict(class_name="Car", anchor_sizes=[[3.9, 1.6, 1.56]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-1.78]),
-        dict(class_name="Pedestrian", anchor_sizes=[[0.8, 0.6, 1.73]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-0.6]),
-        dict(class_name="Cyclist", anchor_sizes=[[1.76, 0.6, 1.73]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-0.6]),
+        dict(class_name="Car", anchor_sizes=[[3.9, 1.6, 1.56]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-1.78],
+             matched_threshold=0.6, unmatched_threshold=0.45),
+        dict(class_name="Pedestrian", anchor_sizes=[[0.8, 0.6, 1.73]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-0.6],
+             matched_threshold=0.5, unmatched_threshold=0.35),
+        dict(class_name="Cyclist", anchor_sizes=[[1.76, 0.6, 1.73]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-0.6],
+             matched_threshold=0.5, unmatched_threshold=0.35),
     ],
+    loss=dict(cls_weight=1.0, loc_weight=2.0, dir_weight=0.2, code_weights=[1.0] * 7),            # second.yaml:78-85
     dir_offset=0.78539, dir_limit_offset=0.0, num_dir_bins=2,
     score_thresh=0.1, nms_thresh=0.01, nms_pre_maxsize=4096, nms_post_maxsize=500,   # second.yaml:88-99
 )
@@ -40,10 +44,14 @@ WAYMO_SECOND_CFG = dict(
     num_bev_features=256,
     layer_nums=[5, 5], layer_strides=[1, 2], num_filters=[128, 256], upsample_strides=[1, 2], num_upsample_filters=[256, 256],
     anchors=[  # tools/cfgs/waymo_models/second.yaml
-        dict(class_name="Vehicle", anchor_sizes=[[4.7, 2.1, 1.7]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[0]),
-        dict(class_name="Pedestrian", anchor_sizes=[[0.91, 0.86, 1.73]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[0]),
-        dict(class_name="Cyclist", anchor_sizes=[[1.78, 0.84, 1.78]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[0]),
+        dict(class_name="Vehicle", anchor_sizes=[[4.7, 2.1, 1.7]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[0],
+             matched_threshold=0.55, unmatched_threshold=0.4),
+        dict(class_name="Pedestrian", anchor_sizes=[[0.91, 0.86, 1.73]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[0],
+             matched_threshold=0.5, unmatched_threshold=0.35),
+        dict(class_name="Cyclist", anchor_sizes=[[1.78, 0.84, 1.78]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[0],
+             matched_threshold=0.5, unmatched_threshold=0.35),
     ],
+    loss=dict(cls_weight=1.0, loc_weight=2.0, dir_weight=0.2, code_weights=[1.0] * 7),
     dir_offset=0.78539, dir_limit_offset=0.0, num_dir_bins=2,
     score_thresh=0.1, nms_thresh=0.7, nms_pre_maxsize=4096, nms_post_maxsize=500,
 )
@@ -283,6 +291,35 @@ class AnchorHeadSingle(nn.Module):
                                               cfg["dir_limit_offset"], cfg["num_dir_bins"])
         self.num_anchors = fm[0] * fm[1] * self.n_loc
 
+    # ---- training path (anchor_head_template.py:88-229): targets and losses on the device (csrc/train_ops.cu)
+    def anchors_device(self, device):
+        a = getattr(self, "_anchors_dev", None)
+        if a is None or a.device != device:
+            a = head_ops.anchors_tensor(self.spec).to(device)
+            self._anchors_dev = a
+        return a
+
+    def assign_targets(self, gt_boxes):
+        """gt_boxes (B, M, 8) -> dict(box_cls_labels (B,A) int32, box_reg_targets (B,A,7), reg_weights (B,A))
+        (AnchorHeadTemplate.assign_targets -> AxisAlignedTargetAssigner.assign_targets)."""
+        from . import train_ops
+        ta = getattr(self, "target_assigner", None)
+        if ta is None:
+            ta = self.target_assigner = train_ops.AxisAlignedTargetAssigner(self.cfg["anchors"], self.cfg["class_names"])
+        return ta.assign_targets(self.anchors_device(gt_boxes.device), gt_boxes)
+
+    def get_loss(self):
+        """rpn_loss = cls + loc + dir of the last training forward, and the reference's tb_dict (tensors, not .item() floats: no
+        host synchronisation inside the training step)."""
+        from . import train_ops
+        r = self.forward_ret_dict
+        cfg = dict(self.cfg["loss"], dir_offset=self.cfg["dir_offset"])
+        losses = train_ops.anchor_head_loss(r["cls_preds"], r["box_preds"], r.get("dir_cls_preds"), r["box_cls_labels"],
+                                            r["box_reg_targets"], self.anchors_device(r["cls_preds"].device), cfg)
+        rpn_loss = losses.sum()
+        return rpn_loss, {"rpn_loss_cls": losses[0].detach(), "rpn_loss_loc": losses[1].detach(), "rpn_loss_dir": losses[2].detach(),
+                          "rpn_loss": rpn_loss.detach()}
+
     def build_inference_plan(self):
         """The three 1x1 head convs as one [n_cls + n_box + n_dir (padded to 80)][C_in] weight for ops.bev_gemm."""
         self._plan = None
@@ -320,6 +357,9 @@ class AnchorHeadSingle(nn.Module):
         batch_dict["cls_preds"] = self.conv_cls(x).permute(0, 2, 3, 1).contiguous().view(B, self.num_anchors, self.num_class)
         batch_dict["box_preds"] = self.conv_box(x).permute(0, 2, 3, 1).contiguous().view(B, self.num_anchors, 7)
         batch_dict["dir_cls_preds"] = self.conv_dir_cls(x).permute(0, 2, 3, 1).contiguous().view(B, self.num_anchors, -1)
+        if self.training and "gt_boxes" in batch_dict:       # anchor_head_single.py:60-66
+            self.forward_ret_dict = {k: batch_dict[k] for k in ("cls_preds", "box_preds", "dir_cls_preds")}
+            self.forward_ret_dict.update(self.assign_targets(batch_dict["gt_boxes"]))
         return batch_dict
 
 
@@ -411,11 +451,14 @@ class SECONDNet(nn.Module):
         books = self.backbone_3d.build_rulebooks(vox["coords"], batch_size)
         return dict(voxel_features=vox["mean"], voxel_coords=vox["coords"], rulebooks=books)
 
-    def forward_features(self, points, frame_offsets, batch_size, geom=None):
-        """points (N, C) or (N, 1+C) with the batch index in column 0 (collate layout). Returns the head outputs."""
+    def forward_features(self, points, frame_offsets, batch_size, geom=None, gt_boxes=None):
+        """points (N, C) or (N, 1+C) with the batch index in column 0 (collate layout). Returns the head outputs. In training
+        mode with gt_boxes (B, M, 8) the head also assigns its targets (dense_head.get_loss() then gives rpn_loss)."""
         if geom is None:
             geom = self.geometry(points, frame_offsets, batch_size)
         bd = dict(batch_size=batch_size, **geom)
+        if gt_boxes is not None:
+            bd["gt_boxes"] = gt_boxes
         bd = self.backbone_3d(bd)
         bd = self.map_to_bev_module(bd)
         bd = self.backbone_2d(bd)

@@ -359,6 +359,10 @@ int launch_tc(const float* feat, int n_in, const int* nbr, const float* weight, 
 
 }  // namespace
 
+int crb3d_spconv_forward_tf32_grouped(const float* feat, const int* nbr, const float* weight, int n_out, int K, int cin, int cout,
+                                      const float* scale, const float* shift, int relu, float* out, const int* n_dev,
+                                      cudaStream_t stream);
+
 // TF32 tensor-core forward. feat: (n_in, C_in) contiguous; weight: contiguous [C_out, K, C_in] (for the input gradient
 // pass the transposed weight [C_in, K, C_out] and the transposed table). Supported: C_in in {16, 32, 64}, C_out in
 // {16, 32, 64, 128}, K <= 27; anything else returns CRB3D_ERR_UNSUPPORTED (callers use crb3d_spconv_forward_f32).
@@ -374,6 +378,12 @@ extern "C" int crb3d_spconv_forward_tf32(const float* feat, int n_in, const int*
     // C_in = 4 / 8 (the first layer: raw voxel features) ride on the 32-channel path: the TMA weight box and the untouched
     // tail of every 128-byte stage row are zero
     if (K > MAX_K || (cin != 4 && cin != 8 && cin != 16 && cin != 32 && cin != 64) || n_in >= (1 << 25)) return CRB3D_ERR_UNSUPPORTED;
+    // narrow layers, forward direction: several offsets per pipeline stage (csrc/spconv_tc_grp.cu); relu bit 2 keeps them on the
+    // one-offset-per-stage kernel below (A/B measurements)
+    if (!kmap && cin <= 8 && !(relu & 4)) {
+        const int rc = crb3d_spconv_forward_tf32_grouped(feat, nbr, weight, n_out, K, cin, cout, scale, shift, relu, out, n_dev, stream);
+        if (rc != CRB3D_ERR_UNSUPPORTED) return rc;
+    }
 #define TC_ARGS feat, n_in, nbr, weight, n_out, K, cin, kmap, scale, shift, relu, out, n_dev, stream
     const int nkb = (cin + 31) / 32;
     if (nkb == 1) {                                        // stage = 16 KB + C_out*128 B

@@ -305,6 +305,30 @@ int crb3d_gather_rows_f32(const float* src, const long long* idx, const int* val
 int crb3d_gather_rows_i32(const int* src, const long long* idx, const int* valid, int B, int K, int64_t n_src,
                           int width, int fill, int* out, cudaStream_t stream);
 
+/* ---- anchor-head training path (csrc/train_ops.cu) -----------------------------------------------------
+ * crb3d_assign_targets_axis_aligned: AxisAlignedTargetAssigner.assign_targets / assign_targets_single
+ *   (pcdet/models/dense_heads/target_assigner/axis_aligned_target_assigner.py:36-210; POS_FRACTION < 0, match_height False:
+ *   box_utils.boxes3d_nearest_bev_iou, box_utils.py:249-298) + ResidualCoder.encode_torch (box_coder_utils.py:13-43) for a whole
+ *   batch. anchors (A,7) in the head's (y, x, type) order; type_class / matched / unmatched: HOST arrays over the n_types anchor
+ *   types of a location (1-based class, thresholds of ANCHOR_GENERATOR_CONFIG); gt_boxes (B,M,gt_stride>=8) with the class in the
+ *   last column (<= 0: padding); M <= 128. labels (B,A) int32: -1 ignore / 0 background / class; reg_targets (B,A,7);
+ *   reg_weights (B,A); num_pos (B) int32.
+ * crb3d_anchor_head_loss: AnchorHeadTemplate.get_loss (anchor_head_template.py:101-229): sigmoid focal loss, smooth-L1 with the
+ *   heading's sin difference, direction-bin cross entropy (loss_utils.py:9-135), normalised by each frame's positives, / B,
+ *   x LOSS_WEIGHTS. losses (DEVICE float[3]) = {rpn_loss_cls, rpn_loss_loc, rpn_loss_dir}; g_* (nullable) = d(sum)/d(pred).
+ *   code_weights (HOST float[7], null = ones), loss_weights3 (HOST {cls, loc, dir}). Deterministic (fixed-order reduction). */
+int crb3d_assign_targets_workspace_bytes(int B, int64_t A, int M, size_t* bytes);
+int crb3d_assign_targets_axis_aligned(const float* anchors, int64_t A, int n_types, const int* type_class, const float* matched,
+                                      const float* unmatched, const float* gt_boxes, int B, int M, int gt_stride, int* labels,
+                                      float* reg_targets, float* reg_weights, int* num_pos, void* ws, size_t ws_bytes,
+                                      cudaStream_t stream);
+int crb3d_anchor_head_loss_workspace_bytes(int B, int64_t A, size_t* bytes);
+int crb3d_anchor_head_loss(const float* cls_preds, const float* box_preds, const float* dir_preds, const int* labels,
+                           const float* reg_targets, const float* anchors, int B, int64_t A, int n_class, int num_dir_bins,
+                           const float* code_weights, float alpha, float gamma, float beta, float dir_offset,
+                           const float* loss_weights3, float* losses, float* g_cls, float* g_box, float* g_dir, void* ws,
+                           size_t ws_bytes, cudaStream_t stream);
+
 /* ---- CRB scoring (pcdet/query_strategies/crb_sampling.py:86-100, 219-226, 276-338) -------------------------- */
 int crb3d_label_entropy(const int* labels, const int* box_off, int B, int num_class, float* entropy, int* class_counts,
                         cudaStream_t stream);
