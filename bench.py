@@ -445,7 +445,7 @@ def run_own(args, rank, world, local_rank):
 
 
 def instrumented_stages(model, batches, ops):
-    """SURVEY 8(d) per-stage table, device side: CUDA events around each stage of the eager path (ms per batch of 4)."""
+    """SURVEY 8(d) per-stage table, device side: CUDA events around each stage of the eager path (ms per batch)."""
     dev = batches[0][0].device
     names = ["voxelize", "rulebooks", "sparse_backbone", "dense", "bev_head", "post", "density_entropy"]
     acc = dict((n, 0.0) for n in names)
@@ -480,7 +480,8 @@ def instrumented_stages(model, batches, ops):
         torch.cuda.synchronize(dev)
         for i, n in enumerate(names):
             acc[n] += ev[i].elapsed_time(ev[i + 1])
-    return {"unit": "ms per batch of 4 frames (eager launches, one stream, CUDA events)", "gpu": dict((n, acc[n] / len(batches)) for n in names)}
+    nb = int(batches[0][1].numel() - 1)
+    return {"unit": "ms per batch of %d frames (eager launches, one stream, CUDA events)" % nb, "gpu": dict((n, acc[n] / len(batches)) for n in names)}
 
 
 def extra_measurements(args, model, ps, frames, device, l2_flush, progress):
