@@ -419,6 +419,15 @@ def run_own(args, rank, world, local_rank):
                "unit": "TFLOP/s", "frac": c2_ach / tf32_peak, "traffic": None,
                "launches_per_replay": len(c2) // max(n_inst, 1), "flops_per_replay": c2_flops / max(n_inst, 1),
                "kernel_ms_per_replay": c2_ms / max(n_inst, 1), "share_of_replay": c2_ms / max(n_inst, 1) / replay_ms}
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this command's replay (profiles/traffic.json); only for the
+    # configuration the capture was made at, otherwise null
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if B == 16 and not args.exact_fp32:
+            roof_c2["traffic"], roof_sp["traffic"] = tj.get("bev_conv_bytes_per_launch"), tj.get("spconv_bytes_per_launch")
+            roof_c2["traffic_source"] = roof_sp["traffic_source"] = "bytes per launch, " + tj.get("_source", "profiles/traffic.json")
+    except Exception:
+        pass
     roofline, roofline2 = (roof_c2, roof_sp) if c2_ms > conv_total_ms else (roof_sp, roof_c2)
     roofline["measured"] = roofline2["measured"] = ("CUDA events around every launch of the kernel on its launching stream during an "
                                                     "instrumented eager pass over %d batches of the pool (the headline region replays one CUDA "

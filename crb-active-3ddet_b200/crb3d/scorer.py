@@ -178,6 +178,20 @@ class PoolScorer(object):
         self._pool_bufs = (key, bufs)
         return bufs
 
+    def prepare_graphs(self, sample_frames, slots=2, margin=1.3, max_points_per_frame=None):
+        """Captures the whole-step graphs for this scorer's batch size with static capacities measured on `sample_frames`
+        (a list of >= batch_size host frames representative of the pool): row capacities = max count per level x margin,
+        point capacity = the largest sample frame + 1024 unless given. score_pool() then streams full batches through them and
+        re-scores any batch that exceeds a capacity on the eager path."""
+        B = self.batch_size
+        batches = [self.to_device(self.stage_host(sample_frames[s:s + B])) for s in range(0, len(sample_frames) - B + 1, B)]
+        if not batches:
+            raise ValueError("prepare_graphs needs at least batch_size sample frames")
+        caps = self.model.calibrate_row_caps([(b[0], b[1], B) for b in batches], margin=margin)
+        mx = max_points_per_frame or (max(len(f) for f in sample_frames) + 1024)
+        self.model.enable_full_graph(B, max_points_per_frame=int(mx), slots=slots, row_caps=caps)
+        return caps
+
     def score_pool(self, frames, frame_ids=None):
         """Scores this rank's shard of `frames` (all ranks pass the same list) and all-gathers the records.
         Returns a dict frame_id -> dict(entropy, labels (n,), density (n,)) identical on every rank.

@@ -327,6 +327,13 @@ def test_pool_scoring_graph_overflow_fallback_and_partial_batch(setup, cuda):
                 host = ps.score_host(ps.stage_host(pool[:2]))
                 for k in host_ref:
                     assert np.array_equal(host[k], host_ref[k]), (growth, k)
+            # capacities measured from sample frames (what bench.py and CRBSampling use): two graph copies, tight caps
+            caps = ps.prepare_graphs(pool[:4], slots=2, margin=1.3)
+            assert len(caps) == 4 and all(c % 128 == 0 for c in caps) and caps[0] < 2.0 * sum(len(f) for f in pool[:2]) + 4096
+            got = ps.score_pool(pool)
+            for i in range(5):
+                assert got[i]["entropy"] == ref[i]["entropy"] and np.array_equal(got[i]["labels"], ref[i]["labels"])
+                assert np.array_equal(got[i]["density"], ref[i]["density"])
         finally:
             model._full_graph = None
             model._full_graphs = None
