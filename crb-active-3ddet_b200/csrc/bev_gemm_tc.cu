@@ -30,6 +30,31 @@ using namespace tc;
 constexpr int TILE_M = 128;
 constexpr int BK = 32;  // floats per k-block = one 128-byte swizzle row
 
+// ---- thread-block clusters: CTAs that consume the same operand k-block fetch it ONCE from L2 (TMA multicast) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the box lands at the same shared-memory offset of every CTA in `mask` and completes bytes on the same barrier offset there
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar,
+                                               uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// arrives on the barrier at this offset in every CTA of `mask` once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 struct GemmOut {
     float* ptr[3];            // up to three column segments, each to its own tensor
     int col_begin[3];
@@ -45,7 +70,7 @@ struct GemmOut {
 // {32 channels, 16 x, 8 y, 1 image} whose traversal stride along x and y is the conv stride and whose out-of-bounds
 // pixels are zero-filled by the TMA unit (that is the padding). Weights: [N][tap][C_in] = K index tap * C_in + c.
 struct ConvArgs {
-    int tiles_x, tiles_y, h_out, w_out, stride, pad, cblocks, ksize;
+    int tiles_x, tiles_y, h_out, w_out, stride, pad, cblocks, ksize, n_img;
 };
 
 template <int N>
@@ -66,7 +91,13 @@ struct Cfg {
 //   BRES = false: weight k-blocks stream with the activations (L2 hits) - used when N*K*4 does not fit.
 // Two TMEM accumulators: the MMA warp fills one while the epilogue warps drain the other, so loads, MMAs and stores of
 // consecutive tiles overlap and the kernel runs at the HBM rate of its activation read + output write.
-template <int N, int STAGES, bool BRES, bool DENSE, bool CONV = false>
+// CLUSTERS (CSA x CSW CTAs, launched with a cluster dimension; OPT-IN, see the measurements at the dispatch sites): the CSA CTAs
+// that hold different weight slices but walk the SAME activation tile each load 1/CSA of every A k-block and multicast it to the
+// group; with streamed weights the CSW CTAs that hold the SAME slice but different tiles do the same for the weight k-blocks.
+// L2 -> SM operand traffic per CTA drops from A + W to A / CSA + W / CSW. A stage is refilled only after every CTA that receives a
+// piece from this one has consumed it: tcgen05.commit is multicast to the writers' empty barriers. Results are bit-identical to the
+// plain launch; it is slower on B200 at the BEV shapes because the ring is latency-bound, not L2-byte-bound.
+template <int N, int STAGES, bool BRES, bool DENSE, bool CONV = false, int CSA = 1, int CSW = 1>
 __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CUtensorMap amap,
                                                       const __grid_constant__ CUtensorMap wmap, int M, int K,
                                                       int ctas_per_slice, int halves, const float* __restrict__ bias, int relu,
@@ -80,15 +111,27 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
     __shared__ long long rowoff_s[8][32];          // ROWS mode: output offset of each staged row, per epilogue warp
     __shared__ int colbase_s[DENSE ? N : 1], colw_s[DENSE ? N : 1];   // DENSE mode: column -> staging offset / segment width
 
+    constexpr int CS = CSA * CSW;
+    static_assert(CS == 1 || (!DENSE && (CSW == 1 || !BRES) && TILE_M / CSA % 8 == 0 && N / CSW % 8 == 0 && 8 % CSA == 0), "cluster geometry");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int slice = blockIdx.x / ctas_per_slice, rank = blockIdx.x - slice * ctas_per_slice;
+    // cluster rank -> (a_idx: which weight slice of the group, w_idx: which tile of the cluster's tile group)
+    const int cr = CS > 1 ? (int)cluster_ctarank() : 0, a_idx = cr % CSA, w_idx = cr / CSA;
+    const int cluster_id = blockIdx.x / CS;
+    const int group = cluster_id / ctas_per_slice, crank = cluster_id - group * ctas_per_slice;   // ctas_per_slice = clusters per slice group
+    const int slice = group * CSA + a_idx;
     const int sub = slice / halves, half = slice - sub * halves;   // transposed-conv sub-position, column block
     const int nkb = K / BK;
     const int n_tiles = CONV ? M : (M + TILE_M - 1) / TILE_M;    // CONV: M counts 8 x 16 pixel tiles
-    const int my_tiles = rank < n_tiles ? (n_tiles - rank + ctas_per_slice - 1) / ctas_per_slice : 0;
+    // tile of iteration i: the same trip count for every CTA of a cluster (a tile index beyond n_tiles loads zeros, stores nothing)
+    const int tile0 = crank * CSW + w_idx, tile_step = ctas_per_slice * CSW;
+    const int my_tiles = crank * CSW < n_tiles ? (n_tiles - crank * CSW + tile_step - 1) / tile_step : 0;
+    const uint16_t mask_a = (uint16_t)(((1u << CSA) - 1u) << (w_idx * CSA));
+    uint16_t mask_w = 0;
+#pragma unroll
+    for (int w = 0; w < CSW; ++w) mask_w |= (uint16_t)(1u << (w * CSA + a_idx));
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CSA + CSW - 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
         mbar_init(&b_full, 1);
         mbar_fence_init();
@@ -109,6 +152,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();              // every CTA's barriers exist before a peer's multicast / commit can reach them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
     // layout: [staging][resident weights (BRES)][stage ring]
@@ -125,7 +169,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
             }
             int it = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                const int t = rank + i * ctas_per_slice;
+                const int t = tile0 + i * tile_step;
                 const int m0 = t * TILE_M;
                 int cb_img = 0, cx0 = 0, cy0 = 0;
                 if (CONV) {
@@ -140,12 +184,28 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
                     if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1, (CRB3D_K_BEV_GEMM << 8) | 9);
                     const uint32_t a_dst = ring_base + stage * STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    if (CONV) {
-                        const int tap = kb / cv.cblocks, cb = kb - tap * cv.cblocks;
-                        tma_load_4d(a_dst, &amap, cb * BK, cx0 + tap % cv.ksize, cy0 + tap / cv.ksize, cb_img, &full_bar[stage]);
-                    } else
-                        tma_load_2d(a_dst, &amap, kb * BK, m0, &full_bar[stage]);
-                    if (!BRES) tma_load_2d(a_dst + C::A_BYTES, &wmap, kb * BK, wrow, &full_bar[stage]);
+                    if (CS == 1) {
+                        if (CONV) {
+                            const int tap = kb / cv.cblocks, cb = kb - tap * cv.cblocks;
+                            tma_load_4d(a_dst, &amap, cb * BK, cx0 + tap % cv.ksize, cy0 + tap / cv.ksize, cb_img, &full_bar[stage]);
+                        } else
+                            tma_load_2d(a_dst, &amap, kb * BK, m0, &full_bar[stage]);
+                        if (!BRES) tma_load_2d(a_dst + C::A_BYTES, &wmap, kb * BK, wrow, &full_bar[stage]);
+                    } else {
+                        // this CTA's piece of the A k-block (rows a_idx * 128 / CSA ..) to every CTA that walks this tile ...
+                        constexpr int RA = TILE_M / CSA;
+                        if (CONV) {
+                            const int tap = kb / cv.cblocks, cb = kb - tap * cv.cblocks;
+                            tma_load_4d_mc(a_dst + a_idx * RA * 128, &amap, cb * BK, cx0 + tap % cv.ksize,
+                                           cy0 + tap / cv.ksize + a_idx * (8 / CSA) * cv.stride, cb_img, &full_bar[stage], mask_a);
+                        } else
+                            tma_load_2d_mc(a_dst + a_idx * RA * 128, &amap, kb * BK, m0 + a_idx * RA, &full_bar[stage], mask_a);
+                        // ... and its piece of the weight k-block (rows w_idx * N / CSW ..) to every CTA that holds this slice
+                        if (!BRES) {
+                            constexpr int RW = N / CSW;
+                            tma_load_2d_mc(a_dst + C::A_BYTES + w_idx * RW * 128, &wmap, kb * BK, wrow + w_idx * RW, &full_bar[stage], mask_w);
+                        }
+                    }
                 }
             }
         }
@@ -168,7 +228,8 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
                     for (int j = 0; j < 4; ++j)
                         umma_tf32(tmem_base + acc * C::TMEM_N, desc_sw128(a_base + j * 32), desc_sw128(b_base + j * 32), idesc,
                                   (kb > 0 || j > 0) ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);
+                    if (CS == 1) umma_commit(&empty_bar[stage]);
+                    else umma_commit_mc(&empty_bar[stage], (uint16_t)(mask_a | mask_w));   // frees the stage for every CTA that writes into it
                 }
                 umma_commit(&acc_full[acc]);
             }
@@ -187,13 +248,13 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
             float* obase = out.ptr[0] + col0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int acc = i & 1;
-                const long long m = (long long)(rank + i * ctas_per_slice) * TILE_M + r;
+                const long long m = (long long)(tile0 + i * tile_step) * TILE_M + r;
                 long long orow = -1;                      // output row of this lane's tile row; -1 = beyond M
                 if (CONV) {                               // tile row r = pixel (y0 + r / 16, x0 + r % 16) of image b
-                    const int t = rank + i * ctas_per_slice, per_img = cv.tiles_x * cv.tiles_y;
+                    const int t = tile0 + i * tile_step, per_img = cv.tiles_x * cv.tiles_y;
                     const int b = t / per_img, rem = t - b * per_img;
                     const int y = (rem / cv.tiles_x) * 8 + (r >> 4), x = (rem % cv.tiles_x) * 16 + (r & 15);
-                    if (y < cv.h_out && x < cv.w_out) orow = ((long long)b * cv.h_out + y) * cv.w_out + x;
+                    if (b < cv.n_img && y < cv.h_out && x < cv.w_out) orow = ((long long)b * cv.h_out + y) * cv.w_out + x;
                 } else if (m < M) {
                     if (out.up == 2) {
                         const int hw = out.in_w * out.in_h;
@@ -250,7 +311,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
             const int tq = h * 32 + lane;                 // thread index within the quarter (0..63)
             for (int i = 0; i < my_tiles; ++i) {
                 const int acc = i & 1;
-                const long long mrow0 = (long long)(rank + i * ctas_per_slice) * TILE_M + q * 32;   // first row of the quarter
+                const long long mrow0 = (long long)(tile0 + i * tile_step) * TILE_M + q * 32;   // first row of the quarter
                 mbar_wait(&acc_full[acc], (i >> 1) & 1, (CRB3D_K_BEV_GEMM << 8) | 5);
                 tc_fence_after();
 #pragma unroll 1
@@ -295,17 +356,42 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();              // a peer may still multicast into this CTA's stages / arrive on its barriers
     if (warp == 1) tmem_dealloc<2 * C::TMEM_N>(tmem_base);
 }
 
-template <int N, int STAGES, bool BRES, bool DENSE>
+// plain launch, or a cluster launch of CS consecutive CTAs
+template <typename Kern, typename... Args>
+int launch_maybe_cluster(Kern kern, unsigned grid, size_t smem, int cs, cudaStream_t stream, Args... args) {
+    if (cs <= 1) {
+        kern<<<grid, 320, smem, stream>>>(args...);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(320);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CRB3D_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    }
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+template <int N, int STAGES, bool BRES, bool DENSE, int CSA = 1>
 int launch_gemm(const float* A, long long M, int K, long long lda, const float* W, int n_slices, int halves, const float* bias,
                 int relu, const GemmOut& out, cudaStream_t stream) {
     using C = Cfg<N>;
     CUtensorMap amap, wmap;
     {
         const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, strides[1] = {(uint64_t)lda * 4};
-        const uint32_t box[2] = {BK, TILE_M};
+        const uint32_t box[2] = {BK, TILE_M / CSA};        // clusters: every CTA loads (and multicasts) its 1/CSA of the rows
         int rc = make_map_f32(&amap, A, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
@@ -318,7 +404,8 @@ int launch_gemm(const float* A, long long M, int K, long long lda, const float* 
     const size_t smem = 1024 + C::staging_bytes(DENSE) + (BRES ? (size_t)(K / BK) * C::B_BYTES : 0) +
                         (size_t)STAGES * (C::A_BYTES + (BRES ? 0 : C::B_BYTES));
     if (smem > 227 * 1024) return CRB3D_ERR_UNSUPPORTED;
-    auto kern = bev_gemm_tc<N, STAGES, BRES, DENSE>;
+    if (n_slices % CSA != 0) return CRB3D_ERR_UNSUPPORTED;
+    auto kern = bev_gemm_tc<N, STAGES, BRES, DENSE, false, CSA, 1>;
     static size_t smem_set[CRB3D_MAX_DEVICES] = {};   // the attribute is per function per device
     const int dev = crb3d_current_device();
     if (smem > smem_set[dev]) {
@@ -326,17 +413,17 @@ int launch_gemm(const float* A, long long M, int K, long long lda, const float* 
         smem_set[dev] = smem;
     }
     const int n_tiles = (int)crb3d_divup(M, TILE_M);
-    int per_slice = crb3d_num_sms() / n_slices;
+    int per_slice = crb3d_num_sms() / n_slices;        // CTAs per slice = clusters per group of CSA slices
     if (per_slice < 1) per_slice = 1;
     if (per_slice > n_tiles) per_slice = n_tiles;
-    kern<<<(unsigned)(n_slices * per_slice), 320, smem, stream>>>(amap, wmap, (int)M, K, per_slice, halves, bias, relu, out, ConvArgs{});
-    CRB3D_CHECK_LAUNCH();
-    return CRB3D_OK;
+    return launch_maybe_cluster(kern, (unsigned)(n_slices * per_slice), smem, CSA, stream, amap, wmap, (int)M, K, per_slice, halves, bias,
+                                relu, out, ConvArgs{});
 }
 
 // k x k conv (stride, zero padding) as an implicit GEMM on the same persistent kernel (CONV mode): N = 128 output channels
-// per CTA (two slices for 256), weights streamed with the activations.
-template <int N, int STAGES>
+// per CTA (two slices for 256), weights streamed with the activations. Clusters of CSA x CSW: the CSA output-channel slices share
+// each activation box, CSW neighbouring tiles share each weight box.
+template <int N, int STAGES, int CSA, int CSW>
 int launch_conv_gemm(const float* in, int B, int H, int W, int cin, const float* w2, int cout, int ksize, int stride, int pad,
                      const float* bias, int relu, float* out_ptr, cudaStream_t stream) {
     using C = Cfg<N>;
@@ -345,27 +432,29 @@ int launch_conv_gemm(const float* in, int B, int H, int W, int cin, const float*
     cv.w_out = (W + 2 * pad - ksize) / stride + 1;
     cv.tiles_x = (int)crb3d_divup(cv.w_out, 16);
     cv.tiles_y = (int)crb3d_divup(cv.h_out, 8);
-    cv.stride = stride; cv.pad = pad; cv.cblocks = cin / BK; cv.ksize = ksize;
+    cv.stride = stride; cv.pad = pad; cv.cblocks = cin / BK; cv.ksize = ksize; cv.n_img = B;
     const int K = ksize * ksize * cin;
     const int n_slices = cout / N;
+    if (n_slices % CSA != 0) return CRB3D_ERR_UNSUPPORTED;
     CUtensorMap amap, wmap;
     {
         const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
         const uint64_t strides[3] = {(uint64_t)cin * 4, (uint64_t)W * cin * 4, (uint64_t)H * W * cin * 4};
-        // with a traversal stride the box is the EXTENT walked in the tensor: ceil(box / stride) elements are copied
-        const uint32_t box[4] = {BK, (uint32_t)(16 * stride), (uint32_t)(8 * stride), 1};
+        // with a traversal stride the box is the EXTENT walked in the tensor: ceil(box / stride) elements are copied.
+        // clusters: a CTA loads 8 / CSA of the tile's 8 pixel rows
+        const uint32_t box[4] = {BK, (uint32_t)(16 * stride), (uint32_t)((8 / CSA) * stride), 1};
         const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         int rc = make_map_f32(&amap, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, es);
         if (rc) return rc;
     }
     {
         const uint64_t dims[2] = {(uint64_t)K, (uint64_t)cout}, strides[1] = {(uint64_t)K * 4};
-        const uint32_t box[2] = {BK, (uint32_t)N};
+        const uint32_t box[2] = {BK, (uint32_t)(N / CSW)};
         int rc = make_map_f32(&wmap, w2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
     const size_t smem = 1024 + C::staging_bytes(false) + (size_t)STAGES * (C::A_BYTES + C::B_BYTES);
-    auto kern = bev_gemm_tc<N, STAGES, false, false, true>;
+    auto kern = bev_gemm_tc<N, STAGES, false, false, true, CSA, CSW>;
     static size_t smem_set[CRB3D_MAX_DEVICES] = {};
     const int dev = crb3d_current_device();
     if (smem > smem_set[dev]) {
@@ -375,12 +464,12 @@ int launch_conv_gemm(const float* in, int B, int H, int W, int cin, const float*
     GemmOut o{};
     o.n_seg = 1; o.up = 0; o.ptr[0] = out_ptr; o.col_begin[0] = 0; o.width[0] = cout; o.row_stride[0] = cout;
     const int n_tiles = B * cv.tiles_x * cv.tiles_y;
-    int per_slice = crb3d_num_sms() / n_slices;
-    if (per_slice < 1) per_slice = 1;
-    if (per_slice > n_tiles) per_slice = n_tiles;
-    kern<<<(unsigned)(n_slices * per_slice), 320, smem, stream>>>(amap, wmap, n_tiles, K, per_slice, n_slices, bias, relu, o, cv);
-    CRB3D_CHECK_LAUNCH();
-    return CRB3D_OK;
+    constexpr int CS = CSA * CSW;
+    int clusters_per_group = crb3d_num_sms() / CS / (n_slices / CSA);      // a group = CSA slices; a cluster walks CSW tiles at a time
+    if (clusters_per_group < 1) clusters_per_group = 1;
+    if (clusters_per_group > (int)crb3d_divup(n_tiles, CSW)) clusters_per_group = (int)crb3d_divup(n_tiles, CSW);
+    return launch_maybe_cluster(kern, (unsigned)((n_slices / CSA) * clusters_per_group * CS), smem, CS, stream, amap, wmap, n_tiles, K,
+                                clusters_per_group, n_slices, bias, relu, o, cv);
 }
 
 }  // namespace
@@ -419,7 +508,15 @@ extern "C" int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long
     // slices = (sub-positions) x (column blocks of the per-CTA width); resident weights when N_cta * K * 4 <= 128 KB
     if (rows) {
         if (N == 256 && K <= 128) return launch_gemm<256, 3, true, false>(A, M, K, lda, W, n_sub, 1, bias, relu, o, stream);
-        if (N == 256 && K <= 256) return launch_gemm<128, 3, true, false>(A, M, K, lda, W, n_sub * 2, 2, bias, relu, o, stream);
+        if (N == 256 && K <= 256) {
+            // relu bit 2 (opt-in, A/B measurements): the 2 column blocks x n_sub sub-positions walk the same activation tiles, so
+            // clusters of 4 (or 2) slices can share every A box by TMA multicast. Measured at 16 x 100 x 88 x 256 -> 4 x 256:
+            // 508 us against 274 us without clusters - the 3-stage ring is latency-bound (one k-block per ~latency / 3) and the
+            // cross-CTA round trip (multicast commit -> refill -> multicast landing, slowest of 4 CTAs) is longer than the local one
+            if ((relu & 4) && (n_sub * 2) % 4 == 0) return launch_gemm<128, 3, true, false, 4>(A, M, K, lda, W, n_sub * 2, 2, bias, relu, o, stream);
+            if (relu & 4) return launch_gemm<128, 3, true, false, 2>(A, M, K, lda, W, n_sub * 2, 2, bias, relu, o, stream);
+            return launch_gemm<128, 3, true, false>(A, M, K, lda, W, n_sub * 2, 2, bias, relu, o, stream);
+        }
         if (N == 256) return launch_gemm<128, 5, false, false>(A, M, K, lda, W, n_sub * 2, 2, bias, relu, o, stream);
         if (N == 128 && K <= 256) return launch_gemm<128, 3, true, false>(A, M, K, lda, W, n_sub, 1, bias, relu, o, stream);
         if (N == 128) return launch_gemm<128, 5, false, false>(A, M, K, lda, W, n_sub, 1, bias, relu, o, stream);
@@ -442,5 +539,10 @@ extern "C" int crb3d_bev_conv_gemm_tf32(const float* in, int B, int H, int W, in
     if (cin % BK != 0 || (cout != 128 && cout != 256) || (ksize != 1 && ksize != 3) || (stride != 1 && stride != 2) || pad < 0 ||
         pad >= ksize || H + 2 * pad < ksize || W + 2 * pad < ksize)
         return CRB3D_ERR_UNSUPPORTED;
-    return launch_conv_gemm<128, 5>(in, B, H, W, cin, w2, cout, ksize, stride, pad, bias, relu, out, stream);
+    // relu bit 2 (opt-in, A/B measurements): 2 x 2 clusters for cout = 256 (both channel halves share the activation boxes, two
+    // neighbouring tiles share the weight boxes), pairs of tiles for cout = 128. Measured at 16 x 200 x 176 x 128 -> 256, stride 2:
+    // 461 us against 247 us without clusters (same reason as the deblock above: ring depth x latency, not L2 bytes, sets the rate)
+    if (!(relu & 4)) return launch_conv_gemm<128, 5, 1, 1>(in, B, H, W, cin, w2, cout, ksize, stride, pad, bias, relu, out, stream);
+    if (cout == 256) return launch_conv_gemm<128, 5, 2, 2>(in, B, H, W, cin, w2, cout, ksize, stride, pad, bias, relu, out, stream);
+    return launch_conv_gemm<128, 5, 1, 2>(in, B, H, W, cin, w2, cout, ksize, stride, pad, bias, relu, out, stream);
 }

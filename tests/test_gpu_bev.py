@@ -211,6 +211,31 @@ def test_bev_conv_gemm_strided_boxes(cuda, B, H, W, cin, cout, k, stride, pad):
     _check(out, ref, "conv gemm")
 
 
+def test_gemm_cluster_multicast_is_bit_identical(cuda, monkeypatch):
+    """The opt-in thread-block-cluster variants of the long-K GEMMs (TMA multicast of the shared operand k-blocks, multicast
+    tcgen05.commit; csrc/bev_gemm_tc.cu) give exactly the plain launch's results: a 2x2 transposed conv (clusters of 4 weight
+    slices), a stride-2 3x3 conv with 256 output channels (2 x 2 clusters) and one with 128 (pairs of tiles, odd tile count)."""
+    from crb3d import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x2 = torch.randn(3, 50, 44, 256, generator=g).to(cuda)
+    w2 = ops.round_tf32((torch.randn(4 * 256, 256, generator=g) / 16).to(cuda))
+    b2 = torch.randn(256, generator=g).to(cuda)
+    x = torch.randn(3, 37, 52, 64, generator=g).to(cuda)
+    res = {}
+    for mode in (False, True):
+        monkeypatch.setattr(ops, "GEMM_CLUSTERS", mode)
+        cat = torch.zeros(3, 100, 88, 512, device=cuda)
+        ops.bev_gemm(x2.view(-1, 256), w2, b2, True, [(cat[..., 256:], 0, 256, 512)], n_sub=4, up=2, in_hw=(50, 44), round_out=True)
+        convs = []
+        for cout in (256, 128):
+            w = ops.round_tf32((torch.randn(cout, 64, 3, 3, generator=torch.Generator().manual_seed(cout)) / 24).to(cuda))
+            convs.append(ops.bev_conv_gemm(x, ops.pack_conv_gemm_weight(w), None, 3, 2, 1, True))
+        res[mode] = [cat] + convs
+    for a, b in zip(res[False], res[True]):
+        assert torch.equal(a, b)
+    assert float(res[True][0][..., 256:].abs().max()) > 0
+
+
 @pytest.mark.parametrize("variant", [4, 8])
 def test_bev_conv3x3_pair_item_sizes(cuda, variant, monkeypatch):
     """Both work-item sizes of the CTA-pair kernel (flag bits 10 / 11 force 1-tile / 2-tile items) on the block-2 shape."""

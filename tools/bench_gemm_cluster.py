@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""A/B timing of the cluster-multicast variants of the long-K BEV GEMMs (csrc/bev_gemm_tc.cu) at the bench shapes.
+  python tools/bench_gemm_cluster.py [--batch 16]"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "crb-active-3ddet_b200"))
+import torch
+
+from crb3d import ops
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--reps", type=int, default=20)
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+B = args.batch
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(args.reps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+g = torch.Generator(device=dev).manual_seed(0)
+# deblock 2: (B,100,88,256) -> ConvTranspose2d(256, 256, 2, 2) into channels [256, 512) of the (B,200,176,512) map
+x2 = torch.randn(B, 100, 88, 256, device=dev, generator=g)
+w2 = ops.round_tf32(torch.randn(4 * 256, 256, device=dev, generator=g) / 16)
+b2 = torch.randn(256, device=dev, generator=g)
+cat = torch.zeros(B, 200, 176, 512, device=dev)
+outs = {}
+for mode in (True, False):
+    ops.GEMM_CLUSTERS = mode
+    fn = lambda: ops.bev_gemm(x2.view(-1, 256), w2, b2, True, [(cat[..., 256:], 0, 256, 512)], n_sub=4, up=2, in_hw=(100, 88), round_out=True)
+    t = timeit(fn)
+    outs[mode] = cat.clone()
+    flops = 2.0 * B * 100 * 88 * 256 * 1024
+    print("deblock2 B%d clusters=%s: %.1f us (%.0f TFLOP/s, %.2f TB/s algorithmic)" % (B, mode, t, flops / t / 1e6,
+                                                                                   (x2.numel() + B * 200 * 176 * 256) * 4 / t / 1e6))
+assert torch.equal(outs[True], outs[False])
+# stride-2 conv: (B,200,176,128) -> (B,100,88,256)
+x = torch.randn(B, 200, 176, 128, device=dev, generator=g)
+w = ops.round_tf32(torch.randn(256, 128, 3, 3, device=dev, generator=g) / 30)
+wp = ops.pack_conv_gemm_weight(w)
+bb = torch.randn(256, device=dev, generator=g)
+res = {}
+for mode in (True, False):
+    ops.GEMM_CLUSTERS = mode
+    fn = lambda: ops.bev_conv_gemm(x, wp, bb, 3, 2, 1, True, round_out=True)
+    t = timeit(fn)
+    res[mode] = fn()
+    flops = 2.0 * B * 100 * 88 * 9 * 128 * 256
+    print("conv3x3 s2 B%d clusters=%s: %.1f us (%.0f TFLOP/s)" % (B, mode, t, flops / t / 1e6))
+assert torch.equal(res[True], res[False])
