@@ -73,6 +73,12 @@ SIGNATURES = {
     "crb3d_anchor_head_loss_workspace_bytes": [c_int, c_int64, POINTER(c_size_t)],
     "crb3d_anchor_head_loss": [P, P, P, P, P, P, c_int, c_int64, c_int, c_int, P, c_float, c_float, c_float, c_float, P, P, P, P, P, P,
                                c_size_t, P],
+    "crb3d_query_stacked_local_neighbor_idxs_workspace_bytes": [c_int, POINTER(c_size_t)],
+    "crb3d_query_stacked_local_neighbor_idxs": [P, P, P, P, c_int, c_int, P, P, P, c_int, c_float, c_int, c_int, P, c_size_t, P],
+    "crb3d_query_three_nn_by_stacked_local_idxs": [P, P, P, P, P, P, c_int, c_int, P],
+    "crb3d_vector_pool_stack": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_int,
+                                P, P, P, P, P, P],
+    "crb3d_vector_pool_grad_stack": [P, P, P, P, c_int, c_int, c_int, c_int, P],
     "crb3d_voxel_query_stack": [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P, P, P, P, P],
     "crb3d_ball_query_batch": [c_int, c_int, c_int, c_float, c_int, P, P, P, P],
     "crb3d_group_points_batch": [c_int, c_int, c_int, c_int, c_int, P, P, P, P],
@@ -143,6 +149,8 @@ KERNELS_PER_CALL = {
     "crb3d_voxel_query_stack": 1, "crb3d_ball_query_batch": 1, "crb3d_group_points_batch": 1, "crb3d_group_points_grad_batch": 1,
     "crb3d_three_nn_batch": 1, "crb3d_three_interpolate_batch": 1, "crb3d_three_interpolate_grad_batch": 1,
     "crb3d_roipoint_pool3d_forward": 1, "crb3d_assign_targets_axis_aligned": 2, "crb3d_anchor_head_loss": 3,
+    "crb3d_query_stacked_local_neighbor_idxs": 8, "crb3d_query_three_nn_by_stacked_local_idxs": 1, "crb3d_vector_pool_stack": 1,
+    "crb3d_vector_pool_grad_stack": 1,
 }
 LAUNCHES = {"kernels": 0, "calls": 0}
 

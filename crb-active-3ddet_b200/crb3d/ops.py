@@ -544,6 +544,65 @@ def roipoint_pool3d_forward(xyz, boxes3d, pts_feature, pooled, empty_flag):
               _p(ws), ws.numel(), _stream(xyz.device))
 
 
+# ----------------------------------------------------------------------------------------------- vector pool (PV-RCNN++)
+def query_stacked_local_neighbor_idxs(support_xyz, xyz_batch_cnt, new_xyz, new_xyz_batch_cnt, stack_neighbor_idxs, start_len, cumsum,
+                                      avg_length_of_neighbor_idxs, max_neighbour_distance, nsample, neighbor_type):
+    """query_stacked_local_neighbor_idxs_wrapper_stack (vector_pool.cpp:35-75), same argument order."""
+    _need_cuda(support_xyz, new_xyz, start_len, cumsum)
+    _check(support_xyz=(support_xyz, torch.float32), xyz_batch_cnt=(xyz_batch_cnt, torch.int32), new_xyz=(new_xyz, torch.float32),
+           new_xyz_batch_cnt=(new_xyz_batch_cnt, torch.int32), stack_neighbor_idxs=(stack_neighbor_idxs, torch.int32),
+           start_len=(start_len, torch.int32), cumsum=(cumsum, torch.int32))
+    M, dev = new_xyz.shape[0], new_xyz.device
+    ws = _ws(_ws_bytes("crb3d_query_stacked_local_neighbor_idxs_workspace_bytes", M), dev)
+    _lib.call("crb3d_query_stacked_local_neighbor_idxs", _p(support_xyz), _p(xyz_batch_cnt), _p(new_xyz), _p(new_xyz_batch_cnt),
+              int(xyz_batch_cnt.shape[0]), M, _p(stack_neighbor_idxs), _p(start_len), _p(cumsum), int(avg_length_of_neighbor_idxs),
+              float(max_neighbour_distance), int(nsample), int(neighbor_type), _p(ws), ws.numel(), _stream(dev))
+
+
+def query_three_nn_by_stacked_local_idxs(support_xyz, new_xyz, new_xyz_grid_centers, new_xyz_grid_idxs, new_xyz_grid_dist2,
+                                         stack_neighbor_idxs, start_len, M, num_total_grids):
+    """query_three_nn_by_stacked_local_idxs_wrapper_stack (vector_pool.cpp:78-113), same argument order."""
+    _need_cuda(support_xyz, new_xyz_grid_centers, new_xyz_grid_idxs, new_xyz_grid_dist2, start_len)
+    _check(support_xyz=(support_xyz, torch.float32), new_xyz_grid_centers=(new_xyz_grid_centers, torch.float32),
+           new_xyz_grid_idxs=(new_xyz_grid_idxs, torch.int32), new_xyz_grid_dist2=(new_xyz_grid_dist2, torch.float32),
+           stack_neighbor_idxs=(stack_neighbor_idxs, torch.int32), start_len=(start_len, torch.int32))
+    if stack_neighbor_idxs.numel() == 0:          # no neighbour anywhere: a valid (never dereferenced) address
+        stack_neighbor_idxs = torch.zeros(1, dtype=torch.int32, device=support_xyz.device)
+    _lib.call("crb3d_query_three_nn_by_stacked_local_idxs", _p(support_xyz), _p(new_xyz_grid_centers), _p(new_xyz_grid_idxs),
+              _p(new_xyz_grid_dist2), _p(stack_neighbor_idxs), _p(start_len), int(M), int(num_total_grids), _stream(support_xyz.device))
+
+
+def vector_pool(support_xyz, xyz_batch_cnt, support_features, new_xyz, new_xyz_batch_cnt, new_features, new_local_xyz,
+                point_cnt_of_grid, grouped_idxs, num_grid_x, num_grid_y, num_grid_z, max_neighbour_distance, use_xyz,
+                num_max_sum_points, nsample, neighbor_type, pooling_type):
+    """vector_pool_wrapper_stack (vector_pool.cpp:116-170), same argument order; returns the cumulative number of grouped points
+    as a host int like the reference (one device -> host read)."""
+    _need_cuda(support_xyz, support_features, new_xyz, new_features)
+    _check(support_xyz=(support_xyz, torch.float32), xyz_batch_cnt=(xyz_batch_cnt, torch.int32),
+           support_features=(support_features, torch.float32), new_xyz=(new_xyz, torch.float32),
+           new_xyz_batch_cnt=(new_xyz_batch_cnt, torch.int32), new_features=(new_features, torch.float32),
+           new_local_xyz=(new_local_xyz, torch.float32), point_cnt_of_grid=(point_cnt_of_grid, torch.int32),
+           grouped_idxs=(grouped_idxs, torch.int32))
+    dev = support_xyz.device
+    cum = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.call("crb3d_vector_pool_stack", _p(support_xyz), _p(support_features), _p(xyz_batch_cnt), _p(new_xyz), _p(new_xyz_batch_cnt),
+              int(xyz_batch_cnt.shape[0]), int(new_xyz.shape[0]), int(support_features.shape[1]), int(new_features.shape[1]),
+              int(num_grid_x), int(num_grid_y), int(num_grid_z), float(max_neighbour_distance), int(use_xyz), int(num_max_sum_points),
+              int(nsample), int(neighbor_type), int(pooling_type), _p(new_features), _p(new_local_xyz), _p(point_cnt_of_grid),
+              _p(grouped_idxs), _p(cum), _stream(dev))
+    return int(cum.item())
+
+
+def vector_pool_grad(grad_new_features, point_cnt_of_grid, grouped_idxs, grad_support_features):
+    """vector_pool_grad_wrapper_stack (vector_pool.cpp:173-204), same argument order."""
+    _need_cuda(grad_new_features, point_cnt_of_grid, grouped_idxs, grad_support_features)
+    _check(grad_new_features=(grad_new_features, torch.float32), point_cnt_of_grid=(point_cnt_of_grid, torch.int32),
+           grouped_idxs=(grouped_idxs, torch.int32), grad_support_features=(grad_support_features, torch.float32))
+    _lib.call("crb3d_vector_pool_grad_stack", _p(grad_new_features), _p(point_cnt_of_grid), _p(grouped_idxs), _p(grad_support_features),
+              int(grad_new_features.shape[1]), int(grad_support_features.shape[1]), int(point_cnt_of_grid.shape[1]),
+              int(grouped_idxs.shape[0]), _stream(grad_new_features.device))
+
+
 # ----------------------------------------------------------------------------------------------- PV-RCNN fused layers
 def sa_group_mlp_maxpool(xyz, xyz_cnt, feat, new_xyz, new_cnt, idx, widths, packed, out):
     """One scale of StackSAModuleMSG fused (csrc/sa_mlp.cu): group + MLP + max-pool. `out` is a (M, stride) VIEW whose first

@@ -1,6 +1,5 @@
 """Stand-in for `pcdet.ops.pointnet2.pointnet2_stack.pointnet2_stack_cuda`
-(pcdet/ops/pointnet2/pointnet2_stack/src/pointnet2_api.cpp:13-30). The PV-RCNN++ entry points (vector_pool*, the stacked
-local-neighbour queries behind them) are outside the CRB hot path and raise NotImplementedError."""
+(pcdet/ops/pointnet2/pointnet2_stack/src/pointnet2_api.cpp:13-30): all 13 entry points, same names and argument order."""
 from crb3d import ops
 
 
@@ -47,14 +46,28 @@ def voxel_query_wrapper(M, R1, R2, R3, nsample, radius, z_range, y_range, x_rang
     return 1
 
 
-def _not_on_path(name):
-    def fn(*args, **kwargs):
-        raise NotImplementedError("%s belongs to PV-RCNN++ and is outside the CRB hot path" % name)
-    fn.__name__ = name
-    return fn
+def query_stacked_local_neighbor_idxs_wrapper_stack(support_xyz, xyz_batch_cnt, new_xyz, new_xyz_batch_cnt, stack_neighbor_idxs, start_len,
+                                                    cumsum, avg_length_of_neighbor_idxs, max_neighbour_distance, nsample, neighbor_type):
+    ops.query_stacked_local_neighbor_idxs(support_xyz, xyz_batch_cnt, new_xyz, new_xyz_batch_cnt, stack_neighbor_idxs, start_len, cumsum,
+                                          avg_length_of_neighbor_idxs, max_neighbour_distance, nsample, neighbor_type)
+    return 0
 
 
-query_stacked_local_neighbor_idxs_wrapper_stack = _not_on_path("query_stacked_local_neighbor_idxs_wrapper_stack")
-query_three_nn_by_stacked_local_idxs_wrapper_stack = _not_on_path("query_three_nn_by_stacked_local_idxs_wrapper_stack")
-vector_pool_wrapper = _not_on_path("vector_pool_wrapper")
-vector_pool_grad_wrapper = _not_on_path("vector_pool_grad_wrapper")
+def query_three_nn_by_stacked_local_idxs_wrapper_stack(support_xyz, new_xyz, new_xyz_grid_centers, new_xyz_grid_idxs, new_xyz_grid_dist2,
+                                                       stack_neighbor_idxs, start_len, M, num_total_grids):
+    ops.query_three_nn_by_stacked_local_idxs(support_xyz, new_xyz, new_xyz_grid_centers, new_xyz_grid_idxs, new_xyz_grid_dist2,
+                                             stack_neighbor_idxs, start_len, M, num_total_grids)
+    return 0
+
+
+def vector_pool_wrapper(support_xyz, xyz_batch_cnt, support_features, new_xyz, new_xyz_batch_cnt, new_features, new_local_xyz,
+                        point_cnt_of_grid, grouped_idxs, num_grid_x, num_grid_y, num_grid_z, max_neighbour_distance, use_xyz,
+                        num_max_sum_points, nsample, neighbor_type, pooling_type):
+    return ops.vector_pool(support_xyz, xyz_batch_cnt, support_features, new_xyz, new_xyz_batch_cnt, new_features, new_local_xyz,
+                           point_cnt_of_grid, grouped_idxs, num_grid_x, num_grid_y, num_grid_z, max_neighbour_distance, use_xyz,
+                           num_max_sum_points, nsample, neighbor_type, pooling_type)
+
+
+def vector_pool_grad_wrapper(grad_new_features, point_cnt_of_grid, grouped_idxs, grad_support_features):
+    ops.vector_pool_grad(grad_new_features, point_cnt_of_grid, grouped_idxs, grad_support_features)
+    return 1

@@ -266,6 +266,34 @@ int crb3d_roipoint_pool3d_forward(int B, int N, int M, int C, int S, const float
                                   const float* pts_feature, float* pooled, int* empty_flag, void* ws, size_t ws_bytes,
                                   cudaStream_t stream);
 
+/* ---- vector-pool aggregation of PV-RCNN++ (pointnet2_stack/src/vector_pool_gpu.cu:19-476, vector_pool.cpp:35-204;
+ * csrc/vector_pool.cu). A warp per query instead of the reference's thread per query; neighbour lists are laid out in query order
+ * (count -> scan -> fill; the reference's layout depends on thread scheduling, `start_len` locates each list either way), sums are
+ * accumulated in the reference's order.
+ *   crb3d_query_stacked_local_neighbor_idxs: start_len (M,2) int32 [offset, length], stack_neighbor_idxs (avg_length * M) int32,
+ *     cumsum (1) int32 in/out running total; neighbor_type 1 = ball, else cube; nsample > 0 limits a list (always <= 1000).
+ *   crb3d_query_three_nn_by_stacked_local_idxs: new_xyz_grid_centers / _idxs / _dist2 (M, num_total_grids, 3).
+ *   crb3d_vector_pool_stack: new_features (M,c_out), new_local_xyz (M,3*G), point_cnt_of_grid (M,G), grouped_idxs (max,3) zero-filled
+ *     by the caller; cum_sum (DEVICE int) = number of grouped entries wanted (> num_max_sum_points: re-run with more room).
+ *   crb3d_vector_pool_grad_stack: grad_support_features (N,c_in) += over the first num_grouped rows of grouped_idxs. */
+int crb3d_query_stacked_local_neighbor_idxs_workspace_bytes(int M, size_t* bytes);
+int crb3d_query_stacked_local_neighbor_idxs(const float* support_xyz, const int* xyz_batch_cnt, const float* new_xyz,
+                                            const int* new_xyz_batch_cnt, int batch_size, int M, int* stack_neighbor_idxs,
+                                            int* start_len, int* cumsum, int avg_length_of_neighbor_idxs,
+                                            float max_neighbour_distance, int nsample, int neighbor_type, void* ws, size_t ws_bytes,
+                                            cudaStream_t stream);
+int crb3d_query_three_nn_by_stacked_local_idxs(const float* support_xyz, const float* new_xyz_grid_centers, int* new_xyz_grid_idxs,
+                                               float* new_xyz_grid_dist2, const int* stack_neighbor_idxs, const int* start_len, int M,
+                                               int num_total_grids, cudaStream_t stream);
+int crb3d_vector_pool_stack(const float* support_xyz, const float* support_features, const int* xyz_batch_cnt, const float* new_xyz,
+                            const int* new_xyz_batch_cnt, int batch_size, int M, int num_c_in, int num_c_out, int num_grid_x,
+                            int num_grid_y, int num_grid_z, float max_neighbour_distance, int use_xyz, int num_max_sum_points,
+                            int nsample, int neighbor_type, int pooling_type, float* new_features, float* new_local_xyz,
+                            int* point_cnt_of_grid, int* grouped_idxs, int* cum_sum, cudaStream_t stream);
+int crb3d_vector_pool_grad_stack(const float* grad_new_features, const int* point_cnt_of_grid, const int* grouped_idxs,
+                                 float* grad_support_features, int num_c_out, int num_c_in, int num_total_grids, int num_grouped,
+                                 cudaStream_t stream);
+
 /* ---- PV-RCNN: fused set-abstraction layer and the RoI-head FC GEMM -------------------------------------------------------
  * crb3d_sa_group_mlp_maxpool: one scale of StackSAModuleMSG.forward (pcdet/ops/pointnet2/pointnet2_stack/
  * pointnet2_modules.py:78-112: QueryAndGroup + shared 1x1-conv MLP + BatchNorm + ReLU + max-pool over the samples) in one

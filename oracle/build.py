@@ -92,9 +92,10 @@ def build_ref_batch(force=False, verbose=False):
     ops = os.path.join(REFERENCE, "pcdet", "ops")
     pb = os.path.join(ops, "pointnet2", "pointnet2_batch", "src")
     srcs = [os.path.join(pb, f) for f in ("ball_query_gpu.cu", "group_points_gpu.cu", "sampling_gpu.cu", "interpolate_gpu.cu")]
-    srcs += [os.path.join(ops, "pointnet2", "pointnet2_stack", "src", "voxel_query_gpu.cu"),
+    ps = os.path.join(ops, "pointnet2", "pointnet2_stack", "src")
+    srcs += [os.path.join(ps, "voxel_query_gpu.cu"), os.path.join(ps, "vector_pool_gpu.cu"),
              os.path.join(ops, "roipoint_pool3d", "src", "roipoint_pool3d_kernel.cu")]
-    return _build_ref_lib(out, os.path.join(HERE, "ref_wrap", "ref_kernels_batch_wrap.cu"), srcs, [pb], force, verbose)
+    return _build_ref_lib(out, os.path.join(HERE, "ref_wrap", "ref_kernels_batch_wrap.cu"), srcs, [pb, ps], force, verbose)
 
 
 STAGE = os.path.join(os.path.dirname(HERE), "baseline", "_ref")

@@ -22,7 +22,41 @@ void voxel_query_kernel_launcher_stack(int M, int R1, int R2, int R3, int nsampl
 void roipool3dLauncher(int batch_size, int pts_num, int boxes_num, int feature_in_len, int sampled_pts_num, const float* xyz,
                        const float* boxes3d, const float* pts_feature, float* pooled_features, int* pooled_empty_flag);
 
+// pointnet2_stack/src/vector_pool_gpu.h
+int query_stacked_local_neighbor_idxs_kernel_launcher_stack(const float* support_xyz, const int* xyz_batch_cnt, const float* new_xyz,
+                                                            const int* new_xyz_batch_cnt, int* stack_neighbor_idxs, int* start_len, int* cumsum,
+                                                            int avg_length_of_neighbor_idxs, float max_neighbour_distance, int batch_size, int M,
+                                                            int nsample, int neighbor_type);
+int query_three_nn_by_stacked_local_idxs_kernel_launcher_stack(const float* support_xyz, const float* new_xyz, const float* new_xyz_grid_centers,
+                                                               int* new_xyz_grid_idxs, float* new_xyz_grid_dist2, const int* stack_neighbor_idxs,
+                                                               const int* start_len, int M, int num_total_grids);
+int vector_pool_kernel_launcher_stack(const float* support_xyz, const float* support_features, const int* xyz_batch_cnt, const float* new_xyz,
+                                      float* new_features, float* new_local_xyz, const int* new_xyz_batch_cnt, int* point_cnt_of_grid,
+                                      int* grouped_idxs, int num_grid_x, int num_grid_y, int num_grid_z, float max_neighbour_distance,
+                                      int batch_size, int N, int M, int num_c_in, int num_c_out, int num_total_grids, int use_xyz,
+                                      int num_max_sum_points, int nsample, int neighbor_type, int pooling_type);
+void vector_pool_grad_kernel_launcher_stack(const float* grad_new_features, const int* point_cnt_of_grid, const int* grouped_idxs,
+                                            float* grad_support_features, int N, int M, int num_c_out, int num_c_in, int num_total_grids,
+                                            int num_max_sum_points);
+
 extern "C" {
+int refb_local_neighbors(const float* sxyz, const int* xc, const float* nxyz, const int* nc, int* stack, int* start_len, int* cumsum, int avg,
+                         float dist, int B, int M, int nsample, int type) {
+    return query_stacked_local_neighbor_idxs_kernel_launcher_stack(sxyz, xc, nxyz, nc, stack, start_len, cumsum, avg, dist, B, M, nsample, type);
+}
+int refb_three_nn_local(const float* sxyz, const float* nxyz, const float* centers, int* idxs, float* d2, const int* stack, const int* start_len,
+                        int M, int G) {
+    return query_three_nn_by_stacked_local_idxs_kernel_launcher_stack(sxyz, nxyz, centers, idxs, d2, stack, start_len, M, G);
+}
+int refb_vector_pool(const float* sxyz, const float* sfeat, const int* xc, const float* nxyz, float* nfeat, float* nlocal, const int* nc,
+                     int* pcnt, int* grouped, int gx, int gy, int gz, float dist, int B, int N, int M, int cin, int cout, int G, int use_xyz,
+                     int max_sum, int nsample, int type, int pooling) {
+    return vector_pool_kernel_launcher_stack(sxyz, sfeat, xc, nxyz, nfeat, nlocal, nc, pcnt, grouped, gx, gy, gz, dist, B, N, M, cin, cout, G,
+                                             use_xyz, max_sum, nsample, type, pooling);
+}
+void refb_vector_pool_grad(const float* g, const int* pcnt, const int* grouped, float* gs, int N, int M, int cout, int cin, int G, int n) {
+    vector_pool_grad_kernel_launcher_stack(g, pcnt, grouped, gs, N, M, cout, cin, G, n);
+}
 int refb_sync() { return (int)cudaDeviceSynchronize(); }
 void refb_ball_query(int b, int n, int m, float radius, int nsample, const float* new_xyz, const float* xyz, int* idx) {
     ball_query_kernel_launcher_fast(b, n, m, radius, nsample, new_xyz, xyz, idx);

@@ -275,3 +275,140 @@ def test_reference_batch_wrappers_over_dropin(cuda):
     assert np.array_equal(vempty.cpu().numpy(), o[:, 0] == -1)
     o[o[:, 0] == -1] = 0
     assert np.array_equal(vi.cpu().numpy(), o)
+
+
+# ---------------------------------------------------------------------------------------------- vector pool (PV-RCNN++)
+def _vp_inputs(rng, cuda, radius):
+    xyz_cnt = np.array([4000, 2500], np.int32)
+    new_cnt = np.array([300, 211], np.int32)
+    xyz = np.concatenate([_cloud(rng, 4000, 6.0), _cloud(rng, 2500, 6.0)])
+    new_xyz = np.concatenate([xyz[:300] + np.float32(0.05), xyz[4000:4211] + np.float32(0.02)])
+    new_xyz[5] = [50, 50, 50]                                        # a query without neighbours
+    ang = rng.uniform(0, 2 * np.pi, 32)                               # support points at distance == radius of query 0
+    xyz[100:132] = new_xyz[0] + np.float32(radius) * np.stack([np.cos(ang), np.sin(ang), np.zeros(32)], 1).astype(np.float32)
+    return xyz, xyz_cnt, new_xyz, new_cnt
+
+
+def _lists(stack, start_len):
+    s, sl = stack.cpu().numpy(), start_len.cpu().numpy()
+    return [s[o:o + n].tolist() for o, n in sl]
+
+
+@pytest.mark.parametrize("neighbor_type,nsample,radius", [(1, -1, 0.8), (0, -1, 0.6), (1, 16, 1.5), (0, 7, 3.0)])
+def test_stacked_local_neighbors_and_three_nn(cuda, neighbor_type, nsample, radius):
+    """Per-query neighbour lists (content and order) and the 3-NN of every grid centre == the reference kernels; the reference
+    places the lists with a global atomicAdd (layout depends on scheduling), this library in query order."""
+    from crb3d import ops
+    rng = np.random.default_rng(int(radius * 10) + neighbor_type)
+    xyz, xyz_cnt, new_xyz, new_cnt = _vp_inputs(rng, cuda, radius)
+    M = len(new_xyz)
+    x, xc, nx, nc = cu(xyz, cuda), cu(xyz_cnt, cuda), cu(new_xyz, cuda), cu(new_cnt, cuda)
+    avg = 1000
+    stack = torch.zeros(avg * M, dtype=torch.int32, device=cuda)
+    start_len = torch.zeros((M, 2), dtype=torch.int32, device=cuda)
+    cumsum = torch.zeros(1, dtype=torch.int32, device=cuda)
+    ops.query_stacked_local_neighbor_idxs(x, xc, nx, nc, stack, start_len, cumsum, avg, radius, nsample, neighbor_type)
+    mine = _lists(stack, start_len)
+    sl = start_len.cpu().numpy()
+    assert int(cumsum.item()) == int(sl[:, 1].sum()) and np.array_equal(sl[:, 0], np.concatenate([[0], np.cumsum(sl[:, 1])[:-1]]))
+    assert len(mine[5]) == 0 and max(len(l) for l in mine) > 3 and (nsample < 0 or max(len(l) for l in mine) == nsample)
+    # brute force in float64 away from the boundary: every list holds frame-local neighbours in ascending order
+    for q in (0, 17, 299, 300, 510):
+        f0 = 0 if q < 300 else 4000
+        assert mine[q] == sorted(mine[q]) and all(f0 <= i < f0 + (4000 if q < 300 else 2500) for i in mine[q])
+    G = 8
+    centers = (new_xyz[:, None, :] + rng.uniform(-radius, radius, (M, G, 3))).astype(np.float32)
+    ct = cu(centers, cuda)
+    idxs = torch.full((M, G, 3), -1, dtype=torch.int32, device=cuda)
+    d2 = torch.zeros((M, G, 3), device=cuda)
+    ops.query_three_nn_by_stacked_local_idxs(x, nx, ct, idxs, d2, stack[: int(cumsum.item())], start_len, M, G)
+    assert int((idxs[5] == -1).all()) == 1
+    ref = ref_batch_kernels()
+    if ref is not None:
+        rstack, rsl, rcs = torch.zeros_like(stack), torch.zeros_like(start_len), torch.zeros_like(cumsum)
+        torch.cuda.synchronize()
+        ref.refb_local_neighbors(P(x), P(xc), P(nx), P(nc), P(rstack), P(rsl), P(rcs), avg, ctypes.c_float(radius), 2, M, nsample, neighbor_type)
+        assert ref.refb_sync() == 0
+        assert int(rcs.item()) == int(cumsum.item())
+        assert _lists(rstack, rsl) == mine                            # same neighbours in the same order, query by query
+        ridx, rd2 = torch.full_like(idxs, -1), torch.zeros_like(d2)
+        ref.refb_three_nn_local(P(x), P(nx), P(ct), P(ridx), P(rd2), P(rstack), P(rsl), M, G)
+        assert ref.refb_sync() == 0
+        assert torch.equal(idxs, ridx) and torch.equal(d2, rd2)
+
+
+@pytest.mark.parametrize("pooling_type,neighbor_type,nsample,c_in,ce", [(0, 0, -1, 32, 16), (0, 1, 24, 16, 16), (1, 0, -1, 32, 8), (0, 0, -1, 5, 5)])
+def test_vector_pool_forward_and_grad(cuda, pooling_type, neighbor_type, nsample, c_in, ce):
+    from crb3d import ops
+    rng = np.random.default_rng(c_in * 3 + pooling_type + nsample % 7)
+    radius = 1.2
+    xyz, xyz_cnt, new_xyz, new_cnt = _vp_inputs(rng, cuda, radius)
+    N, M, (gx, gy, gz) = len(xyz), len(new_xyz), (3, 3, 2)
+    G, c_out = gx * gy * gz, ce * gx * gy * gz
+    feat = rng.normal(size=(N, c_in)).astype(np.float32)
+    x, xc, ft, nx, nc = cu(xyz, cuda), cu(xyz_cnt, cuda), cu(feat, cuda), cu(new_xyz, cuda), cu(new_cnt, cuda)
+    max_sum = 400 * M
+
+    def run(fn_is_ref):
+        nf = torch.zeros((M, c_out), device=cuda)
+        nl = torch.zeros((M, 3 * G), device=cuda)
+        pc = torch.zeros((M, G), dtype=torch.int32, device=cuda)
+        gi = torch.zeros((max_sum, 3), dtype=torch.int32, device=cuda)
+        if fn_is_ref:
+            torch.cuda.synchronize()
+            n = ref_batch_kernels().refb_vector_pool(P(x), P(ft), P(xc), P(nx), P(nf), P(nl), P(nc), P(pc), P(gi), gx, gy, gz, ctypes.c_float(radius),
+                                                     2, N, M, c_in, c_out, G, 1, max_sum, nsample, neighbor_type, pooling_type)
+        else:
+            n = ops.vector_pool(x, xc, ft, nx, nc, nf, nl, pc, gi, gx, gy, gz, radius, 1, max_sum, nsample, neighbor_type, pooling_type)
+        return nf, nl, pc, gi[:n], n
+
+    nf, nl, pc, gi, n = run(False)
+    assert 0 < n <= max_sum and int(pc.sum()) >= n and float(nf.abs().max()) > 0 and int(pc[5].sum()) == 0
+    # grouped rows: (support point, query, sub-voxel); avg pooling: the sub-voxel sums are the sums of the grouped points' features
+    g = gi.cpu().numpy()
+    assert (g[:, 1] >= 0).all() and (g[:, 1] < M).all() and (g[:, 2] < G).all()
+    if pooling_type == 0 and nsample < 0:
+        expect = np.zeros((M, G, ce), np.float64)
+        np.add.at(expect, (g[:, 1], g[:, 2]), feat[g[:, 0]].reshape(len(g), c_in // ce, ce).sum(1).astype(np.float64))
+        assert np.allclose(nf.cpu().numpy().reshape(M, G, ce), expect, rtol=1e-4, atol=1e-4)
+        assert np.array_equal(np.bincount(g[:, 1] * G + g[:, 2], minlength=M * G).reshape(M, G), pc.cpu().numpy())
+    go = torch.randn(M, c_out, device=cuda)
+    gs = torch.zeros((N, c_in), device=cuda)
+    ops.vector_pool_grad(go, pc, gi.contiguous(), gs)
+    if ref_batch_kernels() is not None:
+        rf, rl, rp, rg, rn = run(True)
+        assert rn == n
+        assert torch.equal(pc, rp) and torch.equal(nf, rf) and torch.equal(nl, rl)       # sums accumulated in the same order: bit-equal
+        key = lambda t: np.array(sorted(map(tuple, t.cpu().numpy().tolist())))
+        assert np.array_equal(key(gi), key(rg))                                           # same grouped set (the order is scheduling)
+        rgs = torch.zeros_like(gs)
+        torch.cuda.synchronize()
+        ref_batch_kernels().refb_vector_pool_grad(P(go), P(rp), P(rg.contiguous()), P(rgs), N, M, c_out, c_in, G, rn)
+        assert ref_batch_kernels().refb_sync() == 0
+        assert torch.allclose(gs, rgs, rtol=1e-5, atol=1e-6)
+
+
+def test_reference_vector_pool_functions_over_dropin(cuda):
+    """The reference's VectorPoolWithVoxelQuery / ThreeNNForVectorPoolByTwoStep autograd functions (pointnet2_stack/pointnet2_utils.py:
+    302-448), unmodified, with every pointnet2_stack_cuda entry point answered by this library."""
+    if ref_env.install() is None:
+        pytest.skip("no reference tree (neither /root/reference nor baseline/_ref)")
+    pu = ref_env.ref("pcdet.ops.pointnet2.pointnet2_stack.pointnet2_utils")
+    rng = np.random.default_rng(9)
+    xyz, xyz_cnt, new_xyz, new_cnt = _vp_inputs(rng, cuda, 1.0)
+    x, xc, nx, nc = cu(xyz, cuda), cu(xyz_cnt, cuda), cu(new_xyz, cuda), cu(new_cnt, cuda)
+    feat = torch.randn(len(xyz), 32, device=cuda, requires_grad=True)
+    new_feat, new_local, n_mean, pcnt = pu.vector_pool_with_voxel_query_op(x, xc, feat, nx, nc, 3, 3, 3, 1.0, 16, True, 2, -1, 0, 0)
+    assert new_feat.shape == (len(new_xyz), 16 * 27) and pcnt.shape == (len(new_xyz), 27) and int(pcnt.sum()) > 0
+    (g,) = torch.autograd.grad(new_feat.sum(), feat)
+    # every grouped support point receives 1 / (points in its sub-voxel) per output channel it feeds
+    assert float(g.abs().sum()) > 0 and torch.isfinite(g).all()
+    centers = (new_xyz[:, None, :] + rng.uniform(-1, 1, (len(new_xyz), 27, 3))).astype(np.float32)
+    dist, idx, avg = pu.three_nn_for_vector_pool_by_two_step(x, xc, nx, cu(centers, cuda), nc, 1.0, -1, 1, 5, 27, 2.0)
+    assert dist.shape == idx.shape == (len(new_xyz), 27, 3) and int((idx[5] == -1).all()) == 1 and int((idx[0] >= 0).all()) == 1
+    # nearest of the local list == brute-force nearest within the query radius (2.0) in the frame
+    q = 0
+    d = ((xyz[:4000][None] - centers[q][:, None]) ** 2).sum(-1)
+    inside = ((xyz[:4000] - new_xyz[q]) ** 2).sum(-1) <= 4.0 - 1e-4
+    d[:, ~inside] = np.inf
+    assert np.array_equal(idx[q, :, 0].cpu().numpy(), d.argmin(1))
