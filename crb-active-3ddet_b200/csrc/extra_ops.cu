@@ -307,7 +307,9 @@ extern "C" int crb3d_roipoint_pool3d_forward(int B, int N, int M, int C, int S, 
                                              cudaStream_t stream) {
     if (B < 0 || N < 0 || M < 0 || C < 0 || S <= 0) return CRB3D_ERR_ARG;
     if (B == 0 || M == 0) return CRB3D_OK;
-    if (!xyz || !boxes3d || (C > 0 && !pts_feature) || !pooled || !empty_flag) return CRB3D_ERR_ARG;
+    if (!empty_flag) return CRB3D_ERR_ARG;
+    if (N == 0) return crb3d_fill_i32(empty_flag, (size_t)B * M, 1, stream);      // frames without points: every box is empty
+    if (!xyz || !boxes3d || (C > 0 && !pts_feature) || !pooled) return CRB3D_ERR_ARG;
     WsCursor c(ws, ws_bytes);
     int* pts_idx = c.take<int>((size_t)B * M * S);
     if (!c.ok) return CRB3D_ERR_WORKSPACE;

@@ -412,3 +412,23 @@ def test_reference_vector_pool_functions_over_dropin(cuda):
     inside = ((xyz[:4000] - new_xyz[q]) ** 2).sum(-1) <= 4.0 - 1e-4
     d[:, ~inside] = np.inf
     assert np.array_equal(idx[q, :, 0].cpu().numpy(), d.argmin(1))
+
+
+def test_extra_ops_empty_inputs(cuda):
+    """Zero-sized problems return without a launch and leave the caller's (zero-filled) outputs untouched."""
+    from crb3d import ops
+    z3 = torch.zeros((0, 3), device=cuda)
+    idx = torch.zeros((0, 8), dtype=torch.int32, device=cuda)
+    ops.voxel_query(0, 4, 4, 4, 8, 1.0, 1, 1, 1, z3, torch.zeros((5, 3), device=cuda), torch.zeros((0, 4), dtype=torch.int32, device=cuda),
+                    torch.full((1, 4, 4, 4), -1, dtype=torch.int32, device=cuda), idx)
+    bidx = torch.zeros((2, 0, 4), dtype=torch.int32, device=cuda)
+    ops.ball_query_batch(2, 10, 0, 1.0, 4, torch.zeros((2, 0, 3), device=cuda), torch.zeros((2, 10, 3), device=cuda), bidx)
+    pooled = torch.zeros((1, 0, 16, 5), device=cuda)
+    ops.roipoint_pool3d_forward(torch.zeros((1, 7, 3), device=cuda), torch.zeros((1, 0, 7), device=cuda), torch.zeros((1, 7, 2), device=cuda),
+                                pooled, torch.zeros((1, 0), dtype=torch.int32, device=cuda))
+    # a frame without points: every box is flagged empty
+    ef = torch.zeros((1, 3), dtype=torch.int32, device=cuda)
+    ops.roipoint_pool3d_forward(torch.zeros((1, 0, 3), device=cuda), torch.ones((1, 3, 7), device=cuda), torch.zeros((1, 0, 2), device=cuda),
+                                torch.zeros((1, 3, 4, 5), device=cuda), ef)
+    assert ef.tolist() == [[1, 1, 1]]
+    torch.cuda.synchronize()

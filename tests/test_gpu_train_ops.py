@@ -124,3 +124,13 @@ def test_train_step_with_targets_runs_and_decreases_loss(cuda):
         opt.step()
         hist.append(float(loss))
     assert all(np.isfinite(hist)) and hist[-1] < hist[0], hist
+
+
+def test_target_assignment_without_ground_truth(cuda):
+    """No ground truth at all (M = 0) and only padding rows: every anchor is background, no regression target, no positive."""
+    from crb3d import second
+    head = second.SECONDNet().to_device(cuda).dense_head
+    for gt in (torch.zeros((2, 0, 8), device=cuda), torch.zeros((2, 5, 8), device=cuda)):
+        t = head.assign_targets(gt)
+        assert int(t["box_cls_labels"].abs().sum()) == 0 and float(t["box_reg_targets"].abs().sum()) == 0.0
+        assert int(t["num_pos"].sum()) == 0 and float(t["reg_weights"].sum()) == 0.0
