@@ -409,10 +409,11 @@ def run_own(args, rank, world, local_rank):
     # The kernel is event-timed alone in an eager pass (idle gaps between launches): the BURST figure is the fair denominator.
     c2 = prof_records["conv2d"]
     c2_ms = sum(a.elapsed_time(b) for a, b, _ in c2)
-    c2_flops = sum(f for _, _, f in c2)
+    c2_flops = sum((f() if callable(f) else f) for _, _, f in c2)      # sparse-tile layers report the tiles they computed
     tf32_peak = float(peaks.get("bf16_tflops", 1600.0)) / 2.0
     c2_ach = c2_flops / (c2_ms / 1e3) / 1e12 if c2_ms > 0 else 0.0
-    roof_c2 = {"kernel": "bev_conv3x3_pair_tc / bev_conv3x3_s2 (halo-tile tcgen05 cta_group::2 TF32 convs, %d launches per replay)" % (len(c2) // max(n_inst, 1)),
+    roof_c2 = {"kernel": "bev_conv3x3_pair_tc (halo-tile tcgen05 cta_group::2 TF32 convs, %d launches per replay; block 1 in sparse-tile mode: "
+                         "flops = the tiles that went through the tensor cores, time includes the constant-tile fill)" % (len(c2) // max(n_inst, 1)),
                "bound": "tensor", "achieved": c2_ach, "peak": tf32_peak,
                "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst) / 2 (TF32 = half the bf16 rate; of measured)" if peaks
                                else "fallback 1600/2 TFLOP/s (of fallback)"),

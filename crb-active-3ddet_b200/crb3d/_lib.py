@@ -91,6 +91,10 @@ SIGNATURES = {
     "crb3d_sa_group_mlp_maxpool": [c_int, P, P, P, c_int, P, P, c_int, P, c_int, c_int, P, P, P, c_int, P],
     "crb3d_fc_gemm_workspace_bytes": [c_int64, c_int, c_int, POINTER(c_size_t)],
     "crb3d_fc_gemm_tf32": [P, c_int64, c_int, c_int64, P, c_int, P, P, c_int, P, P, c_size_t, P],
+    "crb3d_bev_conv3x3_num_tiles": [c_int, c_int, c_int, POINTER(c_int)],
+    "crb3d_bev_tile_plan_workspace_bytes": [c_int, c_int, c_int, POINTER(c_size_t)],
+    "crb3d_bev_tile_plan": [P, c_int, P, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P],
+    "crb3d_bev_conv3x3_tf32_tiles": [P, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, P, P, P, P, P],
     "crb3d_bev_conv3x3_trace": [P, c_int],
     "crb3d_anchor_head_scores": [P, c_int64, c_int, P, P, P],
     "crb3d_anchor_head_scores_topk": [P, c_int, c_int64, c_int, c_float, c_int, P, P, P, P, P, P, P, P],
@@ -149,6 +153,7 @@ KERNELS_PER_CALL = {
     "crb3d_voxel_query_stack": 1, "crb3d_ball_query_batch": 1, "crb3d_group_points_batch": 1, "crb3d_group_points_grad_batch": 1,
     "crb3d_three_nn_batch": 1, "crb3d_three_interpolate_batch": 1, "crb3d_three_interpolate_grad_batch": 1,
     "crb3d_roipoint_pool3d_forward": 1, "crb3d_assign_targets_axis_aligned": 2, "crb3d_anchor_head_loss": 3,
+    "crb3d_bev_tile_plan": 5, "crb3d_bev_conv3x3_tf32_tiles": 2,
     "crb3d_query_stacked_local_neighbor_idxs": 8, "crb3d_query_three_nn_by_stacked_local_idxs": 1, "crb3d_vector_pool_stack": 1,
     "crb3d_vector_pool_grad_stack": 1,
 }

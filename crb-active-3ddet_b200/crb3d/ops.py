@@ -393,9 +393,35 @@ def pack_conv3x3_weight(weight, split=None):
     return w.permute(0, 2, 3, 4, 1, 5).contiguous()
 
 
-def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None, round_out=False):
+def bev_conv3x3_num_tiles(B, H, W):
+    n = ctypes.c_int(0)
+    _lib.call("crb3d_bev_conv3x3_num_tiles", int(B), int(H), int(W), byref(n))
+    return int(n.value)
+
+
+def bev_tile_plan(coords, n_dev, B, H, W, n_levels):
+    """Sparse-tile plan of a stack of n_levels 3x3 stride-1 BEV convs whose first input is the dense() of the sparse tensor with
+    rows `coords` (n,4) [b,z,y,x] (n_dev: device row count or None): per level the 128-pixel tiles that can differ from the
+    level's constant (see csrc/bev_conv_tc.cu). Returns dict(lists (L,T) int32, counts (L,) int32, flags (L,T) uint8 = computed,
+    fill_flags (L,T) uint8 = constant tiles somebody reads)."""
+    _need_cuda(coords)
+    coords = _i32c(coords)
+    dev = coords.device
+    T = bev_conv3x3_num_tiles(B, H, W)
+    lists = torch.empty((n_levels, T), dtype=torch.int32, device=dev)
+    counts = torch.empty((n_levels,), dtype=torch.int32, device=dev)
+    flags = torch.empty((n_levels, T), dtype=torch.uint8, device=dev)
+    fill_flags = torch.empty((n_levels, T), dtype=torch.uint8, device=dev)
+    ws = _ws(_ws_bytes("crb3d_bev_tile_plan_workspace_bytes", int(B), int(H), int(W)), dev)
+    _lib.call("crb3d_bev_tile_plan", _p(coords), coords.shape[0], _p(n_dev), int(B), int(H), int(W), int(n_levels), _p(lists), _p(counts),
+              _p(flags), _p(fill_flags), _p(ws), ws.numel(), _stream(dev))
+    return {"lists": lists, "counts": counts, "flags": flags, "fill_flags": fill_flags, "n_tiles": T}
+
+
+def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None, round_out=False, tiles=None):
     """3x3 / stride 1 / pad 1 conv (+bias, ReLU) on the tensor cores. x_nhwc: (B, H, W, C_in) contiguous fp32 CUDA;
-    wpack: pack_conv3x3_weight(...). Returns (B, H, W, C_out) contiguous."""
+    wpack: pack_conv3x3_weight(...). Returns (B, H, W, C_out) contiguous. tiles = (plan, level, fill): compute only the plan's
+    active tiles of that level (bev_tile_plan) and write the constant `fill` (C_out floats) into the others."""
     _need_cuda(x_nhwc, wpack)
     assert x_nhwc.dtype == torch.float32 and x_nhwc.is_contiguous() and wpack.is_contiguous()
     B, H, W, cin = x_nhwc.shape
@@ -408,11 +434,24 @@ def bev_conv3x3(x_nhwc, wpack, bias, relu=True, out=None, round_out=False):
     if timed:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(x_nhwc.device))
-    _lib.call("crb3d_bev_conv3x3_tf32", _p(x_nhwc), B, H, W, cin, _p(wpack), cout, _p(_f32c(bias)) if bias is not None else None,
-              int(bool(relu)) | (2 if round_out else 0) | (CONV_VARIANT << 8), _p(out), _stream(x_nhwc.device))
+    flags_arg = int(bool(relu)) | (2 if round_out else 0) | (CONV_VARIANT << 8)
+    pixels = B * H * W
+    if tiles is None or (CONV_VARIANT & 1):
+        _lib.call("crb3d_bev_conv3x3_tf32", _p(x_nhwc), B, H, W, cin, _p(wpack), cout, _p(_f32c(bias)) if bias is not None else None,
+                  flags_arg, _p(out), _stream(x_nhwc.device))
+    else:
+        plan, level, fill = tiles
+        assert plan["n_tiles"] == bev_conv3x3_num_tiles(B, H, W) and fill.numel() == cout and fill.dtype == torch.float32
+        _lib.call("crb3d_bev_conv3x3_tf32_tiles", _p(x_nhwc), B, H, W, cin, _p(wpack), cout, _p(_f32c(bias)) if bias is not None else None,
+                  flags_arg, _p(out), _p(plan["lists"][level]), _p(plan["counts"][level:level + 1]), _p(plan["fill_flags"][level]),
+                  _p(fill), _stream(x_nhwc.device))
     if timed:
         e1.record(torch.cuda.current_stream(x_nhwc.device))
-        prof["conv2d"].append((e0, e1, 2.0 * 9 * cin * cout * B * H * W))
+        flops = 2.0 * 9 * cin * cout * pixels
+        if tiles is not None and not (CONV_VARIANT & 1):       # flops of the tiles that went through the tensor cores: read after the pass
+            cnt, per_tile = tiles[0]["counts"][tiles[1]], 2.0 * 9 * cin * cout * 128
+            flops = lambda: float(cnt.item()) * per_tile
+        prof["conv2d"].append((e0, e1, flops))
     return out
 
 

@@ -62,6 +62,8 @@ MARKERS = bool(int(os.environ.get("CRB3D_MARKERS", "0")))
 
 # tcgen05 halo-tile kernel for the 3x3 stride-1 BEV convs: "auto" (when its CTA count fills whole waves), True, False
 BEV_CONV_TC = {"0": False, "1": True}.get(os.environ.get("CRB3D_BEV_CONV_TC", ""), "auto")
+# block 1 of the BEV backbone in sparse-tile mode (constant tiles far from every occupied cell are filled, not computed)
+BEV_SPARSE_TILES = os.environ.get("CRB3D_BEV_SPARSE_TILES", "1") != "0"
 
 
 _tf32_weight = ops.tf32_weight
@@ -209,7 +211,29 @@ class BaseBEVBackbone(nn.Module):
                     gemm = (ops.round_tf32(dw.permute(2, 3, 1, 0).reshape(st * st * cout, cin).contiguous()), db, st)
                 plan.append((layers, (dw, db, de[0].stride), gemm))
         self._plan = plan
+        self._sparse_fills = self._build_sparse_fills(plan)
         return plan
+
+    @staticmethod
+    def _build_sparse_fills(plan):
+        """Constants of the sparse-tile mode (ops.bev_tile_plan) for the leading 3x3 stride-1 layers of block 1: the input of the
+        block is zero away from the occupied cells, so far from them (and from the border) layer l outputs one constant vector
+        c_{l+1} = layer_l(constant field c_l), c_0 = 0. Each constant is read off the kernel itself run on a constant image, i.e.
+        it has exactly the bits the dense computation produces there. None when the first block does not start with such layers."""
+        fills = []
+        layers = plan[0][0]
+        c = None
+        for w, b, stride, pad, wpack, w2 in layers:
+            if wpack is None or not w.is_cuda:
+                break
+            cin = w.shape[1]
+            x = torch.zeros((1, 24, 48, cin), dtype=torch.float32, device=w.device) if c is None else c.view(1, 1, 1, cin).expand(1, 24, 48, cin).contiguous()
+            y = ops.bev_conv3x3(x, wpack, b, True, round_out=True)
+            c = y[0, 12, 24].clone()
+            if not bool((y[0, 8:16, 16:32] == c).all()):          # the interior of a constant image must be constant
+                break
+            fills.append(c)
+        return fills or None
 
     @staticmethod
     def _tc_conv_pays(B, H, W, cout, cin=128):
@@ -223,10 +247,16 @@ class BaseBEVBackbone(nn.Module):
         tiles = B * -(-u // 8) * -(-v // 16)
         return tiles * max(1, cout // 128) >= 148
 
-    def forward_inference(self, x, mark=None):
+    def forward_inference(self, x, mark=None, occupancy=None):
+        """occupancy = (coords (n,4) [b,z,y,x], n_dev | None) of the sparse tensor whose dense() is x: block 1 then runs in
+        sparse-tile mode (only the 128-pixel tiles near an occupied cell or the border go through the tensor cores; bit-identical)."""
         B = x.shape[0]
         mark = mark or (lambda stage: None)
         li = 0
+        fills = getattr(self, "_sparse_fills", None)
+        tplan = None
+        if occupancy is not None and fills and BEV_SPARSE_TILES and self._tc_conv_pays(B, x.shape[2], x.shape[3], 128):
+            tplan = ops.bev_tile_plan(occupancy[0], occupancy[1], B, x.shape[2], x.shape[3], len(fills))
         gemm_ok = all(g is not None for _, _, g in self._plan)
         if gemm_ok:
             ctot = sum(g[0].shape[0] // (g[2] * g[2]) for _, _, g in self._plan)
@@ -234,10 +264,11 @@ class BaseBEVBackbone(nn.Module):
         xh = x.permute(0, 2, 3, 1)                                   # (B, H, W, C): the memory order of channels-last
         xh = xh if xh.is_contiguous() else xh.contiguous()
         ups, c0 = [], 0
-        for layers, (dw, db, ds), gemm in self._plan:
-            for w, b, stride, pad, wpack, w2 in layers:
+        for bi, (layers, (dw, db, ds), gemm) in enumerate(self._plan):
+            for lj, (w, b, stride, pad, wpack, w2) in enumerate(layers):
                 if wpack is not None and (w2 is None or self._tc_conv_pays(B, xh.shape[1], xh.shape[2], w.shape[0], w.shape[1])):
-                    xh = ops.bev_conv3x3(xh, wpack, b, True, round_out=True)   # the next layer reads TF32 exactly
+                    tiles = (tplan, lj, fills[lj]) if (tplan is not None and bi == 0 and lj < len(fills)) else None
+                    xh = ops.bev_conv3x3(xh, wpack, b, True, round_out=True, tiles=tiles)   # the next layer reads TF32 exactly
                 elif w2 is not None and BEV_CONV_TC is not False:
                     xh = ops.bev_conv_gemm(xh, w2, b, w.shape[2], stride[0], pad[0], True, round_out=True)
                 else:
@@ -265,7 +296,7 @@ class BaseBEVBackbone(nn.Module):
     def forward(self, batch_dict):
         x = batch_dict["spatial_features"]
         if not self.training and not torch.is_grad_enabled() and getattr(self, "_plan", None) is not None:
-            batch_dict["spatial_features_2d"] = self.forward_inference(x, batch_dict.get("_mark"))
+            batch_dict["spatial_features_2d"] = self.forward_inference(x, batch_dict.get("_mark"), batch_dict.get("_occupancy"))
             return batch_dict
         ups = []
         for i in range(len(self.blocks)):
@@ -466,13 +497,14 @@ class SECONDNet(nn.Module):
         return bd
 
     @torch.no_grad()
-    def dense_and_post(self, spatial_features, points_xyz, pt_begin, pt_end, batch_size, max_pts_per_frame, mark=None):
+    def dense_and_post(self, spatial_features, points_xyz, pt_begin, pt_end, batch_size, max_pts_per_frame, mark=None, occupancy=None):
         """Static-shape half of the step: BEV backbone -> anchor head -> max-class score / top-k / lazy decode -> batched
         rotated NMS -> points-in-boxes density -> label entropy. No host synchronisation and no data-dependent shape, so
         the whole thing is capturable in one CUDA graph (enable_cuda_graph)."""
         cfg = self.cfg
         mark = mark or (lambda stage: None)
-        bd = self.backbone_2d(dict(spatial_features=spatial_features, _mark=mark))
+        # occupancy = (coords, n_dev) of the encoded sparse tensor: lets block 1 of the BEV backbone skip its constant tiles
+        bd = self.backbone_2d(dict(spatial_features=spatial_features, _mark=mark, _occupancy=occupancy))
         mark(40)
         bd = self.dense_head(bd)
         mark(41)
@@ -618,7 +650,7 @@ class SECONDNet(nn.Module):
         ops.sparse_to_dense(feat, coords, B, shape, channels_last_bev=True, out=g["spatial"], n_dev=n_dev)
         mark(30)
         out = self.dense_and_post(g["spatial"].permute(0, 3, 1, 2), g["points"], g["offsets"][:-1], g["offsets"][1:], B,
-                                  g["max_pts"], mark=mark)
+                                  g["max_pts"], mark=mark, occupancy=(coords, n_dev))
         mark(99)
         out["counts"] = torch.cat(counts)
         g["caps"] = caps
@@ -748,7 +780,7 @@ class SECONDNet(nn.Module):
             return g["out"]
         spatial = enc.dense_bev_channels_last()
         return self.dense_and_post(spatial, points[:, xyz_col:], frame_offsets[:-1], frame_offsets[1:], batch_size,
-                                   max_pts_per_frame)
+                                   max_pts_per_frame, occupancy=(enc.indices, None))
 
 
 def calibrate_batchnorm(model, points, frame_offsets, batch_size):

@@ -49,6 +49,10 @@ struct ConvGeom {
     int tiles_u, tiles_v, n_tiles;
     long long su, sv, sb;        // output strides (floats) of u, v, batch; channels are contiguous
     int ku_is_ky;                // 1: u = y (tap row offset moves along u); 0: u = x
+    // sparse-tile mode (CTA-pair kernel): only the tiles tile_list[0 .. *n_active) are computed (device-side list and count,
+    // built by crb3d_bev_tile_plan); null = all n_tiles tiles in order
+    const int* tile_list;
+    const int* n_active;
 };
 
 // 64B swizzle K-major descriptor: rows of 64 bytes (16 channels of one pixel), 8-row groups `sbo` bytes apart. The
@@ -352,7 +356,8 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
     const bool leader = rank == 0;
     const int nh = blockIdx.y;
     const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
-    const int n_items = (g.n_tiles + 2 * IT - 1) / (2 * IT);
+    const int n_tiles = g.n_active ? min(max(__ldg(g.n_active), 0), g.n_tiles) : g.n_tiles;    // the same value in both CTAs of the pair
+    const int n_items = (n_tiles + 2 * IT - 1) / (2 * IT);
     const bool tracing = ((relu >> 8) & 2) && blockIdx.x < 1024 && blockIdx.y == 0;
     long long* tr = g_conv_trace + blockIdx.x * 16;
     if (tracing && tid == 0) { tr[0] = gtime(); uint32_t sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); tr[6] = sm; }
@@ -470,9 +475,10 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
 #pragma unroll
                 for (int t = 0; t < IT; ++t) {
                     const int ti = (item * 2 + (int)rank) * IT + t;
-                    if (ti < g.n_tiles) {
-                        tb[t] = ti / per_img;
-                        const int rem = ti - tb[t] * per_img;
+                    if (ti < n_tiles) {
+                        const int tt = g.tile_list ? __ldg(g.tile_list + ti) : ti;
+                        tb[t] = tt / per_img;
+                        const int rem = tt - tb[t] * per_img;
                         tv0[t] = (rem / g.tiles_u) * TV;
                         tu0[t] = (rem % g.tiles_u) * TU;
                     } else { tb[t] = g.B; tu0[t] = 0; tv0[t] = 0; }   // fully out of bounds: the TMA unit writes zeros
@@ -512,9 +518,10 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
                 continue;
             }
             const int ti = (item * 2 + (int)rank) * IT + t;
-            const bool live = ti < g.n_tiles;        // uniform per warp
+            const bool live = ti < n_tiles;          // uniform per warp
+            const int tt = live ? (g.tile_list ? __ldg(g.tile_list + ti) : ti) : 0;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * (IT * N) + t * N);
-            const int b = live ? ti / per_img : 0, rem = ti - b * per_img;
+            const int b = tt / per_img, rem = tt - b * per_img;
             const int tv = (rem / g.tiles_u) * TV + q * 4, tu = (rem % g.tiles_u) * TU;
             float* obase = out + (long long)b * g.sb + nh * N + (lane & 15) * 4;
             uint32_t va[32], vb[32];
@@ -583,12 +590,196 @@ extern "C" int crb3d_bev_conv3x3_trace(long long* host_out, int n_ctas) {
     return CRB3D_OK;
 }
 
+namespace {
+
+// tile orientation of an H x W map: u (8 pixels per tile) along y or along x, whichever pads less
+bool tile_u_is_y(int H, int W) {
+    return (H % TU == 0) || (W % TU != 0 && (crb3d_divup(H, TU) * TU - H) * W <= (crb3d_divup(W, TU) * TU - W) * H);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sparse-tile plan of a BEV block. The input of the 2-D backbone is the dense() of a sparse tensor: zero except at the occupied
+// cells (13-17 % of a KITTI-synthetic map). Far from every occupied cell and from the image border a stack of 3x3 convs
+// produces, layer after layer, ONE constant vector per layer (conv of a constant field + bias + ReLU). A 128-pixel output tile
+// of layer l (0-based) is constant iff the tile grown by l + 1 pixels lies inside the image and holds no occupied cell; such
+// tiles are filled with the layer's constant (computed once per plan by running the very kernel on a constant image, so the
+// bits are the ones the dense computation would produce) and only the others go through the tensor cores.
+__global__ void __launch_bounds__(256) occ_scatter_kernel(const int* __restrict__ coords, int n, const int* __restrict__ n_dev, int B, int H, int W,
+                                                          unsigned char* __restrict__ occ) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (n_dev && i >= *n_dev)) return;
+    const int4 c = __ldg(reinterpret_cast<const int4*>(coords) + i);     // b, z, y, x
+    if (c.x >= 0 && c.x < B && c.z >= 0 && c.z < H && c.w >= 0 && c.w < W) occ[((size_t)c.x * H + c.z) * W + c.w] = 1;
+}
+// summed-area table sat[b][y + 1][x + 1] = number of occupied cells in [0, y] x [0, x]; row 0 / column 0 stay zero
+__global__ void __launch_bounds__(256) sat_rows_kernel(const unsigned char* __restrict__ occ, int BH, int H, int W, int* __restrict__ sat) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= BH) return;
+    const int b = warp / H, y = warp - b * H;
+    const unsigned char* row = occ + (size_t)warp * W;
+    int* dst = sat + ((size_t)b * (H + 1) + y + 1) * (W + 1) + 1;
+    int carry = 0;
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        int v = x < W ? row[x] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (x < W) dst[x] = v + carry;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+}
+__global__ void __launch_bounds__(256) sat_cols_kernel(int B, int H, int W, int* __restrict__ sat) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * W) return;
+    const int b = t / W, x = t - b * W;
+    int* col = sat + (size_t)b * (H + 1) * (W + 1) + x + 1;
+    int acc = 0;
+    for (int y = 1; y <= H; ++y) { acc += col[(size_t)y * (W + 1)]; col[(size_t)y * (W + 1)] = acc; }
+}
+// one block per level: flags[level][tile] (1 = compute) and the ascending list of the tiles to compute + their count
+__global__ void __launch_bounds__(1024) tile_classify_kernel(const int* __restrict__ sat, int B, int H, int W, int u_is_y, int tiles_u, int tiles_v,
+                                                             int n_tiles, int* __restrict__ lists, int* __restrict__ counts,
+                                                             unsigned char* __restrict__ flags) {
+    __shared__ int sm[33];
+    const int level = blockIdx.x, grow = level + 1;
+    const int per_img = tiles_u * tiles_v;
+    int base = 0;
+    for (int t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const int t = t0 + threadIdx.x;
+        int active = 0;
+        if (t < n_tiles) {
+            const int b = t / per_img, rem = t - b * per_img;
+            const int u0 = (rem % tiles_u) * TU, v0 = (rem / tiles_u) * TV;
+            const int y0 = u_is_y ? u0 : v0, x0 = u_is_y ? v0 : u0;
+            const int y1 = min(y0 + (u_is_y ? TU : TV), H), x1 = min(x0 + (u_is_y ? TV : TU), W);   // exclusive ends, clipped to the image
+            const int gy0 = y0 - grow, gx0 = x0 - grow, gy1 = y1 + grow, gx1 = x1 + grow;
+            if (gy0 < 0 || gx0 < 0 || gy1 > H || gx1 > W || y0 + (u_is_y ? TU : TV) > H || x0 + (u_is_y ? TV : TU) > W) active = 1;   // the padding is in reach
+            else {
+                const int* s = sat + (size_t)b * (H + 1) * (W + 1);
+                const int cnt = s[(size_t)gy1 * (W + 1) + gx1] - s[(size_t)gy0 * (W + 1) + gx1] - s[(size_t)gy1 * (W + 1) + gx0] +
+                                s[(size_t)gy0 * (W + 1) + gx0];
+                active = cnt > 0;
+            }
+            flags[(size_t)level * n_tiles + t] = (unsigned char)active;
+        }
+        int tot;
+        const int pos = block_excl_scan(active, sm, &tot);
+        if (active) lists[(size_t)level * n_tiles + base + pos] = t;
+        base += tot;
+    }
+    if (threadIdx.x == 0) counts[level] = base;
+}
+// which constant tiles actually have to be written: all of them at the last level (the deblock reads the whole map), at the
+// levels before only those a computed tile of the NEXT level can see through its 1-pixel halo (its 8 neighbours)
+__global__ void __launch_bounds__(256) tile_fill_flags_kernel(const unsigned char* __restrict__ flags, int n_levels, int tiles_u, int tiles_v,
+                                                              int n_tiles, unsigned char* __restrict__ fill_flags) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, level = blockIdx.y;
+    if (t >= n_tiles) return;
+    unsigned char f = 0;
+    if (!flags[(size_t)level * n_tiles + t]) {
+        if (level == n_levels - 1) f = 1;
+        else {
+            const int per_img = tiles_u * tiles_v, b = t / per_img, rem = t - b * per_img, iv = rem / tiles_u, iu = rem % tiles_u;
+            const unsigned char* nxt = flags + (size_t)(level + 1) * n_tiles + (size_t)b * per_img;
+            for (int dv = -1; dv <= 1 && !f; ++dv)
+                for (int du = -1; du <= 1; ++du) {
+                    const int v = iv + dv, u = iu + du;
+                    if (v >= 0 && v < tiles_v && u >= 0 && u < tiles_u && nxt[v * tiles_u + u]) { f = 1; break; }
+                }
+        }
+    }
+    fill_flags[(size_t)level * n_tiles + t] = f;
+}
+// constant tiles of a layer: every pixel gets the layer's constant vector
+__global__ void __launch_bounds__(256) tile_fill_kernel(const unsigned char* __restrict__ fill_flags, const float* __restrict__ fill, int cout, ConvGeom g,
+                                                        float* __restrict__ out) {
+    const int t = blockIdx.x;
+    if (!fill_flags[t]) return;
+    const int per_img = g.tiles_u * g.tiles_v;
+    const int b = t / per_img, rem = t - b * per_img;
+    const int u0 = (rem % g.tiles_u) * TU, v0 = (rem / g.tiles_u) * TV;
+    const int c4 = cout >> 2;
+    for (int e = threadIdx.x; e < TU * TV * c4; e += blockDim.x) {
+        const int pix = e / c4, c = (e - pix * c4) * 4;
+        const int u = u0 + (pix % TU), v = v0 + (pix / TU);
+        if (u >= g.U || v >= g.V) continue;
+        *reinterpret_cast<float4*>(out + (long long)b * g.sb + (long long)u * g.su + (long long)v * g.sv + c) =
+            __ldg(reinterpret_cast<const float4*>(fill + c));
+    }
+}
+
+int conv3x3_impl(const float* in, int B, int H, int W, int cin, const float* wpack, int cout, const float* bias, int relu, float* out,
+                 const int* tile_list, const int* n_active, const unsigned char* tile_flags, const float* fill, cudaStream_t stream);
+
+}  // namespace
+
 extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int cin, const float* wpack, int cout,
                                       const float* bias, int relu, float* out, cudaStream_t stream) {
+    return conv3x3_impl(in, B, H, W, cin, wpack, cout, bias, relu, out, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+// number of 128-pixel tiles the halo-tile kernel cuts a (B, H, W) map into (the row stride of the plan arrays below)
+extern "C" int crb3d_bev_conv3x3_num_tiles(int B, int H, int W, int* n_tiles) {
+    if (!n_tiles || B <= 0 || H <= 0 || W <= 0) return CRB3D_ERR_ARG;
+    const bool u_is_y = tile_u_is_y(H, W);
+    *n_tiles = B * (int)crb3d_divup(u_is_y ? H : W, TU) * (int)crb3d_divup(u_is_y ? W : H, TV);
+    return CRB3D_OK;
+}
+
+extern "C" int crb3d_bev_tile_plan_workspace_bytes(int B, int H, int W, size_t* bytes) {
+    if (!bytes || B <= 0 || H <= 0 || W <= 0) return CRB3D_ERR_ARG;
+    *bytes = crb3d_align((size_t)B * H * W) + crb3d_align(sizeof(int) * (size_t)B * (H + 1) * (W + 1));
+    return CRB3D_OK;
+}
+
+// coords (n,4) int32 [b,z,y,x] = the rows of the sparse tensor whose dense() is the block's input (n_dev nullable device count);
+// n_levels = number of stacked 3x3 stride-1 layers. Outputs (device): lists [n_levels][n_tiles] int32, counts [n_levels] int32,
+// flags [n_levels][n_tiles] uint8 (1 = the tile must be computed at that level), fill_flags [n_levels][n_tiles] uint8 (1 = the tile
+// is constant AND somebody reads it: the next level's computed tiles through their halo, or - last level - the consumer of the map).
+extern "C" int crb3d_bev_tile_plan(const int* coords, int n, const int* n_dev, int B, int H, int W, int n_levels, int* lists, int* counts,
+                                   unsigned char* flags, unsigned char* fill_flags, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (n < 0 || B <= 0 || H <= 0 || W <= 0 || n_levels <= 0 || !lists || !counts || !flags || !fill_flags || (n > 0 && !coords))
+        return CRB3D_ERR_ARG;
+    WsCursor c(ws, ws_bytes);
+    unsigned char* occ = c.take<unsigned char>((size_t)B * H * W);
+    int* sat = c.take<int>((size_t)B * (H + 1) * (W + 1));
+    if (!c.ok) return CRB3D_ERR_WORKSPACE;
+    CRB3D_CUDA(cudaMemsetAsync(occ, 0, (size_t)B * H * W, stream));
+    CRB3D_CUDA(cudaMemsetAsync(sat, 0, sizeof(int) * (size_t)B * (H + 1) * (W + 1), stream));
+    if (n > 0) occ_scatter_kernel<<<(unsigned)crb3d_divup(n, 256), 256, 0, stream>>>(coords, n, n_dev, B, H, W, occ);
+    sat_rows_kernel<<<(unsigned)crb3d_divup((int64_t)B * H * 32, 256), 256, 0, stream>>>(occ, B * H, H, W, sat);
+    sat_cols_kernel<<<(unsigned)crb3d_divup(B * W, 256), 256, 0, stream>>>(B, H, W, sat);
+    const bool u_is_y = tile_u_is_y(H, W);
+    const int tiles_u = (int)crb3d_divup(u_is_y ? H : W, TU), tiles_v = (int)crb3d_divup(u_is_y ? W : H, TV);
+    const int n_tiles = B * tiles_u * tiles_v;
+    tile_classify_kernel<<<(unsigned)n_levels, 1024, 0, stream>>>(sat, B, H, W, u_is_y ? 1 : 0, tiles_u, tiles_v, n_tiles, lists, counts, flags);
+    tile_fill_flags_kernel<<<dim3((unsigned)crb3d_divup(n_tiles, 256), (unsigned)n_levels), 256, 0, stream>>>(flags, n_levels, tiles_u, tiles_v,
+                                                                                                           n_tiles, fill_flags);
+    CRB3D_CHECK_LAUNCH();
+    return CRB3D_OK;
+}
+
+// crb3d_bev_conv3x3_tf32 over the tiles tile_list[0 .. *n_active) only (CTA-pair kernel); the tiles with tile_fill != 0 are filled
+// with `fill` (C_out floats, device): one level of a crb3d_bev_tile_plan (lists / counts / fill_flags rows of that level).
+extern "C" int crb3d_bev_conv3x3_tf32_tiles(const float* in, int B, int H, int W, int cin, const float* wpack, int cout, const float* bias,
+                                            int relu, float* out, const int* tile_list, const int* n_active,
+                                            const unsigned char* tile_flags, const float* fill, cudaStream_t stream) {
+    if (!tile_list || !n_active || !tile_flags || !fill || ((relu >> 8) & 1)) return CRB3D_ERR_ARG;
+    return conv3x3_impl(in, B, H, W, cin, wpack, cout, bias, relu, out, tile_list, n_active, tile_flags, fill, stream);
+}
+
+namespace {
+int conv3x3_impl(const float* in, int B, int H, int W, int cin, const float* wpack, int cout, const float* bias, int relu, float* out,
+                 const int* tile_list, const int* n_active, const unsigned char* tile_flags, const float* fill, cudaStream_t stream) {
     if (!in || !wpack || !out || B <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) return CRB3D_ERR_ARG;
     if (cin % KC != 0 || cout % N != 0) return CRB3D_ERR_UNSUPPORTED;
     ConvGeom g;
-    const bool u_is_y = (H % TU == 0) || (W % TU != 0 && (crb3d_divup(H, TU) * TU - H) * W <= (crb3d_divup(W, TU) * TU - W) * H);
+    g.tile_list = tile_list;
+    g.n_active = n_active;
+    const bool u_is_y = tile_u_is_y(H, W);
     g.ku_is_ky = u_is_y ? 1 : 0;
     g.U = u_is_y ? H : W;
     g.V = u_is_y ? W : H;
@@ -641,6 +832,7 @@ extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int 
         else
             pair::bev_conv3x3_pair_tc<2><<<dim3((unsigned)(2 * n_clusters), (unsigned)ny), pair::NTHREADS, pair::smem_bytes(2) + 1024, stream>>>(
                 amap, wmap, cin / KC, bias, relu, out, g);
+        if (tile_flags) tile_fill_kernel<<<(unsigned)g.n_tiles, 256, 0, stream>>>(tile_flags, fill, cout, g, out);
         CRB3D_CHECK_LAUNCH();
         return CRB3D_OK;
     }
@@ -649,5 +841,6 @@ extern "C" int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int 
     CRB3D_CHECK_LAUNCH();
     return CRB3D_OK;
 }
+}  // namespace
 
 CRB3D_DIAG_DEFINE_SETTER(bev_conv)

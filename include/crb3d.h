@@ -209,6 +209,23 @@ int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long lda, const
  *      [C_out/128][ky*3+kx][C_in/16][4][128][4]). Supported: C_in % 16 == 0, C_out % 128 == 0. */
 int crb3d_bev_conv3x3_tf32(const float* in, int B, int H, int W, int cin, const float* wpack, int cout, const float* bias,
                            int relu, float* out, cudaStream_t stream);
+/* Sparse-tile mode of the halo-tile conv for a stack of 3x3 stride-1 layers fed by the dense() of a sparse tensor (block 1 of
+ * BaseBEVBackbone): far from every occupied cell and from the border each layer's output is ONE constant vector, so a 128-pixel
+ * tile whose neighbourhood (grown by level + 1 pixels) is empty and inside the image is filled with that constant instead of
+ * going through the tensor cores. crb3d_bev_tile_plan builds, from the sparse rows (n,4) [b,z,y,x] (n_dev nullable), per level
+ * the list / count / flags of the tiles to compute ([n_levels][n_tiles], n_tiles from crb3d_bev_conv3x3_num_tiles) and fill_flags
+ * (constant tiles that somebody reads: the next level's computed tiles through their halo; every constant tile at the last level);
+ * crb3d_bev_conv3x3_tf32_tiles runs one level: tiles tile_list[0 .. *n_active) on the CTA-pair kernel, `fill` (C_out floats, the
+ * layer's constant: computed by the caller by running the layer on a constant image) in the tiles with tile_flags (= the level's
+ * fill_flags row) != 0.
+ * Bit-identical to crb3d_bev_conv3x3_tf32 on the whole map. */
+int crb3d_bev_conv3x3_num_tiles(int B, int H, int W, int* n_tiles);
+int crb3d_bev_tile_plan_workspace_bytes(int B, int H, int W, size_t* bytes);
+int crb3d_bev_tile_plan(const int* coords, int n, const int* n_dev, int B, int H, int W, int n_levels, int* lists, int* counts,
+                        unsigned char* flags, unsigned char* fill_flags, void* ws, size_t ws_bytes, cudaStream_t stream);
+int crb3d_bev_conv3x3_tf32_tiles(const float* in, int B, int H, int W, int cin, const float* wpack, int cout, const float* bias,
+                                 int relu, float* out, const int* tile_list, const int* n_active, const unsigned char* tile_flags,
+                                 const float* fill, cudaStream_t stream);
 /* k x k convolution (ksize in {1,3}, stride in {1,2}, zero padding) + bias + ReLU over a channels-last map as an implicit
  * GEMM whose A tiles are strided 4-D TMA boxes: the stride-2 first conv of a BEV block (base_bev_backbone.py:33-40) and
  * the fallback for 3x3 stride-1 layers the halo-tile kernel does not take - no cuDNN on the inference path.

@@ -211,6 +211,59 @@ def test_bev_conv_gemm_strided_boxes(cuda, B, H, W, cin, cout, k, stride, pad):
     _check(out, ref, "conv gemm")
 
 
+@pytest.mark.parametrize("n_occ", [0, 1, 400, 6000])
+def test_bev_block1_sparse_tiles_bit_identical(cuda, n_occ):
+    """Block 1 of the BEV backbone in sparse-tile mode (only tiles near an occupied cell or the border on the tensor cores, the
+    rest filled with each layer's constant) == the dense computation, bit for bit, from an empty map (every interior tile is
+    constant, most CTA pairs get no work item) to a map where every tile is active."""
+    from crb3d import ops, second
+    torch.manual_seed(3)
+    net = second.SECONDNet().eval().to_device(cuda)
+    bb = net.backbone_2d
+    bb.build_inference_plan()
+    assert bb._sparse_fills is not None and len(bb._sparse_fills) == 6
+    B, H, W, C = 2, 200, 176, 256
+    rng = np.random.default_rng(n_occ)
+    flat = rng.choice(B * H * W, n_occ, replace=False) if n_occ else np.zeros((0,), np.int64)
+    b, y, x = np.unravel_index(flat, (B, H, W))
+    if n_occ == 400:                                  # clustered: a few blobs, like objects in a scene
+        y = (100 + 20 * rng.standard_normal(n_occ)).clip(0, H - 1).astype(np.int64)
+        x = (60 + 15 * rng.standard_normal(n_occ)).clip(0, W - 1).astype(np.int64)
+    coords = torch.from_numpy(np.stack([b, np.zeros_like(b), y, x], 1).astype(np.int32)).to(cuda)
+    dense = torch.zeros((B, H, W, C), device=cuda)
+    dense[coords[:, 0].long(), coords[:, 2].long(), coords[:, 3].long()] = torch.randn(len(coords), C, device=cuda)
+    xin = dense.permute(0, 3, 1, 2)
+    with torch.no_grad():
+        # capacity-sized coordinate buffer with a device-side count, as in the captured step
+        pad = torch.cat([coords, torch.full((50, 4), 1, dtype=torch.int32, device=cuda)])
+        n_dev = torch.tensor([len(coords)], dtype=torch.int32, device=cuda)
+        # constant tiles nobody reads are NOT written: poison the allocator's free blocks so that a missing fill cannot hide
+        # behind stale values of an earlier (dense) run
+        poison = [torch.full((B, H, W, 128), float("nan"), device=cuda) for _ in range(4)]
+        del poison
+        got = bb.forward_inference(xin, occupancy=(pad, n_dev))
+        assert bool(torch.isfinite(got).all())
+        ref = bb.forward_inference(xin)
+        plan = ops.bev_tile_plan(pad, n_dev, B, H, W, 6)
+    assert torch.equal(got, ref)
+    ff = plan["fill_flags"].cpu().numpy()
+    assert not (ff & plan["flags"].cpu().numpy()).any() and (ff[-1] == 1 - plan["flags"][-1].cpu().numpy()).all()
+    if n_occ == 0:
+        assert ff[0].sum() < ff[-1].sum()              # early levels fill only the ring next to the computed tiles
+    counts = plan["counts"].cpu().numpy()
+    T = plan["n_tiles"]
+    assert (np.diff(counts) >= 0).all() and counts[-1] <= T        # the active set only grows with depth
+    assert np.array_equal(plan["flags"].sum(1).cpu().numpy(), counts)
+    border = 2 * (2 * 25 + 2 * 11 - 4)
+    if n_occ == 0:
+        assert counts[0] == border                                 # only the border tiles (zero padding in reach)
+    if n_occ == 6000:
+        assert counts[-1] > 0.9 * T
+    for l in range(6):                                             # lists = the flagged tiles in ascending order
+        lst = plan["lists"][l, :counts[l]].cpu().numpy()
+        assert np.array_equal(lst, np.nonzero(plan["flags"][l].cpu().numpy())[0])
+
+
 def test_gemm_cluster_multicast_is_bit_identical(cuda, monkeypatch):
     """The opt-in thread-block-cluster variants of the long-K GEMMs (TMA multicast of the shared operand k-blocks, multicast
     tcgen05.commit; csrc/bev_gemm_tc.cu) give exactly the plain launch's results: a 2x2 transposed conv (clusters of 4 weight
