@@ -256,7 +256,10 @@ class BaseBEVBackbone(nn.Module):
         fills = getattr(self, "_sparse_fills", None)
         tplan = None
         if occupancy is not None and fills and BEV_SPARSE_TILES and self._tc_conv_pays(B, x.shape[2], x.shape[3], 128):
-            tplan = ops.bev_tile_plan(occupancy[0], occupancy[1], B, x.shape[2], x.shape[3], len(fills))
+            # a prebuilt plan (dict: the captured step builds it on its geometry branch, off the critical path) or (coords, n_dev)
+            tplan = occupancy if isinstance(occupancy, dict) else ops.bev_tile_plan(occupancy[0], occupancy[1], B, x.shape[2], x.shape[3], len(fills))
+            if tplan["lists"].shape[0] < len(fills) or tplan["n_tiles"] != ops.bev_conv3x3_num_tiles(B, x.shape[2], x.shape[3]):
+                tplan = None
         gemm_ok = all(g is not None for _, _, g in self._plan)
         if gemm_ok:
             ctot = sum(g[0].shape[0] // (g[2] * g[2]) for _, _, g in self._plan)
@@ -637,6 +640,16 @@ class SECONDNet(nn.Module):
                     counts.append(n_dev)
                     caps.append(cap_out)
                 plan.append((conv, bn, relu, nbr, n_dev, ev))
+            # sparse-tile plan of BEV block 1 from the encoded tensor's rows: known as soon as the last rulebook is, so it is built
+            # here on the geometry branch, under the sparse convs
+            occupancy = (coords, n_dev)
+            fills = getattr(self.backbone_2d, "_sparse_fills", None)
+            if fills and BEV_SPARSE_TILES:
+                D2, H2, W2 = shape
+                occupancy = ops.bev_tile_plan(coords, n_dev, B, H2, W2, len(fills))
+                ev_occ = torch.cuda.Event()
+                ev_occ.record(side)
+                g["_tile_plan"] = occupancy
         for li, (conv, bn, relu, nbr, nd, ev) in enumerate(plan):
             main.wait_event(ev)
             scale, shift = spconv.SparseSequential._bn_affine(bn) if bn is not None else (None, None)
@@ -649,8 +662,10 @@ class SECONDNet(nn.Module):
         n_dev = plan[-1][4]
         ops.sparse_to_dense(feat, coords, B, shape, channels_last_bev=True, out=g["spatial"], n_dev=n_dev)
         mark(30)
+        if isinstance(occupancy, dict):
+            main.wait_event(ev_occ)
         out = self.dense_and_post(g["spatial"].permute(0, 3, 1, 2), g["points"], g["offsets"][:-1], g["offsets"][1:], B,
-                                  g["max_pts"], mark=mark, occupancy=(coords, n_dev))
+                                  g["max_pts"], mark=mark, occupancy=occupancy)
         mark(99)
         out["counts"] = torch.cat(counts)
         g["caps"] = caps

@@ -35,7 +35,9 @@ def launches(path, steps):
         total += us(r)
     mine = ("vox_", "scan_", "fill_kernel", "subm_", "sparse_", "bitmap_", "pair_", "spconv_", "dense_kernel", "head_", "gather_rows",
             "nms_", "pairwise_kernel", "points_in_boxes", "box_density", "label_entropy", "roiaware", "ball_query", "group_points",
-            "fps_kernel", "three_", "kde_", "sqdist", "bev_", "topk_", "round_tf32")
+            "fps_kernel", "three_", "kde_", "sqdist", "bev_", "topk_", "round_tf32", "sat_", "tile_", "occ_scatter", "bitmap_", "fps_cluster",
+            "sa_group", "fc_", "assign_", "head_loss", "count_pos", "range_flags", "collate_", "ff_", "row_norms", "voxel_query",
+            "roipoint", "local_neighbors", "vector_pool", "gather_counts")
     own = sum(v for k, (c, v) in agg.items() if k.startswith(mine))
     print("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)")
     print("# last %d bench steps: %d launches, %.1f us per step; kernels of libcrb3d_sm100: %.1f%% of the time" %
