@@ -85,13 +85,16 @@ def accelerate_bev_backbone(module):
     original_forward = module.forward
     module._fold = Ours._fold
     module._tc_conv_pays = Ours._tc_conv_pays
+    module._build_sparse_fills = Ours._build_sparse_fills
     module.build_inference_plan = types.MethodType(Ours.build_inference_plan, module)
     module.forward_inference = types.MethodType(Ours.forward_inference, module)
 
     def forward(self, data_dict):
         x = data_dict["spatial_features"]
         if not self.training and not torch.is_grad_enabled() and getattr(self, "_plan", None) is not None and x.is_cuda:
-            data_dict["spatial_features_2d"] = self.forward_inference(x)
+            # `_occupancy` = (coords, n_dev) of the sparse tensor behind spatial_features, when the caller provides it: block 1 then
+            # runs in sparse-tile mode (crb3d.second.BaseBEVBackbone.forward_inference)
+            data_dict["spatial_features_2d"] = self.forward_inference(x, None, data_dict.get("_occupancy"))
             return data_dict
         return original_forward(data_dict)
 
