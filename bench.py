@@ -289,10 +289,13 @@ def run_own(args, rank, world, local_rank):
     torch.cuda.synchronize(device)
     progress("warm-up done")
     if args.profile_replays > 0:     # the launch list of exactly the kernels one replay of the timed region runs (never a bench value)
+        torch.cuda.synchronize(device)
+        torch.cuda.profiler.start()          # `ncu --profile-from-start off` captures exactly these replays
         for i in range(args.profile_replays):
             model.full_graph_replay(seq[i % len(seq)][0], seq[i % len(seq)][1], slot=0)
             flush.fill_(i & 0xFF)
         torch.cuda.synchronize(device)
+        torch.cuda.profiler.stop()
         progress("profile replays done")
         return
 
