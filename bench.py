@@ -239,7 +239,7 @@ def run_own(args, rank, world, local_rank):
     B = args.batch
     frames = distinct_frames()
     ps = scorer.PoolScorer(model, device, B)
-    cal = ps.to_device(ps.stage_host(frames[:B]))
+    cal = ps.to_device(ps.stage_host([frames[i % len(frames)] for i in range(B)]))     # --batch may exceed the 16 distinct clouds
     second.calibrate_batchnorm(model, cal[0], cal[1], B)      # see the docstring: random init collapses
     second.calibrate_head_bias(model, cal[0], cal[1], B, target_fraction=0.004)
     progress("calibrated; capturing graphs")
@@ -504,7 +504,7 @@ def extra_measurements(args, model, ps, frames, device, l2_flush, progress):
     out = {}
     B = args.batch
     slots = max(1, args.slots)
-    batches = [ps.to_device(ps.stage_host(frames[s:s + B])) for s in range(0, len(frames) - B + 1, B)]
+    batches = [ps.to_device(ps.stage_host([frames[(s + i) % len(frames)] for i in range(B)])) for s in range(0, max(len(frames) - B, 0) + 1, B)]
     b4 = ps.to_device(ps.stage_host(frames[:4]))
     row_caps = model._graph_cfg[4]
 

@@ -117,6 +117,8 @@ def voxelize(points, frame_offsets, batch_size, pc_range, voxel_size, max_pts, m
     _need_cuda(points, frame_offsets)
     points = _f32c(points)
     frame_offsets = _i32c(frame_offsets)
+    if frame_offsets.numel() != batch_size + 1:      # the kernels index frame_offsets[0 .. batch_size]
+        raise ValueError("crb3d: frame_offsets must hold batch_size + 1 = %d entries, got %d" % (batch_size + 1, frame_offsets.numel()))
     n, stride = points.shape
     n_feat = stride - feat_col if n_feat is None else n_feat
     pc_range = [float(x) for x in pc_range]

@@ -286,3 +286,7 @@ def test_raw_pointer_wrappers_reject_wrong_dtype_and_layout(cuda):
         ops.ball_query(1, 10, 0.5, 4, xyz[::10], ncnt, xyz, cnt, idx)
     with pytest.raises(RuntimeError):
         ops.ball_query(1, 10, 0.5, 4, xyz[:10].cpu(), ncnt, xyz, cnt, idx)
+    # a batch size that does not match the offsets vector would read past it on the device
+    with pytest.raises(ValueError):
+        ops.voxelize(torch.rand(100, 4, device=cuda), torch.tensor([0, 50, 100], dtype=torch.int32, device=cuda), 4,
+                     [0, -40, -3, 70.4, 40, 1], [0.05, 0.05, 0.1], 5, 1000)
