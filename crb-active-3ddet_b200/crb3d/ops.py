@@ -56,6 +56,13 @@ def _check(**named):
             raise ValueError("crb3d: %s must be contiguous" % name)
 
 
+def _check_len(**named):
+    """name=(tensor, expected number of elements): count / offset vectors are indexed by the batch size on the device."""
+    for name, (t, n) in named.items():
+        if t is not None and t.numel() != n:
+            raise ValueError("crb3d: %s must hold %d entries, got %d" % (name, n, t.numel()))
+
+
 def _f32c(t):
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
@@ -818,6 +825,7 @@ def roiaware_pool3d_backward(pts_idx_of_voxels, argmax, grad_out, grad_in, pool_
 def ball_query(B, M, radius, nsample, new_xyz, new_xyz_batch_cnt, xyz, xyz_batch_cnt, idx, max_queries_per_frame=0):
     _need_cuda(new_xyz, new_xyz_batch_cnt, xyz, xyz_batch_cnt, idx)
     _check(new_xyz=(new_xyz, torch.float32), new_xyz_batch_cnt=(new_xyz_batch_cnt, torch.int32), xyz=(xyz, torch.float32), xyz_batch_cnt=(xyz_batch_cnt, torch.int32), idx=(idx, torch.int32))
+    _check_len(new_xyz_batch_cnt=(new_xyz_batch_cnt, B), xyz_batch_cnt=(xyz_batch_cnt, B))
     _lib.call("crb3d_ball_query_stack", B, M, float(radius), int(nsample), _p(new_xyz), _p(new_xyz_batch_cnt), _p(xyz),
               _p(xyz_batch_cnt), _p(idx), int(max_queries_per_frame), _stream(idx.device))
 
@@ -825,6 +833,7 @@ def ball_query(B, M, radius, nsample, new_xyz, new_xyz_batch_cnt, xyz, xyz_batch
 def group_points(B, M, C, nsample, features, features_batch_cnt, idx, idx_batch_cnt, out):
     _need_cuda(features, features_batch_cnt, idx, idx_batch_cnt, out)
     _check(features=(features, torch.float32), features_batch_cnt=(features_batch_cnt, torch.int32), idx=(idx, torch.int32), idx_batch_cnt=(idx_batch_cnt, torch.int32), out=(out, torch.float32))
+    _check_len(features_batch_cnt=(features_batch_cnt, B), idx_batch_cnt=(idx_batch_cnt, B))
     _lib.call("crb3d_group_points_stack", B, M, C, nsample, _p(features), _p(features_batch_cnt), _p(idx),
               _p(idx_batch_cnt), _p(out), _stream(out.device))
 
@@ -832,6 +841,7 @@ def group_points(B, M, C, nsample, features, features_batch_cnt, idx, idx_batch_
 def group_points_grad(B, M, C, N, nsample, grad_out, idx, idx_batch_cnt, features_batch_cnt, grad_features):
     _need_cuda(grad_out, idx, idx_batch_cnt, features_batch_cnt, grad_features)
     _check(grad_out=(grad_out, torch.float32), idx=(idx, torch.int32), idx_batch_cnt=(idx_batch_cnt, torch.int32), features_batch_cnt=(features_batch_cnt, torch.int32), grad_features=(grad_features, torch.float32))
+    _check_len(features_batch_cnt=(features_batch_cnt, B), idx_batch_cnt=(idx_batch_cnt, B))
     _lib.call("crb3d_group_points_grad_stack", B, M, C, N, nsample, _p(grad_out), _p(idx), _p(idx_batch_cnt),
               _p(features_batch_cnt), _p(grad_features), _stream(grad_out.device))
 
@@ -855,6 +865,7 @@ def stack_farthest_point_sampling(points, temp, xyz_batch_cnt, idx, num_sampled_
 def three_nn(B, N, M, unknown, unknown_batch_cnt, known, known_batch_cnt, dist2, idx):
     _need_cuda(unknown, unknown_batch_cnt, known, known_batch_cnt, dist2, idx)
     _check(unknown=(unknown, torch.float32), unknown_batch_cnt=(unknown_batch_cnt, torch.int32), known=(known, torch.float32), known_batch_cnt=(known_batch_cnt, torch.int32), dist2=(dist2, torch.float32), idx=(idx, torch.int32))
+    _check_len(unknown_batch_cnt=(unknown_batch_cnt, B), known_batch_cnt=(known_batch_cnt, B))
     _lib.call("crb3d_three_nn_stack", B, N, M, _p(unknown), _p(unknown_batch_cnt), _p(known), _p(known_batch_cnt),
               _p(dist2), _p(idx), _stream(idx.device))
 
