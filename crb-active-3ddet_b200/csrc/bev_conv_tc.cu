@@ -832,9 +832,11 @@ int conv3x3_impl(const float* in, int B, int H, int W, int cin, const float* wpa
         const int ny = cout / N;
         int n_clusters = crb3d_num_sms() / 2 / ny;
         if (n_clusters < 1) n_clusters = 1;
-        // item size: rounds(IT) * IT = time in units of one tile per CTA; 1-tile items when they save a whole such unit
+        // item size: rounds(IT) * IT = time in units of one tile per CTA. A tile of a 2-tile item costs ~0.88 of a tile of a 1-tile
+        // item (the weight stage feeds two tiles: 217 vs 232 us at 16 x 100 x 88, 256 -> 256, i.e. 12.1 vs 13.7 us per tile round),
+        // so 1-tile items only when their finer rounds save more than that
         const long long items2 = crb3d_divup(g.n_tiles, 4), items1 = crb3d_divup(g.n_tiles, 2);
-        const long long cost2 = crb3d_divup(items2, n_clusters) * 2, cost1 = crb3d_divup(items1, n_clusters);
+        const long long cost2 = crb3d_divup(items2, n_clusters) * 2 * 88, cost1 = crb3d_divup(items1, n_clusters) * 100;
         const int it_sel = (((relu >> 8) & 4) || cost1 < cost2) && !((relu >> 8) & 8) ? 1 : 2;
         const int n_items = (int)(it_sel == 1 ? items1 : items2);
         if (n_clusters > n_items) n_clusters = n_items;

@@ -55,6 +55,11 @@ def case(B, H, W, cin, cout, stride):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "b16":         # the bench's batch: item-size choice of the pair kernel
+        case(16, 100, 88, 256, 256, 1)
+        case(16, 200, 176, 128, 128, 1)
+        case(16, 200, 176, 256, 128, 1)
+        sys.exit(0)
     case(4, 200, 176, 128, 256, 2)
     case(4, 100, 88, 256, 256, 1)
     case(4, 200, 176, 128, 128, 1)
