@@ -7,6 +7,7 @@
 #include <string.h>
 
 extern "C" int crb3d_diag_set_spconv_tc(void*, unsigned int);
+extern "C" int crb3d_diag_set_spconv_grp(void*, unsigned int);
 extern "C" int crb3d_diag_set_bev_conv(void*, unsigned int);
 extern "C" int crb3d_diag_set_bev_gemm(void*, unsigned int);
 extern "C" int crb3d_diag_set_rulebook(void*, unsigned int);
@@ -54,6 +55,7 @@ extern "C" int crb3d_diag_init(void) {
     CRB3D_CUDA(cudaHostGetDevicePointer(&dptr, g_host_rec, 0));
     int rc;
     if ((rc = crb3d_diag_set_spconv_tc(dptr, (unsigned)d))) return rc;
+    if ((rc = crb3d_diag_set_spconv_grp(dptr, (unsigned)d))) return rc;
     if ((rc = crb3d_diag_set_bev_conv(dptr, (unsigned)d))) return rc;
     if ((rc = crb3d_diag_set_bev_gemm(dptr, (unsigned)d))) return rc;
     if ((rc = crb3d_diag_set_rulebook(dptr, (unsigned)d))) return rc;

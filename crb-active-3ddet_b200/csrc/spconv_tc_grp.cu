@@ -303,6 +303,8 @@ int launch_grp(const float* feat, const int* nbr, const float* weight, int n_out
 
 }  // namespace
 
+CRB3D_DIAG_DEFINE_SETTER(spconv_grp)
+
 // Forward of a narrow layer with grouped stages (no kmap: the forward direction only). Returns CRB3D_ERR_UNSUPPORTED for shapes it
 // does not take; crb3d_spconv_forward_tf32 then uses the one-offset-per-stage kernel. Not part of include/crb3d.h.
 int crb3d_spconv_forward_tf32_grouped(const float* feat, const int* nbr, const float* weight, int n_out, int K, int cin, int cout,
