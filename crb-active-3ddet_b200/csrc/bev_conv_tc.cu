@@ -316,7 +316,12 @@ __device__ __forceinline__ uint32_t leader_addr(const void* local) {        // t
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): what the epilogue hands over is tensor-memory
+// state, ordered by the tcgen05 fences on both sides; `.release.cluster` would make the warp drain its global stores first
 __device__ __forceinline__ void remote_arrive(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void remote_arrive_release(uint32_t cluster_addr) {      // A/B only (variant bit 4)
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -563,7 +568,7 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
             // every column of this warp's accumulator slice is in registers: hand the TMEM set back to the MMA issuer
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) remote_arrive(acc_empty_leader[set]);
+            if (lane == 0) { if ((relu >> 8) & 16) remote_arrive_release(acc_empty_leader[set]); else remote_arrive(acc_empty_leader[set]); }
             convert(vb, 96, 32);
             store_half(64);
         }

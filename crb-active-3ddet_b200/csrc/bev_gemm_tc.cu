@@ -474,6 +474,11 @@ int launch_conv_gemm(const float* in, int B, int H, int W, int cin, const float*
 
 }  // namespace
 
+int crb3d_bev_gemm_pair_tf32(const float* A, long long M, int K, long long lda, const float* W, int n_sub, const float* bias, int relu,
+                             float* out_ptr, long long row_stride, int up, int in_h, int in_w, cudaStream_t stream);   // bev_gemm_pair.cu
+int crb3d_bev_conv_gemm_pair_tf32(const float* in, int B, int H, int W, int cin, const float* w2, int ksize, int stride, int pad,
+                                  const float* bias, int relu, float* out_ptr, cudaStream_t stream);                           // bev_gemm_pair.cu
+
 // A: (M, K) fp32 rows `lda` floats apart (channels-last activations); W: contiguous [n_sub][N][K]; bias: N floats or null.
 // Output: n_seg column segments (seg s = columns [col_begin[s], col_begin[s]+width[s]) -> out_ptr[s] + row*row_stride[s]).
 // up = 0: output row = GEMM row, n_sub must be 1. up = 2: ConvTranspose2d(kernel = stride = 2): n_sub = 4 weight slices
@@ -508,6 +513,11 @@ extern "C" int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long
     // slices = (sub-positions) x (column blocks of the per-CTA width); resident weights when N_cta * K * 4 <= 128 KB
     if (rows) {
         if (N == 256 && K <= 128) return launch_gemm<256, 3, true, false>(A, M, K, lda, W, n_sub, 1, bias, relu, o, stream);
+        if (N == 256 && K <= 256 && !(relu & 12)) {
+            // CTA pairs: all 256 columns from one pass over the activations (csrc/bev_gemm_pair.cu); relu bit 3 = the single-CTA kernel
+            int rc = crb3d_bev_gemm_pair_tf32(A, M, K, lda, W, n_sub, bias, relu, out_ptr[0], row_stride[0], up, in_h, in_w, stream);
+            if (rc != CRB3D_ERR_UNSUPPORTED) return rc;
+        }
         if (N == 256 && K <= 256) {
             // relu bit 2 (opt-in, A/B measurements): the 2 column blocks x n_sub sub-positions walk the same activation tiles, so
             // clusters of 4 (or 2) slices can share every A box by TMA multicast. Measured at 16 x 100 x 88 x 256 -> 4 x 256:
@@ -542,6 +552,10 @@ extern "C" int crb3d_bev_conv_gemm_tf32(const float* in, int B, int H, int W, in
     // relu bit 2 (opt-in, A/B measurements): 2 x 2 clusters for cout = 256 (both channel halves share the activation boxes, two
     // neighbouring tiles share the weight boxes), pairs of tiles for cout = 128. Measured at 16 x 200 x 176 x 128 -> 256, stride 2:
     // 461 us against 247 us without clusters (same reason as the deblock above: ring depth x latency, not L2 bytes, sets the rate)
+    if (cout == 256 && !(relu & 12)) {   // CTA pairs, all 256 channels per activation box (csrc/bev_gemm_pair.cu); relu bit 3 = this file's kernel
+        int rc = crb3d_bev_conv_gemm_pair_tf32(in, B, H, W, cin, w2, ksize, stride, pad, bias, relu, out, stream);
+        if (rc != CRB3D_ERR_UNSUPPORTED) return rc;
+    }
     if (!(relu & 4)) return launch_conv_gemm<128, 5, 1, 1>(in, B, H, W, cin, w2, cout, ksize, stride, pad, bias, relu, out, stream);
     if (cout == 256) return launch_conv_gemm<128, 5, 2, 2>(in, B, H, W, cin, w2, cout, ksize, stride, pad, bias, relu, out, stream);
     return launch_conv_gemm<128, 5, 1, 2>(in, B, H, W, cin, w2, cout, ksize, stride, pad, bias, relu, out, stream);

@@ -10,6 +10,7 @@ extern "C" int crb3d_diag_set_spconv_tc(void*, unsigned int);
 extern "C" int crb3d_diag_set_spconv_grp(void*, unsigned int);
 extern "C" int crb3d_diag_set_bev_conv(void*, unsigned int);
 extern "C" int crb3d_diag_set_bev_gemm(void*, unsigned int);
+extern "C" int crb3d_diag_set_bev_gemm_pair(void*, unsigned int);
 extern "C" int crb3d_diag_set_rulebook(void*, unsigned int);
 extern "C" int crb3d_diag_set_voxelize(void*, unsigned int);
 extern "C" int crb3d_diag_set_fc_gemm(void*, unsigned int);
@@ -58,6 +59,7 @@ extern "C" int crb3d_diag_init(void) {
     if ((rc = crb3d_diag_set_spconv_grp(dptr, (unsigned)d))) return rc;
     if ((rc = crb3d_diag_set_bev_conv(dptr, (unsigned)d))) return rc;
     if ((rc = crb3d_diag_set_bev_gemm(dptr, (unsigned)d))) return rc;
+    if ((rc = crb3d_diag_set_bev_gemm_pair(dptr, (unsigned)d))) return rc;
     if ((rc = crb3d_diag_set_rulebook(dptr, (unsigned)d))) return rc;
     if ((rc = crb3d_diag_set_voxelize(dptr, (unsigned)d))) return rc;
     if ((rc = crb3d_diag_set_fc_gemm(dptr, (unsigned)d))) return rc;

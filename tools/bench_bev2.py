@@ -46,7 +46,7 @@ def case(B, H, W, cin, cout, stride):
         stride, B, H, W, cin, cout, t_dnn, fl / t_dnn / 1e6, t_gemm, fl / t_gemm / 1e6)
     if stride == 1:
         wp = ops.pack_conv3x3_weight(w, split=True)
-        for name, var in (("pair auto", 0), ("pair 1-tile items", 4), ("pair 2-tile items", 8)):
+        for name, var in (("pair auto", 0), ("pair auto, release.cluster arrive", 16), ("pair 1-tile items", 4), ("pair 2-tile items", 8)):
             ops.CONV_VARIANT = var
             t = timeit(lambda: ops.bev_conv3x3(x, wp, b, True))
             res += " | %s %.1f us (%.0f TF/s)" % (name, t, fl / t / 1e6)

@@ -41,6 +41,26 @@ w2 = ops.round_tf32(torch.randn(4 * 256, 256, device=dev, generator=g) / 16)
 b2 = torch.randn(256, device=dev, generator=g)
 cat = torch.zeros(B, 200, 176, 512, device=dev)
 outs = {}
+ops.GEMM_CLUSTERS = False
+for pairs in (True, False):      # CTA pairs (csrc/bev_gemm_pair.cu) against the single-CTA kernel
+    ops.GEMM_PAIRS = pairs
+    cat.zero_()
+    fn = lambda: ops.bev_gemm(x2.view(-1, 256), w2, b2, True, [(cat[..., 256:], 0, 256, 512)], n_sub=4, up=2, in_hw=(100, 88), round_out=True)
+    t = timeit(fn)
+    outs["pairs%d" % pairs] = cat.clone()
+    print("deblock2 B%d pairs=%s: %.1f us (%.0f TFLOP/s)" % (B, pairs, t, 2.0 * B * 100 * 88 * 256 * 1024 / t / 1e6))
+ops.GEMM_PAIRS, ops.GEMM_PAIR_STREAM = True, True
+cat.zero_()
+t = timeit(fn)
+print("deblock2 B%d pairs, streamed weights: %.1f us, equal=%s" % (B, t, torch.equal(cat, outs["pairs1"])))
+ops.GEMM_PAIR_STREAM = False
+d = (outs["pairs1"] - outs["pairs0"]).abs().max().item()
+print("pairs vs single: max abs diff %.3g (max |value| %.3g), equal=%s" % (d, outs["pairs0"].abs().max().item(), torch.equal(outs["pairs1"], outs["pairs0"])))
+ref = torch.relu(torch.nn.functional.conv_transpose2d(x2.permute(0, 3, 1, 2).double(), w2.view(2, 2, 256, 256).permute(3, 2, 0, 1).double(),
+                                                      b2.double(), stride=2)).permute(0, 2, 3, 1)
+err = (outs["pairs1"][..., 256:].double() - ref).pow(2).mean().sqrt().item() / ref.pow(2).mean().sqrt().item()
+print("pairs vs fp64 conv_transpose2d: rel RMS %.3g" % err)
+ops.GEMM_PAIRS = False
 for mode in (True, False):
     ops.GEMM_CLUSTERS = mode
     fn = lambda: ops.bev_gemm(x2.view(-1, 256), w2, b2, True, [(cat[..., 256:], 0, 256, 512)], n_sub=4, up=2, in_hw=(100, 88), round_out=True)
@@ -56,6 +76,12 @@ w = ops.round_tf32(torch.randn(256, 128, 3, 3, device=dev, generator=g) / 30)
 wp = ops.pack_conv_gemm_weight(w)
 bb = torch.randn(256, device=dev, generator=g)
 res = {}
+ops.GEMM_CLUSTERS, ops.GEMM_PAIRS = False, True
+fn = lambda: ops.bev_conv_gemm(x, wp, bb, 3, 2, 1, True, round_out=True)
+t = timeit(fn)
+res["pairs"] = fn()
+print("conv3x3 s2 B%d pairs: %.1f us (%.0f TFLOP/s)" % (B, t, 2.0 * B * 100 * 88 * 9 * 128 * 256 / t / 1e6))
+ops.GEMM_PAIRS = False
 for mode in (True, False):
     ops.GEMM_CLUSTERS = mode
     fn = lambda: ops.bev_conv_gemm(x, wp, bb, 3, 2, 1, True, round_out=True)
@@ -64,3 +90,4 @@ for mode in (True, False):
     flops = 2.0 * B * 100 * 88 * 9 * 128 * 256
     print("conv3x3 s2 B%d clusters=%s: %.1f us (%.0f TFLOP/s)" % (B, mode, t, flops / t / 1e6))
 assert torch.equal(res[True], res[False])
+print("conv pairs vs single: equal=%s, max abs diff %.3g" % (torch.equal(res["pairs"], res[False]), (res["pairs"] - res[False]).abs().max().item()))
