@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(THREADS, 1) bev_conv3x3_tc(const __grid_consta
                                                               const float* __restrict__ bias, int relu, float* __restrict__ out,
                                                               const __grid_constant__ ConvGeom g) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     __shared__ uint64_t full_a[NSTAGE_A], empty_a[NSTAGE_A], full_b[NSTAGE_B], empty_b[NSTAGE_B], acc_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_s[N];
@@ -351,7 +351,7 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
     constexpr int ITEM_A = IT * TILE_A;             // bytes per (item, chunk) and CTA
     extern __shared__ uint8_t smem_raw[];
     // the dynamic window starts at the same offset in both CTAs; descriptors address both CTAs with one offset
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     __shared__ uint64_t full_a[NSA], empty_a[NSA], full_b[NSB], empty_b[NSB], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_s[N];

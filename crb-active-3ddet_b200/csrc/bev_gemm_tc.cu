@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
     using C = Cfg<N>;
     constexpr int STAGE_BYTES = C::A_BYTES + (BRES ? 0 : C::B_BYTES);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2], b_full;
     __shared__ uint32_t tmem_base_s;
     __shared__ long long rowoff_s[8][32];          // ROWS mode: output offset of each staged row, per epilogue warp
@@ -512,7 +512,7 @@ extern "C" int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long
     }
     // slices = (sub-positions) x (column blocks of the per-CTA width); resident weights when N_cta * K * 4 <= 128 KB
     if (rows) {
-        if (N == 256 && K <= 128) return launch_gemm<256, 3, true, false>(A, M, K, lda, W, n_sub, 1, bias, relu, o, stream);
+        if (N == 256 && K <= 128 && !(relu & 32)) return launch_gemm<256, 3, true, false>(A, M, K, lda, W, n_sub, 1, bias, relu, o, stream);
         if (N == 256 && K <= 256 && !(relu & 12)) {
             // CTA pairs: all 256 columns from one pass over the activations (csrc/bev_gemm_pair.cu); relu bit 3 = the single-CTA kernel
             int rc = crb3d_bev_gemm_pair_tf32(A, M, K, lda, W, n_sub, bias, relu, out_ptr[0], row_stride[0], up, in_h, in_w, stream);

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(192, 1) fc_gemm_tc(const __grid_constant__ CUt
                                                      const __grid_constant__ CUtensorMap wmap, int M, int N, int kb_per_split,
                                                      int nkb, float* __restrict__ partial) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

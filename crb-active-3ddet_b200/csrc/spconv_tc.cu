@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     __shared__ int act[MAX_K];
     __shared__ int act_flag[MAX_K];
     __shared__ unsigned int list_v[2][2][TILE_M], list_z[2][2][TILE_M];   // [group][double buffer][entries]: per-stage work lists

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc_grp(const flo
     const int nv = n_dev ? min(n_out, *n_dev) : n_out;
     if ((int)blockIdx.x * TILE_M >= nv) return;     // uniform per CTA, before any barrier / TMEM allocation
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     __shared__ int act[MAX_K];                       // active STAGE ids, ascending
     __shared__ int act_flag[MAX_K + 5];              // per offset: some row of the tile has this neighbour
     __shared__ int list_src[2][NBUF][LIST_CAP];

@@ -70,6 +70,20 @@ for mode in (True, False):
     print("deblock2 B%d clusters=%s: %.1f us (%.0f TFLOP/s, %.2f TB/s algorithmic)" % (B, mode, t, flops / t / 1e6,
                                                                                    (x2.numel() + B * 200 * 176 * 256) * 4 / t / 1e6))
 assert torch.equal(outs[True], outs[False])
+# deblock 1: (B,200,176,128) -> ConvTranspose2d(128, 256, 1, 1) = a plain GEMM into channels [0, 256)
+x1 = torch.randn(B, 200, 176, 128, device=dev, generator=g)
+w1 = ops.round_tf32(torch.randn(256, 128, device=dev, generator=g) / 11)
+ops.GEMM_CLUSTERS, ops.GEMM_PAIRS = False, True
+r1 = {}
+for shortk, stream in ((False, False), (True, False), (True, True)):
+    ops.GEMM_PAIR_SHORTK, ops.GEMM_PAIR_STREAM = shortk, stream
+    cat.zero_()
+    fn = lambda: ops.bev_gemm(x1.view(-1, 128), w1, b2, True, [(cat, 0, 256, 512)], round_out=True)
+    t = timeit(fn)
+    r1[(shortk, stream)] = cat.clone()
+    print("deblock1 B%d pair kernel=%s streamed=%s: %.1f us (%.2f TB/s)" % (B, shortk, stream, t, (x1.numel() + B * 200 * 176 * 256) * 4 / t / 1e6))
+print("deblock1 equal:", torch.equal(r1[(False, False)], r1[(True, False)]), torch.equal(r1[(False, False)], r1[(True, True)]))
+ops.GEMM_PAIR_SHORTK, ops.GEMM_PAIR_STREAM = False, True
 # stride-2 conv: (B,200,176,128) -> (B,100,88,256)
 x = torch.randn(B, 200, 176, 128, device=dev, generator=g)
 w = ops.round_tf32(torch.randn(256, 128, 3, 3, device=dev, generator=g) / 30)
