@@ -102,7 +102,11 @@ __global__ void __launch_bounds__(THREADS, 1) bev_conv3x3_tc(const __grid_consta
     __shared__ __align__(16) float bias_s[N];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef CRB3D_CONV_TRACE   // phase trace (variant bit 1): compiled in on request only - the clock reads sit in the MMA issue loop
     const bool tracing = ((relu >> 8) & 2) && blockIdx.x < 1024;
+#else
+    constexpr bool tracing = false;
+#endif
     long long* tr = g_conv_trace + blockIdx.x * 16;
     if (tracing && tid == 0) { tr[0] = gtime(); uint32_t sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); tr[6] = sm; }
     const int tile0 = blockIdx.x * NT;
@@ -363,7 +367,11 @@ bev_conv3x3_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_const
     const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
     const int n_tiles = g.n_active ? min(max(__ldg(g.n_active), 0), g.n_tiles) : g.n_tiles;    // the same value in both CTAs of the pair
     const int n_items = (n_tiles + 2 * IT - 1) / (2 * IT);
+#ifdef CRB3D_CONV_TRACE
     const bool tracing = ((relu >> 8) & 2) && blockIdx.x < 1024 && blockIdx.y == 0;
+#else
+    constexpr bool tracing = false;
+#endif
     long long* tr = g_conv_trace + blockIdx.x * 16;
     if (tracing && tid == 0) { tr[0] = gtime(); uint32_t sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); tr[6] = sm; }
 

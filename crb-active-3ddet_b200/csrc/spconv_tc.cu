@@ -29,8 +29,15 @@ constexpr int THREADS = (PW + 1) * 32;
 constexpr int MAX_K = 27;
 
 // optional timeline trace of one CTA (clock64 stamps per offset: producer after empty-wait / after issuing its copies,
-// MMA thread after full-wait / after issuing + committing); set through crb3d_debug_set_tc_trace, null in production
+// MMA thread after full-wait / after issuing + committing); set through crb3d_debug_set_tc_trace. The stamps are compiled in only with
+// -DCRB3D_TC_TRACE (tools/trace_spconv.py): even predicated off, four clock reads + stores per stage cost the producers ~4 % of their
+// stall samples (ncu source view)
 __device__ long long* g_tc_trace = nullptr;
+#ifdef CRB3D_TC_TRACE
+#define TC_TRACE(ptr, idx) do { if (ptr) (ptr)[idx] = clock64(); } while (0)
+#else
+#define TC_TRACE(ptr, idx) do { } while (0)
+#endif
 
 using tc::smem_u32;
 using tc::mbar_init;
@@ -174,7 +181,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
         const int o = row0 + r;
         const int cpr = cin >> 2;                         // 16-byte chunks per row (1, 2, 4, 8 or 16)
         const int cshift = 31 - __clz(cpr);
+#ifdef CRB3D_TC_TRACE
         long long* const trace_base = (blockIdx.x == gridDim.x / 2 && gtid == 0) ? g_tc_trace : nullptr;   // read once
+#endif
         uint32_t dirty = 0u;
         int src_next = (grp < n_act && o < nv) ? __ldg(&nbr[(size_t)act[grp] * n_out + o]) : -1;
         for (int it = grp, li = 0; it < n_act; it += NG, ++li) {
@@ -183,8 +192,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
             if (it + NG < n_act) src_next = (o < nv) ? __ldg(&nbr[(size_t)act[it + NG] * n_out + o]) : -1;
             if (gtid == 0) { cnt_v[grp][(li + 2) & 3] = 0; cnt_z[grp][(li + 2) & 3] = 0; }
             if (it >= STAGES) mbar_wait(&empty_bar[stage], ((it / STAGES) - 1) & 1, (CRB3D_K_SPCONV_TC << 8) | 9, it);
+#ifdef CRB3D_TC_TRACE
             long long* trace = (trace_base && it < 32) ? trace_base + 128 : nullptr;
-            if (trace) trace[it * 4 + 0] = clock64();
+#endif
+            TC_TRACE(trace, it * 4 + 0);
             const uint32_t a_base = smem_base + stage * STAGE_BYTES, b_base = a_base + A_BYTES;
             if (gtid == GT - 1) {   // one thread of the group fetches the weight slice: one 3-D TMA box per k-block
                 const int kw = kmap ? kmap[act[it]] : act[it];
@@ -214,13 +225,41 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
                 if (stale) list_z[grp][lb][bz + __popc(mz & lt)] = (unsigned int)r;
             }
             asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GT) : "memory");   // this group's lists are complete
-            if (trace) trace[it * 4 + 2] = clock64();
+            TC_TRACE(trace, it * 4 + 2);
             const int n_v = cnt_v[grp][li & 3] << cshift, n_z = cnt_z[grp][li & 3] << cshift;
-            for (int i = gtid; i < n_v; i += GT) {
-                const unsigned int e = list_v[grp][lb][i >> cshift];
-                const int row = (int)(e >> 25), c16 = i & (cpr - 1);
-                cp_async16(a_base + (row >> 3) * 1024 + (row & 7) * 128 + (c16 >> 3) * (TILE_M * 128) + (((c16 & 7) ^ (row & 7)) << 4),
-                           feat + (size_t)(e & 0x1FFFFFFu) * cin + c16 * 4);
+            if constexpr (NKB == 2) {
+                // 64-channel rows (16 chunks, 4-5 list passes per stage): thread -> (list entry j0 + k * entries-per-pass, its fixed
+                // 16-byte chunk) with four list reads in flight - the loop is a chain of shared-memory load -> address arithmetic ->
+                // LDGSTS whose latency, not its issue rate, is what the stage waits for (conv3.1 137 -> 131 us, conv4.1 83 -> 78;
+                // the narrower layers have 1-2 passes and lose 5-10 % to the extra loop structure, so they keep the plain loop)
+                const int epp = GT >> cshift, c16 = gtid & (cpr - 1);
+                const int n_rows = n_v >> cshift;
+                const uint32_t col = a_base + (c16 >> 3) * (TILE_M * 128), cx = (uint32_t)(c16 & 7);
+                const float* fsrc = feat + c16 * 4;
+                const unsigned int* lst = list_v[grp][lb];
+                int j = gtid >> cshift;
+                for (; j + 3 * epp < n_rows; j += 4 * epp) {
+                    unsigned int e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) e[u] = lst[j + u * epp];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t row = e[u] >> 25;
+                        cp_async16(col + (row >> 3) * 1024 + (row & 7) * 128 + ((cx ^ (row & 7)) << 4), fsrc + (size_t)(e[u] & 0x1FFFFFFu) * cin);
+                    }
+                }
+                for (; j < n_rows; j += epp) {
+                    const unsigned int e = lst[j];
+                    const uint32_t row = e >> 25;
+                    cp_async16(col + (row >> 3) * 1024 + (row & 7) * 128 + ((cx ^ (row & 7)) << 4), fsrc + (size_t)(e & 0x1FFFFFFu) * cin);
+                }
+            } else {
+                for (int i = gtid; i < n_v; i += GT) {
+                    const unsigned int e = list_v[grp][lb][i >> cshift];
+                    const int row = (int)(e >> 25), c16 = i & (cpr - 1);
+                    cp_async16(a_base + (row >> 3) * 1024 + (row & 7) * 128 + (c16 >> 3) * (TILE_M * 128) + (((c16 & 7) ^ (row & 7)) << 4),
+                               feat + (size_t)(e & 0x1FFFFFFu) * cin + c16 * 4);
+                }
             }
             if (n_z > 0) {   // stale rows: plain 16-byte zero stores (the LDGSTS path is the scarce resource) + proxy fence
                 for (int i = gtid; i < n_z; i += GT) {
@@ -229,9 +268,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
-            if (trace) trace[it * 4 + 3] = clock64();
+            TC_TRACE(trace, it * 4 + 3);
             cp_async_arrive(&full_bar[stage]);            // arrives when this thread's copies (if any) have landed
-            if (trace) trace[it * 4 + 1] = clock64();
+            TC_TRACE(trace, it * 4 + 1);
         }
     } else if (warp == PW) {
         // ================================ MMA issuer ================================
@@ -240,12 +279,16 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
         // before each UTCHMMA (~100 issue cycles per MMA, 800 cycles per stage in tools/trace_spconv.py)
         const uint32_t idesc = make_idesc_tf32(TILE_M, COUT);
         const uint64_t desc0 = make_desc_sw128(smem_base);
+#ifdef CRB3D_TC_TRACE
         long long* const trace_mma = (blockIdx.x == gridDim.x / 2 && lane == 0) ? g_tc_trace : nullptr;
+#endif
         for (int it = 0; it < n_act; ++it) {
             const int stage = it % STAGES;
             mbar_wait(&full_bar[stage], (it / STAGES) & 1, (CRB3D_K_SPCONV_TC << 8) | 8, it);
+#ifdef CRB3D_TC_TRACE
             long long* trace = (trace_mma && it < 32) ? trace_mma : nullptr;
-            if (trace) trace[it * 4 + 2] = clock64();
+#endif
+            TC_TRACE(trace, it * 4 + 2);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint64_t da = desc0 + (uint64_t)((stage * STAGE_BYTES) >> 4), db = da + (uint64_t)(A_BYTES >> 4);
@@ -263,7 +306,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
                 if (it == n_act - 1) umma_commit(&acc_bar);       // accumulator complete
             }
             __syncwarp();
-            if (trace) trace[it * 4 + 3] = clock64();
+            TC_TRACE(trace, it * 4 + 3);
         }
     }
 

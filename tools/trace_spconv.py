@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Timeline of one CTA of the tcgen05 sparse-conv kernel (debug hook crb3d_debug_set_tc_trace)."""
+"""Timeline of one CTA of the tcgen05 sparse-conv kernel (debug hook crb3d_debug_set_tc_trace).
+The clock stamps are compiled into csrc/spconv_tc.cu only with -DCRB3D_TC_TRACE (add it to the nvcc flags in __graft_entry__.py)."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "crb-active-3ddet_b200"))
