@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
     __shared__ uint32_t tmem_base_s;
     __shared__ long long rowoff_s[8][32];          // ROWS mode: output offset of each staged row, per epilogue warp
     __shared__ int colbase_s[DENSE ? N : 1], colw_s[DENSE ? N : 1];   // DENSE mode: column -> staging offset / segment width
+    __shared__ __align__(16) float bias_s[N];      // this slice's bias (zeros when absent): no global load in the epilogue's inner loop
 
     constexpr int CS = CSA * CSW;
     static_assert(CS == 1 || (!DENSE && (CSW == 1 || !BRES) && TILE_M / CSA % 8 == 0 && N / CSW % 8 == 0 && 8 % CSA == 0), "cluster geometry");
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
         tma_prefetch_desc(&wmap);
     }
     if (warp == 1) tmem_alloc<2 * C::TMEM_N>(&tmem_base_s);
+    for (int c = tid; c < N; c += blockDim.x) bias_s[c] = bias ? __ldg(&bias[half * N + c]) : 0.0f;
     if (DENSE) {
         for (int c = tid; c < N; c += blockDim.x) {
             int base = 0, cb = -1, w = 0;
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             float x = __uint_as_float(v[j + u]);
-                            if (bias) x += __ldg(&bias[col0 + c0 + j + u]);
+                            x += bias_s[c0 + j + u];
                             if (relu & 1) x = fmaxf(x, 0.0f);
                             if (relu & 2) x = tf32_rn(x);
                             wp[u] = x;
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(320, 1) bev_gemm_tc(const __grid_constant__ CU
                         const int cbse = colbase_s[c];
                         if (cbse < 0) continue;            // padding column
                         float x = __uint_as_float(v[j]);
-                        if (bias) x += __ldg(&bias[col0 + c]);
+                        x += bias_s[c];
                         if (relu & 1) x = fmaxf(x, 0.0f);
                         if (relu & 2) x = tf32_rn(x);
                         stage_q[cbse + lane * colw_s[c]] = x;

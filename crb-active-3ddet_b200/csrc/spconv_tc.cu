@@ -155,8 +155,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
         float4* z = reinterpret_cast<float4*>(smem);
         for (int t = tid; t < STAGES * STAGE_BYTES / 16; t += THREADS) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if constexpr (COUT >= 64)
-        for (int c = tid; c < COUT; c += THREADS) { scale_s[c] = scale ? __ldg(&scale[c]) : 1.0f; shift_s[c] = shift ? __ldg(&shift[c]) : 0.0f; }
+    for (int c = tid; c < COUT; c += THREADS) { scale_s[c] = scale ? __ldg(&scale[c]) : 1.0f; shift_s[c] = shift ? __ldg(&shift[c]) : 0.0f; }
     if (warp < PW) {
 #pragma unroll
         for (int u = 0; u < SCAN; ++u) {
@@ -334,102 +333,49 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc(const float* 
         }
     }
 
-    if constexpr (COUT >= 64) {
-        // ---- epilogue: TMEM -> registers -> global. A warp may only touch TMEM lanes 32*(warp%4)..+31: warps 0-3 take the first half of
-        // the columns, warps 4-7 the second (C_out >= 64); the affine comes from shared memory (two global loads per element stalled
-        // every FMA of the old epilogue). fmaf(x, 1, shift) and fmaf(x, scale, 0) are exact, so absent terms change no bit.
-        constexpr int EP_SPLIT = COUT >= 64 ? 2 : 1, EP_COLS = COUT / EP_SPLIT;
-        if (warp < 4 * EP_SPLIT) {
-            if (n_act > 0) {
-                mbar_wait(&acc_bar, 0, (CRB3D_K_SPCONV_TC << 8) | 7);
-                asm volatile("tcgen05.fence::after_thread_sync;");
-            }
-            const int quarter = warp & 3, cbase = (warp >> 2) * EP_COLS;
-            const int r = quarter * 32 + lane;
-            const int o = row0 + r;
-    #pragma unroll
-            for (int cc = 0; cc < EP_COLS; cc += 32) {
-                const int c0 = cbase + cc;
-                uint32_t v[32];
-                if (n_act > 0) {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + c0;
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;");
-                } else {
-    #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 0u;
-                }
-                if (o < nv) {
-                    float* dst = out + (size_t)o * COUT + c0;
-    #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (c0 + j >= COUT) break;  // C_out = 16: only half of the 32 loaded columns exist
-                        const float4 sc = *reinterpret_cast<const float4*>(scale_s + c0 + j), sh = *reinterpret_cast<const float4*>(shift_s + c0 + j);
-                        float4 w = make_float4(fmaf(__uint_as_float(v[j]), sc.x, sh.x), fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y),
-                                               fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z), fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w));
-                        if (relu & 1) { w.x = fmaxf(w.x, 0.0f); w.y = fmaxf(w.y, 0.0f); w.z = fmaxf(w.z, 0.0f); w.w = fmaxf(w.w, 0.0f); }
-                        if (relu & 2) { w.x = tc::tf32_rn(w.x); w.y = tc::tf32_rn(w.y); w.z = tc::tf32_rn(w.z); w.w = tc::tf32_rn(w.w); }   // the next tensor-core layer reads exactly what was stored
-                        *reinterpret_cast<float4*>(dst + j) = w;
-                    }
-                }
-            }
+    // ---- epilogue: TMEM -> registers -> global. A warp may only touch TMEM lanes 32*(warp%4)..+31: warps 0-3 take the first half of
+    // the columns, warps 4-7 the second (C_out >= 64); the affine comes from shared memory (two global loads per element stalled
+    // every FMA of the old epilogue: sparse backbone 1.23 -> 1.01 ms per batch of 16). fmaf(x, 1, shift) and fmaf(x, scale, 0) are exact, so absent terms change no bit.
+    constexpr int EP_SPLIT = COUT >= 64 ? 2 : 1, EP_COLS = COUT / EP_SPLIT;
+    if (warp < 4 * EP_SPLIT) {
+        if (n_act > 0) {
+            mbar_wait(&acc_bar, 0, (CRB3D_K_SPCONV_TC << 8) | 7);
+            asm volatile("tcgen05.fence::after_thread_sync;");
         }
-    } else {   // narrow outputs: one 32-column pass by warps 0-3 (the wide-output epilogue costs these layers 3-8 %: measured)
-        // ---- epilogue: TMEM -> registers -> global (warps 0..3; a warp may only touch TMEM lanes 32*(warp%4)..+31)
-        if (warp < 4) {
+        const int quarter = warp & 3, cbase = (warp >> 2) * EP_COLS;
+        const int r = quarter * 32 + lane;
+        const int o = row0 + r;
+#pragma unroll
+        for (int cc = 0; cc < EP_COLS; cc += 32) {
+            const int c0 = cbase + cc;
+            uint32_t v[32];
             if (n_act > 0) {
-                mbar_wait(&acc_bar, 0, (CRB3D_K_SPCONV_TC << 8) | 7);
-                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            const int quarter = warp & 3;
-            const int r = quarter * 32 + lane;
-            const int o = row0 + r;
-    #pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += 32) {
-                uint32_t v[32];
-                if (n_act > 0) {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + c0;
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;");
-                } else {
-    #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 0u;
-                }
-                if (o < nv) {
-                    float* dst = out + (size_t)o * COUT + c0;
-    #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (c0 + j >= COUT) break;  // C_out = 16: only half of the 32 loaded columns exist
-                        float4 w;
-                        float* wp = reinterpret_cast<float*>(&w);
-    #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            float x = __uint_as_float(v[j + u]);
-                            const int c = c0 + j + u;
-                            if (scale) x = fmaf(x, __ldg(&scale[c]), shift ? __ldg(&shift[c]) : 0.0f);
-                            else if (shift) x += __ldg(&shift[c]);
-                            if (relu & 1) x = fmaxf(x, 0.0f);
-                            if (relu & 2) x = tc::tf32_rn(x);   // the next tensor-core layer then reads exactly what was stored
-                            wp[u] = x;
-                        }
-                        *reinterpret_cast<float4*>(dst + j) = w;
-                    }
+            if (o < nv) {
+                float* dst = out + (size_t)o * COUT + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (c0 + j >= COUT) break;  // C_out = 16: only half of the 32 loaded columns exist
+                    const float4 sc = *reinterpret_cast<const float4*>(scale_s + c0 + j), sh = *reinterpret_cast<const float4*>(shift_s + c0 + j);
+                    float4 w = make_float4(fmaf(__uint_as_float(v[j]), sc.x, sh.x), fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y),
+                                           fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z), fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w));
+                    if (relu & 1) { w.x = fmaxf(w.x, 0.0f); w.y = fmaxf(w.y, 0.0f); w.z = fmaxf(w.z, 0.0f); w.w = fmaxf(w.w, 0.0f); }
+                    if (relu & 2) { w.x = tc::tf32_rn(w.x); w.y = tc::tf32_rn(w.y); w.z = tc::tf32_rn(w.z); w.w = tc::tf32_rn(w.w); }   // the next tensor-core layer reads exactly what was stored
+                    *reinterpret_cast<float4*>(dst + j) = w;
                 }
             }
         }

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc_grp(const flo
     __shared__ unsigned short list_z[2][NBUF][SPLIT ? 1 : LIST_CAP];
     __shared__ int cnt_v[2][4], cnt_z[2][4];
     __shared__ int n_act_s;
+    __shared__ __align__(16) float scale_s[128], shift_s[128];   // BatchNorm affine of the epilogue (identity where absent)
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
     __shared__ uint32_t tmem_base_s;
 
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc_grp(const flo
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
+    for (int c = threadIdx.x; c < COUT; c += blockDim.x) { scale_s[c] = scale ? __ldg(&scale[c]) : 1.0f; shift_s[c] = shift ? __ldg(&shift[c]) : 0.0f; }
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
@@ -256,18 +258,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) spconv_fwd_tc_grp(const flo
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     if (c0 + j >= COUT) break;
-                    float4 w;
-                    float* wp = reinterpret_cast<float*>(&w);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float x = __uint_as_float(v[j + u]);
-                        const int c = c0 + j + u;
-                        if (scale) x = fmaf(x, __ldg(&scale[c]), shift ? __ldg(&shift[c]) : 0.0f);
-                        else if (shift) x += __ldg(&shift[c]);
-                        if (relu & 1) x = fmaxf(x, 0.0f);
-                        if (relu & 2) x = tf32_rn(x);
-                        wp[u] = x;
-                    }
+                    // affine from shared memory (as in spconv_tc.cu); fmaf(x, 1, shift) and fmaf(x, scale, 0) are exact
+                    const float4 sc = *reinterpret_cast<const float4*>(scale_s + c0 + j), sh = *reinterpret_cast<const float4*>(shift_s + c0 + j);
+                    float4 w = make_float4(fmaf(__uint_as_float(v[j]), sc.x, sh.x), fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y),
+                                           fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z), fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w));
+                    if (relu & 1) { w.x = fmaxf(w.x, 0.0f); w.y = fmaxf(w.y, 0.0f); w.z = fmaxf(w.z, 0.0f); w.w = fmaxf(w.w, 0.0f); }
+                    if (relu & 2) { w.x = tf32_rn(w.x); w.y = tf32_rn(w.y); w.z = tf32_rn(w.z); w.w = tf32_rn(w.w); }
                     *reinterpret_cast<float4*>(dst + j) = w;
                 }
             }
