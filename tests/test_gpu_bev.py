@@ -289,6 +289,36 @@ def test_gemm_cluster_multicast_is_bit_identical(cuda, monkeypatch):
     assert float(res[True][0][..., 256:].abs().max()) > 0
 
 
+def test_bev_gemm_pair_kernel_identical_to_single_cta(cuda, monkeypatch):
+    """The CTA-pair GEMM (csrc/bev_gemm_pair.cu: cta_group::2 M256 x N256 MMAs, weights streamed or resident) gives exactly the
+    single-CTA kernel's results on a ragged deblock (6600 rows = 25.8 tile pairs, 2x2 pixel interleave into a channel slice)
+    and on the stride-2 3x3 conv in CONV mode (19 x 26 outputs: partial tiles in both directions, odd tile count)."""
+    from crb3d import ops
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x2 = torch.randn(3, 50, 44, 256, generator=g).to(cuda)
+    w2 = ops.round_tf32((torch.randn(4 * 256, 256, generator=g) / 16).to(cuda))
+    b2 = torch.randn(256, generator=g).to(cuda)
+    x = torch.randn(3, 37, 52, 64, generator=g).to(cuda)
+    w = ops.round_tf32((torch.randn(256, 64, 3, 3, generator=g) / 24).to(cuda))
+    bc = torch.randn(256, generator=g).to(cuda)
+    monkeypatch.setattr(ops, "GEMM_CLUSTERS", False)
+    res = {}
+    for name, pairs, stream in (("single", False, False), ("pair_resident", True, False), ("pair_streamed", True, True)):
+        monkeypatch.setattr(ops, "GEMM_PAIRS", pairs)
+        monkeypatch.setattr(ops, "GEMM_PAIR_STREAM", stream)
+        cat = torch.zeros(3, 100, 88, 512, device=cuda)
+        ops.bev_gemm(x2.view(-1, 256), w2, b2, True, [(cat[..., 256:], 0, 256, 512)], n_sub=4, up=2, in_hw=(50, 44), round_out=True)
+        conv = ops.bev_conv_gemm(x, ops.pack_conv_gemm_weight(w), bc, 3, 2, 1, True, round_out=True)
+        res[name] = (cat, conv)
+    for name in ("pair_resident", "pair_streamed"):
+        assert torch.equal(res[name][0], res["single"][0]), name
+        assert torch.equal(res[name][1], res["single"][1]), name
+    assert float(res["single"][0][..., :256].abs().max()) == 0.0 and float(res["single"][0][..., 256:].abs().max()) > 0
+    ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bc.double(), stride=2, padding=1)).permute(0, 2, 3, 1)
+    err = float((res["pair_streamed"][1].double() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    assert err < 1e-3, err          # TF32 operands (weights pre-rounded, activations truncated by the tensor core), fp32 accumulate
+
+
 @pytest.mark.parametrize("variant", [4, 8])
 def test_bev_conv3x3_pair_item_sizes(cuda, variant, monkeypatch):
     """Both work-item sizes of the CTA-pair kernel (flag bits 10 / 11 force 1-tile / 2-tile items) on the block-2 shape."""
