@@ -284,6 +284,21 @@ bev_gemm_pair_tc(const __grid_constant__ CUtensorMap amap, const __grid_constant
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
 }
 
+constexpr size_t PAIR_SMEM_BUDGET = 227 * 1024 - 8192;   // dynamic window any configuration may ask for; the kernel's static shared memory
+                                                         // (barriers, row offsets, bias: 4272 B) has to fit beside it in the 227 KB opt-in limit
+
+// The dynamic shared-memory opt-in is per function and per device, and both launchers below launch the same kernel with sizes that
+// depend on K: opt in ONCE per device for the whole budget instead of tracking a high-water mark per launcher.
+int pair_smem_opt_in() {
+    static bool done[CRB3D_MAX_DEVICES] = {};
+    const int dev = crb3d_current_device();
+    if (!done[dev]) {
+        CRB3D_CUDA(cudaFuncSetAttribute(bev_gemm_pair_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM_BUDGET));
+        done[dev] = true;
+    }
+    return CRB3D_OK;
+}
+
 }  // namespace
 
 CRB3D_DIAG_DEFINE_SETTER(bev_gemm_pair)
@@ -309,19 +324,14 @@ int crb3d_bev_gemm_pair_tf32(const float* A, long long M, int K, long long lda, 
         int rc = make_map_f32(&wmap, W, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    const size_t budget = 227 * 1024 - 4096;     // static shared memory (barriers, row offsets) + alignment slack
+    const size_t budget = PAIR_SMEM_BUDGET;
     const int bres = (relu & 16) ? 0 : 1;        // relu bit 4 (A/B runs): weights streamed with the activations instead of resident
     const size_t stage_bytes = bres ? A_BYTES : A_BYTES + B_BYTES, fixed = 1024 + STAGING + (bres ? (size_t)nkb * B_BYTES : 0);
     int stages = (int)((budget - fixed) / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return CRB3D_ERR_UNSUPPORTED;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
-    static size_t smem_set[CRB3D_MAX_DEVICES] = {};   // the attribute is per function per device
-    const int dev = crb3d_current_device();
-    if (smem > smem_set[dev]) {
-        CRB3D_CUDA(cudaFuncSetAttribute(bev_gemm_pair_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[dev] = smem;
-    }
+    { int rc = pair_smem_opt_in(); if (rc) return rc; }
     const int n_pairs = (int)crb3d_divup(M, 2 * TILE_M);
     int cps = crb3d_num_sms() / 2 / n_sub;      // clusters per sub-position
     if (cps < 1) cps = 1;
@@ -364,16 +374,11 @@ int crb3d_bev_conv_gemm_pair_tf32(const float* in, int B, int H, int W, int cin,
         int rc = make_map_f32(&wmap, w2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    const size_t budget = 227 * 1024 - 4096, stage_bytes = A_BYTES + B_BYTES, fixed = 1024 + STAGING;
+    const size_t budget = PAIR_SMEM_BUDGET, stage_bytes = A_BYTES + B_BYTES, fixed = 1024 + STAGING;
     int stages = (int)((budget - fixed) / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
-    static size_t smem_set[CRB3D_MAX_DEVICES] = {};
-    const int dev = crb3d_current_device();
-    if (smem > smem_set[dev]) {
-        CRB3D_CUDA(cudaFuncSetAttribute(bev_gemm_pair_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[dev] = smem;
-    }
+    { int rc = pair_smem_opt_in(); if (rc) return rc; }
     const int n_tiles = B * cv.tiles_x * cv.tiles_y, n_pairs = (n_tiles + 1) / 2;
     int cps = crb3d_num_sms() / 2;
     if (cps < 1) cps = 1;
