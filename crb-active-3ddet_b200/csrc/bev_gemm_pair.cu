@@ -1,15 +1,18 @@
 // CTA-pair variant of the BEV GEMM (csrc/bev_gemm_tc.cu) for the long-K deblock: ConvTranspose2d(256 -> 256, k = s = 2) + BN + ReLU
 // of pcdet/models/backbones_2d/base_bev_backbone.py:60-78 as four GEMMs D[m, n] = sum_k A[m, k] W[sub][n, k] whose rows land on the
-// interleaved output pixels (2y+dy, 2x+dx) of the channel slice of the concatenated map.
+// interleaved output pixels (2y+dy, 2x+dx) of the channel slice of the concatenated map -
+// and, in CONV mode, for the stride-2 3x3 conv that opens BEV block 2 (base_bev_backbone.py:33-40) as an implicit GEMM.
 //
 // Why a second kernel: with K = 256 the single-CTA kernel keeps a 128-column weight block resident (128 KB), which leaves room for
 // 3 activation stages - the ring, not L2 bytes or the tensor pipe, sets its rate (274 us at 16 x 100 x 88, 270 TFLOP/s) - and it
 // reads every activation tile once per 128-column block (8 times). Here two CTAs of a cluster issue ONE M256 x N256 x K8
-// tcgen05.mma.cta_group::2: each CTA holds its own 128 rows of A and HALF of the sub-position's weight rows (128 of 256, still
-// 128 KB resident), so all 256 output columns come from one pass over the activations (4 passes instead of 8) with the same
-// ring depth; a 16-column epilogue staging buys a fourth stage.
-//   warp 0 (both CTAs) : TMA producer - resident weight half once, then one 128 x 32 box of A per k-block (.cta_group::2 loads
-//                        complete on the LEADER's barriers)
+// tcgen05.mma.cta_group::2: each CTA holds its own 128 rows of A and HALF of the sub-position's weight rows (128 of 256), so all
+// 256 output columns come from one pass over the activations (4 passes instead of 8). The weight half either stays resident
+// (128 KB, 4 activation stages of 16 KB: 184 us) or - the default - streams with the activations through 6 stages of 32 KB
+// (169 us: twice the L2 -> SM bytes, but 1.5x the latency cover, and the ring is what bounds the kernel). A 16-column epilogue
+// staging (20 KB instead of 36) pays for the extra stage.
+//   warp 0 (both CTAs) : TMA producer - per k-block one 128 x 32 box of A (2-D, or the 4-D strided box of a conv tap) and this CTA's
+//                        half of the weight k-block (.cta_group::2 loads complete on the LEADER's barriers)
 //   warp 1 (leader)    : MMA issuer, two TMEM accumulators of 256 columns; commits are multicast to both CTAs
 //   warps 2-9 (both)   : epilogue of the other accumulator (tcgen05.ld, bias / ReLU / TF32 rounding, rows staged in shared memory,
 //                        64-byte row pieces out); they hand the accumulator back on the leader's barrier
