@@ -383,7 +383,7 @@ def bev_gemm(a, weight, bias, relu, segs, n_sub=1, up=0, in_hw=(0, 0), round_out
     wd = (ctypes.c_int * 3)(*[int(s[2]) for s in segs], *([0] * (3 - len(segs))))
     rs = (ctypes.c_longlong * 3)(*[int(s[3]) for s in segs], *([0] * (3 - len(segs))))
     _lib.call("crb3d_bev_gemm_tf32", _p(a), M, K, a.stride(0), _p(weight), N, n_sub, _p(_f32c(bias)) if bias is not None else None,
-              int(bool(relu)) | (2 if round_out else 0) | (4 if GEMM_CLUSTERS else 0) | (0 if GEMM_PAIRS else 8) | (16 if GEMM_PAIR_STREAM else 0) | (32 if GEMM_PAIR_SHORTK else 0), len(segs), ptrs, cb, wd, rs, int(up), int(in_hw[0]), int(in_hw[1]),
+              int(bool(relu)) | (2 if round_out else 0) | (4 if GEMM_CLUSTERS else 0) | (0 if GEMM_PAIRS else 8) | (0 if GEMM_PAIR_STREAM else 16) | (32 if GEMM_PAIR_SHORTK else 0), len(segs), ptrs, cb, wd, rs, int(up), int(in_hw[0]), int(in_hw[1]),
               _stream(a.device))
 
 

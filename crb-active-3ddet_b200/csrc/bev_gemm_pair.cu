@@ -328,7 +328,7 @@ int crb3d_bev_gemm_pair_tf32(const float* A, long long M, int K, long long lda, 
         if (rc) return rc;
     }
     const size_t budget = PAIR_SMEM_BUDGET;
-    const int bres = (relu & 16) ? 0 : 1;        // relu bit 4 (A/B runs): weights streamed with the activations instead of resident
+    const int bres = (relu & 16) ? 1 : 0;        // relu bit 4 (A/B runs): weights resident instead of streamed with the activations
     const size_t stage_bytes = bres ? A_BYTES : A_BYTES + B_BYTES, fixed = 1024 + STAGING + (bres ? (size_t)nkb * B_BYTES : 0);
     int stages = (int)((budget - fixed) / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;

@@ -196,7 +196,11 @@ int crb3d_three_interpolate_grad_stack(int N, int C, const float* grad_out, cons
  *      Column segment s = [col_begin[s], +width[s]) is written to out_ptr[s] + row * row_stride[s] (1 <= n_seg <= 3).
  *      up = 0: n_sub = 1, output row = GEMM row. up = 2: n_sub = 4 (dy,dx) slices of a kernel=stride=2 transposed
  *      conv; GEMM row (b,y,x) of an in_h x in_w map lands on output pixel (b, 2y+dy, 2x+dx).
- *      Supported: K % 32 == 0, N in {80, 128, 256}, lda % 4 == 0. */
+ *      Supported: K % 32 == 0, N in {80, 128, 256}, lda % 4 == 0.
+ *      relu: bit 0 = ReLU, bit 1 = round the stored values to TF32 (a following tensor-core layer then reads them exactly).
+ *      Bits 2-5 select kernel variants for A/B measurements and never change a result bit: 2 = thread-block clusters with TMA
+ *      multicast, 3 = the single-CTA kernel where the CTA-pair kernel (N = 256, 128 < K <= 256) would run, 4 = the pair kernel with
+ *      resident instead of streamed weights, 5 = the pair kernel for K <= 128 too. */
 int crb3d_bev_gemm_tf32(const float* A, long long M, int K, long long lda, const float* W, int N, int n_sub,
                         const float* bias, int relu, int n_seg, float* const* out_ptr, const int* col_begin,
                         const int* width, const long long* row_stride, int up, int in_h, int in_w, cudaStream_t stream);
