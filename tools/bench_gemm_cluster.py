@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""A/B timing of the cluster-multicast variants of the long-K BEV GEMMs (csrc/bev_gemm_tc.cu) at the bench shapes.
+"""A/B timing of the BEV GEMM variants at the bench shapes: the CTA-pair kernel (csrc/bev_gemm_pair.cu, streamed / resident weights)
+against the single-CTA kernel and its opt-in cluster-multicast variants (csrc/bev_gemm_tc.cu) on deblock 2, deblock 1 and the
+stride-2 3x3 conv; every variant is checked bit for bit against the single-CTA kernel.
   python tools/bench_gemm_cluster.py [--batch 16]"""
 import argparse
 import os
